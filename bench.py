@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- PCM samples/sec encoded by the B200 frame-encode path (BASELINE.json metric).
+
+A "step" is one pass of the hot path (ingest -> analysis -> Rice search -> bit packing -> CRC) over one
+batch: BASELINE config 2, one hour of 44.1 kHz / 16-bit stereo (38 760 frames of 4096), default encoder
+config, synthetic noisy-sine PCM (flacenc_rs_b200.sigen.noisy_sine_pcm).
+
+  value : inter-channel samples/s, whole job, inputs and outputs resident in HBM (fb200_encode_device),
+          timed with CUDA events on the library's stream, max over ranks.
+  e2e   : same metric through fb200_encode_interleaved with pinned HOST buffers, H2D and D2H inside the
+          timed region.
+  roofline     : dominant kernel of the step vs the measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline : the C oracle (a port of the reference's scalar path) on the host cores, bounded sample.
+
+`--impl reference` times that CPU port with all host threads instead (the reference itself is a Rust
+crate and cannot be built in this image).  N > 1: one process per GPU (torchrun), every rank encodes its
+own one-hour stream (frames are independent; no collective on the data path), weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHANNELS, BPS, RATE, BLOCK = 2, 16, 44100, 4096
+SECONDS = 3600
+N_SAMPLES = SECONDS * RATE  # 158 760 000 per channel -> 38 760 frames (tail 3136)
+WORKLOAD = "C2: 1 h 44.1 kHz 16-bit stereo, default config::Encoder, block 4096 (38760 frames)"
+
+
+def make_pcm(rank: int, n: int) -> np.ndarray:
+    """Synthetic noisy sine; generated in chunks of 10 s and tiled with per-minute seeds to keep start-up short."""
+    from flacenc_rs_b200 import sigen
+    return sigen.noisy_sine_pcm(n, CHANNELS, BPS, RATE, config_id=2 + 16 * rank)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for name, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(pcm: np.ndarray, threads: int, target_seconds: float):
+    """Times the oracle (port of the reference's CPU path, par.rs-style frame workers) on a bounded sample."""
+    from oracle import oracle as O
+    cfg = O.default_config()
+    probe_frames = max(threads * 8, 64)
+    probe = pcm[: probe_frames * BLOCK]
+    t0 = time.perf_counter()
+    O.encode_frames(cfg, probe, CHANNELS, BPS, RATE, BLOCK, nthreads=threads)
+    dt = time.perf_counter() - t0
+    rate = len(probe) / dt
+    frames = int(min(len(pcm) // BLOCK, max(probe_frames, rate * target_seconds / BLOCK)))
+    sample = pcm[: frames * BLOCK]
+    t0 = time.perf_counter()
+    data, sizes = O.encode_frames(cfg, sample, CHANNELS, BPS, RATE, BLOCK, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return len(sample) / dt, frames, dt, len(data)
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = min(N_SAMPLES, 120 * RATE)  # the bounded sample is drawn from the first two minutes of the workload
+    pcm = make_pcm(0, n)
+    vals = []
+    frames = secs = 0
+    for i in range(args.warmup + args.steps):
+        v, frames, secs, _ = cpu_port_throughput(pcm, threads, target_seconds=max(2.0, 20.0 / max(1, args.steps)))
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    sample = f"{frames} frames ({frames * BLOCK / RATE:.1f} s of audio) of the C2 signal per step, {secs:.2f} s CPU wall"
+    line = {
+        "impl": "reference", "metric": "PCM inter-channel samples/sec encoded", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * frames * BLOCK / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample,
+                   "note": "CPU port (C oracle) of the reference's scalar path with par.rs-style frame workers; "
+                           "the Rust reference cannot be built in this image"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seconds", type=int, default=SECONDS, help="audio seconds per rank (default: the 1 h workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from flacenc_rs_b200.config import Encoder
+    from flacenc_rs_b200.encoder import Context, pack_samples
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; flacenc_rs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.seconds * RATE
+    n_frames = (n + BLOCK - 1) // BLOCK
+    pcm_i32 = make_pcm(rank, n)
+    packed = pack_samples(pcm_i32, 2)  # packed LE16 interleaved: what Fill::fill_le_bytes receives
+    in_bytes = packed.nbytes
+
+    ctx = Context(Encoder().into_verified(), CHANNELS, BPS, RATE, BLOCK, device=local_rank)
+    cap = n_frames * ctx.max_frame_bytes()
+    # device-resident buffers (value) and pinned host buffers (e2e)
+    d_in = torch.from_numpy(packed).cuda()
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_in_t = torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True)
+    h_in = h_in_t.numpy()
+    h_in[:] = packed
+    h_out_t = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    h_out = h_out_t.numpy()
+    sizes = np.zeros(n_frames, np.uint32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        olen, _ = ctx.encode_device(d_in.data_ptr(), 2, n, d_out.data_ptr(), cap, 0, sizes)
+        return olen, ctx.timing()
+
+    def step_host():
+        got, _, _ = ctx.encode_interleaved(h_in, 2, n, 0, out=h_out)
+        return len(got), ctx.timing()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        out_len, _ = step_device()
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+
+    # ---- timed: device-resident (value).  Inputs (635 MB) and the planar working set (2.5 GB) are far larger
+    # than the 126 MB L2, so every step streams from HBM.
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, kern = 0.0, {"ingest": 0.0, "analyze": 0.0, "rice": 0.0, "pack": 0.0, "gather": 0.0}
+    launches = 0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_len, t = step_device()
+        dev_ms += t.total_ms
+        kern["ingest"] += t.k_ingest_ms
+        kern["analyze"] += t.k_analyze_ms
+        kern["rice"] += t.k_rice_ms
+        kern["pack"] += t.k_pack_ms
+        kern["gather"] += t.k_gather_ms
+        launches += t.launches
+    barrier()
+    wall_dev = time.perf_counter() - w0
+    clocks = sampler.stop()
+
+    # ---- timed: end to end with host buffers (e2e)
+    barrier()
+    e2e_ms = 0.0
+    h2d_ms = d2h_ms = 0.0
+    for _ in range(args.steps):
+        out_len_h, t = step_host()
+        e2e_ms += t.total_ms
+        h2d_ms += t.h2d_ms
+        d2h_ms += t.d2h_ms
+    barrier()
+    assert out_len_h == out_len
+
+    # max over ranks of the device time; aggregate = all ranks' samples / that time
+    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = times.tolist()
+    total_samples = float(n) * world * args.steps
+    value = total_samples / (dev_ms_max / 1000.0)
+    e2e_value = total_samples / (e2e_ms_max / 1000.0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        dom = max(kern, key=kern.get)
+        alg_bytes = float(in_bytes + out_len)  # algorithmic bytes of one step: packed PCM in + frame bytes out
+        dom_s = kern[dom] / args.steps / 1000.0
+        achieved = alg_bytes / dom_s / 1e9
+        whole = alg_bytes / (dev_ms / args.steps / 1000.0) / 1e9
+        line = {
+            "metric": "PCM inter-channel samples/sec encoded", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.seconds == SECONDS else f"{args.seconds} s slice of " + WORKLOAD,
+                       "pcm_samples_per_s": value * CHANNELS, "frames_per_step": n_frames,
+                       "stream_size_ratio": out_len / in_bytes,
+                       "l2": "inputs (635 MB/step) and working set exceed the 126 MB L2; no flush needed",
+                       "timing": "CUDA events on the library stream (fb200_last_timing), max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(in_bytes),
+                    "d2h_bytes_per_step": int(out_len + 4 * n_frames + 16),
+                    "h2d_ms_per_step": h2d_ms / args.steps, "d2h_ms_per_step": d2h_ms / args.steps,
+                    "ms_per_step": e2e_ms_max / args.steps, "api": "fb200_encode_interleaved, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": dom, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_step": alg_bytes,
+                         "whole_step_achieved_gbs": whole, "whole_step_frac": whole / peak,
+                         "note": "compute/issue-bound path (~700 integer/FP ops per inter-channel sample): the HBM "
+                                 "fraction is low by construction, see DESIGN.md"},
+            "clocks": clocks,
+            "wall_s_device_loop": wall_dev,
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, frames, secs, _ = cpu_port_throughput(pcm_i32[: min(n, 120 * RATE)], threads, target_seconds=15.0)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": f"{frames} frames ({frames * BLOCK / RATE:.1f} s of audio) of the same "
+                                              f"signal, {secs:.2f} s wall, C oracle with {threads} frame workers"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,289 @@
+// fb_common.h -- shared definitions of the B200 FLAC frame-encode pipeline.
+//
+// This header is compiled two ways:
+//   * by nvcc for sm_100a (the product: libflacenc_b200.so), and
+//   * by g++ with FB_EMULATE defined (tests/emu): the same kernel bodies are run on the CPU
+//     by executing each barrier-delimited phase for tid = 0..T-1 in turn.  That build exists
+//     only so kernel logic can be checked against the oracle on machines without a GPU; it is
+//     never linked into the product library and is not a fallback.
+//
+// Reference citations are relative to /root/reference/.
+#pragma once
+
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/flacenc_b200.h"
+
+#if defined(__CUDACC__) && !defined(FB_EMULATE)
+#define FB_GPU 1
+#define FB_HD __host__ __device__ __forceinline__
+#define FB_DEV __device__ __forceinline__
+#else
+#define FB_GPU 0
+#define FB_HD inline
+#define FB_DEV inline
+#include <math.h>
+struct int4 { int32_t x, y, z, w; };
+struct float4 { float x, y, z, w; };
+#endif
+
+// ---- phase macros: a "phase" is a region between two CTA barriers --------------------------
+#if FB_GPU
+#define FB_PHASE(tid, T) { const int tid = (int)threadIdx.x; (void)tid;
+#define FB_PHASE_END } __syncthreads();
+#else
+#define FB_PHASE(tid, T) for (int tid = 0; tid < (T); ++tid) {
+#define FB_PHASE_END }
+#endif
+
+#define FB_RICE_SAT ((1u << 27) - 1u)   // src/rice.rs:51
+#define FB_MIN_PRED_BLOCK 64            // src/constant.rs:51 MIN_BLOCK_SIZE_FOR_PREDICTION
+#define FB_MAX_ENT_PARTS 64             // src/constant.rs:63
+
+// ---- atomics (plain ops under emulation: phases run one thread at a time) -------------------
+#if FB_GPU
+FB_DEV void fb_atomic_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+FB_DEV void fb_atomic_max_u32(uint32_t *p, uint32_t v) { atomicMax(p, v); }
+FB_DEV void fb_atomic_min_u32(uint32_t *p, uint32_t v) { atomicMin(p, v); }
+FB_DEV void fb_atomic_add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+#else
+FB_DEV void fb_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
+FB_DEV void fb_atomic_max_u32(uint32_t *p, uint32_t v) { if (v > *p) *p = v; }
+FB_DEV void fb_atomic_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
+FB_DEV void fb_atomic_add_u64(unsigned long long *p, unsigned long long v) { *p += v; }
+#endif
+
+// ---- job description passed by value to every kernel ----------------------------------------
+struct FbJob {
+    fb200_config cfg;
+    int32_t channels;
+    int32_t bps;             // stream bits per sample
+    int32_t sample_rate;
+    int32_t block_size;
+    int32_t nvar;            // channel variants per frame: 4 (L,R,M,S) for stereo, else channels
+    int32_t stride;          // planar stride in samples (block_size rounded up to 32)
+    int32_t container_bytes; // 2, 3 (packed LE) or 4 (int32)
+    int32_t tail_n;          // size of the last frame of the batch (== block_size when full)
+    uint32_t n_frames;
+    uint32_t first_frame_number;
+    uint64_t n_samples;      // per channel
+    uint32_t slot_bytes;     // stride of the per-frame output slots (multiple of 16)
+    int32_t  pack_in_smem;   // 1: frames are assembled in shared memory, 0: in their global slot
+};
+
+// Output of the analysis kernel (K1), one per channel variant.
+struct FbAnalysis {
+    int32_t  is_constant;
+    int32_t  fixed_order;        // ApproxEnt winner, -1 = None
+    int32_t  qlp_order;
+    int32_t  qlp_shift;
+    uint64_t fixed_est[5];
+    int16_t  qlp[32];
+};
+
+FB_HD int fb_frame_len(const FbJob &J, uint32_t frame) {
+    return (frame + 1 == J.n_frames) ? J.tail_n : J.block_size;
+}
+
+// bits per sample of a variant (ChannelAssignment::bits_per_sample_offset, src/component/datatype.rs:1145-1171)
+FB_HD int fb_variant_bps(const FbJob &J, int v) { return J.bps + ((J.channels == 2 && v == 3) ? 1 : 0); }
+
+// src/rice.rs:169-171 encode_signbit: (|v| << 1) - (v < 0)
+FB_HD uint32_t fb_zigzag(int32_t v) { return ((uint32_t)v << 1) ^ (uint32_t)(v >> 31); }
+
+// src/rice.rs:157-165 finest_partition_order(size, max(64, warmup)); warmup <= 24 so min part is 64
+FB_HD int fb_finest_partition_order(int n) {
+    uint32_t max_splits = (uint32_t)(n / 64);
+    if (max_splits == 0) return 0;
+    int lg = 0;
+    while ((max_splits >> (lg + 1)) != 0) lg++;
+    int tz = 0;
+    while (((n >> tz) & 1) == 0 && tz < 31) tz++;
+    int r = lg < tz ? lg : tz;
+    return r < 15 ? r : 15;
+}
+
+// ---- glibc-compatible log2f ------------------------------------------------------------------
+// The reference's estimate_entropy (src/coding.rs:200-227) calls f32::log2, i.e. the platform libm
+// (glibc on Linux).  CUDA's log2f rounds differently in the last place, which can flip an order
+// decision, so the device evaluates the published table-driven algorithm glibc >= 2.27 uses
+// (ARM optimized-routines log2f: 16-entry table, degree-4 polynomial in double).
+// tests/test_log2f_compat.py checks this function against the host libm for all 2^31 positive floats.
+FB_HD uint32_t fb_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+FB_HD float fb_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+#if FB_GPU
+__device__ __constant__ double FB_LOG2F_TAB[32] = {
+#else
+static const double FB_LOG2F_TAB[32] = {
+#endif
+    0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2, 0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2,
+    0x1.49539f0f010bp+0,  -0x1.7418b0a1fb77bp-2, 0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2,
+    0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2, 0x1.25e227b0b8eap+0,  -0x1.97c1d1b3b7afp-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3, 0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4,
+    0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5, 0x1p+0,               0x0p+0,
+    0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4,  0x1.ca4b31f026aap-1,  0x1.476a9543891bap-3,
+    0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3,  0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2,
+    0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2,  0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2};
+
+#if FB_GPU
+#define FB_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define FB_FMAF(a, b, c) __fmaf_rn((a), (b), (c))
+#define FB_DMUL(a, b) __dmul_rn((a), (b))
+#define FB_DADD(a, b) __dadd_rn((a), (b))
+#define FB_FMUL(a, b) __fmul_rn((a), (b))
+#define FB_FADD(a, b) __fadd_rn((a), (b))
+#define FB_FDIV(a, b) __fdiv_rn((a), (b))
+#define FB_DDIV(a, b) __ddiv_rn((a), (b))
+#else
+#define FB_FMA(a, b, c) fma((a), (b), (c))
+#define FB_FMAF(a, b, c) fmaf((a), (b), (c))
+#define FB_DMUL(a, b) ((a) * (b))
+#define FB_DADD(a, b) ((a) + (b))
+#define FB_FMUL(a, b) ((a) * (b))
+#define FB_FADD(a, b) ((a) + (b))
+#define FB_FDIV(a, b) ((a) / (b))
+#define FB_DDIV(a, b) ((a) / (b))
+#endif
+
+FB_DEV float fb_log2f(float x) {
+    uint32_t ix = fb_f2u(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2 == 0) return fb_u2f(0xff800000u);           // -inf
+        if (ix == 0x7f800000u) return x;                        // +inf
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return fb_u2f(0x7fc00000u); // NaN
+        ix = fb_f2u(FB_FMUL(x, 8388608.0f));                    // subnormal: scale by 2^23
+        ix -= 23u << 23;
+    }
+    uint32_t tmp = ix - 0x3f330000u;
+    int i = (int)((tmp >> 19) & 15u);
+    uint32_t top = tmp & 0xff800000u;
+    uint32_t iz = ix - top;
+    int k = (int32_t)tmp >> 23;
+    double invc = FB_LOG2F_TAB[2 * i], logc = FB_LOG2F_TAB[2 * i + 1];
+    double z = (double)fb_u2f(iz);
+    double r = FB_DADD(FB_DMUL(z, invc), -1.0);
+    double y0 = FB_DADD(logc, (double)k);
+    double r2 = FB_DMUL(r, r);
+    double y = FB_DADD(FB_DMUL(0x1.ecabf496832ep-2, r), -0x1.715479ffae3dep-1);
+    y = FB_DADD(FB_DMUL(-0x1.712b6f70a7e4dp-2, r2), y);
+    double p = FB_DADD(FB_DMUL(0x1.715475f35c8b8p0, r), y0);
+    y = FB_DADD(FB_DMUL(y, r2), p);
+    return (float)y;
+}
+
+// Rust `f32 as usize`: saturating, NaN -> 0 (src/coding.rs:222)
+FB_HD uint64_t fb_f32_as_u64(float v) {
+    if (!(v == v)) return 0;
+    if (v <= 0.0f) return 0;
+    if (v >= 18446744073709551616.0f) return 0xFFFFFFFFFFFFFFFFull;
+    return (uint64_t)v;
+}
+
+// One partition of estimate_entropy (src/coding.rs:216-222); `sum` is the sequential f32 sum of |e|.
+FB_DEV uint64_t fb_entropy_partition_bits(float sum, int sample_count) {
+    float cnt = (float)sample_count;
+    float avg = FB_FDIV(FB_FMUL(sum, 2.0f), FB_FADD(cnt, 0.00001f));
+    float geom_p = FB_FDIV(1.0f, FB_FADD(avg, 1.0f));
+    float xent = FB_FMAF(avg, -fb_log2f(FB_FADD(1.0f, -geom_p)), -fb_log2f(geom_p));
+    return fb_f32_as_u64(FB_FMUL(xent, cnt));
+}
+
+// ---- frame header (src/component/bitrepr.rs:359-420, src/component/datatype.rs:1239-1249,
+//      1350-1360, 1427-1453) ---------------------------------------------------------------
+FB_HD int fb_block_size_tag(int size, int *extra_bits, uint32_t *extra) {
+    *extra_bits = 0; *extra = 0;
+    if (size == 192) return 1;
+    if (size == 576) return 2;
+    if (size == 1152) return 3;
+    if (size == 2304) return 4;
+    if (size == 4608) return 5;
+    for (int k = 0; k <= 7; k++) if (size == (256 << k)) return 8 + k;
+    if (size <= 256) { *extra_bits = 8; *extra = (uint32_t)(size - 1); return 6; }
+    *extra_bits = 16; *extra = (uint32_t)(size - 1); return 7;
+}
+
+FB_HD int fb_sample_size_tag(int bits) {
+    switch (bits) {
+    case 8: return 1; case 12: return 2; case 16: return 4; case 20: return 5; case 24: return 6; case 32: return 7;
+    default: return 0;
+    }
+}
+
+FB_HD int fb_sample_rate_tag(uint32_t f, int *extra_bits, uint32_t *extra) {
+    *extra_bits = 0; *extra = 0;
+    switch (f) {
+    case 88200: return 1; case 176400: return 2; case 192000: return 3; case 8000: return 4;
+    case 16000: return 5; case 22050: return 6; case 24000: return 7; case 32000: return 8;
+    case 44100: return 9; case 48000: return 10; case 96000: return 11; default: break;
+    }
+    if (f % 1000 == 0 && f / 1000 <= 255) { *extra_bits = 8; *extra = f / 1000; return 12; }
+    if (f % 10 == 0 && f / 10 <= 65535) { *extra_bits = 16; *extra = f / 10; return 14; }
+    if (f <= 65535) { *extra_bits = 16; *extra = f; return 13; }
+    return 0;
+}
+
+// CRC-8/SMBUS: poly 0x07, init 0 (src/component/bitrepr.rs:39,356-357)
+FB_HD uint8_t fb_crc8(const uint8_t *d, int len) {
+    uint32_t crc = 0;
+    for (int i = 0; i < len; i++) {
+        crc ^= d[i];
+        for (int b = 0; b < 8; b++) crc = (crc & 0x80) ? (((crc << 1) ^ 0x07) & 0xFF) : ((crc << 1) & 0xFF);
+    }
+    return (uint8_t)crc;
+}
+
+// Fixed-blocking frame header incl. CRC-8; returns the number of bytes (<= 16).
+FB_HD int fb_frame_header(int n, int ch_tag, int bps, int sample_rate, uint32_t frame_number, uint8_t *out) {
+    int bs_bits, sr_bits;
+    uint32_t bs_extra, sr_extra;
+    int bs_tag = fb_block_size_tag(n, &bs_bits, &bs_extra);
+    int sr_tag = fb_sample_rate_tag((uint32_t)sample_rate, &sr_bits, &sr_extra);
+    int k = 0;
+    out[k++] = 0xFF;
+    out[k++] = 0xF8; // fixed blocking (FrameOffset::Frame, src/coding.rs:603-604)
+    out[k++] = (uint8_t)((bs_tag << 4) | sr_tag);
+    out[k++] = (uint8_t)((ch_tag << 4) | (fb_sample_size_tag(bps) << 1));
+    // encode_to_utf8like(frame_number) (src/component/bitrepr.rs:121-159); frame_number < 2^31
+    uint32_t v = frame_number;
+    int code_bits = 0;
+    while (code_bits < 32 && (v >> code_bits) != 0) code_bits++;
+    if (code_bits <= 7) {
+        out[k++] = (uint8_t)v;
+    } else {
+        int trailing = (code_bits - 2) / 5;
+        const uint8_t heads[7] = {0x80, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
+        out[k++] = (trailing == 6) ? 0xFE : (uint8_t)(heads[trailing] | (uint8_t)(v >> (6 * trailing)));
+        for (int i = trailing - 1; i >= 0; i--) out[k++] = (uint8_t)(0x80 | ((v >> (6 * i)) & 0x3F));
+    }
+    if (bs_bits == 8) out[k++] = (uint8_t)bs_extra;
+    if (bs_bits == 16) { out[k++] = (uint8_t)(bs_extra >> 8); out[k++] = (uint8_t)bs_extra; }
+    if (sr_bits == 8) out[k++] = (uint8_t)sr_extra;
+    if (sr_bits == 16) { out[k++] = (uint8_t)(sr_extra >> 8); out[k++] = (uint8_t)sr_extra; }
+    out[k] = fb_crc8(out, k);
+    return k + 1;
+}
+
+// Upper bound of a frame in bytes: header (16) + per channel a verbatim subframe at bps+1 + CRC-16.
+FB_HD uint32_t fb_max_frame_bytes(int channels, int bps, int block_size) {
+    uint64_t bits = 16 * 8 + (uint64_t)channels * (8 + (uint64_t)block_size * (uint64_t)(bps + 1)) + 7 + 16;
+    return (uint32_t)(bits >> 3) + 8;
+}
+
+// GF(2) helpers for the CRC-16 (poly 0x8005, init 0; src/component/bitrepr.rs:40,270-271)
+FB_HD uint32_t fb_crc16_mulmod(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 15; i >= 0; i--) {
+        r = (r & 0x8000u) ? (((r << 1) ^ 0x8005u) & 0xFFFFu) : ((r << 1) & 0xFFFFu);
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+
+FB_HD uint32_t fb_crc16_table_entry(uint32_t i) {
+    uint32_t c = i << 8;
+    for (int b = 0; b < 8; b++) c = (c & 0x8000u) ? (((c << 1) ^ 0x8005u) & 0xFFFFu) : ((c << 1) & 0xFFFFu);
+    return c;
+}

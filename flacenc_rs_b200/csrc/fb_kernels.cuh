@@ -1,0 +1,1197 @@
+// fb_kernels.cuh -- kernel bodies of the B200 FLAC frame-encode pipeline.
+//
+//   K0 ingest   : interleaved packed PCM -> planar int32 channel variants (L,R,M,S for stereo),
+//                 range check                                   [thread per inter-channel sample]
+//   K1 analyze  : constant detection, fixed-predictor entropy estimate, windowed autocorrelation
+//                 (sequential f64 FMA, bit-identical to the scalar reference), Levinson-Durbin,
+//                 qlp quantisation                              [thread per channel variant]
+//   K2 rice     : residual of the fixed winner and of the LPC candidate, partitioned Rice search,
+//                 exact bit counts, per-variant subframe decision [CTA per channel variant]
+//   K3 pack     : stereo decision, frame header + CRC-8, bit packing from a prefix scan of code
+//                 lengths, CRC-16                               [CTA per frame]
+//   K4 gather   : exclusive scan of frame sizes, compaction into one contiguous byte stream
+//
+// Every body is written as barrier-delimited phases (FB_PHASE ... FB_PHASE_END) so the same source
+// also runs under the CPU emulation used by the logic tests (see fb_common.h).
+// Reference citations are relative to /root/reference/.
+#pragma once
+
+#include "fb_common.h"
+
+#if !FB_GPU
+static unsigned long long fb_emu_mode_count[4] = {0, 0, 0, 0};
+#endif
+
+#define FB_K2_THREADS 128
+#define FB_K3_THREADS 256
+#define FB_RUN 16 // samples packed sequentially by one thread in K3
+
+// =================================================================================================
+// K0: ingest.  Mirrors Fill::fill_le_bytes / fill_interleaved + deinterleave
+// (src/source.rs:278-299, src/arrayutils.rs:248-264,345-364), FrameBuf::verify_samples
+// (src/source.rs:262-275) and the M/S synthesis of try_stereo_coding (src/coding.rs:476-484).
+// xv layout: [frame][variant][stride] int32.
+// =================================================================================================
+FB_DEV int32_t fb_load_sample(const uint8_t *pcm, uint64_t idx, int container_bytes) {
+    if (container_bytes == 1) {
+        return (int32_t)(int8_t)pcm[idx];
+    } else if (container_bytes == 2) {
+        const uint8_t *p = pcm + idx * 2;
+        return (int32_t)(int16_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8));
+    } else if (container_bytes == 3) {
+        const uint8_t *p = pcm + idx * 3;
+        uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+        return (int32_t)(v << 8) >> 8;
+    } else {
+        const uint8_t *p = pcm + idx * 4;
+        return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+    }
+}
+
+// one inter-channel sample `s` (global index within the batch)
+FB_DEV void fb_k0_sample(const FbJob &J, const uint8_t *pcm, int32_t *xv, uint32_t *err_flag, uint64_t s) {
+    uint32_t f = (uint32_t)(s / (uint64_t)J.block_size);
+    int t = (int)(s - (uint64_t)f * (uint64_t)J.block_size);
+    int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
+    int32_t *dst = xv + (size_t)f * (size_t)J.nvar * (size_t)J.stride + t;
+    bool bad = false;
+    if (J.channels == 2) {
+        int32_t l, r;
+        if (J.container_bytes == 2) {
+            // one aligned 32-bit load per stereo sample
+            uint32_t w = ((const uint32_t *)pcm)[s];
+            l = (int32_t)(int16_t)(w & 0xFFFFu);
+            r = (int32_t)(int16_t)(w >> 16);
+        } else {
+            l = fb_load_sample(pcm, s * 2, J.container_bytes);
+            r = fb_load_sample(pcm, s * 2 + 1, J.container_bytes);
+        }
+        bad = (l < lo) | (l > hi) | (r < lo) | (r > hi);
+        dst[0] = l;
+        dst[(size_t)J.stride] = r;
+        dst[2 * (size_t)J.stride] = (l + r) >> 1; // M
+        dst[3 * (size_t)J.stride] = l - r;        // S
+    } else {
+        for (int c = 0; c < J.channels; c++) {
+            int32_t v = fb_load_sample(pcm, s * (uint64_t)J.channels + (uint64_t)c, J.container_bytes);
+            bad |= (v < lo) | (v > hi);
+            dst[(size_t)c * (size_t)J.stride] = v;
+        }
+    }
+    if (bad) fb_atomic_or(err_flag, 1u);
+}
+
+// same for a planar FrameBuf input (fb200_encode_planar_frame): src[ch * src_stride + t]
+FB_DEV void fb_k0_planar_sample(const FbJob &J, const int32_t *src, int src_stride, int32_t *xv,
+                                uint32_t *err_flag, int t) {
+    int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
+    bool bad = false;
+    for (int c = 0; c < J.channels; c++) {
+        int32_t v = src[(size_t)c * (size_t)src_stride + t];
+        bad |= (v < lo) | (v > hi);
+        xv[(size_t)c * (size_t)J.stride + t] = v;
+    }
+    if (J.channels == 2) {
+        int32_t l = src[t], r = src[(size_t)src_stride + t];
+        xv[2 * (size_t)J.stride + t] = (l + r) >> 1;
+        xv[3 * (size_t)J.stride + t] = l - r;
+    }
+    if (bad) fb_atomic_or(err_flag, 1u);
+}
+
+// =================================================================================================
+// K1: analyze one channel variant with a single sequential pass (thread per variant).
+//
+// Everything whose result depends on floating-point evaluation order is done here in exactly the
+// reference's (stable build) order, so the floats are bit-identical to the scalar CPU code:
+//   * estimate_entropy's per-partition f32 running sums of |e_k|   (src/coding.rs:200-227,
+//     src/arrayutils.rs:496-506), fixed residuals by zero-history differences (src/coding.rs:182-197)
+//   * y[t] = (f32)x[t] * w[t] (src/lpc.rs:739-756) and r[tau] += y[t-tau]*y[t] as sequential f64
+//     FMAs starting at t = lpc_order for every lag (src/lpc.rs:533-548)
+//   * symmetric_levinson_recursion::<f64> (src/lpc.rs:633-705), quantize_parameters (:234-302)
+// R = ring size = lpc_order rounded up to a multiple of 4; lags 0..R are accumulated, lags above
+// lpc_order are ignored.  Independent variants give the parallelism (32 per warp), the R+1
+// independent FMA chains per thread give the ILP.
+// =================================================================================================
+
+// src/lpc.rs:633-705
+FB_DEV void fb_levinson(const double *coefs, const double *ys, int order, double *dest) {
+    for (int i = 0; i < order; i++) dest[i] = 0.0;
+    if (order <= 0) return;
+    if (coefs[0] == 0.0) return; // digital silence -> all-zero coefficients (:648-658)
+    double forward[FB200_MAX_LPC_ORDER + 1], forward_next[FB200_MAX_LPC_ORDER + 1];
+    for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) forward[i] = forward_next[i] = 0.0;
+    forward[0] = FB_DDIV(1.0, coefs[0]);
+    dest[0] = FB_DDIV(ys[0], coefs[0]);
+    for (int n = 1; n < order; n++) {
+        double error = 0.0;
+        for (int d = 0; d < n; d++) error = FB_FMA(coefs[n - d], forward[d], error);
+        double denom = FB_FMA(error, -error, 1.0);
+        if (denom == 0.0) continue; // :679-682 (the loading term is never used again)
+        double alpha = FB_DDIV(1.0, denom);
+        double beta = FB_DMUL(-alpha, error);
+        for (int d = 0; d <= n; d++) forward_next[d] = FB_FMA(alpha, forward[d], FB_DMUL(beta, forward[n - d]));
+        for (int d = 0; d <= n; d++) forward[d] = forward_next[d];
+        double delta = 0.0;
+        for (int d = 0; d < n; d++) delta = FB_FMA(coefs[n - d], dest[d], delta);
+        double g = FB_DADD(ys[n], -delta);
+        for (int d = 0; d <= n; d++) dest[d] = FB_FMA(g, forward[n - d], dest[d]);
+    }
+}
+
+// src/lpc.rs:234-255 find_shift.  ceil(log2(max|a|)) is taken from the binary exponent (exact);
+// libm's log2 agrees except when max|a| >= 16 sits one ulp above a power of two.
+FB_DEV int fb_find_shift(const double *coefs, int n, int precision) {
+    double max_abs = 0.0;
+    for (int i = 0; i < n; i++) {
+        double a = coefs[i] < 0 ? -coefs[i] : coefs[i];
+        if (a > max_abs) max_abs = a;
+    }
+    uint64_t bits;
+    memcpy(&bits, &max_abs, 8);
+    int e = (int)((bits >> 52) & 0x7FF);
+    uint64_t mant = bits & 0xFFFFFFFFFFFFFull;
+    int abs_log2;
+    if (e == 0) abs_log2 = -32752;                 // zero / subnormal: shift saturates at 15
+    else abs_log2 = (e - 1023) + (mant != 0 ? 1 : 0); // 2^k exactly -> k, otherwise k+1
+    int shift = (precision - 1) - abs_log2;
+    if (shift < 0) shift = 0;
+    if (shift > 15) shift = 15;
+    return shift;
+}
+
+// src/lpc.rs:258-302 quantize_parameter(s); returns the truncated order
+FB_DEV int fb_quantize(const double *coefs, int n, int precision, int16_t *q, int *shift_out) {
+    for (int i = 0; i < 32; i++) q[i] = 0;
+    int shift = fb_find_shift(coefs, n, precision);
+    double scale = (double)(1 << shift);
+    int lo = -(1 << (precision - 1)), hi = (1 << (precision - 1)) - 1;
+    for (int i = 0; i < n; i++) {
+        double s = FB_DMUL(coefs[i], scale);
+#if FB_GPU
+        double r = round(s); // half away from zero, exact
+#else
+        double r = round(s);
+#endif
+        if (r < -32768.0) r = -32768.0;
+        if (r > 32767.0) r = 32767.0;
+        int v = (int)r;
+        v = v < lo ? lo : (v > hi ? hi : v);
+        q[i] = (int16_t)v;
+    }
+    int order = FB200_MAX_LPC_ORDER;
+    while (order > 0 && q[order - 1] == 0) order--;
+    if (order < 1) order = 1;
+    *shift_out = shift;
+    return order;
+}
+
+template <int R>
+FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, const float *win,
+                          FbAnalysis *out, fb200_variant_taps *taps) {
+    const int P = J.cfg.lpc_order;
+    const bool too_short = n < FB_MIN_PRED_BLOCK;
+    const bool do_ent = !too_short && J.cfg.use_fixed && J.cfg.fixed_order_sel == 1;
+    const bool do_lpc = !too_short && J.cfg.use_lpc;
+    const int n_orders = (J.cfg.fixed_max_order < 4 ? J.cfg.fixed_max_order : 4) + 1;
+    const int parts = J.cfg.approx_ent_partitions;
+    const int psize = (n + parts - 1) / parts;
+
+    float psum[FB_MAX_ENT_PARTS][5]; // per-partition sequential f32 sums of |e_k|
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+    int32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
+    int part = 0, pend = psize < n ? psize : n;
+    bool allsame = true;
+    const int32_t x0 = x[0];
+
+    double acc[R + 1];
+    double ring[R];
+#pragma unroll
+    for (int i = 0; i <= R; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) ring[i] = 0.0;
+
+    for (int t0 = 0; t0 < n; t0 += R) {
+        int32_t xs[R];
+#pragma unroll
+        for (int i = 0; i < R; i += 4) {
+            // stride is a multiple of 32 samples and t0 a multiple of 4: aligned 16-byte loads
+            const int4 v = *reinterpret_cast<const int4 *>(x + t0 + i);
+            xs[i] = v.x; xs[i + 1] = v.y; xs[i + 2] = v.z; xs[i + 3] = v.w;
+        }
+        float ws[R];
+        if (do_lpc) {
+#pragma unroll
+            for (int i = 0; i < R; i += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(win + t0 + i);
+                ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < R; s++) {
+            const int t = t0 + s;
+            if (t < n) {
+                const int32_t xt = xs[s];
+                allsame = allsame && (xt == x0);
+                if (do_ent) {
+                    // zero-history differences, wrapping i32 (src/coding.rs:188-195)
+                    const int32_t e0 = xt;
+                    const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)pe0);
+                    const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)pe1);
+                    const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)pe2);
+                    const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)pe3);
+                    pe0 = e0; pe1 = e1; pe2 = e2; pe3 = e3;
+                    s0 = FB_FADD((float)(e0 < 0 ? -e0 : e0), s0);
+                    s1 = FB_FADD((float)(e1 < 0 ? -e1 : e1), s1);
+                    s2 = FB_FADD((float)(e2 < 0 ? -e2 : e2), s2);
+                    s3 = FB_FADD((float)(e3 < 0 ? -e3 : e3), s3);
+                    s4 = FB_FADD((float)(e4 < 0 ? -e4 : e4), s4);
+                    if (t + 1 == pend) {
+                        psum[part][0] = s0; psum[part][1] = s1; psum[part][2] = s2;
+                        psum[part][3] = s3; psum[part][4] = s4;
+                        s0 = s1 = s2 = s3 = s4 = 0.f;
+                        part++;
+                        pend = (pend + psize < n) ? pend + psize : n;
+                    }
+                }
+                if (do_lpc) {
+                    const double y = (double)FB_FMUL((float)xt, ws[s]);
+                    if (t >= P) {
+                        acc[0] = FB_FMA(y, y, acc[0]);
+#pragma unroll
+                        for (int j = 0; j < R; j++) {
+                            // logical y[t-1-j] lives in ring[(s-1-j) mod R]; static after unrolling
+                            acc[j + 1] = FB_FMA(ring[(s - 1 - j + 2 * R) % R], y, acc[j + 1]);
+                        }
+                    }
+                    ring[s] = y; // overwrites y[t-R]
+                }
+            }
+        }
+    }
+
+    out->is_constant = allsame ? 1 : 0;
+    out->fixed_order = -1;
+    out->qlp_order = 0;
+    out->qlp_shift = 0;
+    for (int k = 0; k < 5; k++) out->fixed_est[k] = 0;
+    for (int i = 0; i < 32; i++) out->qlp[i] = 0;
+    if (taps) {
+        memset(taps, 0, sizeof(*taps));
+        taps->is_constant = allsame ? 1 : 0;
+        taps->fixed_order = -1;
+    }
+
+    if (do_ent) {
+        // estimate_entropy per order + bits_per_sample * order; first minimum wins; accepted only
+        // if below the verbatim size (src/coding.rs:264-285, :396-401)
+        const uint64_t verbatim_bits = 8 + (uint64_t)n * (uint64_t)bps_v;
+        int best = -1;
+        uint64_t best_bits = 0;
+        for (int k = 0; k < n_orders; k++) {
+            uint64_t bits = 0;
+            int offset = 0;
+            for (int p = 0; p < parts; p++) {
+                int end = offset + psize < n ? offset + psize : n;
+                int len = end - offset;
+                if (len > 0 && end >= k) {
+                    int cnt = (end - k) < len ? (end - k) : len;
+                    bits += fb_entropy_partition_bits(psum[p][k], cnt);
+                }
+                offset = end;
+            }
+            bits += (uint64_t)bps_v * (uint64_t)k;
+            out->fixed_est[k] = bits;
+            if (taps) taps->fixed_est_bits[k] = bits;
+            if (best < 0 || bits < best_bits) { best = k; best_bits = bits; }
+        }
+        if (best >= 0 && best_bits < verbatim_bits) out->fixed_order = best;
+        if (taps) taps->fixed_order = out->fixed_order;
+    }
+
+    if (do_lpc) {
+        double corr[FB200_MAX_LPC_ORDER + 1];
+#pragma unroll
+        for (int i = 0; i <= R; i++)
+            if (i <= FB200_MAX_LPC_ORDER) corr[i] = acc[i];
+        double lpc[FB200_MAX_LPC_ORDER];
+        fb_levinson(corr, corr + 1, P, lpc);
+        int16_t q[32];
+        int shift;
+        int order = fb_quantize(lpc, P, J.cfg.quant_precision, q, &shift);
+        out->qlp_order = order;
+        out->qlp_shift = shift;
+        for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
+        if (taps) {
+            for (int i = 0; i <= P; i++) taps->autocorr[i] = corr[i];
+            for (int i = 0; i < P; i++) taps->lpc[i] = lpc[i];
+            for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
+            taps->qlp_order = order;
+            taps->qlp_shift = shift;
+        }
+    }
+}
+
+// R must equal fb_k1_ring(J.cfg.lpc_order); one kernel instantiation per R keeps the register
+// allocation of the common small orders independent of the order-24 case.
+FB_HD int fb_k1_ring(int lpc_order) { return (lpc_order + 3) & ~3; }
+
+template <int R>
+FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
+                         FbAnalysis *ana, fb200_variant_taps *taps, uint32_t gv) {
+    uint32_t f = gv / (uint32_t)J.nvar;
+    int v = (int)(gv - f * (uint32_t)J.nvar);
+    int n = fb_frame_len(J, f);
+    const int32_t *x = xv + (size_t)gv * (size_t)J.stride;
+    const float *win = (n == J.block_size) ? win_full : win_tail;
+    int bps_v = fb_variant_bps(J, v);
+    fb200_variant_taps *tp = taps ? taps + gv : nullptr;
+    fb_k1_variant<R>(J, x, n, bps_v, win, ana + gv, tp);
+}
+
+#if !FB_GPU
+inline void fb_k1_dispatch(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
+                           FbAnalysis *ana, fb200_variant_taps *taps, uint32_t gv) {
+    switch (fb_k1_ring(J.cfg.lpc_order)) {
+    case 4: fb_k1_thread<4>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    case 8: fb_k1_thread<8>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    case 12: fb_k1_thread<12>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    case 16: fb_k1_thread<16>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    case 20: fb_k1_thread<20>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    default: fb_k1_thread<24>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    }
+}
+#endif
+
+// =================================================================================================
+// K2: per-variant residual coding search and subframe decision (CTA per variant).
+// =================================================================================================
+
+// residual of sample t for a candidate: kind 0 = fixed order `order`, kind 1 = LPC.
+// fixed (src/coding.rs:182-197): zero-history k-th difference == sum_j (-1)^j C(k,j) x[t-j] for t >= k.
+// lpc (src/lpc.rs:306-390): x[t] - ((sum_j q[j] x[t-1-j]) >> shift); the i32 and i64 paths of the
+// reference agree modulo 2^32, so the sum is always formed in 64 bits and truncated.
+FB_DEV int32_t fb_residual_at(const int32_t *x, int t, int kind, int order, const int16_t *q, int shift) {
+    if (t < order) return 0;
+    if (kind == 0) {
+        uint32_t a = (uint32_t)x[t];
+        switch (order) {
+        case 0: return (int32_t)a;
+        case 1: return (int32_t)(a - (uint32_t)x[t - 1]);
+        case 2: return (int32_t)(a - 2u * (uint32_t)x[t - 1] + (uint32_t)x[t - 2]);
+        case 3: return (int32_t)(a - 3u * (uint32_t)x[t - 1] + 3u * (uint32_t)x[t - 2] - (uint32_t)x[t - 3]);
+        default:
+            return (int32_t)(a - 4u * (uint32_t)x[t - 1] + 6u * (uint32_t)x[t - 2] - 4u * (uint32_t)x[t - 3] +
+                             (uint32_t)x[t - 4]);
+        }
+    }
+    int64_t acc = 0;
+    for (int j = 0; j < order; j++) acc += (int64_t)q[j] * (int64_t)x[t - 1 - j];
+    return (int32_t)(uint32_t)((uint64_t)(int64_t)x[t] - (uint64_t)(acc >> shift));
+}
+
+// shared-memory layout of K2 (offsets in bytes), identical on host and device
+struct FbK2Layout {
+    uint32_t off_u, off_tbl_a, off_tbl_b, off_part, off_lvl_params, off_lvl_bits, off_unit_sum, off_misc, total;
+};
+
+FB_HD FbK2Layout fb_k2_layout(int n_max, int leaves_max) {
+    FbK2Layout L;
+    uint32_t o = 0;
+    L.off_u = o;          o += (uint32_t)((n_max + 3) & ~3) * 4u;
+    L.off_tbl_a = o;      o += (uint32_t)leaves_max * 32u * 4u;
+    L.off_tbl_b = o;      o += (uint32_t)leaves_max * 32u * 4u;
+    uint32_t units = (uint32_t)(leaves_max > FB_K2_THREADS ? leaves_max : FB_K2_THREADS);
+    L.off_part = o;       o += units * 32u * 4u;
+    L.off_unit_sum = o;   o += units * 8u;
+    L.off_lvl_bits = o;   o += 16u * 8u;
+    L.off_lvl_params = o; o += 2u * (uint32_t)leaves_max;
+    o = (o + 15u) & ~15u;
+    L.off_misc = o;       o += 256u;
+    L.total = o;
+    return L;
+}
+
+// result of one residual search, kept in shared memory between candidates
+struct FbRiceResult {
+    int32_t  part_order;
+    int32_t  rice2;
+    uint64_t res_bits; // Residual::count_bits()
+    uint64_t code_bits;
+    uint8_t  params[FB200_MAX_RICE_PARTS];
+};
+
+struct FbK2Misc {
+    uint32_t maxu;
+    uint32_t pmin, pmax;
+    uint32_t fail;
+    int32_t  win_a, win_b;
+    int32_t  mode;
+    int32_t  best_level;
+    unsigned long long sum_q;
+    uint32_t any_gt14;
+    uint32_t pad;
+};
+
+// Partitioned Rice parameter search for one candidate (src/rice.rs:246-298) + Residual::count_bits
+// (src/component/bitrepr.rs:532-544).
+//
+// The reference evaluates, for every finest partition, the cost of all 31 parameters
+// (bits[p] = sum(u >> p) + len*(p+1) + 4, saturated to 2^27-1) and merges tables bottom-up.
+// bits[p] is convex in p, so the minimiser of every node of the partition tree lies between the
+// smallest and the largest leaf minimiser.  The kernel therefore evaluates only a window [a, b] of
+// parameters around per-leaf estimates, then *verifies* on every leaf that the window brackets the
+// minimum (bits[a] > bits[a+1] or a == 0; bits[b-1] <= bits[b] or b == max_p; nothing saturated).
+// If the check fails the search is repeated over the full range, which reproduces the reference's
+// tables entry for entry.  When a residual is >= 2^27 the reference's 16-sample chunked saturating
+// u32 accumulation (src/rice.rs:75-98) is replayed literally (mode 2).  Either way the chosen
+// partition order, parameters and bit count are identical to the reference's.
+FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind, int order, const int16_t *q,
+                              int shift, uint8_t *smem, const FbK2Layout &L, FbRiceResult *res) {
+    const int T = FB_K2_THREADS;
+    uint32_t *u = (uint32_t *)(smem + L.off_u);
+    uint32_t *tbl_a = (uint32_t *)(smem + L.off_tbl_a);
+    uint32_t *tbl_b = (uint32_t *)(smem + L.off_tbl_b);
+    uint32_t *part = (uint32_t *)(smem + L.off_part);
+    unsigned long long *unit_sum = (unsigned long long *)(smem + L.off_unit_sum);
+    unsigned long long *lvl_bits = (unsigned long long *)(smem + L.off_lvl_bits);
+    uint8_t *lvl_params = smem + L.off_lvl_params;
+    FbK2Misc *M = (FbK2Misc *)(smem + L.off_misc);
+
+    const int warm = order;
+    const int max_p = J.cfg.prc_max_parameter;
+    const int o0 = fb_finest_partition_order(n);
+    const int leaves = 1 << o0;
+    const int leaf_len = n >> o0;
+    int nsub = 1;
+    while (leaves * nsub * 2 <= T && (leaf_len / (nsub * 2)) >= 16) nsub *= 2;
+    const int units = leaves * nsub;
+
+    // ---- phase 1: residual -> zigzag u[] (warm-up slots 0), block maximum
+    FB_PHASE(tid, T)
+        if (tid == 0) { M->maxu = 0; M->pmin = 31; M->pmax = 0; M->fail = 0; M->sum_q = 0; M->any_gt14 = 0; }
+    FB_PHASE_END
+    FB_PHASE(tid, T)
+        uint32_t mx = 0;
+        for (int t = tid; t < n; t += T) {
+            uint32_t v = fb_zigzag(fb_residual_at(x, t, kind, order, q, shift));
+            u[t] = v;
+            mx = v > mx ? v : mx;
+        }
+        if (mx) fb_atomic_max_u32(&M->maxu, mx);
+    FB_PHASE_END
+
+    // ---- phase 2: per-unit sums of u (unit = contiguous piece of a leaf)
+    FB_PHASE(tid, T)
+        for (int unit = tid; unit < units; unit += T) {
+            int leaf = unit / nsub, sub = unit - leaf * nsub;
+            int lstart = leaf * leaf_len;
+            int a0 = lstart + (int)(((long long)leaf_len * sub) / nsub);
+            int a1 = lstart + (int)(((long long)leaf_len * (sub + 1)) / nsub);
+            if (a0 < warm) a0 = warm;
+            unsigned long long sacc = 0;
+            for (int t = a0; t < a1; t++) sacc += u[t];
+            unit_sum[unit] = sacc;
+        }
+    FB_PHASE_END
+
+    // ---- phase 3: per-leaf parameter estimate floor(log2(mean)) -> window bounds
+    FB_PHASE(tid, T)
+        for (int leaf = tid; leaf < leaves; leaf += T) {
+            unsigned long long sacc = 0;
+            for (int s = 0; s < nsub; s++) sacc += unit_sum[leaf * nsub + s];
+            int cnt = leaf_len - (leaf == 0 ? warm : 0);
+            unsigned long long mean = cnt > 0 ? sacc / (unsigned long long)cnt : 0;
+            uint32_t pe = 0;
+            while (pe < 31 && (mean >> (pe + 1)) != 0) pe++;
+            fb_atomic_min_u32(&M->pmin, pe);
+            fb_atomic_max_u32(&M->pmax, pe);
+        }
+    FB_PHASE_END
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            int a = (int)M->pmin - 2, b = (int)M->pmax + 1;
+            if (b > max_p) b = max_p;
+            if (a > b - 1) a = b - 1;
+            if (a < 0) a = 0;
+            int mode = 0;
+            if (M->maxu >= (1u << 27)) { mode = 2; a = 0; b = max_p; }
+            M->win_a = a; M->win_b = b; M->mode = mode;
+        }
+    FB_PHASE_END
+
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int a = M->win_a, b = M->win_b, mode = M->mode;
+        const int W = b - a + 1;
+#if !FB_GPU
+        fb_emu_mode_count[mode]++; // emulation-only statistics: which search mode ran
+        fb_emu_mode_count[3] += (unsigned long long)W;
+#endif
+
+        if (mode != 2) {
+            // ---- phase 4: per-unit partial sums S(p) = sum(u >> p), p in [a, b]
+            FB_PHASE(tid, T)
+                for (int unit = tid; unit < units; unit += T) {
+                    int leaf = unit / nsub, sub = unit - leaf * nsub;
+                    int lstart = leaf * leaf_len;
+                    int a0 = lstart + (int)(((long long)leaf_len * sub) / nsub);
+                    int a1 = lstart + (int)(((long long)leaf_len * (sub + 1)) / nsub);
+                    if (a0 < warm) a0 = warm;
+                    for (int pc = 0; pc < W; pc += 4) {
+                        unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                        const int p0 = a + pc;
+                        for (int t = a0; t < a1; t++) {
+                            uint32_t v = u[t] >> p0;
+                            c0 += v; c1 += v >> 1; c2 += v >> 2; c3 += v >> 3;
+                        }
+                        unsigned long long c[4] = {c0, c1, c2, c3};
+                        for (int k = 0; k < 4 && pc + k < W; k++)
+                            part[unit * 32 + pc + k] = c[k] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c[k];
+                    }
+                }
+            FB_PHASE_END
+            // ---- phase 5: leaf tables  min(S + 4 + cnt*(p+1), 2^27-1)
+            FB_PHASE(tid, T)
+                for (int e = tid; e < leaves * W; e += T) {
+                    int leaf = e / W, j = e - leaf * W;
+                    unsigned long long sacc = 0;
+                    for (int s = 0; s < nsub; s++) sacc += part[(leaf * nsub + s) * 32 + j];
+                    int cnt = leaf_len - (leaf == 0 ? warm : 0);
+                    sacc += 4ull + (unsigned long long)cnt * (unsigned long long)(a + j + 1);
+                    tbl_a[leaf * 32 + j] = sacc > FB_RICE_SAT ? FB_RICE_SAT : (uint32_t)sacc;
+                }
+            FB_PHASE_END
+        } else {
+            // ---- mode 2: literal replay of PrcBitTable::from_errors (src/rice.rs:65-105):
+            // u32 wrapping adds, clamp after every 16 samples, offset added at the end
+            FB_PHASE(tid, T)
+                for (int e = tid; e < leaves * W; e += T) {
+                    int leaf = e / W, j = e - leaf * W;
+                    int p = a + j;
+                    int start = leaf * leaf_len;
+                    int end = start + leaf_len;
+                    if (start < warm) start = warm;
+                    uint32_t accv = 0;
+                    for (int c = start; c < end; c += 16) {
+                        int ce = c + 16 < end ? c + 16 : end;
+                        for (int t = c; t < ce; t++) accv += u[t] >> p;
+                        accv = accv < FB_RICE_SAT ? accv : FB_RICE_SAT;
+                    }
+                    accv += 4u + (uint32_t)(end - start) * (uint32_t)(p + 1);
+                    tbl_a[leaf * 32 + j] = accv < FB_RICE_SAT ? accv : FB_RICE_SAT;
+                }
+            FB_PHASE_END
+        }
+
+        // ---- phase 6: bracket verification on the leaves (narrow window only)
+        if (mode == 0) {
+            FB_PHASE(tid, T)
+                for (int leaf = tid; leaf < leaves; leaf += T) {
+                    const uint32_t *row = tbl_a + leaf * 32;
+                    bool ok = true;
+                    for (int j = 0; j < W; j++) ok = ok && (row[j] < FB_RICE_SAT);
+                    if (a > 0) ok = ok && (W >= 2) && (row[0] > row[1]);
+                    if (b < max_p) ok = ok && (W >= 2) && (row[W - 2] <= row[W - 1]);
+                    if (!ok) M->fail = 1; // benign race: every writer stores 1
+                }
+            FB_PHASE_END
+        }
+
+        // ---- phase 7: tree search, finest level first (src/rice.rs:276-291)
+        if (!(mode == 0 && M->fail)) {
+            uint32_t *cur = tbl_a, *nxt = tbl_b;
+            int pbase = 0;
+            for (int lvl = o0; lvl >= 0; lvl--) {
+                const int nodes = 1 << lvl;
+                FB_PHASE(tid, T)
+                    if (tid == 0) lvl_bits[lvl] = 0;
+                FB_PHASE_END
+                FB_PHASE(tid, T)
+                    unsigned long long local = 0;
+                    for (int node = tid; node < nodes; node += T) {
+                        const uint32_t *row = cur + node * 32;
+                        // minimizer: smallest (bits << 5 | p) (src/rice.rs:117-141)
+                        uint32_t best = row[0], bp = (uint32_t)a;
+                        for (int j = 1; j < W; j++)
+                            if (row[j] < best) { best = row[j]; bp = (uint32_t)(a + j); }
+                        lvl_params[pbase + node] = (uint8_t)bp;
+                        local += best;
+                        if (mode == 0 && best >= FB_RICE_SAT) M->fail = 1;
+                    }
+                    if (local) fb_atomic_add_u64(&lvl_bits[lvl], local);
+                FB_PHASE_END
+                if (lvl > 0) {
+                    // merge pairs: min(a + b - 4, 2^27-1) with u32 wrapping (src/rice.rs:144-152)
+                    FB_PHASE(tid, T)
+                        for (int e = tid; e < (nodes / 2) * W; e += T) {
+                            int node = e / W, j = e - node * W;
+                            uint32_t v = cur[(2 * node) * 32 + j] + cur[(2 * node + 1) * 32 + j] - 4u;
+                            if (mode == 0 && v >= FB_RICE_SAT) M->fail = 1;
+                            nxt[node * 32 + j] = v < FB_RICE_SAT ? v : FB_RICE_SAT;
+                        }
+                    FB_PHASE_END
+                    uint32_t *tmp = cur; cur = nxt; nxt = tmp;
+                }
+                pbase += nodes;
+            }
+        }
+
+        if (mode == 0 && M->fail) {
+            // widen to the full parameter range and repeat (exact by construction)
+            FB_PHASE(tid, T)
+                if (tid == 0) { M->win_a = 0; M->win_b = max_p; M->mode = 1; M->fail = 0; }
+            FB_PHASE_END
+            continue;
+        }
+        break;
+    }
+
+    // ---- phase 8: pick the partition order: strictly smaller total wins while going coarser
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            unsigned long long min_bits = lvl_bits[o0];
+            int best = o0;
+            for (int lvl = o0 - 1; lvl >= 0; lvl--)
+                if (lvl_bits[lvl] < min_bits) { min_bits = lvl_bits[lvl]; best = lvl; }
+            M->best_level = best;
+            res->part_order = best;
+            res->code_bits = min_bits;
+        }
+    FB_PHASE_END
+    {
+        const int best = M->best_level;
+        int pbase = 0;
+        for (int lvl = o0; lvl > best; lvl--) pbase += 1 << lvl;
+        const int nparts = 1 << best;
+        const int plen = n >> best;
+        FB_PHASE(tid, T)
+            for (int j = tid; j < nparts; j += T) {
+                uint8_t p = lvl_params[pbase + j];
+                res->params[j] = p;
+                if (p > 14) M->any_gt14 = 1;
+            }
+            // exact quotient sum for Residual::count_bits (src/component/datatype.rs:2328-2335)
+            unsigned long long local = 0;
+            for (int t = tid; t < n; t += T) {
+                if (t >= warm) local += u[t] >> lvl_params[pbase + t / plen];
+            }
+            if (local) fb_atomic_add_u64(&M->sum_q, local);
+        FB_PHASE_END
+        FB_PHASE(tid, T)
+            if (tid == 0) {
+                unsigned long long sum_p = 0;
+                for (int j = 0; j < nparts; j++) sum_p += res->params[j];
+                int rice2 = M->any_gt14 ? 1 : 0;
+                res->rice2 = rice2;
+                // src/component/bitrepr.rs:532-544
+                res->res_bits = 2 + 4 + (unsigned long long)nparts * (rice2 ? 5 : 4) + M->sum_q +
+                                (unsigned long long)(n - warm) + sum_p * (unsigned long long)plen -
+                                (unsigned long long)warm * res->params[0];
+            }
+        FB_PHASE_END
+    }
+}
+
+// K2 body: one CTA per channel variant.  Implements fixed_lpc / estimated_qlpc / encode_subframe
+// (src/coding.rs:298-418) on top of K1's analysis.
+FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, fb200_subframe_info *choice,
+                       uint32_t gv, uint8_t *smem, const FbK2Layout &L) {
+    const int T = FB_K2_THREADS;
+    const uint32_t f = gv / (uint32_t)J.nvar;
+    const int v = (int)(gv - f * (uint32_t)J.nvar);
+    const int n = fb_frame_len(J, f);
+    const int bps_v = fb_variant_bps(J, v);
+    const int32_t *x = xv + (size_t)gv * (size_t)J.stride;
+    const FbAnalysis &A = ana[gv];
+    fb200_subframe_info *out = choice + gv;
+    FbRiceResult *res_fixed = (FbRiceResult *)(smem + L.total);
+    FbRiceResult *res_lpc = res_fixed + 1;
+    FbRiceResult *res_tmp = res_fixed + 2;
+    const unsigned long long verbatim_bits = 8ull + (unsigned long long)n * (unsigned long long)bps_v;
+    const bool too_short = n < FB_MIN_PRED_BLOCK;
+
+    // common fields
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            out->type = FB200_SF_VERBATIM;
+            out->order = 0;
+            out->bits_per_sample = bps_v;
+            out->precision = 0;
+            out->shift = 0;
+            out->partition_order = 0;
+            out->rice2 = 0;
+            out->reserved = n;
+            out->bits = verbatim_bits;
+        }
+        for (int i = tid; i < 32; i += T) out->qlp[i] = 0;
+    FB_PHASE_END
+
+    if (J.cfg.use_constant && A.is_constant) {
+        FB_PHASE(tid, T)
+            if (tid == 0) { out->type = FB200_SF_CONSTANT; out->bits = 8ull + (unsigned long long)bps_v; }
+        FB_PHASE_END
+        return;
+    }
+    if (too_short) return;
+
+    // ---- fixed candidate (src/coding.rs:298-331)
+    int kf = -1;
+    unsigned long long fixed_bits = 0;
+    if (J.cfg.use_fixed) {
+        if (J.cfg.fixed_order_sel == 1) {
+            kf = A.fixed_order;
+            if (kf >= 0) fb_k2_rice_search(J, x, n, 0, kf, nullptr, 0, smem, L, res_fixed);
+        } else {
+            // OrderSel::BitCount: exact Rice search per order, key = bps*order + code_bits,
+            // first minimum wins (src/coding.rs:241-262)
+            const int n_orders = (J.cfg.fixed_max_order < 4 ? J.cfg.fixed_max_order : 4) + 1;
+            unsigned long long best_key = 0;
+            for (int k = 0; k < n_orders; k++) {
+                fb_k2_rice_search(J, x, n, 0, k, nullptr, 0, smem, L, res_tmp);
+                unsigned long long key = (unsigned long long)bps_v * (unsigned long long)k + res_tmp->code_bits;
+                bool better = (kf < 0) || key < best_key;
+                if (better) {
+                    kf = k;
+                    best_key = key;
+                    FB_PHASE(tid, T)
+                        for (int i = tid; i < (int)sizeof(FbRiceResult); i += T)
+                            ((uint8_t *)res_fixed)[i] = ((const uint8_t *)res_tmp)[i];
+                    FB_PHASE_END
+                }
+            }
+            if (!(best_key < verbatim_bits)) kf = -1;
+        }
+        if (kf >= 0) fixed_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res_fixed->res_bits;
+    }
+    const unsigned long long baseline_bits =
+        kf >= 0 ? (fixed_bits < verbatim_bits ? fixed_bits : verbatim_bits) : verbatim_bits;
+
+    // ---- LPC candidate (src/coding.rs:360-381)
+    bool lpc_ok = false;
+    unsigned long long lpc_bits = 0;
+    if (J.cfg.use_lpc) {
+        fb_k2_rice_search(J, x, n, 1, A.qlp_order, A.qlp, A.qlp_shift, smem, L, res_lpc);
+        lpc_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
+                   (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res_lpc->res_bits;
+        lpc_ok = lpc_bits < baseline_bits;
+    }
+
+    // ---- decision (src/coding.rs:403-416)
+    int pick = -1; // 0 fixed, 1 lpc
+    if (lpc_ok) pick = 1;
+    else if (kf >= 0) pick = 0;
+    if (pick == 1 && !(lpc_bits < verbatim_bits)) pick = -1;
+    if (pick == 0 && !(fixed_bits < verbatim_bits)) pick = -1;
+    if (pick < 0) return; // verbatim (already written)
+
+    const FbRiceResult *R = pick == 1 ? res_lpc : res_fixed;
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            out->type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED;
+            out->order = pick == 1 ? A.qlp_order : kf;
+            out->precision = pick == 1 ? J.cfg.quant_precision : 0;
+            out->shift = pick == 1 ? A.qlp_shift : 0;
+            out->partition_order = R->part_order;
+            out->rice2 = R->rice2;
+            out->bits = pick == 1 ? lpc_bits : fixed_bits;
+        }
+        if (pick == 1)
+            for (int i = tid; i < 32; i += T) out->qlp[i] = A.qlp[i];
+        for (int i = tid; i < (1 << R->part_order); i += T) out->rice_params[i] = R->params[i];
+    FB_PHASE_END
+}
+
+// =================================================================================================
+// K3: frame assembly (CTA per frame).
+// =================================================================================================
+
+// MSB-first bit writer of a thread-private run of the frame (src/bitsink.rs semantics).  Words are
+// big-endian 32-bit groups of the byte stream; the buffer is zero-initialised, so runs of zero bits
+// are skipped.  Only the first and last word of a run can be shared with a neighbour (atomic OR);
+// interior words are owned by the run (plain store).
+struct FbBitRun {
+    uint32_t *words;
+    uint32_t w_first, w_last, cur_w, acc, pos;
+};
+
+FB_DEV void fb_run_init(FbBitRun &r, uint32_t *words, uint32_t pos_start, uint32_t pos_end) {
+    r.words = words;
+    r.w_first = pos_start >> 5;
+    r.w_last = pos_end > pos_start ? ((pos_end - 1) >> 5) : r.w_first;
+    r.cur_w = r.w_first;
+    r.acc = 0;
+    r.pos = pos_start;
+}
+
+FB_DEV void fb_run_flush(FbBitRun &r) {
+    if (r.acc) {
+        if (r.cur_w == r.w_first || r.cur_w == r.w_last) fb_atomic_or(&r.words[r.cur_w], r.acc);
+        else r.words[r.cur_w] = r.acc;
+        r.acc = 0;
+    }
+}
+
+FB_DEV void fb_run_skip(FbBitRun &r, uint32_t q) {
+    r.pos += q;
+    uint32_t nw = r.pos >> 5;
+    if (nw != r.cur_w) { fb_run_flush(r); r.cur_w = nw; }
+}
+
+// append the k (1..32) low bits of v (v < 2^k)
+FB_DEV void fb_run_put(FbBitRun &r, uint32_t v, uint32_t k) {
+    uint32_t space = 32u - (r.pos & 31u);
+    if (k <= space) {
+        r.acc |= (k == 32u) ? v : (v << (space - k));
+        r.pos += k;
+        if (k == space) { fb_run_flush(r); r.cur_w++; }
+    } else {
+        uint32_t rem = k - space; // 1..31
+        r.acc |= v >> rem;
+        fb_run_flush(r);
+        r.cur_w++;
+        r.acc = v << (32u - rem);
+        r.pos += k;
+    }
+}
+
+struct FbK3Sub {
+    int32_t  variant;       // index into the frame's variants
+    int32_t  type, order, bps, precision, shift, part_order, rice2;
+    uint32_t start_bit;     // first bit of the subframe
+    uint32_t res_bit;       // first bit of the residual section (method field)
+    uint32_t code_bit;      // first bit after the 6-bit residual header
+};
+
+struct FbK3Shared {
+    FbK3Sub sub[FB200_MAX_CHANNELS];
+    uint8_t header[16];
+    int32_t header_len;
+    int32_t ch_tag;
+    uint32_t data_bytes;    // bytes covered by the CRC-16
+    uint32_t crc_xpow[9];
+    uint32_t crc_tab[256];
+    uint32_t crc_part[FB_K3_THREADS];
+    uint32_t scan_part[FB_K3_THREADS];
+};
+
+FB_HD uint32_t fb_k3_smem_bytes(uint32_t frame_bytes_max, int block_size, int pack_in_smem) {
+    uint32_t runs = (uint32_t)((block_size + FB_RUN - 1) / FB_RUN);
+    uint32_t o = (uint32_t)((sizeof(FbK3Shared) + 15) & ~(size_t)15);
+    o += ((runs + 1 + 3) & ~3u) * 4u;                                   // run offsets
+    if (pack_in_smem) o += ((frame_bytes_max + 3u) & ~3u) + 16u;        // frame words
+    return o;
+}
+
+FB_DEV void fb_k3_body(const FbJob &J, const int32_t *xv, const fb200_subframe_info *choice, uint8_t *slots,
+                       uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t f, uint8_t *smem) {
+    const int T = FB_K3_THREADS;
+    FbK3Shared *S = (FbK3Shared *)smem;
+    uint32_t off = (uint32_t)((sizeof(FbK3Shared) + 15) & ~(size_t)15);
+    const int n = fb_frame_len(J, f);
+    const uint32_t runs_cap = (uint32_t)((J.block_size + FB_RUN - 1) / FB_RUN);
+    uint32_t *run_off = (uint32_t *)(smem + off);
+    off += ((runs_cap + 1 + 3) & ~3u) * 4u;
+    uint8_t *slot = slots + (size_t)f * (size_t)J.slot_bytes;
+    uint32_t *words = J.pack_in_smem ? (uint32_t *)(smem + off) : (uint32_t *)slot;
+    const uint32_t max_bytes = fb_max_frame_bytes(J.channels, J.bps, J.block_size);
+    const uint32_t max_words = (max_bytes + 3u) / 4u;
+    const fb200_subframe_info *var = choice + (size_t)f * (size_t)J.nvar;
+    const int nruns = (n + FB_RUN - 1) / FB_RUN;
+
+    // ---- phase 0: zero the word buffer, CRC table; thread 0: stereo decision, header, offsets
+    FB_PHASE(tid, T)
+        for (uint32_t w = (uint32_t)tid; w < max_words; w += T) words[w] = 0;
+        for (int i = tid; i < 256; i += T) S->crc_tab[i] = fb_crc16_table_entry((uint32_t)i);
+        if (tid == 0) {
+            int ch_tag = J.channels - 1;
+            int sel[FB200_MAX_CHANNELS];
+            for (int c = 0; c < J.channels; c++) sel[c] = c;
+            if (J.channels == 2) {
+                // try_stereo_coding (src/coding.rs:469-527): strict <, order I, L/S, R/S, M/S
+                unsigned long long bl = var[0].bits, br = var[1].bits, bm = var[2].bits, bs = var[3].bits;
+                unsigned long long min_bits = bl + br;
+                if (J.cfg.use_leftside && bl + bs < min_bits) { min_bits = bl + bs; ch_tag = 8; }
+                if (J.cfg.use_rightside && br + bs < min_bits) { min_bits = br + bs; ch_tag = 9; }
+                if (J.cfg.use_midside && bm + bs < min_bits) { min_bits = bm + bs; ch_tag = 10; }
+                // select_channels (src/component/datatype.rs:1171-1184)
+                if (ch_tag == 8) { sel[0] = 0; sel[1] = 3; }
+                else if (ch_tag == 9) { sel[0] = 3; sel[1] = 1; }
+                else if (ch_tag == 10) { sel[0] = 2; sel[1] = 3; }
+            }
+            S->ch_tag = ch_tag;
+            S->header_len = fb_frame_header(n, ch_tag, J.bps, J.sample_rate, J.first_frame_number + f, S->header);
+            uint32_t bit = (uint32_t)S->header_len * 8u;
+            for (int c = 0; c < J.channels; c++) {
+                const fb200_subframe_info &V = var[sel[c]];
+                FbK3Sub &D = S->sub[c];
+                D.variant = sel[c];
+                D.type = V.type; D.order = V.order; D.bps = V.bits_per_sample;
+                D.precision = V.precision; D.shift = V.shift; D.part_order = V.partition_order; D.rice2 = V.rice2;
+                D.start_bit = bit;
+                uint32_t hb = 8;
+                if (V.type == FB200_SF_FIXED) hb += (uint32_t)(V.order * V.bits_per_sample);
+                if (V.type == FB200_SF_LPC)
+                    hb += (uint32_t)(V.order * V.bits_per_sample) + 4u + 5u + (uint32_t)(V.precision * V.order);
+                D.res_bit = bit + hb;
+                D.code_bit = D.res_bit + 6u;
+                bit += (uint32_t)V.bits;
+            }
+            S->data_bytes = (bit + 7u) >> 3;
+        }
+    FB_PHASE_END
+
+    // ---- phase 1: header bytes and the fixed-position leading fields of every subframe
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            FbBitRun r;
+            fb_run_init(r, words, 0, 1); // every word through the atomic path
+            r.w_last = 0xFFFFFFFFu;
+            for (int i = 0; i < S->header_len; i++) {
+                r.w_first = r.cur_w; // force atomic OR on each flush
+                fb_run_put(r, S->header[i], 8);
+            }
+            r.w_first = r.cur_w;
+            fb_run_flush(r);
+        }
+        if (tid >= 1 && tid <= J.channels) {
+            const FbK3Sub &D = S->sub[tid - 1];
+            const int32_t *x = xv + ((size_t)f * (size_t)J.nvar + (size_t)D.variant) * (size_t)J.stride;
+            const fb200_subframe_info &V = var[D.variant];
+            FbBitRun r;
+            fb_run_init(r, words, D.start_bit, D.start_bit + 1);
+            r.w_last = 0xFFFFFFFFu;
+            const uint32_t mask = D.bps >= 32 ? 0xFFFFFFFFu : ((1u << D.bps) - 1u);
+#define FB_PUT_ATOMIC(val, nb) do { r.w_first = r.cur_w; fb_run_put(r, (uint32_t)(val), (uint32_t)(nb)); } while (0)
+            if (D.type == FB200_SF_CONSTANT) {
+                FB_PUT_ATOMIC(0x00, 8);
+                FB_PUT_ATOMIC((uint32_t)x[0] & mask, D.bps);
+            } else if (D.type == FB200_SF_VERBATIM) {
+                FB_PUT_ATOMIC(0x02, 8);
+            } else if (D.type == FB200_SF_FIXED) {
+                FB_PUT_ATOMIC(0x10 | (D.order << 1), 8);
+                for (int t = 0; t < D.order; t++) FB_PUT_ATOMIC((uint32_t)x[t] & mask, D.bps);
+                FB_PUT_ATOMIC(((D.rice2 ? 1 : 0) << 4) | D.part_order, 6);
+            } else {
+                FB_PUT_ATOMIC(0x40 | ((D.order - 1) << 1), 8);
+                for (int t = 0; t < D.order; t++) FB_PUT_ATOMIC((uint32_t)x[t] & mask, D.bps);
+                FB_PUT_ATOMIC(D.precision - 1, 4);
+                FB_PUT_ATOMIC((uint32_t)D.shift & 31u, 5);
+                const uint32_t pmask = (1u << D.precision) - 1u;
+                for (int j = 0; j < D.order; j++) FB_PUT_ATOMIC((uint32_t)(int32_t)V.qlp[j] & pmask, D.precision);
+                FB_PUT_ATOMIC(((D.rice2 ? 1 : 0) << 4) | D.part_order, 6);
+            }
+#undef FB_PUT_ATOMIC
+            r.w_first = r.cur_w;
+            fb_run_flush(r);
+        }
+    FB_PHASE_END
+
+    // ---- per subframe: samples
+    for (int c = 0; c < J.channels; c++) {
+        const FbK3Sub D = S->sub[c];
+        const int32_t *x = xv + ((size_t)f * (size_t)J.nvar + (size_t)D.variant) * (size_t)J.stride;
+        const fb200_subframe_info &V = var[D.variant];
+        if (D.type == FB200_SF_CONSTANT) continue;
+        if (D.type == FB200_SF_VERBATIM) {
+            // Verbatim::write (src/component/bitrepr.rs:463-470): bps bits per sample, fixed positions
+            FB_PHASE(tid, T)
+                const uint32_t mask = D.bps >= 32 ? 0xFFFFFFFFu : ((1u << D.bps) - 1u);
+                for (int run = tid; run < nruns; run += T) {
+                    int t0 = run * FB_RUN, t1 = t0 + FB_RUN < n ? t0 + FB_RUN : n;
+                    uint32_t p0 = D.start_bit + 8u + (uint32_t)t0 * (uint32_t)D.bps;
+                    uint32_t p1 = D.start_bit + 8u + (uint32_t)t1 * (uint32_t)D.bps;
+                    FbBitRun r;
+                    fb_run_init(r, words, p0, p1);
+                    for (int t = t0; t < t1; t++) fb_run_put(r, (uint32_t)x[t] & mask, (uint32_t)D.bps);
+                    fb_run_flush(r);
+                }
+            FB_PHASE_END
+            continue;
+        }
+        // Residual::write (src/component/bitrepr.rs:550-597): per partition a 4/5-bit parameter,
+        // then per sample q zeros, a one, and the p low bits.
+        const int kind = D.type == FB200_SF_LPC ? 1 : 0;
+        const int warm = D.order;
+        const int plen = n >> D.part_order;
+        const uint32_t pbits = D.rice2 ? 5u : 4u;
+        // pass A: bits of each run (codes + the parameter fields that start inside it)
+        FB_PHASE(tid, T)
+            for (int run = tid; run < nruns; run += T) {
+                int t0 = run * FB_RUN, t1 = t0 + FB_RUN < n ? t0 + FB_RUN : n;
+                uint32_t bits = 0;
+                int pj = t0 / plen;
+                int pstart = pj * plen;
+                if (pstart < warm) pstart = warm; // partition 0 starts after the warm-up
+                uint32_t rp = V.rice_params[pj];
+                int pnext = (pj + 1) * plen;
+                for (int t = t0; t < t1; t++) {
+                    if (t == pnext) { pj++; pstart = pnext; pnext += plen; rp = V.rice_params[pj]; }
+                    if (t < warm) continue;
+                    if (t == pstart) bits += pbits;
+                    uint32_t uu = fb_zigzag(fb_residual_at(x, t, kind, D.order, V.qlp, D.shift));
+                    bits += (uu >> rp) + 1u + rp;
+                }
+                run_off[run] = bits;
+            }
+        FB_PHASE_END
+        // exclusive scan of run_off[0..nruns) (three steps: slice sums, scan of T partials, fix-up)
+        {
+            const int per = (nruns + T - 1) / T;
+            FB_PHASE(tid, T)
+                uint32_t s = 0;
+                for (int i = tid * per; i < (tid + 1) * per && i < nruns; i++) s += run_off[i];
+                S->scan_part[tid] = s;
+            FB_PHASE_END
+            FB_PHASE(tid, T)
+                if (tid == 0) {
+                    uint32_t s = 0;
+                    for (int i = 0; i < T; i++) { uint32_t v2 = S->scan_part[i]; S->scan_part[i] = s; s += v2; }
+                }
+            FB_PHASE_END
+            FB_PHASE(tid, T)
+                uint32_t s = S->scan_part[tid];
+                for (int i = tid * per; i < (tid + 1) * per && i < nruns; i++) { uint32_t v2 = run_off[i]; run_off[i] = s; s += v2; }
+                if (tid == T - 1) run_off[nruns] = s;
+            FB_PHASE_END
+        }
+        // pass B: pack
+        FB_PHASE(tid, T)
+            for (int run = tid; run < nruns; run += T) {
+                int t0 = run * FB_RUN, t1 = t0 + FB_RUN < n ? t0 + FB_RUN : n;
+                uint32_t p0 = D.code_bit + run_off[run];
+                uint32_t p1 = D.code_bit + run_off[run + 1];
+                if (p1 == p0) continue;
+                FbBitRun r;
+                fb_run_init(r, words, p0, p1);
+                int pj = t0 / plen;
+                int pstart = pj * plen;
+                if (pstart < warm) pstart = warm;
+                uint32_t rp = V.rice_params[pj];
+                int pnext = (pj + 1) * plen;
+                for (int t = t0; t < t1; t++) {
+                    if (t == pnext) { pj++; pstart = pnext; pnext += plen; rp = V.rice_params[pj]; }
+                    if (t < warm) continue;
+                    if (t == pstart) fb_run_put(r, rp, pbits);
+                    uint32_t uu = fb_zigzag(fb_residual_at(x, t, kind, D.order, V.qlp, D.shift));
+                    fb_run_skip(r, uu >> rp);
+                    fb_run_put(r, (uu & ((1u << rp) - 1u)) | (1u << rp), rp + 1u);
+                }
+                fb_run_flush(r);
+            }
+        FB_PHASE_END
+    }
+
+    // ---- CRC-16 over data_bytes (Frame::write, src/component/bitrepr.rs:289-320).
+    // Chunks of L bytes are aligned to the END of the data (leading zero bytes do not change a
+    // CRC with init 0); partial CRCs are combined pairwise with x^(8*L*2^k) mod P.
+    const uint32_t B = S->data_bytes;
+    const uint32_t Lc = (B + (uint32_t)T - 1u) / (uint32_t)T;
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            // x^(8*Lc) mod P by square-and-multiply, then successive squares
+            uint32_t result = 1, base = 2; // polynomial "x"
+            uint32_t e = 8u * Lc;
+            while (e) { if (e & 1u) result = fb_crc16_mulmod(result, base); base = fb_crc16_mulmod(base, base); e >>= 1; }
+            S->crc_xpow[0] = result;
+            for (int k = 1; k < 9; k++) S->crc_xpow[k] = fb_crc16_mulmod(S->crc_xpow[k - 1], S->crc_xpow[k - 1]);
+        }
+        // chunk tid covers bytes [B - (T - tid)*Lc, B - (T - tid - 1)*Lc) intersected with [0, B)
+        long long lo = (long long)B - (long long)(T - tid) * (long long)Lc;
+        long long hi = lo + (long long)Lc;
+        if (lo < 0) lo = 0;
+        uint32_t crc = 0;
+        for (long long i = lo; i < hi; i++) {
+            uint32_t byte = (words[i >> 2] >> (24u - 8u * (uint32_t)(i & 3))) & 0xFFu;
+            crc = ((crc << 8) & 0xFFFFu) ^ S->crc_tab[((crc >> 8) ^ byte) & 0xFFu];
+        }
+        S->crc_part[tid] = crc;
+    FB_PHASE_END
+    for (int k = 0; (1 << k) < T; k++) {
+        FB_PHASE(tid, T)
+            const int span = 1 << (k + 1);
+            if ((tid % span) == 0) {
+                uint32_t left = S->crc_part[tid], right = S->crc_part[tid + (1 << k)];
+                S->crc_part[tid] = fb_crc16_mulmod(left, S->crc_xpow[k]) ^ right;
+            }
+        FB_PHASE_END
+    }
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            uint32_t crc = S->crc_part[0];
+            // the two CRC bytes follow the (byte-aligned) data, big-endian
+            for (int i = 0; i < 2; i++) {
+                uint32_t pos = B + (uint32_t)i;
+                uint32_t byte = (crc >> (8 * (1 - i))) & 0xFFu;
+                fb_atomic_or(&words[pos >> 2], byte << (24u - 8u * (pos & 3u)));
+            }
+            frame_bytes[f] = B + 2u;
+            if (infos) {
+                fb200_frame_info &I = infos[f];
+                I.channel_assignment = S->ch_tag;
+                I.block_size = n;
+                I.frame_number = J.first_frame_number + f;
+                I.frame_bytes = B + 2u;
+            }
+        }
+        if (infos) {
+            // decision records of the emitted subframes
+            fb200_frame_info &I = infos[f];
+            for (int c = 0; c < J.channels; c++) {
+                const uint8_t *src = (const uint8_t *)&var[S->sub[c].variant];
+                uint8_t *dst = (uint8_t *)&I.sub[c];
+                for (int i = tid; i < (int)sizeof(fb200_subframe_info); i += T) dst[i] = src[i];
+            }
+        }
+    FB_PHASE_END
+    // ---- store: big-endian words -> bytes of the slot
+    FB_PHASE(tid, T)
+        const uint32_t total = B + 2u;
+        const uint32_t nwords = (total + 3u) / 4u;
+        uint32_t *dstw = (uint32_t *)slot;
+        for (uint32_t w = (uint32_t)tid; w < nwords; w += T) {
+            uint32_t v = words[w];
+            dstw[w] = ((v & 0xFFu) << 24) | ((v & 0xFF00u) << 8) | ((v >> 8) & 0xFF00u) | (v >> 24);
+        }
+    FB_PHASE_END
+}
+
+// =================================================================================================
+// K4: exclusive scan of frame sizes (single CTA) and gather into a contiguous stream.
+// =================================================================================================
+#define FB_K4_THREADS 1024
+
+FB_DEV void fb_k4_scan_body(const uint32_t *frame_bytes, unsigned long long *offsets, uint32_t n_frames,
+                            unsigned long long *partials /* smem, T entries */) {
+    const int T = FB_K4_THREADS;
+    const uint32_t per = (n_frames + (uint32_t)T - 1u) / (uint32_t)T;
+    FB_PHASE(tid, T)
+        unsigned long long s = 0;
+        for (uint32_t i = (uint32_t)tid * per; i < ((uint32_t)tid + 1u) * per && i < n_frames; i++) s += frame_bytes[i];
+        partials[tid] = s;
+    FB_PHASE_END
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            unsigned long long s = 0;
+            for (int i = 0; i < T; i++) { unsigned long long v = partials[i]; partials[i] = s; s += v; }
+        }
+    FB_PHASE_END
+    FB_PHASE(tid, T)
+        unsigned long long s = partials[tid];
+        for (uint32_t i = (uint32_t)tid * per; i < ((uint32_t)tid + 1u) * per && i < n_frames; i++) {
+            offsets[i] = s;
+            s += frame_bytes[i];
+        }
+        if (tid == T - 1) offsets[n_frames] = s;
+    FB_PHASE_END
+}
+
+// copies frame f from its slot to out + offsets[f]; `tid`/`T` index the bytes
+FB_DEV void fb_k4_gather_thread(const uint8_t *slots, uint32_t slot_bytes, const uint32_t *frame_bytes,
+                                const unsigned long long *offsets, uint8_t *out, unsigned long long out_cap,
+                                uint32_t f, int tid, int T) {
+    const uint8_t *src = slots + (size_t)f * (size_t)slot_bytes;
+    unsigned long long o = offsets[f];
+    uint32_t len = frame_bytes[f];
+    if (o + len > out_cap) return; // capacity error is reported by the host from offsets[n_frames]
+    for (uint32_t i = (uint32_t)tid; i < len; i += (uint32_t)T) out[o + i] = src[i];
+}

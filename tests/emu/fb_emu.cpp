@@ -1,0 +1,165 @@
+// fb_emu.cpp -- CPU emulation of the CUDA kernel bodies, for logic tests on machines without a GPU.
+//
+// TEST INFRASTRUCTURE.  It compiles flacenc_rs_b200/csrc/fb_kernels.cuh with FB_EMULATE, which turns
+// every barrier-delimited phase of a kernel into a loop over the CTA's threads, and drives the same
+// K0..K4 sequence as fb_api.cu.  It lets `pytest -m "not gpu"` compare the kernels' logic with the
+// oracle byte for byte.  It is not part of libflacenc_b200.so and is not a fallback.
+#define FB_EMULATE 1
+#include "../../flacenc_rs_b200/csrc/fb_host.h"
+
+#include <stdlib.h>
+#include <vector>
+
+extern "C" {
+
+float fbemu_log2f(float x) { return fb_log2f(x); }
+
+// Rice-search statistics: [0] narrow-window runs, [1] full-range reruns, [2] chunk-exact runs, [3] sum of widths
+void fbemu_mode_counts(unsigned long long *out4, int reset) {
+    for (int i = 0; i < 4; i++) { out4[i] = fb_emu_mode_count[i]; if (reset) fb_emu_mode_count[i] = 0; }
+}
+
+void fbemu_config_default(fb200_config *c) { fbh_config_default(c); }
+int fbemu_config_verify(const fb200_config *c) { return fbh_config_verify(c); }
+
+int fbemu_frame_header(int n, int ch_tag, int bps, int rate, uint32_t number, uint8_t *out) {
+    return fb_frame_header(n, ch_tag, bps, rate, number, out);
+}
+
+struct EmuBuffers {
+    std::vector<int32_t> xv;
+    std::vector<float> win_full, win_tail;
+    std::vector<FbAnalysis> ana;
+    std::vector<fb200_variant_taps> taps;
+    std::vector<fb200_subframe_info> choice;
+    std::vector<uint8_t> slots;
+    std::vector<uint32_t> frame_bytes;
+    std::vector<unsigned long long> offsets;
+    std::vector<fb200_frame_info> infos;
+};
+
+static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *planar, int planar_stride,
+                   int container_bytes, uint64_t n_samples, int channels, int bps, int rate, int block_size,
+                   uint32_t first_frame, bool analyze_only, EmuBuffers &B, FbJob &Jout) {
+    int rc = fbh_config_verify(cfg);
+    if (rc) return rc;
+    rc = fbh_format_verify(channels, bps, rate, block_size);
+    if (rc) return rc;
+    if (!planar && (container_bytes < 1 || container_bytes > 4 || container_bytes * 8 < bps)) return FB200_ERR_SOURCE;
+    FbJob J = fbh_make_job(*cfg, channels, bps, rate, block_size, container_bytes, n_samples, first_frame);
+    Jout = J;
+    if (J.n_frames == 0) return FB200_OK;
+    if ((uint64_t)first_frame + J.n_frames > (1ull << 31)) return FB200_ERR_CONFIG;
+    const size_t nvars = (size_t)J.n_frames * J.nvar;
+    B.xv.assign(nvars * J.stride + 64, 0x55555555); // poison: padding must never influence results
+    B.win_full.assign(J.block_size + 64, 0.f);
+    B.win_tail.assign(J.tail_n + 64, 0.f);
+    fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.block_size, B.win_full.data());
+    fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.tail_n, B.win_tail.data());
+    B.ana.resize(nvars);
+    B.taps.resize(nvars);
+    B.choice.resize(nvars);
+    uint32_t err_flag = 0;
+
+    // K0
+    if (planar) {
+        for (int t = 0; t < J.tail_n; t++) fb_k0_planar_sample(J, planar, planar_stride, B.xv.data(), &err_flag, t);
+    } else {
+        for (uint64_t s = 0; s < n_samples; s++) fb_k0_sample(J, (const uint8_t *)pcm, B.xv.data(), &err_flag, s);
+    }
+    if (err_flag) return FB200_ERR_CONFIG;
+    // K1
+    for (uint32_t gv = 0; gv < nvars; gv++)
+        fb_k1_dispatch(J, B.xv.data(), B.win_full.data(), B.win_tail.data(), B.ana.data(), B.taps.data(), gv);
+    if (analyze_only) return FB200_OK;
+    // K2
+    {
+        int nmax = J.block_size;
+        FbK2Layout L = fb_k2_layout(nmax, fbh_leaves_max(J));
+        std::vector<uint8_t> smem(L.total + 3 * sizeof(FbRiceResult) + 64);
+        for (uint32_t gv = 0; gv < nvars; gv++) {
+            memset(smem.data(), 0xAB, smem.size());
+            fb_k2_body(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L);
+        }
+    }
+    // K3
+    B.slots.assign((size_t)J.n_frames * J.slot_bytes, 0xCD);
+    B.frame_bytes.assign(J.n_frames, 0);
+    B.infos.resize(J.n_frames);
+    {
+        uint32_t mb = fb_max_frame_bytes(J.channels, J.bps, J.block_size);
+        std::vector<uint8_t> smem(fb_k3_smem_bytes(mb, J.block_size, J.pack_in_smem) + 64);
+        for (uint32_t f = 0; f < J.n_frames; f++) {
+            memset(smem.data(), 0xEF, smem.size());
+            fb_k3_body(J, B.xv.data(), B.choice.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), f,
+                       smem.data());
+        }
+    }
+    // K4 scan
+    B.offsets.assign(J.n_frames + 1, 0);
+    {
+        std::vector<unsigned long long> partials(FB_K4_THREADS);
+        fb_k4_scan_body(B.frame_bytes.data(), B.offsets.data(), J.n_frames, partials.data());
+    }
+    return FB200_OK;
+}
+
+int fbemu_encode_interleaved(const fb200_config *cfg, const void *pcm, int container_bytes, uint64_t n_samples,
+                             int channels, int bps, int rate, int block_size, uint32_t first_frame, uint8_t *out,
+                             size_t out_cap, uint32_t *frame_sizes, fb200_frame_info *infos, size_t *n_frames,
+                             size_t *out_len, int force_global_pack) {
+    EmuBuffers B;
+    FbJob J;
+    (void)force_global_pack;
+    int rc = emu_run(cfg, pcm, nullptr, 0, container_bytes, n_samples, channels, bps, rate, block_size, first_frame,
+                     false, B, J);
+    if (rc) return rc;
+    if (n_frames) *n_frames = J.n_frames;
+    if (J.n_frames == 0) {
+        if (out_len) *out_len = 0;
+        return FB200_OK;
+    }
+    unsigned long long total = B.offsets[J.n_frames];
+    if (out_len) *out_len = (size_t)total;
+    if (total > out_cap) return FB200_ERR_CAPACITY;
+    for (uint32_t f = 0; f < J.n_frames; f++)
+        for (int tid = 0; tid < 256; tid++)
+            fb_k4_gather_thread(B.slots.data(), J.slot_bytes, B.frame_bytes.data(), B.offsets.data(), out, out_cap, f,
+                                tid, 256);
+    if (frame_sizes) memcpy(frame_sizes, B.frame_bytes.data(), sizeof(uint32_t) * J.n_frames);
+    if (infos) memcpy(infos, B.infos.data(), sizeof(fb200_frame_info) * J.n_frames);
+    return FB200_OK;
+}
+
+int fbemu_encode_planar_frame(const fb200_config *cfg, const int32_t *planar, int stride, int n, int channels, int bps,
+                              int rate, uint32_t frame_number, uint8_t *out, size_t out_cap, size_t *out_len,
+                              fb200_frame_info *info) {
+    EmuBuffers B;
+    FbJob J;
+    if (n < 1 || n > 32767) return FB200_ERR_SOURCE;
+    int block_size = n < 32 ? 32 : n; // FrameBuf sizes are >= 32; a short frame is a tail of a 32-block
+    int rc = emu_run(cfg, nullptr, planar, stride, 4, (uint64_t)n, channels, bps, rate, block_size, frame_number,
+                     false, B, J);
+    if (rc) return rc;
+    unsigned long long total = B.offsets[1];
+    if (out_len) *out_len = (size_t)total;
+    if (total > out_cap) return FB200_ERR_CAPACITY;
+    memcpy(out, B.slots.data(), (size_t)total);
+    if (info) *info = B.infos[0];
+    return FB200_OK;
+}
+
+int fbemu_analyze(const fb200_config *cfg, const void *pcm, int container_bytes, uint64_t n_samples, int channels,
+                  int bps, int rate, int block_size, fb200_variant_taps *taps, size_t taps_cap, size_t *n_variants) {
+    EmuBuffers B;
+    FbJob J;
+    int rc = emu_run(cfg, pcm, nullptr, 0, container_bytes, n_samples, channels, bps, rate, block_size, 0, true, B, J);
+    if (rc) return rc;
+    size_t nv = (size_t)J.n_frames * J.nvar;
+    if (n_variants) *n_variants = nv;
+    if (nv > taps_cap) return FB200_ERR_CAPACITY;
+    if (nv) memcpy(taps, B.taps.data(), nv * sizeof(fb200_variant_taps));
+    return FB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libflacenc_b200.so via ctypes), against the
+CPU oracle on the same seeded inputs.  Bar: frame bytes bit-exact; floats of the analysis tier within 1e-5
+relative (they are in fact bit-identical); decoded PCM identical to the input (tier 1).
+Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_fixture, pack_pcm
+from flacenc_rs_b200 import _ffi, sigen
+from flacenc_rs_b200.config import Encoder, Fixed, OrderSel, Qlpc, StereoCoding, SubFrameCoding, Window, Prc
+from flacenc_rs_b200.encoder import (Context, StreamInfo, encode_fixed_size_frame, encode_with_fixed_block_size)
+from flacenc_rs_b200.error import VerifyError
+from flacenc_rs_b200.source import FrameBuf, MemSource
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_config(**kw) -> Encoder:
+    """flat oracle-style keywords -> config::Encoder mirror"""
+    e = Encoder()
+    s = e.subframe_coding
+    for k, v in kw.items():
+        if k in ("use_leftside", "use_rightside", "use_midside"):
+            setattr(e.stereo_coding, k, bool(v))
+        elif k in ("use_constant", "use_fixed", "use_lpc"):
+            setattr(s, k, bool(v))
+        elif k == "fixed_max_order":
+            s.fixed.max_order = v
+        elif k == "fixed_order_sel":
+            s.fixed.order_sel.type = "BitCount" if v == 0 else "ApproxEnt"
+        elif k == "approx_ent_partitions":
+            s.fixed.order_sel.partitions = v
+        elif k == "lpc_order":
+            s.qlpc.lpc_order = v
+        elif k == "quant_precision":
+            s.qlpc.quant_precision = v
+        elif k == "window_type":
+            s.qlpc.window.type = "Rectangle" if v == 0 else "Tukey"
+        elif k == "tukey_alpha":
+            s.qlpc.window.alpha = v
+        elif k == "prc_max_parameter":
+            s.prc.max_parameter = v
+        elif k == "block_size":
+            e.block_size = v
+        else:
+            raise KeyError(k)
+    return e
+
+
+def _compare(signal, channels, bps, rate, block_size, container=None, first_frame=0, check_infos=False, **cfgkw):
+    ocfg = O.default_config(**cfgkw)
+    vcfg = make_config(**cfgkw).into_verified()
+    assert bytes(vcfg.pod) == bytes(ocfg)  # the POD the C ABI receives equals the oracle's config
+    signal = np.ascontiguousarray(signal, np.int32).reshape(-1, channels)
+    n = len(signal)
+    container = container or (bps + 7) // 8
+    ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
+    with Context(vcfg, channels, bps, rate, block_size) as ctx:
+        got, sizes, infos = ctx.encode_interleaved(pack_pcm(signal, container), container, n, first_frame,
+                                                   want_infos=check_infos)
+        got = got.tobytes()
+        t = ctx.timing()
+        assert t.launches >= 6 and t.kernels_ms > 0
+    assert list(sizes) == list(ref_sizes)
+    if got != ref:
+        off = 0
+        for i, s in enumerate(ref_sizes):
+            assert got[off:off + s] == ref[off:off + s], f"frame {i} differs (size {s})"
+            off += s
+    assert got == ref
+    out, nf = O.decode_frames(got, channels, bps)
+    assert np.array_equal(out, signal)
+    return infos
+
+
+def test_cd_stereo_c1_full():
+    """BASELINE config 1: 10 s, 44.1 kHz, 16-bit stereo, block 4096 (108 frames, tail 2728)"""
+    x = sigen.noisy_sine_pcm(441000, 2, 16, 44100, config_id=1)
+    infos = _compare(x, 2, 16, 44100, 4096, check_infos=True)
+    assert infos[107].block_size == 2728 and infos[0].block_size == 4096
+
+
+@pytest.mark.parametrize("name", ["sus109", "sus6", "ras22", "ras103"])
+def test_fixture_clips(name):
+    x = np.stack([load_fixture(name, 0), load_fixture(name, 1)], axis=1)
+    _compare(x, 2, 16, 44100, 4096)
+    _compare(x[:, 0], 1, 16, 44100, 4096)
+
+
+def test_96k_24bit_order24_block4608_c3():
+    x = sigen.noisy_sine_pcm(4608 * 20, 2, 24, 96000, config_id=3)
+    _compare(x, 2, 24, 96000, 4608, lpc_order=24, quant_precision=15)
+
+
+def test_8ch_24bit_c5_slice():
+    x = sigen.noisy_sine_pcm(4096 * 6 + 1000, 8, 24, 48000, config_id=5)
+    _compare(x, 8, 24, 48000, 4096)
+
+
+def test_rectangle_window_c4_shape():
+    x = sigen.noisy_sine_pcm(4096 * 10, 2, 16, 44100, config_id=4)
+    _compare(x, 2, 16, 44100, 4096, window_type=0)
+
+
+@pytest.mark.parametrize("cfgkw", [
+    dict(use_lpc=0), dict(use_fixed=0), dict(use_constant=0), dict(fixed_order_sel=0),
+    dict(use_leftside=0, use_rightside=0), dict(use_midside=0), dict(use_leftside=0, use_rightside=0, use_midside=0),
+    dict(lpc_order=1, quant_precision=3), dict(lpc_order=7, quant_precision=12, tukey_alpha=0.1),
+    dict(fixed_max_order=0), dict(fixed_max_order=2, approx_ent_partitions=32), dict(approx_ent_partitions=1),
+    dict(approx_ent_partitions=64), dict(prc_max_parameter=0), dict(prc_max_parameter=3), dict(prc_max_parameter=14),
+    dict(fixed_max_order=9), dict(tukey_alpha=1.0), dict(tukey_alpha=0.0), dict(lpc_order=16), dict(lpc_order=20),
+])
+def test_config_variations(cfgkw):
+    x = sigen.Sine(60, 0.5).noise(0.05, seed=2).to_vec_quantized(16, 2 * 3000).reshape(3000, 2)
+    _compare(x, 2, 16, 44100, 1024, **cfgkw)
+
+
+@pytest.mark.parametrize("block_size", [32, 63, 64, 65, 100, 192, 576, 1000, 1152, 4000, 4095, 4097, 16384])
+def test_block_sizes(block_size):
+    n = block_size * 2 + block_size // 3 + 1
+    x = sigen.Sine(77, 0.6).noise(0.02, seed=block_size).to_vec_quantized(16, n)
+    _compare(x, 1, 16, 32000, block_size)
+
+
+def test_max_block_size_8ch_global_pack_path():
+    x = sigen.noisy_sine_pcm(32767 + 500, 8, 24, 96000, config_id=7)
+    _compare(x, 8, 24, 96000, 32767)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("bps,container", [(8, 1), (12, 2), (16, 2), (20, 3), (24, 3), (24, 4), (16, 4)])
+def test_channels_and_sample_formats(channels, bps, container):
+    n = 2500
+    chans = [sigen.Sine(30 + 7 * c, 0.7).noise(0.01, seed=c).to_vec_quantized(bps, n) for c in range(channels)]
+    _compare(np.stack(chans, axis=1), channels, bps, 48000, 1024, container=container)
+
+
+def test_special_signals():
+    _compare(np.zeros((3000, 2), np.int32), 2, 16, 44100, 1024)
+    c = np.full((3000, 2), -1234, np.int32)
+    c[:, 1] = 77
+    _compare(c, 2, 16, 44100, 1024)
+    fs = np.tile(np.array([[32767, -32768], [-32768, 32767]], np.int32), (1500, 1))
+    _compare(fs, 2, 16, 44100, 1024)
+    rng = np.random.default_rng(5)
+    _compare(rng.integers(-(1 << 23), 1 << 23, (3000, 2)).astype(np.int32), 2, 24, 96000, 1024)
+    imp = np.zeros((4096, 1), np.int32)
+    imp[1000] = 30000
+    _compare(imp, 1, 16, 44100, 4096)
+    loudquiet = np.concatenate([rng.integers(-30000, 30000, 2048), rng.integers(-3, 3, 2048)]).astype(np.int32)
+    _compare(loudquiet.reshape(-1, 1), 1, 16, 44100, 4096)
+
+
+def test_pathological_residuals():
+    """residuals >= 2^27: chunked saturating Rice tables (src/rice.rs:75-98) and 32-bit wrap (src/lpc.rs:375-389)"""
+    t = np.arange(4096)
+    smooth = (np.sin(t / 300.0) * 8000000).astype(np.int32)
+    smooth[3000:] = np.where(np.arange(1096) % 2 == 0, 8388607, -8388608)
+    _compare(smooth.reshape(-1, 1), 1, 24, 96000, 4096, lpc_order=24)
+    _compare(np.stack([smooth, smooth[::-1]], axis=1), 2, 24, 96000, 4096, lpc_order=12, prc_max_parameter=5)
+    alt = np.where(np.arange(4096) % 2 == 0, 8388607, -8388608).astype(np.int32).reshape(-1, 1)
+    _compare(alt, 1, 24, 96000, 4096, fixed_order_sel=0)
+
+
+def test_first_frame_number_and_utf8_lengths():
+    x = sigen.Sine(50, 0.3).noise(0.01, seed=1).to_vec_quantized(16, 600).reshape(300, 2)
+    for first in (0, 127, 128, 2047, 65535, (1 << 21) - 1, (1 << 26), (1 << 31) - 3):
+        _compare(x, 2, 16, 44100, 128, first_frame=first)
+
+
+def test_errors_map_to_reference_error_kinds():
+    cfg = Encoder().into_verified()
+    x = np.zeros((200, 2), np.int32)
+    x[77, 1] = 2048
+    with Context(cfg, 2, 12, 44100, 64) as ctx:
+        with pytest.raises(VerifyError):          # sample out of range (src/source.rs:262-275)
+            ctx.encode_interleaved(pack_pcm(x, 2), 2, 200)
+        x[77, 1] = -2048
+        ctx.encode_interleaved(pack_pcm(x, 2), 2, 200)
+        with pytest.raises(VerifyError):          # frame number >= 2^31 (src/coding.rs:587-591)
+            ctx.encode_interleaved(pack_pcm(x, 2), 2, 200, (1 << 31) - 2)
+        got, sizes, _ = ctx.encode_interleaved(pack_pcm(x, 2), 2, 0)   # empty input: zero frames
+        assert len(got) == 0 and len(sizes) == 0
+    bad = Encoder()
+    bad.subframe_coding.qlpc.lpc_order = 25
+    with pytest.raises(VerifyError):
+        bad.into_verified()
+    with pytest.raises(VerifyError):
+        Context(cfg, 9, 16, 44100, 4096)
+
+
+def test_float_tier_taps():
+    """north_star tier 2: autocorrelation and LPC floats within 1e-5 relative (bit-identical in practice),
+    quantised coefficients exact"""
+    x = sigen.noisy_sine_pcm(4096 * 2 + 999, 2, 16, 44100)
+    with Context(Encoder().into_verified(), 2, 16, 44100, 4096) as ctx:
+        taps, nv = ctx.analyze(pack_pcm(x, 2), 2, len(x))
+    assert nv == 12
+    for f in range(3):
+        blk = x[f * 4096:(f + 1) * 4096]
+        L, R = blk[:, 0], blk[:, 1]
+        for v, sig in enumerate([L, R, (L + R) >> 1, L - R]):
+            coefs, corr = O.lpc_from_autocorr(sig, 1, 0.4, 10)
+            tp = taps[f * 4 + v]
+            np.testing.assert_allclose(np.array(tp.autocorr[:11]), corr, rtol=1e-5)
+            np.testing.assert_allclose(np.array(tp.lpc[:10]), coefs, rtol=1e-5, atol=1e-12)
+            assert np.array_equal(np.array(tp.autocorr[:11]), corr)
+            assert np.array_equal(np.array(tp.lpc[:10]), coefs)
+            q, order, shift = O.quantize_parameters(coefs, 15)
+            assert tp.qlp_order == order and tp.qlp_shift == shift and list(tp.qlp[:order]) == q.tolist()
+            e5 = O.fixed_lpc_errors(sig)
+            bps_v = 17 if v == 3 else 16
+            assert list(tp.fixed_est_bits) == [O.estimate_entropy(e5[k], k, 16) + bps_v * k for k in range(5)]
+
+
+def test_encode_fixed_size_frame_api():
+    """encode_fixed_size_frame on a FrameBuf (src/coding.rs:581-606); short fills and decision records"""
+    cfg = Encoder().into_verified()
+    x = sigen.Sine(90, 0.5).noise(0.03, seed=4).to_vec_quantized(16, 2 * 1024).reshape(1024, 2)
+    fb = FrameBuf.with_size(2, 1024)
+    si = StreamInfo.new(44100, 2, 16)
+    for filled in (1024, 700, 40):
+        fb.fill_interleaved(x[:filled])
+        frame = encode_fixed_size_frame(cfg, fb, 5, si)
+        planar = np.zeros((2, 1024), np.int32)
+        planar[:, :filled] = x[:filled].T
+        ref, rec = O.encode_frame(O.default_config(), planar, 16, 44100, 5, n=filled)
+        assert frame.bitstream == ref
+        assert frame.channel_assignment == (rec["ch_assignment"] or 1)
+        for c in range(2):
+            assert frame.subframes[c].type == rec["subframes"][c]["type"]
+            assert frame.subframes[c].bits == rec["subframes"][c]["bits"]
+            if frame.subframes[c].type in (2, 3):
+                assert frame.subframes[c].rice_params == rec["subframes"][c]["rice_params"]
+            if frame.subframes[c].type == 3:
+                assert frame.subframes[c].qlp == rec["subframes"][c]["qlp"]
+    with pytest.raises(VerifyError):
+        encode_fixed_size_frame(cfg, fb, 1 << 31, si)
+
+
+def test_encode_with_fixed_block_size_stream():
+    """encode_with_fixed_block_size (src/coding.rs:645-695): whole stream incl. STREAMINFO and MD5"""
+    for ch, bps, rate, bs, n in ((2, 16, 44100, 4096, 16123), (1, 16, 44100, 4096, 102), (2, 24, 16000, 128, 1024),
+                                 (3, 8, 8000, 256, 5000)):
+        chans = [sigen.Sine(100 + 13 * c, 0.4).noise(0.05, seed=c).to_vec_quantized(bps, n) for c in range(ch)]
+        signal = np.stack(chans, axis=1)
+        src = MemSource.from_samples(signal, ch, bps, rate)
+        stream = encode_with_fixed_block_size(Encoder().into_verified(), src, bs)
+        ref = O.encode_stream(O.default_config(), signal, ch, bps, rate, bs)
+        assert stream.write() == ref
+        out, info = O.decode_stream(stream.write())
+        assert np.array_equal(out, signal)
+        assert bytes(info.md5) == O.md5_of_samples(signal, (bps + 7) // 8)
+        assert info.min_block == info.max_block and info.total_samples == n
+    # the reference's MD5 known answer (src/coding.rs:737-769)
+    signal = np.full((1024, 2), 23, np.int32)
+    s = encode_with_fixed_block_size(Encoder().into_verified(), MemSource.from_samples(signal, 2, 24, 16000), 128)
+    assert s.write()[26:42] == bytes([0xEE, 0x78, 0x7A, 0x6E, 0x99, 0x01, 0x36, 0x79, 0xA5, 0xBB, 0x6D, 0x5C, 0x10,
+                                      0xAF, 0x0B, 0x87])
+    # empty stream = 42 bytes (src/component/bitrepr.rs:610-621)
+    e = encode_with_fixed_block_size(Encoder().into_verified(), MemSource.from_samples([], 2, 16, 44100), 4096)
+    assert len(e) == 42
+
+
+def test_device_resident_api_matches_host_api():
+    """fb200_encode_device (HBM in, HBM out) returns the same bytes as the host-buffer call"""
+    import torch
+    x = sigen.noisy_sine_pcm(4096 * 37 + 123, 2, 16, 44100, config_id=2)
+    pcm = pack_pcm(x, 2)
+    with Context(Encoder().into_verified(), 2, 16, 44100, 4096) as ctx:
+        host_bytes, host_sizes, _ = ctx.encode_interleaved(pcm, 2, len(x))
+        host_bytes = host_bytes.tobytes()
+        d_in = torch.from_numpy(pcm.copy()).cuda()
+        d_out = torch.empty(38 * ctx.max_frame_bytes(), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        olen, sizes = ctx.encode_device(d_in.data_ptr(), 2, len(x), d_out.data_ptr(), d_out.numel())
+        assert olen == len(host_bytes) and list(sizes) == list(host_sizes)
+        assert d_out[:olen].cpu().numpy().tobytes() == host_bytes
+
+
+def test_large_batch_properties_c2_slice():
+    """size-independent checks on a large batch (2000 frames of config 2): lossless decode, both CRCs valid
+    (the decoder verifies them), sizes sum to the stream, stream size equals the oracle's on a sample"""
+    n = 4096 * 2000 + 3136
+    x = sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=2)
+    with Context(Encoder().into_verified(), 2, 16, 44100, 4096) as ctx:
+        got, sizes, _ = ctx.encode_interleaved(pack_pcm(x, 2), 2, n)
+    assert int(sizes.sum()) == len(got) and len(sizes) == 2001
+    out, nf = O.decode_frames(got.tobytes(), 2, 16)
+    assert nf == 2001 and np.array_equal(out, x)
+    # frame bytes of a random sample of frames against the oracle
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    rng = np.random.default_rng(0)
+    for f in sorted(set(rng.integers(0, 2001, 40).tolist() + [0, 2000])):
+        blk = x[f * 4096:(f + 1) * 4096]
+        ref, _ = O.encode_frames(O.default_config(), blk, 2, 16, 44100, 4096, first_frame_number=f)
+        assert got[offs[f]:offs[f + 1]].tobytes() == ref, f

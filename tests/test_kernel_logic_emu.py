@@ -1,0 +1,226 @@
+"""Checks the CUDA kernel bodies' logic against the oracle on the CPU, by running
+flacenc_rs_b200/csrc/fb_kernels.cuh under the phase-by-phase CTA emulation in tests/emu.
+The same comparisons run against the real kernels in tests/test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import load_fixture, pack_pcm
+from flacenc_rs_b200 import sigen
+from oracle import oracle as O
+from emu import emu as E
+
+
+def _cfg_pair(**kw):
+    return O.default_config(**kw), E.default_config(**kw)
+
+
+def _compare(signal, channels, bps, rate, block_size, container=None, first_frame=0, **cfgkw):
+    ocfg, ecfg = _cfg_pair(**cfgkw)
+    signal = np.ascontiguousarray(signal, np.int32).reshape(-1, channels)
+    n = len(signal)
+    container = container or (bps + 7) // 8
+    ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
+    rc, got, sizes, _ = E.encode_interleaved(ecfg, pack_pcm(signal, container), container, n, channels, bps, rate,
+                                             block_size, first_frame)
+    assert rc == 0
+    assert list(sizes) == list(ref_sizes)
+    if got != ref:
+        # locate the first differing frame for the report
+        off = 0
+        for i, s in enumerate(ref_sizes):
+            if got[off:off + s] != ref[off:off + s]:
+                raise AssertionError(f"frame {i} differs (size {s})")
+            off += s
+    assert got == ref
+    out, nf = O.decode_frames(got, channels, bps)
+    assert np.array_equal(out, signal)
+
+
+def test_log2f_matches_libm_sampled():
+    """fb_log2f (device code) vs glibc log2f; the exhaustive run is tests/test_log2f_compat.py (slow)"""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    libm.log2f.restype = C.c_float
+    libm.log2f.argtypes = [C.c_float]
+    rng = np.random.default_rng(1)
+    bits = np.concatenate([rng.integers(1, 0x7F800000, 200000, dtype=np.uint32),
+                           np.array([1, 0x00800000, 0x3F800000, 0x3F7FFFFF, 0x3F800001, 0x7F7FFFFF, 0], np.uint32)])
+    xs = bits.view(np.float32)
+    L = E.lib()
+    for x in xs[:20000].tolist() + xs[-7:].tolist():
+        a, b = L.fbemu_log2f(x), libm.log2f(x)
+        assert a == b or (a != a and b != b), x
+
+
+def test_default_config_matches_oracle():
+    o, e = _cfg_pair()
+    assert bytes(o) == bytes(e)
+
+
+def test_frame_header_matches_oracle():
+    L = E.lib()
+    for n in (192, 256, 576, 1000, 4096, 4608, 100, 2728, 32767, 16384):
+        for ch_tag in (0, 1, 7, 8, 9, 10):
+            for bps, rate in ((16, 44100), (24, 96000), (8, 12345), (20, 48000), (16, 11025), (24, 95800)):
+                for num in (0, 1, 127, 128, 2047, 2048, 65535, 65536, (1 << 21), (1 << 26) + 5, (1 << 31) - 1):
+                    a = np.zeros(16, np.uint8)
+                    b = np.zeros(16, np.uint8)
+                    ka = L.fbemu_frame_header(n, ch_tag, bps, rate, num, a.ctypes.data_as(E.C.POINTER(E.C.c_uint8)))
+                    kb = O.lib().fo_frame_header_bytes(n, ch_tag, bps, rate, 0, num, O._p(b, O.C.c_uint8))
+                    assert ka == kb and bytes(a[:ka]) == bytes(b[:kb])
+
+
+def test_cd_stereo_noisy_sine_c1_slice():
+    """config 1 shape: 44.1 kHz / 16-bit / stereo, block 4096, short tail"""
+    x = sigen.noisy_sine_pcm(4096 * 3 + 2728, 2, 16, 44100)
+    _compare(x, 2, 16, 44100, 4096)
+
+
+@pytest.mark.parametrize("name", ["sus109", "sus6", "ras22", "ras103"])
+def test_fixture_clips(name):
+    x = np.stack([load_fixture(name, 0), load_fixture(name, 1)], axis=1)
+    _compare(x, 2, 16, 44100, 4096)
+    _compare(x[:, 0], 1, 16, 44100, 4096)
+
+
+def test_96k_24bit_order24_block4608():
+    """config 3 shape"""
+    x = sigen.noisy_sine_pcm(4608 * 2, 2, 24, 96000, config_id=3)
+    _compare(x, 2, 24, 96000, 4608, lpc_order=24, quant_precision=15)
+
+
+def test_8ch_24bit():
+    """config 5 shape"""
+    x = sigen.noisy_sine_pcm(4096 + 1000, 8, 24, 48000, config_id=5)
+    _compare(x, 8, 24, 48000, 4096)
+
+
+def test_rectangle_window_c4_shape():
+    x = sigen.noisy_sine_pcm(4096 * 2, 2, 16, 44100, config_id=4)
+    _compare(x, 2, 16, 44100, 4096, window_type=0)
+
+
+@pytest.mark.parametrize("cfgkw", [
+    dict(use_lpc=0), dict(use_fixed=0), dict(use_constant=0), dict(fixed_order_sel=0),
+    dict(use_leftside=0, use_rightside=0), dict(use_midside=0), dict(use_leftside=0, use_rightside=0, use_midside=0),
+    dict(lpc_order=1, quant_precision=3), dict(lpc_order=7, quant_precision=12, tukey_alpha=0.1),
+    dict(fixed_max_order=0), dict(fixed_max_order=2, approx_ent_partitions=32), dict(approx_ent_partitions=1),
+    dict(approx_ent_partitions=64), dict(prc_max_parameter=0), dict(prc_max_parameter=3), dict(prc_max_parameter=14),
+    dict(fixed_max_order=9), dict(tukey_alpha=1.0), dict(tukey_alpha=0.0),
+])
+def test_config_variations(cfgkw):
+    x = sigen.Sine(60, 0.5).noise(0.05, seed=2).to_vec_quantized(16, 2 * 3000).reshape(3000, 2)
+    _compare(x, 2, 16, 44100, 1024, **cfgkw)
+
+
+@pytest.mark.parametrize("block_size", [32, 63, 64, 65, 100, 192, 576, 1000, 1152, 4000, 4095, 4097, 16384])
+def test_block_sizes(block_size):
+    n = block_size * 2 + block_size // 3 + 1
+    x = sigen.Sine(77, 0.6).noise(0.02, seed=block_size).to_vec_quantized(16, n)
+    _compare(x, 1, 16, 32000, block_size)
+
+
+def test_max_block_size_8ch_global_pack_path():
+    """32767-sample blocks with 8 channels do not fit shared memory: frames are assembled in their global slot"""
+    x = sigen.noisy_sine_pcm(32767 + 500, 8, 24, 96000, config_id=7)
+    _compare(x, 8, 24, 96000, 32767)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("bps,container", [(8, 1), (12, 2), (16, 2), (20, 3), (24, 3), (24, 4), (16, 4)])
+def test_channels_and_sample_formats(channels, bps, container):
+    n = 2500
+    chans = [sigen.Sine(30 + 7 * c, 0.7).noise(0.01, seed=c).to_vec_quantized(bps, n) for c in range(channels)]
+    _compare(np.stack(chans, axis=1), channels, bps, 48000, 1024, container=container)
+
+
+def test_8bit_in_16bit_container():
+    x = sigen.Sine(40, 0.9).noise(0.1, seed=3).to_vec_quantized(8, 5000).reshape(2500, 2)
+    _compare(x, 2, 8, 22050, 512, container=2)
+
+
+def test_special_signals():
+    z = np.zeros((3000, 2), np.int32)
+    _compare(z, 2, 16, 44100, 1024)                                  # constant zero
+    c = np.full((3000, 2), -1234, np.int32)
+    c[:, 1] = 77
+    _compare(c, 2, 16, 44100, 1024)                                  # constant non-zero, S constant too
+    fs = np.tile(np.array([[32767, -32768], [-32768, 32767]], np.int32), (1500, 1))
+    _compare(fs, 2, 16, 44100, 1024)                                 # full-scale alternation: verbatim / huge residuals
+    rng = np.random.default_rng(5)
+    w = rng.integers(-(1 << 23), 1 << 23, (3000, 2)).astype(np.int32)
+    _compare(w, 2, 24, 96000, 1024)                                  # white noise 24-bit: verbatim
+    imp = np.zeros((4096, 1), np.int32)
+    imp[1000] = 30000
+    _compare(imp, 1, 16, 44100, 4096)                                # impulse: mixed leaf parameters
+    step = np.concatenate([np.zeros(2000, np.int32), np.full(2096, 20000, np.int32)]).reshape(-1, 1)
+    _compare(step, 1, 16, 44100, 4096)
+    loudquiet = np.concatenate([rng.integers(-30000, 30000, 2048), rng.integers(-3, 3, 2048)]).astype(np.int32)
+    _compare(loudquiet.reshape(-1, 1), 1, 16, 44100, 4096)           # wide spread of leaf parameters
+
+
+def test_pathological_lpc_gain_chunked_saturation_path():
+    """smooth signal then full-scale alternation: the LPC residual exceeds 2^27 (mode 2 of the Rice search,
+    src/rice.rs:75-98 chunked saturating accumulation) and wraps in 32 bits (src/lpc.rs:375-389)"""
+    t = np.arange(4096)
+    smooth = (np.sin(t / 300.0) * 8000000).astype(np.int32)
+    smooth[3000:] = np.where(np.arange(1096) % 2 == 0, 8388607, -8388608)
+    _compare(smooth.reshape(-1, 1), 1, 24, 96000, 4096, lpc_order=24)
+    _compare(np.stack([smooth, smooth[::-1]], axis=1), 2, 24, 96000, 4096, lpc_order=12, prc_max_parameter=5)
+
+
+def test_first_frame_number_and_utf8_lengths():
+    x = sigen.Sine(50, 0.3).noise(0.01, seed=1).to_vec_quantized(16, 600).reshape(300, 2)
+    for first in (0, 127, 128, 2047, 65535, (1 << 21) - 1, (1 << 26), (1 << 31) - 3):
+        _compare(x, 2, 16, 44100, 128, first_frame=first)
+
+
+def test_out_of_range_sample_is_a_config_error():
+    """src/coding.rs:587-593 + src/source.rs:262-275: VerifyError -> FB200_ERR_CONFIG"""
+    x = np.zeros((200, 2), np.int32)
+    x[77, 1] = 2048  # 12-bit range is [-2048, 2047]
+    rc, _, _, _ = E.encode_interleaved(E.default_config(), pack_pcm(x, 2), 2, 200, 2, 12, 44100, 64)
+    assert rc == 1
+    x[77, 1] = -2048
+    rc, _, _, _ = E.encode_interleaved(E.default_config(), pack_pcm(x, 2), 2, 200, 2, 12, 44100, 64)
+    assert rc == 0
+    # frame number must stay below 2^31
+    rc, _, _, _ = E.encode_interleaved(E.default_config(), pack_pcm(x, 2), 2, 200, 2, 12, 44100, 64, (1 << 31) - 2)
+    assert rc == 1
+
+
+def test_config_verify_matches_oracle():
+    cases = [dict(), dict(lpc_order=0), dict(lpc_order=25), dict(quant_precision=0), dict(quant_precision=16),
+             dict(tukey_alpha=1.5), dict(tukey_alpha=-0.1), dict(prc_max_parameter=31), dict(use_direct_mse=1),
+             dict(mae_optimization_steps=2), dict(block_size=31), dict(block_size=32768), dict(fixed_max_order=9),
+             dict(window_type=0, tukey_alpha=9.0)]
+    for kw in cases:
+        o, e = _cfg_pair(**kw)
+        assert O.lib().fo_config_verify(O.C.byref(o)) == E.lib().fbemu_config_verify(E.C.byref(e)), kw
+
+
+def test_float_tier_taps_match_oracle():
+    """autocorrelation / LPC floats are bit-identical to the scalar reference order (tolerance tier: 1e-5 rel)"""
+    x = sigen.noisy_sine_pcm(4096 * 2, 2, 16, 44100)
+    ecfg = E.default_config()
+    rc, taps, nv = E.analyze(ecfg, pack_pcm(x, 2), 2, len(x), 2, 16, 44100, 4096)
+    assert rc == 0 and nv == 8
+    for f in range(2):
+        blk = x[f * 4096:(f + 1) * 4096]
+        L, R = blk[:, 0], blk[:, 1]
+        variants = [L, R, (L + R) >> 1, L - R]
+        for v, sig in enumerate(variants):
+            coefs, corr = O.lpc_from_autocorr(sig, 1, 0.4, 10)
+            tp = taps[f * 4 + v]
+            got_corr = np.array(tp.autocorr[:11])
+            got_lpc = np.array(tp.lpc[:10])
+            np.testing.assert_allclose(got_corr, corr, rtol=1e-5)
+            np.testing.assert_allclose(got_lpc, coefs, rtol=1e-5, atol=1e-12)
+            assert np.array_equal(got_corr, corr) and np.array_equal(got_lpc, coefs)  # in fact bit-identical
+            q, order, shift = O.quantize_parameters(coefs, 15)
+            assert tp.qlp_order == order and tp.qlp_shift == shift
+            assert list(tp.qlp[:order]) == q.tolist()
+            e5 = O.fixed_lpc_errors(sig)
+            bps_v = 17 if v == 3 else 16
+            est = [O.estimate_entropy(e5[k], k, 16) + bps_v * k for k in range(5)]
+            assert list(tp.fixed_est_bits) == est
