@@ -51,18 +51,31 @@ static void fb_launch_k1(const FbJob &J, const int32_t *xv, const float *win_ful
     }
 }
 
+template <int G>
 __global__ void __launch_bounds__(FB_K2_THREADS) fb_k2_rice(FbJob J, const int32_t *xv, const FbAnalysis *ana,
                                                            fb200_subframe_info *choice, FbK2Layout L) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_k2_body(J, xv, ana, choice, blockIdx.x, fb_smem, L);
+    fb_k2_body<G>(J, xv, ana, choice, blockIdx.x, fb_smem, L);
 }
 
+template <int G>
 __global__ void __launch_bounds__(FB_K3_THREADS) fb_k3_pack(FbJob J, const int32_t *xv, const fb200_subframe_info *choice,
                                                            uint8_t *slots, uint32_t *frame_bytes,
                                                            fb200_frame_info *infos) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_k3_body(J, xv, choice, slots, frame_bytes, infos, blockIdx.x, fb_smem);
+    fb_k3_body<G>(J, xv, choice, slots, frame_bytes, infos, blockIdx.x, fb_smem);
 }
+
+// one instantiation per ring size G = fb_k1_ring(lpc_order)
+#define FB_DISPATCH_G(G_VALUE, STMT)                                                                \
+    switch (G_VALUE) {                                                                              \
+    case 4: { constexpr int G = 4; STMT; } break;                                                   \
+    case 8: { constexpr int G = 8; STMT; } break;                                                   \
+    case 12: { constexpr int G = 12; STMT; } break;                                                 \
+    case 16: { constexpr int G = 16; STMT; } break;                                                 \
+    case 20: { constexpr int G = 20; STMT; } break;                                                 \
+    default: { constexpr int G = 24; STMT; } break;                                                 \
+    }
 
 // offsets[i] = *total + exclusive prefix; *total advances by the chunk's bytes (single CTA)
 __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *frame_bytes, unsigned long long *offsets,
@@ -337,12 +350,15 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
         ctx->last_error = "internal: shared memory budget exceeded";
         return FB200_ERR_CUDA;
     }
+    const int ring = fb_k1_ring(ctx->cfg.lpc_order);
     if ((int)k2_smem > ctx->k2_smem_set) {
-        FB_CUDA(ctx, cudaFuncSetAttribute(fb_k2_rice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
+        FB_DISPATCH_G(ring, FB_CUDA(ctx, cudaFuncSetAttribute(fb_k2_rice<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                              (int)k2_smem)));
         ctx->k2_smem_set = (int)k2_smem;
     }
     if ((int)k3_smem > ctx->k3_smem_set) {
-        FB_CUDA(ctx, cudaFuncSetAttribute(fb_k3_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem));
+        FB_DISPATCH_G(ring, FB_CUDA(ctx, cudaFuncSetAttribute(fb_k3_pack<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                              (int)k3_smem)));
         ctx->k3_smem_set = (int)k3_smem;
     }
 
@@ -395,14 +411,14 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
             continue;
         }
         // K2
-        fb_k2_rice<<<nvars, FB_K2_THREADS, k2_smem, st>>>(J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
-                                                          (fb200_subframe_info *)ctx->choice.p, L);
+        FB_DISPATCH_G(ring, (fb_k2_rice<G><<<nvars, FB_K2_THREADS, k2_smem, st>>>(
+                                J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
+                                (fb200_subframe_info *)ctx->choice.p, L)));
         FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
         // K3
-        fb_k3_pack<<<J.n_frames, FB_K3_THREADS, k3_smem, st>>>(J, (const int32_t *)ctx->xv.p,
-                                                              (const fb200_subframe_info *)ctx->choice.p,
-                                                              (uint8_t *)ctx->slots.p, d_fb,
-                                                              A.infos ? (fb200_frame_info *)ctx->infos.p : nullptr);
+        FB_DISPATCH_G(ring, (fb_k3_pack<G><<<J.n_frames, FB_K3_THREADS, k3_smem, st>>>(
+                                J, (const int32_t *)ctx->xv.p, (const fb200_subframe_info *)ctx->choice.p,
+                                (uint8_t *)ctx->slots.p, d_fb, A.infos ? (fb200_frame_info *)ctx->infos.p : nullptr)));
         FB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
         // K4
         fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)ctx->offsets.p, J.n_frames, d_total);

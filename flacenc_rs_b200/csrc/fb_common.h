@@ -29,12 +29,18 @@ struct float4 { float x, y, z, w; };
 #endif
 
 // ---- phase macros: a "phase" is a region between two CTA barriers --------------------------
+// Rule for code between phases (executed by every thread on the GPU, once under emulation): it may
+// read shared memory for uniform control flow, but a value read there must not be overwritten by
+// the next phase unless an FB_SYNC() separates the read from that phase (a fast thread could
+// otherwise change the value before a slow thread has read it and the CTA would diverge).
 #if FB_GPU
 #define FB_PHASE(tid, T) { const int tid = (int)threadIdx.x; (void)tid;
 #define FB_PHASE_END } __syncthreads();
+#define FB_SYNC() __syncthreads()
 #else
 #define FB_PHASE(tid, T) for (int tid = 0; tid < (T); ++tid) {
 #define FB_PHASE_END }
+#define FB_SYNC() ((void)0)
 #endif
 
 #define FB_RICE_SAT ((1u << 27) - 1u)   // src/rice.rs:51

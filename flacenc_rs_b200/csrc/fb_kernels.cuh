@@ -390,6 +390,88 @@ FB_DEV int32_t fb_residual_at(const int32_t *x, int t, int kind, int order, cons
     return (int32_t)(uint32_t)((uint64_t)(int64_t)x[t] - (uint64_t)(acc >> shift));
 }
 
+// ---- run-based residuals: one thread produces the zigzag residuals of FB_RUN consecutive samples
+// from a register window of the signal, so every tap is one multiply-add with static operands
+// (no per-tap loads, no loop overhead).  G = number of taps evaluated (order rounded up to 4, 8, 12,
+// 16 or 24); coefficients beyond `order` are zero.  Results equal fb_residual_at() sample for sample.
+
+// u[i] for t = t0 + i, i < FB_RUN; samples at t >= n give 0.  x must be readable up to index
+// ((n + 3) & ~3) - 1 (the planar stride is a multiple of 32).
+template <int G>
+FB_DEV void fb_run_residual_lpc(const int32_t *x, int n, int t0, const int16_t *q, int order, int shift,
+                                uint32_t *u) {
+    int32_t win[G + FB_RUN]; // win[i] = x[t0 - G + i]
+    if (t0 >= G) {
+#pragma unroll
+        for (int i = 0; i < G + FB_RUN; i += 4) {
+            const int4 v = *reinterpret_cast<const int4 *>(x + t0 - G + i); // t0, G multiples of 4: aligned
+            win[i] = v.x; win[i + 1] = v.y; win[i + 2] = v.z; win[i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < G + FB_RUN; i++) {
+            const int idx = t0 - G + i;
+            win[i] = (idx >= 0) ? x[idx] : 0;
+        }
+    }
+    int32_t qq[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) qq[j] = (j < order) ? (int32_t)q[j] : 0;
+#pragma unroll
+    for (int i = 0; i < FB_RUN; i++) {
+        const int t = t0 + i;
+        int64_t acc = 0;
+#pragma unroll
+        for (int j = 0; j < G; j++) acc += (int64_t)qq[j] * (int64_t)win[G + i - 1 - j];
+        const int32_t e = (int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> shift));
+        u[i] = (t >= order && t < n) ? fb_zigzag(e) : 0u;
+    }
+}
+
+FB_DEV void fb_run_residual_fixed(const int32_t *x, int n, int t0, int order, uint32_t *u) {
+    uint32_t win[4 + FB_RUN]; // win[i] = x[t0 - 4 + i]
+    if (t0 >= 4) {
+#pragma unroll
+        for (int i = 0; i < 4 + FB_RUN; i += 4) {
+            const int4 v = *reinterpret_cast<const int4 *>(x + t0 - 4 + i);
+            win[i] = (uint32_t)v.x; win[i + 1] = (uint32_t)v.y; win[i + 2] = (uint32_t)v.z; win[i + 3] = (uint32_t)v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 + FB_RUN; i++) {
+            const int idx = t0 - 4 + i;
+            win[i] = (idx >= 0) ? (uint32_t)x[idx] : 0u;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FB_RUN; i++) {
+        const int t = t0 + i;
+        const uint32_t a = win[4 + i], b = win[3 + i], c = win[2 + i], d = win[1 + i], e4 = win[i];
+        uint32_t e;
+        switch (order) {
+        case 0: e = a; break;
+        case 1: e = a - b; break;
+        case 2: e = a - 2u * b + c; break;
+        case 3: e = a - 3u * b + 3u * c - d; break;
+        default: e = a - 4u * b + 6u * c - 4u * d + e4; break;
+        }
+        u[i] = (t >= order && t < n) ? fb_zigzag((int32_t)e) : 0u;
+    }
+}
+
+// G >= order is fixed per kernel instantiation (fb_k1_ring(cfg.lpc_order)), so the register allocation
+// of the default order-10 build does not pay for the order-24 window.
+template <int G>
+FB_DEV void fb_run_residual(const int32_t *x, int n, int t0, int kind, int order, const int16_t *q, int shift,
+                            uint32_t *u) {
+    if (kind == 0) fb_run_residual_fixed(x, n, t0, order, u);
+    else fb_run_residual_lpc<G>(x, n, t0, q, order, shift, u);
+}
+
+// index of u[t] in shared memory: one pad word per 32 keeps both the per-sample (stride 1) and the
+// per-run (stride 16) access patterns free of bank conflicts
+FB_HD int fb_uidx(int t) { return t + (t >> 5); }
+
 // shared-memory layout of K2 (offsets in bytes), identical on host and device
 struct FbK2Layout {
     uint32_t off_u, off_tbl_a, off_tbl_b, off_part, off_lvl_params, off_lvl_bits, off_unit_sum, off_misc, total;
@@ -398,7 +480,7 @@ struct FbK2Layout {
 FB_HD FbK2Layout fb_k2_layout(int n_max, int leaves_max) {
     FbK2Layout L;
     uint32_t o = 0;
-    L.off_u = o;          o += (uint32_t)((n_max + 3) & ~3) * 4u;
+    L.off_u = o;          o += (uint32_t)((n_max + (n_max >> 5) + 4 + 3) & ~3) * 4u; // padded, see fb_uidx
     L.off_tbl_a = o;      o += (uint32_t)leaves_max * 32u * 4u;
     L.off_tbl_b = o;      o += (uint32_t)leaves_max * 32u * 4u;
     uint32_t units = (uint32_t)(leaves_max > FB_K2_THREADS ? leaves_max : FB_K2_THREADS);
@@ -446,6 +528,7 @@ struct FbK2Misc {
 // tables entry for entry.  When a residual is >= 2^27 the reference's 16-sample chunked saturating
 // u32 accumulation (src/rice.rs:75-98) is replayed literally (mode 2).  Either way the chosen
 // partition order, parameters and bit count are identical to the reference's.
+template <int G>
 FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind, int order, const int16_t *q,
                               int shift, uint8_t *smem, const FbK2Layout &L, FbRiceResult *res) {
     const int T = FB_K2_THREADS;
@@ -473,15 +556,22 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
     FB_PHASE_END
     FB_PHASE(tid, T)
         uint32_t mx = 0;
-        for (int t = tid; t < n; t += T) {
-            uint32_t v = fb_zigzag(fb_residual_at(x, t, kind, order, q, shift));
-            u[t] = v;
-            mx = v > mx ? v : mx;
+        const int nruns = (n + FB_RUN - 1) / FB_RUN;
+        for (int run = tid; run < nruns; run += T) {
+            uint32_t uu[FB_RUN];
+            fb_run_residual<G>(x, n, run * FB_RUN, kind, order, q, shift, uu);
+#pragma unroll
+            for (int i = 0; i < FB_RUN; i++) {
+                const int t = run * FB_RUN + i;
+                if (t < n) u[fb_uidx(t)] = uu[i];
+                mx = uu[i] > mx ? uu[i] : mx;
+            }
         }
         if (mx) fb_atomic_max_u32(&M->maxu, mx);
     FB_PHASE_END
 
-    // ---- phase 2: per-unit sums of u (unit = contiguous piece of a leaf)
+    // ---- phase 2: per-unit sums of u (unit = contiguous piece of a leaf).  Integer sums do not
+    // depend on the order, so every lane starts at a different offset of its piece (no bank conflicts).
     FB_PHASE(tid, T)
         for (int unit = tid; unit < units; unit += T) {
             int leaf = unit / nsub, sub = unit - leaf * nsub;
@@ -489,8 +579,13 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
             int a0 = lstart + (int)(((long long)leaf_len * sub) / nsub);
             int a1 = lstart + (int)(((long long)leaf_len * (sub + 1)) / nsub);
             if (a0 < warm) a0 = warm;
+            const int m = a1 - a0;
+            int t = a0 + (m > 0 ? (tid % m) : 0);
             unsigned long long sacc = 0;
-            for (int t = a0; t < a1; t++) sacc += u[t];
+            for (int i = 0; i < m; i++) {
+                sacc += u[fb_uidx(t)];
+                t = (t + 1 < a1) ? t + 1 : a0;
+            }
             unit_sum[unit] = sacc;
         }
     FB_PHASE_END
@@ -537,12 +632,16 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
                     int a0 = lstart + (int)(((long long)leaf_len * sub) / nsub);
                     int a1 = lstart + (int)(((long long)leaf_len * (sub + 1)) / nsub);
                     if (a0 < warm) a0 = warm;
+                    const int m = a1 - a0;
+                    const int tstart = a0 + (m > 0 ? (tid % m) : 0);
                     for (int pc = 0; pc < W; pc += 4) {
                         unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
                         const int p0 = a + pc;
-                        for (int t = a0; t < a1; t++) {
-                            uint32_t v = u[t] >> p0;
+                        int t = tstart;
+                        for (int i = 0; i < m; i++) {
+                            uint32_t v = u[fb_uidx(t)] >> p0;
                             c0 += v; c1 += v >> 1; c2 += v >> 2; c3 += v >> 3;
+                            t = (t + 1 < a1) ? t + 1 : a0;
                         }
                         unsigned long long c[4] = {c0, c1, c2, c3};
                         for (int k = 0; k < 4 && pc + k < W; k++)
@@ -574,7 +673,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
                     uint32_t accv = 0;
                     for (int c = start; c < end; c += 16) {
                         int ce = c + 16 < end ? c + 16 : end;
-                        for (int t = c; t < ce; t++) accv += u[t] >> p;
+                        for (int t = c; t < ce; t++) accv += u[fb_uidx(t)] >> p;
                         accv = accv < FB_RICE_SAT ? accv : FB_RICE_SAT;
                     }
                     accv += 4u + (uint32_t)(end - start) * (uint32_t)(p + 1);
@@ -636,7 +735,10 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
             }
         }
 
-        if (mode == 0 && M->fail) {
+        // every thread must have read the flag before thread 0 clears it below
+        const bool failed = (mode == 0) && (M->fail != 0);
+        FB_SYNC();
+        if (failed) {
             // widen to the full parameter range and repeat (exact by construction)
             FB_PHASE(tid, T)
                 if (tid == 0) { M->win_a = 0; M->win_b = max_p; M->mode = 1; M->fail = 0; }
@@ -672,8 +774,13 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
             }
             // exact quotient sum for Residual::count_bits (src/component/datatype.rs:2328-2335)
             unsigned long long local = 0;
+            const float inv_plen = 1.0f / (float)plen;
             for (int t = tid; t < n; t += T) {
-                if (t >= warm) local += u[t] >> lvl_params[pbase + t / plen];
+                // partition index t / plen without an integer division (t < 2^15: one correction step each way)
+                int pj = (int)((float)t * inv_plen);
+                if ((pj + 1) * plen <= t) pj++;
+                if (pj * plen > t) pj--;
+                if (t >= warm) local += u[fb_uidx(t)] >> lvl_params[pbase + pj];
             }
             if (local) fb_atomic_add_u64(&M->sum_q, local);
         FB_PHASE_END
@@ -694,6 +801,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
 
 // K2 body: one CTA per channel variant.  Implements fixed_lpc / estimated_qlpc / encode_subframe
 // (src/coding.rs:298-418) on top of K1's analysis.
+template <int G>
 FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, fb200_subframe_info *choice,
                        uint32_t gv, uint8_t *smem, const FbK2Layout &L) {
     const int T = FB_K2_THREADS;
@@ -740,14 +848,14 @@ FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     if (J.cfg.use_fixed) {
         if (J.cfg.fixed_order_sel == 1) {
             kf = A.fixed_order;
-            if (kf >= 0) fb_k2_rice_search(J, x, n, 0, kf, nullptr, 0, smem, L, res_fixed);
+            if (kf >= 0) fb_k2_rice_search<G>(J, x, n, 0, kf, nullptr, 0, smem, L, res_fixed);
         } else {
             // OrderSel::BitCount: exact Rice search per order, key = bps*order + code_bits,
             // first minimum wins (src/coding.rs:241-262)
             const int n_orders = (J.cfg.fixed_max_order < 4 ? J.cfg.fixed_max_order : 4) + 1;
             unsigned long long best_key = 0;
             for (int k = 0; k < n_orders; k++) {
-                fb_k2_rice_search(J, x, n, 0, k, nullptr, 0, smem, L, res_tmp);
+                fb_k2_rice_search<G>(J, x, n, 0, k, nullptr, 0, smem, L, res_tmp);
                 unsigned long long key = (unsigned long long)bps_v * (unsigned long long)k + res_tmp->code_bits;
                 bool better = (kf < 0) || key < best_key;
                 if (better) {
@@ -770,7 +878,7 @@ FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     bool lpc_ok = false;
     unsigned long long lpc_bits = 0;
     if (J.cfg.use_lpc) {
-        fb_k2_rice_search(J, x, n, 1, A.qlp_order, A.qlp, A.qlp_shift, smem, L, res_lpc);
+        fb_k2_rice_search<G>(J, x, n, 1, A.qlp_order, A.qlp, A.qlp_shift, smem, L, res_lpc);
         lpc_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
                    (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res_lpc->res_bits;
         lpc_ok = lpc_bits < baseline_bits;
@@ -878,10 +986,12 @@ FB_HD uint32_t fb_k3_smem_bytes(uint32_t frame_bytes_max, int block_size, int pa
     uint32_t runs = (uint32_t)((block_size + FB_RUN - 1) / FB_RUN);
     uint32_t o = (uint32_t)((sizeof(FbK3Shared) + 15) & ~(size_t)15);
     o += ((runs + 1 + 3) & ~3u) * 4u;                                   // run offsets
+    o += (uint32_t)((block_size + (block_size >> 5) + 4 + 3) & ~3) * 4u; // zigzag residuals (fb_uidx layout)
     if (pack_in_smem) o += ((frame_bytes_max + 3u) & ~3u) + 16u;        // frame words
     return o;
 }
 
+template <int G>
 FB_DEV void fb_k3_body(const FbJob &J, const int32_t *xv, const fb200_subframe_info *choice, uint8_t *slots,
                        uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t f, uint8_t *smem) {
     const int T = FB_K3_THREADS;
@@ -891,6 +1001,8 @@ FB_DEV void fb_k3_body(const FbJob &J, const int32_t *xv, const fb200_subframe_i
     const uint32_t runs_cap = (uint32_t)((J.block_size + FB_RUN - 1) / FB_RUN);
     uint32_t *run_off = (uint32_t *)(smem + off);
     off += ((runs_cap + 1 + 3) & ~3u) * 4u;
+    uint32_t *ubuf = (uint32_t *)(smem + off);
+    off += (uint32_t)((J.block_size + (J.block_size >> 5) + 4 + 3) & ~3) * 4u;
     uint8_t *slot = slots + (size_t)f * (size_t)J.slot_bytes;
     uint32_t *words = J.pack_in_smem ? (uint32_t *)(smem + off) : (uint32_t *)slot;
     const uint32_t max_bytes = fb_max_frame_bytes(J.channels, J.bps, J.block_size);
@@ -1024,12 +1136,19 @@ FB_DEV void fb_k3_body(const FbJob &J, const int32_t *xv, const fb200_subframe_i
                 if (pstart < warm) pstart = warm; // partition 0 starts after the warm-up
                 uint32_t rp = V.rice_params[pj];
                 int pnext = (pj + 1) * plen;
-                for (int t = t0; t < t1; t++) {
-                    if (t == pnext) { pj++; pstart = pnext; pnext += plen; rp = V.rice_params[pj]; }
-                    if (t < warm) continue;
-                    if (t == pstart) bits += pbits;
-                    uint32_t uu = fb_zigzag(fb_residual_at(x, t, kind, D.order, V.qlp, D.shift));
-                    bits += (uu >> rp) + 1u + rp;
+                uint32_t uu16[FB_RUN];
+                fb_run_residual<G>(x, n, t0, kind, D.order, V.qlp, D.shift, uu16);
+#pragma unroll
+                for (int i = 0; i < FB_RUN; i++) {
+                    const int t = t0 + i;
+                    if (t < t1) {
+                        ubuf[fb_uidx(t)] = uu16[i];
+                        if (t == pnext) { pj++; pstart = pnext; pnext += plen; rp = V.rice_params[pj]; }
+                        if (t >= warm) {
+                            if (t == pstart) bits += pbits;
+                            bits += (uu16[i] >> rp) + 1u + rp;
+                        }
+                    }
                 }
                 run_off[run] = bits;
             }
@@ -1072,7 +1191,7 @@ FB_DEV void fb_k3_body(const FbJob &J, const int32_t *xv, const fb200_subframe_i
                     if (t == pnext) { pj++; pstart = pnext; pnext += plen; rp = V.rice_params[pj]; }
                     if (t < warm) continue;
                     if (t == pstart) fb_run_put(r, rp, pbits);
-                    uint32_t uu = fb_zigzag(fb_residual_at(x, t, kind, D.order, V.qlp, D.shift));
+                    const uint32_t uu = ubuf[fb_uidx(t)];
                     fb_run_skip(r, uu >> rp);
                     fb_run_put(r, (uu & ((1u << rp) - 1u)) | (1u << rp), rp + 1u);
                 }

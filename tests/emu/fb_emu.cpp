@@ -79,7 +79,14 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<uint8_t> smem(L.total + 3 * sizeof(FbRiceResult) + 64);
         for (uint32_t gv = 0; gv < nvars; gv++) {
             memset(smem.data(), 0xAB, smem.size());
-            fb_k2_body(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L);
+            switch (fb_k1_ring(J.cfg.lpc_order)) {
+            case 4: fb_k2_body<4>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 8: fb_k2_body<8>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 12: fb_k2_body<12>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 16: fb_k2_body<16>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 20: fb_k2_body<20>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            default: fb_k2_body<24>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            }
         }
     }
     // K3
@@ -91,8 +98,16 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<uint8_t> smem(fb_k3_smem_bytes(mb, J.block_size, J.pack_in_smem) + 64);
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xEF, smem.size());
-            fb_k3_body(J, B.xv.data(), B.choice.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), f,
-                       smem.data());
+#define EMU_K3(GG) fb_k3_body<GG>(J, B.xv.data(), B.choice.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), f, smem.data())
+            switch (fb_k1_ring(J.cfg.lpc_order)) {
+            case 4: EMU_K3(4); break;
+            case 8: EMU_K3(8); break;
+            case 12: EMU_K3(12); break;
+            case 16: EMU_K3(16); break;
+            case 20: EMU_K3(20); break;
+            default: EMU_K3(24); break;
+            }
+#undef EMU_K3
         }
     }
     // K4 scan

@@ -292,7 +292,7 @@ def test_large_batch_properties_c2_slice():
     out, nf = O.decode_frames(got.tobytes(), 2, 16)
     assert nf == 2001 and np.array_equal(out, x)
     # frame bytes of a random sample of frames against the oracle
-    offs = np.concatenate([[0], np.cumsum(sizes)])
+    offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))]).astype(np.int64)
     rng = np.random.default_rng(0)
     for f in sorted(set(rng.integers(0, 2001, 40).tolist() + [0, 2000])):
         blk = x[f * 4096:(f + 1) * 4096]
