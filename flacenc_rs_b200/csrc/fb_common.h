@@ -43,6 +43,20 @@ struct float4 { float x, y, z, w; };
 #define FB_SYNC() ((void)0)
 #endif
 
+// Warp-0 regions: a stretch of work done by the first warp only, split into warp-synchronous
+// sub-phases (FB_WPHASE ... FB_WPHASE_END, lanes 0..31).  The other warps wait at FB_WARP0_END.
+#if FB_GPU
+#define FB_WARP0_BEGIN if (threadIdx.x < 32) {
+#define FB_WARP0_END } __syncthreads();
+#define FB_WPHASE(lane) { const int lane = (int)threadIdx.x; (void)lane;
+#define FB_WPHASE_END } __syncwarp();
+#else
+#define FB_WARP0_BEGIN {
+#define FB_WARP0_END }
+#define FB_WPHASE(lane) for (int lane = 0; lane < 32; ++lane) {
+#define FB_WPHASE_END }
+#endif
+
 #define FB_RICE_SAT ((1u << 27) - 1u)   // src/rice.rs:51
 #define FB_MIN_PRED_BLOCK 64            // src/constant.rs:51 MIN_BLOCK_SIZE_FOR_PREDICTION
 #define FB_MAX_ENT_PARTS 64             // src/constant.rs:63
@@ -94,6 +108,17 @@ FB_HD int fb_frame_len(const FbJob &J, uint32_t frame) {
 
 // bits per sample of a variant (ChannelAssignment::bits_per_sample_offset, src/component/datatype.rs:1145-1171)
 FB_HD int fb_variant_bps(const FbJob &J, int v) { return J.bps + ((J.channels == 2 && v == 3) ? 1 : 0); }
+
+// c + a * b with a 64-bit accumulator: one IMAD.WIDE on the GPU (mad.wide.s32)
+FB_DEV int64_t fb_mad_wide(int32_t a, int32_t b, int64_t c) {
+#if FB_GPU
+    long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((long long)c));
+    return (int64_t)r;
+#else
+    return c + (int64_t)a * (int64_t)b;
+#endif
+}
 
 // src/rice.rs:169-171 encode_signbit: (|v| << 1) - (v < 0)
 FB_HD uint32_t fb_zigzag(int32_t v) { return ((uint32_t)v << 1) ^ (uint32_t)(v >> 31); }

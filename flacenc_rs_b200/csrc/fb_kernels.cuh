@@ -422,7 +422,7 @@ FB_DEV void fb_run_residual_lpc(const int32_t *x, int n, int t0, const int16_t *
         const int t = t0 + i;
         int64_t acc = 0;
 #pragma unroll
-        for (int j = 0; j < G; j++) acc += (int64_t)qq[j] * (int64_t)win[G + i - 1 - j];
+        for (int j = 0; j < G; j++) acc = fb_mad_wide(qq[j], win[G + i - 1 - j], acc);
         const int32_t e = (int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> shift));
         u[i] = (t >= order && t < n) ? fb_zigzag(e) : 0u;
     }
