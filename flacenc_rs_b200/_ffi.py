@@ -89,6 +89,7 @@ class Timing(C.Structure):
         ("k_ingest_ms", C.c_float), ("k_analyze_ms", C.c_float), ("k_rice_ms", C.c_float),
         ("k_pack_ms", C.c_float), ("k_gather_ms", C.c_float),
         ("launches", C.c_uint64), ("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64),
+        ("fused_frames", C.c_uint64), ("fallback_frames", C.c_uint64),
     ]
 
 

@@ -6,6 +6,8 @@
 // returns FB200_ERR_CUDA.  Reference citations are relative to /root/reference/.
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <mutex>
 #include <string>
@@ -13,6 +15,7 @@
 #include <vector>
 
 #include "fb_host.h"
+#include "fb_launch.h"
 #include "fb_md5.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -28,54 +31,6 @@ __global__ void __launch_bounds__(256) fb_k0_ingest_planar(FbJob J, const int32_
     int t = (int)(blockIdx.x * 256u + threadIdx.x);
     if (t < J.tail_n) fb_k0_planar_sample(J, src, src_stride, xv, err_flag, t);
 }
-
-#define FB_K1_THREADS 128
-template <int R>
-__global__ void __launch_bounds__(FB_K1_THREADS) fb_k1_analyze(FbJob J, const int32_t *xv, const float *win_full,
-                                                               const float *win_tail, FbAnalysis *ana,
-                                                               fb200_variant_taps *taps, uint32_t n_variants) {
-    uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
-    if (gv < n_variants) fb_k1_thread<R>(J, xv, win_full, win_tail, ana, taps, gv);
-}
-
-static void fb_launch_k1(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
-                         FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
-    const unsigned grid = (nvars + FB_K1_THREADS - 1) / FB_K1_THREADS;
-    switch (fb_k1_ring(J.cfg.lpc_order)) {
-    case 4: fb_k1_analyze<4><<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars); break;
-    case 8: fb_k1_analyze<8><<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars); break;
-    case 12: fb_k1_analyze<12><<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars); break;
-    case 16: fb_k1_analyze<16><<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars); break;
-    case 20: fb_k1_analyze<20><<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars); break;
-    default: fb_k1_analyze<24><<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars); break;
-    }
-}
-
-template <int G>
-__global__ void __launch_bounds__(FB_K2_THREADS) fb_k2_rice(FbJob J, const int32_t *xv, const FbAnalysis *ana,
-                                                           fb200_subframe_info *choice, FbK2Layout L) {
-    extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_k2_body<G>(J, xv, ana, choice, blockIdx.x, fb_smem, L);
-}
-
-template <int G>
-__global__ void __launch_bounds__(FB_K3_THREADS) fb_k3_pack(FbJob J, const int32_t *xv, const fb200_subframe_info *choice,
-                                                           uint8_t *slots, uint32_t *frame_bytes,
-                                                           fb200_frame_info *infos) {
-    extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_k3_body<G>(J, xv, choice, slots, frame_bytes, infos, blockIdx.x, fb_smem);
-}
-
-// one instantiation per ring size G = fb_k1_ring(lpc_order)
-#define FB_DISPATCH_G(G_VALUE, STMT)                                                                \
-    switch (G_VALUE) {                                                                              \
-    case 4: { constexpr int G = 4; STMT; } break;                                                   \
-    case 8: { constexpr int G = 8; STMT; } break;                                                   \
-    case 12: { constexpr int G = 12; STMT; } break;                                                 \
-    case 16: { constexpr int G = 16; STMT; } break;                                                 \
-    case 20: { constexpr int G = 20; STMT; } break;                                                 \
-    default: { constexpr int G = 24; STMT; } break;                                                 \
-    }
 
 // offsets[i] = *total + exclusive prefix; *total advances by the chunk's bytes (single CTA)
 __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *frame_bytes, unsigned long long *offsets,
@@ -109,13 +64,14 @@ struct fb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16];
     int n_ev = 0;
-    DevBuf pcm, xv, win_full, win_tail, ana, taps, choice, slots, frame_bytes, offsets, out, infos, scalars;
+    DevBuf pcm, xv, win_full, win_tail, ana, taps, choice, slots, frame_bytes, offsets, out, infos, scalars, fb_list;
     int win_tail_n = -1;
     void *pinned = nullptr; // small pinned staging: err flag, total bytes
     size_t pinned_cap = 0;
     fb200_timing timing;
     std::string last_error;
-    int k2_smem_set = 0, k3_smem_set = 0;
+    int k2_smem_set = 0, k3_smem_set = 0, kf_smem_set = 0;
+    bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
     std::mutex mu;
 };
 
@@ -186,6 +142,10 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
     ctx->block_size = block_size;
     ctx->device = device;
     memset(&ctx->timing, 0, sizeof(ctx->timing));
+    {
+        const char *fg = getenv("FB200_FORCE_GENERIC");
+        ctx->force_generic = fg && fg[0] == '1';
+    }
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 16; i++) {
@@ -207,7 +167,7 @@ void fb200_destroy(fb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->pcm, &ctx->xv, &ctx->win_full, &ctx->win_tail, &ctx->ana, &ctx->taps, &ctx->choice,
-                      &ctx->slots, &ctx->frame_bytes, &ctx->offsets, &ctx->out, &ctx->infos, &ctx->scalars};
+                      &ctx->slots, &ctx->frame_bytes, &ctx->offsets, &ctx->out, &ctx->infos, &ctx->scalars, &ctx->fb_list};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < ctx->n_ev; i++) cudaEventDestroy(ctx->ev[i]);
@@ -299,12 +259,13 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     uint64_t chunk_frames = std::max<uint64_t>(64, (2048ull << 20) / per_frame);
     chunk_frames = std::min<uint64_t>(chunk_frames, total_frames);
 
-    // device scalars: [0] err flag (u32), [8] running total bytes (u64)
+    // device scalars: [0] err flag (u32), [8] running total bytes (u64), [16] fallback-list length (u32)
     int rc;
     if ((rc = fb_reserve(ctx, ctx->scalars, 64))) return rc;
     FB_CUDA(ctx, cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->stream));
     uint32_t *d_err = (uint32_t *)ctx->scalars.p;
     unsigned long long *d_total = (unsigned long long *)((uint8_t *)ctx->scalars.p + 8);
+    uint32_t *d_fb_count = (uint32_t *)((uint8_t *)ctx->scalars.p + 16);
 
     if ((rc = fb_reserve(ctx, ctx->frame_bytes, total_frames * 4u))) return rc;
     if ((rc = fb_reserve(ctx, ctx->offsets, (chunk_frames + 1) * 8u))) return rc;
@@ -315,6 +276,7 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     } else {
         if ((rc = fb_reserve(ctx, ctx->choice, chunk_frames * (uint64_t)nvar * sizeof(fb200_subframe_info)))) return rc;
         if ((rc = fb_reserve(ctx, ctx->slots, chunk_frames * (uint64_t)((mb + 15u) & ~15u)))) return rc;
+        if ((rc = fb_reserve(ctx, ctx->fb_list, (chunk_frames + 1) * 4u))) return rc;
         if (A.infos && (rc = fb_reserve(ctx, ctx->infos, chunk_frames * sizeof(fb200_frame_info)))) return rc;
         if (A.out_host && (rc = fb_reserve(ctx, ctx->out, A.out_cap ? A.out_cap : 16))) return rc;
     }
@@ -351,20 +313,26 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
         return FB200_ERR_CUDA;
     }
     const int ring = fb_k1_ring(ctx->cfg.lpc_order);
+    FbKfLayout KL;
+    const bool fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, tail_n, &KL);
+    if (fused && (int)KL.total > ctx->kf_smem_set) {
+        FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_KF, (int)KL.total));
+        ctx->kf_smem_set = (int)KL.total;
+    }
     if ((int)k2_smem > ctx->k2_smem_set) {
-        FB_DISPATCH_G(ring, FB_CUDA(ctx, cudaFuncSetAttribute(fb_k2_rice<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                              (int)k2_smem)));
+        FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_K2, (int)k2_smem));
         ctx->k2_smem_set = (int)k2_smem;
     }
     if ((int)k3_smem > ctx->k3_smem_set) {
-        FB_DISPATCH_G(ring, FB_CUDA(ctx, cudaFuncSetAttribute(fb_k3_pack<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                              (int)k3_smem)));
+        FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_K3, (int)k3_smem));
         ctx->k3_smem_set = (int)k3_smem;
     }
 
     cudaStream_t st = ctx->stream;
     float ms_h2d = 0, ms_k[5] = {0, 0, 0, 0, 0};
-    uint64_t launches = 0;
+    uint64_t launches = 0, n_chunks = 0, fused_frames = 0;
+    uint32_t *h_fb_counts = (uint32_t *)((uint8_t *)ctx->pinned + 64); // per-chunk fallback counts
+    const uint64_t max_counts = (ctx->pinned_cap - 64) / 4;
     FB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st)); // start of the call
 
     for (uint64_t f0 = 0; f0 < total_frames; f0 += chunk_frames) {
@@ -400,7 +368,7 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
         }
         FB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
         // K1
-        fb_launch_k1(J, (const int32_t *)ctx->xv.p, (const float *)ctx->win_full.p, d_win_tail,
+        fb_launch_k1(ring, J, (const int32_t *)ctx->xv.p, (const float *)ctx->win_full.p, d_win_tail,
                      (FbAnalysis *)ctx->ana.p, A.analyze_only ? (fb200_variant_taps *)ctx->taps.p : nullptr, nvars, st);
         FB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
         launches += 2;
@@ -410,23 +378,40 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
             FB_CUDA(ctx, cudaStreamSynchronize(st));
             continue;
         }
-        // K2
-        FB_DISPATCH_G(ring, (fb_k2_rice<G><<<nvars, FB_K2_THREADS, k2_smem, st>>>(
-                                J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
-                                (fb200_subframe_info *)ctx->choice.p, L)));
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-        // K3
-        FB_DISPATCH_G(ring, (fb_k3_pack<G><<<J.n_frames, FB_K3_THREADS, k3_smem, st>>>(
-                                J, (const int32_t *)ctx->xv.p, (const fb200_subframe_info *)ctx->choice.p,
-                                (uint8_t *)ctx->slots.p, d_fb, A.infos ? (fb200_frame_info *)ctx->infos.p : nullptr)));
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+        fb200_frame_info *d_infos = A.infos ? (fb200_frame_info *)ctx->infos.p : nullptr;
+        if (fused) {
+            // KF: Rice search + frame assembly per frame; frames it cannot reproduce exactly go to the list
+            FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
+            fb_launch_kf(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p, (uint8_t *)ctx->slots.p, d_fb,
+                         d_infos, (uint32_t *)ctx->fb_list.p, d_fb_count, KL, st);
+            FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+            fb_launch_k2(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
+                         (fb200_subframe_info *)ctx->choice.p, L, (const uint32_t *)ctx->fb_list.p, d_fb_count, 296,
+                         k2_smem, st);
+            fb_launch_k3(ring, J, (const int32_t *)ctx->xv.p, (const fb200_subframe_info *)ctx->choice.p,
+                         (uint8_t *)ctx->slots.p, d_fb, d_infos, (const uint32_t *)ctx->fb_list.p, d_fb_count, 148,
+                         k3_smem, st);
+            FB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+            if (n_chunks < max_counts)
+                FB_CUDA(ctx, cudaMemcpyAsync(&h_fb_counts[n_chunks], d_fb_count, 4, cudaMemcpyDeviceToHost, st));
+            n_chunks++;
+            fused_frames += J.n_frames;
+            launches += 3;
+        } else {
+            fb_launch_k2(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
+                         (fb200_subframe_info *)ctx->choice.p, L, nullptr, nullptr, nvars, k2_smem, st);
+            FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+            fb_launch_k3(ring, J, (const int32_t *)ctx->xv.p, (const fb200_subframe_info *)ctx->choice.p,
+                         (uint8_t *)ctx->slots.p, d_fb, d_infos, nullptr, nullptr, J.n_frames, k3_smem, st);
+            FB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+        }
         // K4
         fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)ctx->offsets.p, J.n_frames, d_total);
         fb_k4_gather<<<J.n_frames, 256, 0, st>>>((const uint8_t *)ctx->slots.p, J.slot_bytes, d_fb,
                                                  (const unsigned long long *)ctx->offsets.p, d_out,
                                                  (unsigned long long)A.out_cap);
         FB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
-        launches += 4;
+        launches += fused ? 2 : 4;
         FB_CUDA(ctx, cudaGetLastError());
         if (A.infos) {
             FB_CUDA(ctx, cudaMemcpyAsync(A.infos + f0, ctx->infos.p, (size_t)J.n_frames * sizeof(fb200_frame_info),
@@ -477,6 +462,10 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     ctx->timing.d2h_ms = t_d2h;
     ctx->timing.total_ms = t_total;
     ctx->timing.launches = launches;
+    uint64_t fallback = 0;
+    for (uint64_t i = 0; i < n_chunks && i < max_counts; i++) fallback += h_fb_counts[i];
+    ctx->timing.fused_frames = fused_frames - fallback;
+    ctx->timing.fallback_frames = fallback;
     ctx->timing.in_bytes = in_bytes_total;
     ctx->timing.out_bytes = total;
     return FB200_OK;

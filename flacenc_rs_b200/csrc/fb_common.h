@@ -48,7 +48,7 @@ struct float4 { float x, y, z, w; };
 #if FB_GPU
 #define FB_WARP0_BEGIN if (threadIdx.x < 32) {
 #define FB_WARP0_END } __syncthreads();
-#define FB_WPHASE(lane) { const int lane = (int)threadIdx.x; (void)lane;
+#define FB_WPHASE(lane) { const int lane = (int)(threadIdx.x & 31u); (void)lane;
 #define FB_WPHASE_END } __syncwarp();
 #else
 #define FB_WARP0_BEGIN {
@@ -98,6 +98,8 @@ struct FbAnalysis {
     int32_t  fixed_order;        // ApproxEnt winner, -1 = None
     int32_t  qlp_order;
     int32_t  qlp_shift;
+    uint32_t max_abs;            // max |x| of the variant (selects the i32 / i64 residual accumulation, src/lpc.rs:361-374)
+    uint32_t pad;
     uint64_t fixed_est[5];
     int16_t  qlp[32];
 };

@@ -6,7 +6,7 @@
 #include <math.h>
 #include <vector>
 
-#include "fb_kernels.cuh"
+#include "fb_fused.cuh"
 
 // config::Encoder::default() (src/config.rs:97-107,143-151,180-191,218-222,257-264,287-297,352-358,411-417)
 inline void fbh_config_default(fb200_config *c) {
@@ -117,4 +117,15 @@ inline int fbh_leaves_max(const FbJob &J) {
     int a = 1 << fb_finest_partition_order(J.block_size);
     int b = 1 << fb_finest_partition_order(J.tail_n);
     return a > b ? a : b;
+}
+
+// The fused per-frame kernel (fb_fused.cuh) serves a batch when the fixed order comes from K1's entropy
+// estimate (OrderSel::ApproxEnt, the default; BitCount needs one Rice search per order and stays on the
+// generic kernels) and the frame's working set fits in shared memory.
+#define FB_KF_SMEM_LIMIT (200u * 1024u)
+inline bool fbh_fused_ok(const FbJob &J, int tail_n_call, FbKfLayout *Lout) {
+    if (J.cfg.use_fixed && J.cfg.fixed_order_sel != 1) return false;
+    FbKfLayout L = fb_kf_layout(J.channels, J.nvar, J.bps, J.block_size, tail_n_call);
+    if (Lout) *Lout = L;
+    return L.total <= FB_KF_SMEM_LIMIT;
 }

@@ -1,0 +1,100 @@
+// fb_inst.cu -- the kernels that depend on the tap-window size G, compiled once per -DFB_INST_G=<4|8|12|16|20|24>
+// (flacenc_rs_b200/build.py runs the six compilations in parallel).
+#ifndef FB_INST_G
+#error "compile with -DFB_INST_G=<G>"
+#endif
+#include "fb_launch.h"
+
+#define FB_CAT2(a, b) a##b
+#define FB_CAT(a, b) FB_CAT2(a, b)
+#define FB_NAME(base) FB_CAT(base, FB_INST_G)
+
+#define FB_K1_THREADS 128
+__global__ void __launch_bounds__(FB_K1_THREADS) FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xv, const float *win_full,
+                                                                          const float *win_tail, FbAnalysis *ana,
+                                                                          fb200_variant_taps *taps, uint32_t n_variants) {
+    uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
+    if (gv < n_variants) fb_k1_thread<FB_INST_G>(J, xv, win_full, win_tail, ana, taps, gv);
+}
+
+// generic Rice search: one CTA per channel variant.  list == nullptr: variant blockIdx.x; else the variants of the
+// frames in list[0..*count) (the fused kernel's fallback list, normally empty)
+__global__ void __launch_bounds__(FB_K2_THREADS) FB_NAME(fb_k2_rice_g)(FbJob J, const int32_t *xv, const FbAnalysis *ana,
+                                                                       fb200_subframe_info *choice, FbK2Layout L,
+                                                                       const uint32_t *list, const uint32_t *count) {
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    if (!list) {
+        fb_k2_body<FB_INST_G>(J, xv, ana, choice, blockIdx.x, fb_smem, L);
+        return;
+    }
+    const uint32_t total = *count * (uint32_t)J.nvar;
+    for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
+        const uint32_t f = list[i / (uint32_t)J.nvar];
+        fb_k2_body<FB_INST_G>(J, xv, ana, choice, f * (uint32_t)J.nvar + i % (uint32_t)J.nvar, fb_smem, L);
+        __syncthreads();
+    }
+}
+
+// generic frame assembly: one CTA per frame (same list convention)
+__global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, const int32_t *xv,
+                                                                       const fb200_subframe_info *choice, uint8_t *slots,
+                                                                       uint32_t *frame_bytes, fb200_frame_info *infos,
+                                                                       const uint32_t *list, const uint32_t *count) {
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    if (!list) {
+        fb_k3_body<FB_INST_G>(J, xv, choice, slots, frame_bytes, infos, blockIdx.x, fb_smem);
+        return;
+    }
+    const uint32_t total = *count;
+    for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
+        fb_k3_body<FB_INST_G>(J, xv, choice, slots, frame_bytes, infos, list[i], fb_smem);
+        __syncthreads();
+    }
+}
+
+// fused per-frame kernel (fb_fused.cuh): one CTA of 32 * nvar threads per frame
+__global__ void __launch_bounds__(256) FB_NAME(fb_kf_frame_g)(FbJob J, const int32_t *xv, const FbAnalysis *ana,
+                                                              uint8_t *slots, uint32_t *frame_bytes,
+                                                              fb200_frame_info *infos, uint32_t *fb_list,
+                                                              uint32_t *fb_count, FbKfLayout L) {
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    fb_kf_body<FB_INST_G>(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, blockIdx.x, fb_smem, L);
+}
+
+void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
+                             FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
+    const unsigned grid = (nvars + FB_K1_THREADS - 1) / FB_K1_THREADS;
+    FB_NAME(fb_k1_analyze_g)<<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars);
+}
+
+void FB_NAME(fb_launch_k2_g)(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, fb200_subframe_info *choice,
+                             const FbK2Layout &L, const uint32_t *list, const uint32_t *count, uint32_t grid, size_t smem,
+                             cudaStream_t st) {
+    FB_NAME(fb_k2_rice_g)<<<grid, FB_K2_THREADS, smem, st>>>(J, xv, ana, choice, L, list, count);
+}
+
+void FB_NAME(fb_launch_k3_g)(const FbJob &J, const int32_t *xv, const fb200_subframe_info *choice, uint8_t *slots,
+                             uint32_t *frame_bytes, fb200_frame_info *infos, const uint32_t *list, const uint32_t *count,
+                             uint32_t grid, size_t smem, cudaStream_t st) {
+    FB_NAME(fb_k3_pack_g)<<<grid, FB_K3_THREADS, smem, st>>>(J, xv, choice, slots, frame_bytes, infos, list, count);
+}
+
+void FB_NAME(fb_launch_kf_g)(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots, uint32_t *frame_bytes,
+                             fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const FbKfLayout &L,
+                             cudaStream_t st) {
+    FB_NAME(fb_kf_frame_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xv, ana, slots, frame_bytes, infos, fb_list,
+                                                                      fb_count, L);
+}
+
+cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {
+    switch (kernel) {
+    case FB_KERNEL_K2:
+        return cudaFuncSetAttribute(FB_NAME(fb_k2_rice_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case FB_KERNEL_K3:
+        return cudaFuncSetAttribute(FB_NAME(fb_k3_pack_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case FB_KERNEL_KF:
+        return cudaFuncSetAttribute(FB_NAME(fb_kf_frame_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    default:
+        return cudaErrorInvalidValue;
+    }
+}

@@ -203,6 +203,7 @@ FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, co
     int part = 0, pend = psize < n ? psize : n;
     bool allsame = true;
     const int32_t x0 = x[0];
+    int32_t xmin = x0, xmax = x0;
 
     double acc[R + 1];
     double ring[R];
@@ -233,6 +234,8 @@ FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, co
             if (t < n) {
                 const int32_t xt = xs[s];
                 allsame = allsame && (xt == x0);
+                xmin = xt < xmin ? xt : xmin;
+                xmax = xt > xmax ? xt : xmax;
                 if (do_ent) {
                     // zero-history differences, wrapping i32 (src/coding.rs:188-195)
                     const int32_t e0 = xt;
@@ -271,6 +274,12 @@ FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, co
     }
 
     out->is_constant = allsame ? 1 : 0;
+    {
+        const uint32_t a = xmin < 0 ? (uint32_t)(-(int64_t)xmin) : (uint32_t)xmin;
+        const uint32_t b = xmax < 0 ? (uint32_t)(-(int64_t)xmax) : (uint32_t)xmax;
+        out->max_abs = a > b ? a : b;
+        out->pad = 0;
+    }
     out->fixed_order = -1;
     out->qlp_order = 0;
     out->qlp_shift = 0;

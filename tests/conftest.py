@@ -35,3 +35,22 @@ def pack_pcm(signal: np.ndarray, container_bytes: int) -> np.ndarray:
         b = x.astype("<i4").view(np.uint8).reshape(-1, 4)
         return np.ascontiguousarray(b[:, :3]).reshape(-1)
     raise ValueError(container_bytes)
+
+
+def crafted_huge_residual_stereo(order: int = 24) -> np.ndarray:
+    """4096 x 2 samples of 24-bit stereo whose side channel drives the LPC residual above 2^26 (zigzag >= 2^27):
+    six near-Nyquist tones give a high-gain predictor; the last `order` samples (where the Tukey window is ~0, so
+    they barely move the coefficients) are full scale with the signs of the coefficients.  R = -L doubles it."""
+    from oracle import oracle as O
+    t = np.arange(4096)
+    x = np.zeros(4096)
+    for k in range(6):
+        x += np.cos((np.pi - 0.03 - 0.05 * k) * t + 0.3 * k)
+    s = (x / np.abs(x).max() * 8000000).astype(np.int32)
+    for _ in range(3):
+        coefs, _corr = O.lpc_from_autocorr(s, 1, 0.4, order)
+        q, o, _shift = O.quantize_parameters(coefs, 15)
+        for j in range(o):
+            s[len(s) - 2 - j] = 8388607 if q[j] > 0 else -8388607
+        s[len(s) - 1] = -8388607
+    return np.stack([s, -s], axis=1)

@@ -81,6 +81,18 @@ def analyze(cfg, pcm_bytes: np.ndarray, container_bytes: int, n_samples: int, ch
     return rc, taps, nv.value
 
 
+def set_force_generic(flag: bool) -> None:
+    """True: run only the generic K2/K3 kernels; False (default): the fused kernel when eligible, like the library."""
+    lib().fbemu_set_force_generic(1 if flag else 0)
+
+
+def fused_counts(reset: bool = True):
+    """(frames encoded by the fused kernel, frames it handed to the generic kernels)"""
+    out = (C.c_ulonglong * 2)()
+    lib().fbemu_fused_counts(out, 1 if reset else 0)
+    return list(out)
+
+
 def mode_counts(reset: bool = True):
     out = (C.c_ulonglong * 4)()
     lib().fbemu_mode_counts(out, 1 if reset else 0)

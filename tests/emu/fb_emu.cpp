@@ -19,6 +19,15 @@ void fbemu_mode_counts(unsigned long long *out4, int reset) {
     for (int i = 0; i < 4; i++) { out4[i] = fb_emu_mode_count[i]; if (reset) fb_emu_mode_count[i] = 0; }
 }
 
+// 0 = fused kernel when eligible (like the library), 1 = generic K2/K3 kernels only
+static int fb_emu_force_generic = 0;
+static unsigned long long fb_emu_fused_frames = 0, fb_emu_fallback_frames = 0;
+void fbemu_set_force_generic(int v) { fb_emu_force_generic = v; }
+void fbemu_fused_counts(unsigned long long *out2, int reset) {
+    out2[0] = fb_emu_fused_frames; out2[1] = fb_emu_fallback_frames;
+    if (reset) fb_emu_fused_frames = fb_emu_fallback_frames = 0;
+}
+
 void fbemu_config_default(fb200_config *c) { fbh_config_default(c); }
 int fbemu_config_verify(const fb200_config *c) { return fbh_config_verify(c); }
 
@@ -72,12 +81,43 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     for (uint32_t gv = 0; gv < nvars; gv++)
         fb_k1_dispatch(J, B.xv.data(), B.win_full.data(), B.win_tail.data(), B.ana.data(), B.taps.data(), gv);
     if (analyze_only) return FB200_OK;
+    B.slots.assign((size_t)J.n_frames * J.slot_bytes, 0xCD);
+    B.frame_bytes.assign(J.n_frames, 0);
+    B.infos.resize(J.n_frames);
+    // frames for the generic kernels: all of them, or the fused kernel's fallback list
+    std::vector<uint32_t> todo;
+    FbKfLayout KL;
+    const bool fused = !fb_emu_force_generic && fbh_fused_ok(J, J.tail_n, &KL);
+    if (fused) {
+        std::vector<uint32_t> list(J.n_frames + 1, 0);
+        uint32_t count = 0;
+        std::vector<uint8_t> smem(KL.total + 64);
+        for (uint32_t f = 0; f < J.n_frames; f++) {
+            memset(smem.data(), 0xAB, smem.size());
+#define EMU_KF(GG) fb_kf_body<GG>(J, B.xv.data(), B.ana.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, f, smem.data(), KL)
+            switch (fb_k1_ring(J.cfg.lpc_order)) {
+            case 4: EMU_KF(4); break;
+            case 8: EMU_KF(8); break;
+            case 12: EMU_KF(12); break;
+            case 16: EMU_KF(16); break;
+            case 20: EMU_KF(20); break;
+            default: EMU_KF(24); break;
+            }
+#undef EMU_KF
+        }
+        todo.assign(list.begin(), list.begin() + count);
+        fb_emu_fused_frames += J.n_frames - count;
+        fb_emu_fallback_frames += count;
+    } else {
+        for (uint32_t f = 0; f < J.n_frames; f++) todo.push_back(f);
+    }
     // K2
     {
         int nmax = J.block_size;
         FbK2Layout L = fb_k2_layout(nmax, fbh_leaves_max(J));
         std::vector<uint8_t> smem(L.total + 3 * sizeof(FbRiceResult) + 64);
-        for (uint32_t gv = 0; gv < nvars; gv++) {
+        for (uint32_t f : todo)
+          for (uint32_t gv = f * J.nvar; gv < (f + 1) * (uint32_t)J.nvar; gv++) {
             memset(smem.data(), 0xAB, smem.size());
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: fb_k2_body<4>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
@@ -87,16 +127,13 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
             case 20: fb_k2_body<20>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
             default: fb_k2_body<24>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
             }
-        }
+          }
     }
     // K3
-    B.slots.assign((size_t)J.n_frames * J.slot_bytes, 0xCD);
-    B.frame_bytes.assign(J.n_frames, 0);
-    B.infos.resize(J.n_frames);
     {
         uint32_t mb = fb_max_frame_bytes(J.channels, J.bps, J.block_size);
         std::vector<uint8_t> smem(fb_k3_smem_bytes(mb, J.block_size, J.pack_in_smem) + 64);
-        for (uint32_t f = 0; f < J.n_frames; f++) {
+        for (uint32_t f : todo) {
             memset(smem.data(), 0xEF, smem.size());
 #define EMU_K3(GG) fb_k3_body<GG>(J, B.xv.data(), B.choice.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), f, smem.data())
             switch (fb_k1_ring(J.cfg.lpc_order)) {

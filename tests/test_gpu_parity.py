@@ -3,11 +3,12 @@ CPU oracle on the same seeded inputs.  Bar: frame bytes bit-exact; floats of the
 relative (they are in fact bit-identical); decoded PCM identical to the input (tier 1).
 Nothing here reads /root/reference."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
-from conftest import load_fixture, pack_pcm
+from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm
 from flacenc_rs_b200 import _ffi, sigen
 from flacenc_rs_b200.config import Encoder, Fixed, OrderSel, Qlpc, StereoCoding, SubFrameCoding, Window, Prc
 from flacenc_rs_b200.encoder import (Context, StreamInfo, encode_fixed_size_frame, encode_with_fixed_block_size)
@@ -58,19 +59,27 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
     n = len(signal)
     container = container or (bps + 7) // 8
     ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
-    with Context(vcfg, channels, bps, rate, block_size) as ctx:
-        got, sizes, infos = ctx.encode_interleaved(pack_pcm(signal, container), container, n, first_frame,
-                                                   want_infos=check_infos)
-        got = got.tobytes()
-        t = ctx.timing()
-        assert t.launches >= 6 and t.kernels_ms > 0
-    assert list(sizes) == list(ref_sizes)
-    if got != ref:
-        off = 0
-        for i, s in enumerate(ref_sizes):
-            assert got[off:off + s] == ref[off:off + s], f"frame {i} differs (size {s})"
-            off += s
-    assert got == ref
+    # both device paths: the fused per-frame kernel (default, when the batch is eligible) and the generic kernels
+    for force_generic in ("0", "1"):
+        os.environ["FB200_FORCE_GENERIC"] = force_generic
+        try:
+            with Context(vcfg, channels, bps, rate, block_size) as ctx:
+                got, sizes, infos = ctx.encode_interleaved(pack_pcm(signal, container), container, n, first_frame,
+                                                           want_infos=check_infos)
+                got = got.tobytes()
+                t = ctx.timing()
+                assert t.launches >= 6 and t.kernels_ms > 0
+                if force_generic == "1":
+                    assert t.fused_frames == 0 and t.fallback_frames == 0
+        finally:
+            os.environ.pop("FB200_FORCE_GENERIC", None)
+        assert list(sizes) == list(ref_sizes), f"force_generic={force_generic}"
+        if got != ref:
+            off = 0
+            for i, s in enumerate(ref_sizes):
+                assert got[off:off + s] == ref[off:off + s], f"frame {i} differs (size {s}), generic={force_generic}"
+                off += s
+        assert got == ref
     out, nf = O.decode_frames(got, channels, bps)
     assert np.array_equal(out, signal)
     return infos
@@ -163,6 +172,35 @@ def test_pathological_residuals():
     _compare(np.stack([smooth, smooth[::-1]], axis=1), 2, 24, 96000, 4096, lpc_order=12, prc_max_parameter=5)
     alt = np.where(np.arange(4096) % 2 == 0, 8388607, -8388608).astype(np.int32).reshape(-1, 1)
     _compare(alt, 1, 24, 96000, 4096, fixed_order_sel=0)
+
+
+def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
+    """Default config: every frame is encoded by the fused per-frame kernel.  A residual >= 2^26 (zigzag >= 2^27)
+    or a saturated table minimum hands the frame to the generic kernels; results stay byte-identical."""
+    vcfg = Encoder().into_verified()
+    n = 4096 * 5 + 2728
+    x = sigen.noisy_sine_pcm(n, 2, 16, 44100)
+    with Context(vcfg, 2, 16, 44100, 4096) as ctx:
+        ctx.encode_interleaved(pack_pcm(x, 2), 2, n)
+        t = ctx.timing()
+        assert (t.fused_frames, t.fallback_frames) == (6, 0)
+    y = crafted_huge_residual_stereo()
+    _compare(y, 2, 24, 96000, 4096, lpc_order=24)
+    with Context(make_config(lpc_order=24).into_verified(), 2, 24, 96000, 4096) as ctx:
+        ctx.encode_interleaved(pack_pcm(np.concatenate([y, y // 4, y]), 3), 3, 3 * 4096)
+        t = ctx.timing()
+        assert (t.fused_frames, t.fallback_frames) == (1, 2)
+    with Context(make_config(fixed_order_sel=0).into_verified(), 2, 16, 44100, 4096) as ctx:
+        ctx.encode_interleaved(pack_pcm(x, 2), 2, n)
+        t = ctx.timing()
+        assert (t.fused_frames, t.fallback_frames) == (0, 0)  # BitCount selection: generic kernels only
+
+
+def test_fused_geometry_odd_block_sizes():
+    rng = np.random.default_rng(11)
+    for n in (64, 66, 127, 128, 341 * 8, 3136, 98 * 32, 5000, 4100, 8192, 9216, 12345, 16383):
+        x = (rng.normal(0, 300, n + 17).cumsum() % 20000 - 10000).astype(np.int32)
+        _compare(x, 1, 16, 44100, n)
 
 
 def test_first_frame_number_and_utf8_lengths():

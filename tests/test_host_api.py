@@ -52,7 +52,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ffi.SubframeInfo) == 8 * 4 + 64 + 256 + 8
     assert C.sizeof(_ffi.FrameInfo) == 16 + 8 * C.sizeof(_ffi.SubframeInfo)
     assert C.sizeof(_ffi.VariantTaps) == 25 * 8 + 24 * 8 + 64 + 4 * 4 + 5 * 8
-    assert C.sizeof(_ffi.Timing) == 9 * 4 + 4 + 3 * 8
+    assert C.sizeof(_ffi.Timing) == 9 * 4 + 4 + 5 * 8
 
 
 def test_no_device_means_error_not_fallback():

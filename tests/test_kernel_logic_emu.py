@@ -4,7 +4,7 @@ The same comparisons run against the real kernels in tests/test_gpu_parity.py (-
 import numpy as np
 import pytest
 
-from conftest import load_fixture, pack_pcm
+from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm
 from flacenc_rs_b200 import sigen
 from oracle import oracle as O
 from emu import emu as E
@@ -20,18 +20,24 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
     n = len(signal)
     container = container or (bps + 7) // 8
     ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
-    rc, got, sizes, _ = E.encode_interleaved(ecfg, pack_pcm(signal, container), container, n, channels, bps, rate,
-                                             block_size, first_frame)
-    assert rc == 0
-    assert list(sizes) == list(ref_sizes)
-    if got != ref:
-        # locate the first differing frame for the report
-        off = 0
-        for i, s in enumerate(ref_sizes):
-            if got[off:off + s] != ref[off:off + s]:
-                raise AssertionError(f"frame {i} differs (size {s})")
-            off += s
-    assert got == ref
+    # both device paths: the fused per-frame kernel (when the batch is eligible) and the generic K2/K3 kernels
+    for force_generic in (False, True):
+        E.set_force_generic(force_generic)
+        try:
+            rc, got, sizes, _ = E.encode_interleaved(ecfg, pack_pcm(signal, container), container, n, channels, bps,
+                                                     rate, block_size, first_frame)
+        finally:
+            E.set_force_generic(False)
+        assert rc == 0
+        assert list(sizes) == list(ref_sizes), f"force_generic={force_generic}"
+        if got != ref:
+            # locate the first differing frame for the report
+            off = 0
+            for i, s in enumerate(ref_sizes):
+                if got[off:off + s] != ref[off:off + s]:
+                    raise AssertionError(f"frame {i} differs (size {s}), force_generic={force_generic}")
+                off += s
+        assert got == ref
     out, nf = O.decode_frames(got, channels, bps)
     assert np.array_equal(out, signal)
 
@@ -167,6 +173,39 @@ def test_pathological_lpc_gain_chunked_saturation_path():
     smooth[3000:] = np.where(np.arange(1096) % 2 == 0, 8388607, -8388608)
     _compare(smooth.reshape(-1, 1), 1, 24, 96000, 4096, lpc_order=24)
     _compare(np.stack([smooth, smooth[::-1]], axis=1), 2, 24, 96000, 4096, lpc_order=12, prc_max_parameter=5)
+
+
+def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
+    """Default config: every frame goes through the fused kernel.  Residuals >= 2^27 (the reference's chunked
+    saturating sums become order dependent) are handed to the generic kernels; BitCount order selection and
+    frames that do not fit shared memory never enter the fused kernel."""
+    E.fused_counts()
+    x = sigen.noisy_sine_pcm(4096 * 3 + 2728, 2, 16, 44100)
+    _compare(x, 2, 16, 44100, 4096)
+    assert E.fused_counts() == [4, 0]
+    E.mode_counts()
+    _compare(crafted_huge_residual_stereo(), 2, 24, 96000, 4096, lpc_order=24)
+    assert E.fused_counts() == [0, 1]
+    assert E.mode_counts()[2] > 0  # the generic kernels replayed the chunked saturating sums (mode 2)
+    t = np.arange(4096)
+    smooth = (np.sin(t / 300.0) * 8000000).astype(np.int32)
+    smooth[3000:] = np.where(np.arange(1096) % 2 == 0, 8388607, -8388608)
+    _compare(np.stack([smooth, smooth[::-1]], axis=1), 2, 24, 96000, 4096, lpc_order=12, prc_max_parameter=5)
+    assert E.fused_counts() == [0, 1]  # saturated table minimum (max_parameter too small for the residuals)
+    _compare(x, 2, 16, 44100, 4096, fixed_order_sel=0)
+    assert E.fused_counts() == [0, 0]
+    y = sigen.noisy_sine_pcm(32767 + 500, 8, 24, 96000, config_id=7)
+    _compare(y, 8, 24, 96000, 32767)
+    assert E.fused_counts() == [0, 0]
+
+
+def test_fused_geometry_covers_every_block_size():
+    """units tile every leaf exactly, are <= 112 samples and there are >= 32 of them (host-side geometry check
+    through the encode of odd sizes, incl. leaves that are not a multiple of 4 samples)"""
+    rng = np.random.default_rng(11)
+    for n in (64, 66, 127, 128, 341 * 8, 3136, 98 * 32, 5000, 4100, 8192, 9216, 12345, 16383):
+        x = (rng.normal(0, 300, n + 17).cumsum() % 20000 - 10000).astype(np.int32)
+        _compare(x, 1, 16, 44100, n)
 
 
 def test_first_frame_number_and_utf8_lengths():
