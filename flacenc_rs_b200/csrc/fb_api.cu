@@ -64,13 +64,14 @@ struct fb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16];
     int n_ev = 0;
-    DevBuf pcm, xv, win_full, win_tail, ana, taps, choice, slots, frame_bytes, offsets, out, infos, scalars, fb_list;
+    DevBuf pcm, xv, win_full, win_tail, ana, taps, choice, slots, frame_bytes, offsets, out, infos, scalars, fb_list, ktab;
     int win_tail_n = -1;
     void *pinned = nullptr; // small pinned staging: err flag, total bytes
     size_t pinned_cap = 0;
     fb200_timing timing;
     std::string last_error;
     int k2_smem_set = 0, k3_smem_set = 0, kf_smem_set = 0;
+    uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
     std::mutex mu;
 };
@@ -167,7 +168,7 @@ void fb200_destroy(fb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->pcm, &ctx->xv, &ctx->win_full, &ctx->win_tail, &ctx->ana, &ctx->taps, &ctx->choice,
-                      &ctx->slots, &ctx->frame_bytes, &ctx->offsets, &ctx->out, &ctx->infos, &ctx->scalars, &ctx->fb_list};
+                      &ctx->slots, &ctx->frame_bytes, &ctx->offsets, &ctx->out, &ctx->infos, &ctx->scalars, &ctx->fb_list, &ctx->ktab};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < ctx->n_ev; i++) cudaEventDestroy(ctx->ev[i]);
@@ -315,6 +316,14 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     const int ring = fb_k1_ring(ctx->cfg.lpc_order);
     FbKfLayout KL;
     const bool fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, tail_n, &KL);
+    if (fused && ctx->ktab_chunk != KL.crc_chunk) {
+        std::vector<uint32_t> kt(fb_kf_ktab_words(KL.crc_chunk));
+        fb_kf_build_ktab(KL.crc_chunk, kt.data());
+        if ((rc = fb_reserve(ctx, ctx->ktab, kt.size() * 4u))) return rc;
+        FB_CUDA(ctx, cudaMemcpyAsync(ctx->ktab.p, kt.data(), kt.size() * 4u, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
+        ctx->ktab_chunk = KL.crc_chunk;
+    }
     if (fused && (int)KL.total > ctx->kf_smem_set) {
         FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_KF, (int)KL.total));
         ctx->kf_smem_set = (int)KL.total;
@@ -383,7 +392,7 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
             // KF: Rice search + frame assembly per frame; frames it cannot reproduce exactly go to the list
             FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
             fb_launch_kf(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p, (uint8_t *)ctx->slots.p, d_fb,
-                         d_infos, (uint32_t *)ctx->fb_list.p, d_fb_count, KL, st);
+                         d_infos, (uint32_t *)ctx->fb_list.p, d_fb_count, (const uint32_t *)ctx->ktab.p, KL, st);
             FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
             fb_launch_k2(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
                          (fb200_subframe_info *)ctx->choice.p, L, (const uint32_t *)ctx->fb_list.p, d_fb_count, 296,

@@ -13,7 +13,8 @@
 //                 sum_t (u_t >> p)  ==  sum_j (w_j >> p) << j          for every p,
 //             so any entry of the reference's PrcBitTable (src/rice.rs:65-105) costs 7 shifts per unit
 //             instead of one shift per sample.
-//     pass 2  per finest partition: the exact minimiser, found by walking the convex cost function
+//     pass 2  per finest partition: the exact minimiser, found by walking the convex cost function (done
+//             in registers right after the unit's last run when a unit is a whole partition)
 //     pass 3  bottom-up partition tree (src/rice.rs:246-298) over the parameter window
 //             [min leaf minimiser, max leaf minimiser] -- the minimiser of every merged node lies in it
 //             (sum of convex functions) -- in passes of 8 parameters
@@ -64,9 +65,8 @@ FB_DEV int fb_clz64(unsigned long long v) { return v ? __builtin_clzll(v) : 64; 
 // ---- geometry of one frame length -----------------------------------------------------------------
 struct FbKfGeom {
     int n, o0, leaves, leaf_len;
-    int m;        // units per leaf (power of two)
-    int U;        // units per variant = leaves * m, a power of two >= 32
-    int lgU;
+    int m, lgm;   // units per leaf (power of two)
+    int U, lgU;   // units per variant = leaves * m, a power of two >= 32
     int unit_len; // samples per unit (multiple of 4, <= FB_KF_UNIT_MAX); the last unit of a leaf may be shorter
 };
 
@@ -76,20 +76,20 @@ FB_HD FbKfGeom fb_kf_geom(int n) {
     g.o0 = fb_finest_partition_order(n);
     g.leaves = 1 << g.o0;
     g.leaf_len = n >> g.o0;
-    int m = 1;
-    while (g.leaves * m < 32) m <<= 1;
-    while (((((g.leaf_len + m - 1) / m) + 3) & ~3) > FB_KF_UNIT_MAX) m <<= 1;
+    int m = 1, lgm = 0;
+    while (g.leaves * m < 32) { m <<= 1; lgm++; }
+    while (((((g.leaf_len + m - 1) / m) + 3) & ~3) > FB_KF_UNIT_MAX) { m <<= 1; lgm++; }
     g.m = m;
+    g.lgm = lgm;
     g.unit_len = (((g.leaf_len + m - 1) / m) + 3) & ~3;
     g.U = g.leaves * m;
-    g.lgU = 0;
-    while ((1 << g.lgU) < g.U) g.lgU++;
+    g.lgU = g.o0 + lgm;
     return g;
 }
 
 // sample range [t0, t1) of unit u
 FB_HD void fb_kf_unit_range(const FbKfGeom &g, int u, int *t0, int *t1) {
-    const int leaf = u / g.m, k = u - leaf * g.m;
+    const int leaf = u >> g.lgm, k = u & (g.m - 1);
     const int ls = leaf * g.leaf_len, le = ls + g.leaf_len;
     int a = ls + k * g.unit_len, b = a + g.unit_len;
     if (a > le) a = le;
@@ -101,6 +101,35 @@ FB_HD void fb_kf_unit_range(const FbKfGeom &g, int u, int *t0, int *t1) {
 // index of sample t in a staged plane: 4 pad words per 64 samples keep 16-byte loads of lanes that are
 // 64 samples apart on different banks
 FB_HD int fb_xidx(int t) { return t + ((t >> 6) << 2); }
+
+// ---- CRC-16 tables (poly 0x8005, init 0, MSB first; src/component/bitrepr.rs:40,270-271) ------------
+// Built on the host once per context and read by the kernel:
+//   [0, 1024)            slicing-by-4 tables: T[k][b] = CRC of byte b followed by k zero bytes
+//   [1024, 1280)         xp[j] = x^(8 * Lc * j) mod P, j < 256   (Lc = bytes per CRC chunk, see fb_kf_crc_chunk)
+//   [1280, 1280 + Lc+4)  xb[i] = x^(8 * i) mod P, i <= Lc
+#define FB_KTAB_XP 1024
+#define FB_KTAB_XB 1280
+FB_HD uint32_t fb_kf_crc_chunk(int channels, int bps, int block_size, int threads) {
+    const uint32_t mb = fb_max_frame_bytes(channels, bps, block_size);
+    return ((mb + (uint32_t)threads - 1u) / (uint32_t)threads + 3u) & ~3u;
+}
+FB_HD uint32_t fb_kf_ktab_words(uint32_t Lc) { return FB_KTAB_XB + Lc + 4u; }
+inline void fb_kf_build_ktab(uint32_t Lc, uint32_t *t) {
+    for (uint32_t b = 0; b < 256; b++) {
+        uint32_t c = fb_crc16_table_entry(b);
+        t[b] = c;
+        for (int k = 1; k < 4; k++) {
+            c = ((c << 8) & 0xFFFFu) ^ fb_crc16_table_entry((c >> 8) & 0xFFu);
+            t[k * 256 + b] = c;
+        }
+    }
+    // x^(8*i): start from 1 and multiply by x^8 (= 0x100 reduced: as a 16-bit polynomial x^8 is 0x0100)
+    uint32_t v = 1;
+    for (uint32_t i = 0; i <= Lc + 3; i++) { t[FB_KTAB_XB + i] = v; v = fb_crc16_mulmod(v, 0x0100u); }
+    const uint32_t step = t[FB_KTAB_XB + Lc];
+    v = 1;
+    for (uint32_t j = 0; j < 256; j++) { t[FB_KTAB_XP + j] = v; v = fb_crc16_mulmod(v, step); }
+}
 
 // ---- shared-memory layout (bytes), identical on host and device ---------------------------------
 struct FbKfLayout {
@@ -116,6 +145,7 @@ struct FbKfLayout {
     uint32_t s_words, s_tbl_a, s_tbl_b, s_best_val, s_best_p, s_lvl_bits, s_misc;
     uint32_t words_bytes; // bytes of the frame word buffer
     uint32_t U_max, leaves_max;
+    uint32_t crc_chunk;   // Lc
     uint32_t total;
 };
 
@@ -129,7 +159,6 @@ struct FbKfRes {
 struct FbKfMisc {
     uint32_t ormask, pmin, pmax, fail;
     int32_t  best_level, any_gt14;
-    unsigned long long sum_bits;
 };
 
 struct FbKfSub {
@@ -145,9 +174,8 @@ struct FbKfFrame {
     uint32_t data_bytes;
     uint32_t frame_fail;
     int32_t  cand[FB200_MAX_CHANNELS]; // per variant: result set of the chosen coding (0 fixed, 1 lpc)
-    uint32_t crc_xpow[9];
-    uint32_t crc_tab[256];
-    uint32_t crc_part[256];
+    uint32_t crc_acc, crc_last;
+    uint32_t crc_tab[1024];
 };
 
 FB_HD uint32_t fb_align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -159,6 +187,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     const uint32_t leaves = (uint32_t)(ga.leaves > gb.leaves ? ga.leaves : gb.leaves);
     L.U_max = U;
     L.leaves_max = leaves;
+    L.crc_chunk = fb_kf_crc_chunk(channels, bps, block_size, 32 * nvar);
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
     uint32_t o = 0;
     L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
@@ -174,8 +203,9 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     // scratch per warp
     uint32_t s = 0;
     L.s_words = s;      s += fb_align16(FB_KF_NWORDS * U * 4u);
-    L.s_tbl_a = s;      s += fb_align16(leaves * FB_KF_ROW * 4u + 64u * 4u); // also level-sum exchange (16 x 32)
-    if (leaves * FB_KF_ROW < 16u * 32u) s = L.s_tbl_a + fb_align16(16u * 32u * 4u);
+    uint32_t ta = leaves * FB_KF_ROW * 4u;
+    if (ta < 16u * 32u * 4u) ta = 16u * 32u * 4u; // also the level-sum exchange (16 levels x 32 lanes)
+    L.s_tbl_a = s;      s += fb_align16(ta);
     L.s_tbl_b = s;      s += fb_align16((leaves / 2u + 1u) * FB_KF_ROW * 4u);
     L.s_best_val = s;   s += fb_align16(2u * leaves * 4u);
     L.s_best_p = s;     s += fb_align16(2u * leaves);
@@ -220,12 +250,63 @@ FB_DEV void fb_kf_csa16(uint32_t *cw, const uint32_t *d) {
     cw[6] ^= c2;
 }
 
-// sum_t (u_t >> p) of one unit from its counter words (stored [word][unit], stride U)
-FB_DEV unsigned long long fb_kf_eval(const uint32_t *words, int U, int unit, int p) {
+// sum_t (u_t >> p) of one unit from its counter words: in registers (cw[j]) or in shared memory
+// ([word][unit], stride U).  The 32-bit forms are exact when every u < 2^24 (112 * 2^24 < 2^31).
+FB_DEV unsigned long long fb_kf_evalr64(const uint32_t *cw, int p) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < FB_KF_NWORDS; j++) s += (unsigned long long)(cw[j] >> p) << j;
+    return s;
+}
+FB_DEV uint32_t fb_kf_evalr32(const uint32_t *cw, int p) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < FB_KF_NWORDS; j++) s += (cw[j] >> p) << j;
+    return s;
+}
+FB_DEV unsigned long long fb_kf_eval64(const uint32_t *words, int U, int unit, int p) {
     unsigned long long s = 0;
 #pragma unroll
     for (int j = 0; j < FB_KF_NWORDS; j++) s += (unsigned long long)(words[j * U + unit] >> p) << j;
     return s;
+}
+FB_DEV uint32_t fb_kf_eval32(const uint32_t *words, int U, int unit, int p) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < FB_KF_NWORDS; j++) s += (words[j * U + unit] >> p) << j;
+    return s;
+}
+FB_DEV unsigned long long fb_kf_eval(const uint32_t *words, int U, int unit, int p, bool small) {
+    return small ? (unsigned long long)fb_kf_eval32(words, U, unit, p) : fb_kf_eval64(words, U, unit, p);
+}
+
+// Smallest minimiser of the convex cost f over [0, max_p], starting the walk at p (any start gives the same
+// result).  Going up requires a strict decrease, going down accepts ties, so ties resolve to the smallest p
+// like PrcBitTable::minimizer (src/rice.rs:117-141).
+template <class F>
+FB_DEV int fb_kf_walk(F f, int p, int max_p, unsigned long long *fmin) {
+    unsigned long long fc = f(p);
+    bool moved = false;
+    while (p < max_p) {
+        const unsigned long long fu = f(p + 1);
+        if (fu < fc) { fc = fu; p++; moved = true; } else break;
+    }
+    if (!moved) {
+        while (p > 0) {
+            const unsigned long long fd = f(p - 1);
+            if (fd <= fc) { fc = fd; p--; } else break;
+        }
+    }
+    *fmin = fc;
+    return p;
+}
+
+// starting point of the walk: ~ log2(mean)
+FB_DEV int fb_kf_pstart(unsigned long long s0, int cnt, int max_p) {
+    int p = 0;
+    if (cnt > 0 && s0 > (unsigned long long)cnt) p = (63 - fb_clz64(s0)) - (31 - fb_clz32((uint32_t)cnt));
+    if (p < 0) p = 0;
+    return p > max_p ? max_p : p;
 }
 
 // M = (L + R) >> 1 (arithmetic), S = L - R (src/coding.rs:476-484); unsigned adds so that stale padding
@@ -234,75 +315,111 @@ FB_HD int32_t fb_mid(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uin
 FB_HD int32_t fb_side(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
 // ---- residual runs out of the staged planes ------------------------------------------------------
-// vm: 0 = plane xa as is, 2 = mid (xa + xb) >> 1, 3 = side xa - xb   (src/coding.rs:476-484)
-// win[i] = x[t0 - G + i], i < G + FB_RUN; samples outside [0, n) read as 0 (their results are masked anyway)
-template <int G>
-FB_DEV void fb_kf_window(const int32_t *xa, const int32_t *xb, int vm, int t0, int n, int32_t *win) {
-    if (((t0 & 3) == 0) && t0 >= G) {
-#pragma unroll
-        for (int i = 0; i < G + FB_RUN; i += 4) {
-            const int o = fb_xidx(t0 - G + i);
-            const int4 a = *reinterpret_cast<const int4 *>(xa + o);
-            if (vm < 2) {
-                win[i] = a.x; win[i + 1] = a.y; win[i + 2] = a.z; win[i + 3] = a.w;
-            } else {
-                const int4 b = *reinterpret_cast<const int4 *>(xb + o);
-                if (vm == 2) {
-                    win[i] = fb_mid(a.x, b.x); win[i + 1] = fb_mid(a.y, b.y);
-                    win[i + 2] = fb_mid(a.z, b.z); win[i + 3] = fb_mid(a.w, b.w);
-                } else {
-                    win[i] = fb_side(a.x, b.x); win[i + 1] = fb_side(a.y, b.y);
-                    win[i + 2] = fb_side(a.z, b.z); win[i + 3] = fb_side(a.w, b.w);
-                }
-            }
-        }
+// vm: 0 = plane xa as is, 2 = mid, 3 = side.  A run's window is win[i] = x[t0 - G + i], i < G + FB_RUN:
+// the G history samples are loaded once per unit and then slide in registers, the 16 new samples come
+// from 16-byte shared-memory loads (scalar loads when the unit is not 4-aligned).
+
+// four samples t..t+3 (t a multiple of 4, inside the plane incl. its slack)
+FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
+    const int o = fb_xidx(t);
+    const int4 a = *reinterpret_cast<const int4 *>(xa + o);
+    if (vm < 2) {
+        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
     } else {
-#pragma unroll
-        for (int i = 0; i < G + FB_RUN; i++) {
-            const int t = t0 - G + i;
-            int32_t v = 0;
-            if (t >= 0 && t < n) {
-                const int o = fb_xidx(t);
-                v = xa[o];
-                if (vm == 2) v = fb_mid(v, xb[o]);
-                else if (vm == 3) v = fb_side(v, xb[o]);
-            }
-            win[i] = v;
+        const int4 b = *reinterpret_cast<const int4 *>(xb + o);
+        if (vm == 2) {
+            dst[0] = fb_mid(a.x, b.x); dst[1] = fb_mid(a.y, b.y); dst[2] = fb_mid(a.z, b.z); dst[3] = fb_mid(a.w, b.w);
+        } else {
+            dst[0] = fb_side(a.x, b.x); dst[1] = fb_side(a.y, b.y); dst[2] = fb_side(a.z, b.z); dst[3] = fb_side(a.w, b.w);
         }
     }
 }
 
-// zigzag residuals of the run t0..t0+15 from its window; samples outside [lo, hi) give 0.
-// kind 0: fixed predictor of `order` (zero-history differences, wrapping i32);
-// kind 1: LPC, narrow = the reference's i32 accumulation is safe (src/lpc.rs:361-374), else 64-bit.
+FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
+    const int o = fb_xidx(t);
+    const int32_t a = xa[o];
+    if (vm < 2) return a;
+    return vm == 2 ? fb_mid(a, xb[o]) : fb_side(a, xb[o]);
+}
+
+// win[0..G) = x[ta - G .. ta), zeros before the start of the frame
 template <int G>
-FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, int kind, int order, const int32_t *qq, int shift,
-                        bool narrow, uint32_t *u) {
-    if (kind == 0) {
+FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, int32_t *win) {
+    if ((ta & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < G; i += 4) {
+            const int t = ta - G + i;
+            if (t >= 0) fb_kf_load4(xa, xb, vm, t, win + i);
+            else { win[i] = 0; win[i + 1] = 0; win[i + 2] = 0; win[i + 3] = 0; }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            const int t = ta - G + i;
+            win[i] = t >= 0 ? fb_kf_load1(xa, xb, vm, t) : 0;
+        }
+    }
+}
+
+// win[G..G+16) = x[t0 .. t0+16); samples at t >= n are don't-cares (their results are masked)
+template <int G>
+FB_DEV void fb_kf_fetch16(const int32_t *xa, const int32_t *xb, int vm, int t0, int n, int32_t *win) {
+    if ((t0 & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < FB_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < FB_RUN; i++) win[G + i] = (t0 + i < n) ? fb_kf_load1(xa, xb, vm, t0 + i) : 0;
+    }
+}
+
+template <int G>
+FB_DEV void fb_kf_slide(int32_t *win) {
+#pragma unroll
+    for (int i = 0; i < G; i++) win[i] = win[i + FB_RUN];
+}
+
+// description of one residual candidate of a variant
+struct FbKfCand {
+    int kind, order, shift; // kind 0: fixed predictor of `order`, 1: LPC
+    bool narrow;            // LPC: the reference's i32 accumulation is safe (src/lpc.rs:361-374), else 64-bit
+    int32_t fc[4];          // fixed: e[t] = x[t] + fc0 x[t-1] + fc1 x[t-2] + fc2 x[t-3] + fc3 x[t-4] (wrapping i32)
+    const int16_t *q;
+};
+
+FB_DEV void fb_kf_fixed_coefs(int order, int32_t *fc) {
+    // zero-history k-th differences (src/coding.rs:182-197) == binomial predictors
+    // (-1)^j C(k, j):  k=1: -1 | k=2: -2 1 | k=3: -3 3 -1 | k=4: -4 6 -4 1
+    const int k = order < 0 ? 0 : (order > 4 ? 4 : order);
+    fc[0] = -k;
+    fc[1] = k * (k - 1) / 2;
+    fc[2] = -(k * (k - 1) * (k - 2)) / 6;
+    fc[3] = k == 4 ? 1 : 0;
+}
+
+// zigzag residuals of the run t0..t0+15 from its window; samples outside [lo, hi) give 0.
+template <int G>
+FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCand &cd, const int32_t *qq, uint32_t *u) {
+    // bit i of vmask: sample t0 + i lies in [lo, hi)
+    const int a = lo - t0, b = hi - t0;
+    const uint32_t m_hi = b >= FB_RUN ? 0xFFFFu : (b <= 0 ? 0u : ((1u << b) - 1u));
+    const uint32_t m_lo = a <= 0 ? 0u : (a >= FB_RUN ? 0xFFFFu : ((1u << a) - 1u));
+    const uint32_t vmask = m_hi & ~m_lo;
+    if (cd.kind == 0) {
 #pragma unroll
         for (int i = 0; i < FB_RUN; i++) {
-            const uint32_t a = (uint32_t)win[G + i], b = (uint32_t)win[G + i - 1], c = (uint32_t)win[G + i - 2],
-                           d = (uint32_t)win[G + i - 3], e4 = (uint32_t)win[G + i - 4];
-            uint32_t e;
-            switch (order) {
-            case 0: e = a; break;
-            case 1: e = a - b; break;
-            case 2: e = a - 2u * b + c; break;
-            case 3: e = a - 3u * b + 3u * c - d; break;
-            default: e = a - 4u * b + 6u * c - 4u * d + e4; break;
-            }
-            const int t = t0 + i;
-            u[i] = (t >= lo && t < hi) ? fb_zigzag((int32_t)e) : 0u;
+            const uint32_t e = (uint32_t)win[G + i] + (uint32_t)cd.fc[0] * (uint32_t)win[G + i - 1] +
+                               (uint32_t)cd.fc[1] * (uint32_t)win[G + i - 2] + (uint32_t)cd.fc[2] * (uint32_t)win[G + i - 3] +
+                               (uint32_t)cd.fc[3] * (uint32_t)win[G + i - 4];
+            u[i] = fb_zigzag((int32_t)e);
         }
-    } else if (narrow) {
+    } else if (cd.narrow) {
 #pragma unroll
         for (int i = 0; i < FB_RUN; i++) {
             uint32_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) acc += (uint32_t)qq[j] * (uint32_t)win[G + i - 1 - j];
-            const int32_t e = (int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> shift));
-            const int t = t0 + i;
-            u[i] = (t >= lo && t < hi) ? fb_zigzag(e) : 0u;
+            u[i] = fb_zigzag((int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> cd.shift)));
         }
     } else {
 #pragma unroll
@@ -310,29 +427,23 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, int kind, in
             int64_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) acc = fb_mad_wide(qq[j], win[G + i - 1 - j], acc);
-            const int32_t e = (int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> shift));
-            const int t = t0 + i;
-            u[i] = (t >= lo && t < hi) ? fb_zigzag(e) : 0u;
+            u[i] = fb_zigzag((int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> cd.shift)));
         }
+    }
+    if (vmask != 0xFFFFu) {
+#pragma unroll
+        for (int i = 0; i < FB_RUN; i++) u[i] = ((vmask >> i) & 1u) ? u[i] : 0u;
     }
 }
 
-// description of one residual candidate of a variant
-struct FbKfCand {
-    int kind, order, shift;
-    bool narrow;
-    const int16_t *q;
-};
-
 // =====================================================================================================
 // Rice search of one candidate by one warp.  xa/xb/vm select the variant's samples.  Writes res and
-// unit_bits[0..U] (bits of every unit without the parameter fields; [U] unused here).
+// unit_bits[0..U) (bits of every unit without the parameter fields).
 // Sets M->fail when the frame must be redone by the literal path.
 // =====================================================================================================
 template <int G>
 FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, const int32_t *xb, int vm,
-                         const FbKfCand &cd, uint8_t *scratch, const FbKfLayout &L, uint32_t *unit_bits,
-                         uint32_t *xch, FbKfRes *res) {
+                         const FbKfCand &cd, uint8_t *scratch, const FbKfLayout &L, uint32_t *unit_bits, FbKfRes *res) {
     uint32_t *words = (uint32_t *)(scratch + L.s_words);
     uint32_t *tbl_a = (uint32_t *)(scratch + L.s_tbl_a);
     uint32_t *tbl_b = (uint32_t *)(scratch + L.s_tbl_b);
@@ -344,10 +455,10 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
     const int slots = U >> 5;
 
     FB_WPHASE(lane)
-        if (lane == 0) { M->ormask = 0; M->pmin = 31; M->pmax = 0; M->any_gt14 = 0; M->sum_bits = 0; }
+        if (lane == 0) { M->ormask = 0; M->pmin = 31; M->pmax = 0; M->any_gt14 = 0; }
     FB_WPHASE_END
 
-    // ---- pass 1: residuals -> bit-sliced counters per unit
+    // ---- pass 1: residuals -> bit-sliced counters per unit (+ pass 2 in registers when unit == leaf)
     FB_WPHASE(lane)
         int32_t qq[G];
 #pragma unroll
@@ -361,15 +472,39 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 #pragma unroll
             for (int j = 0; j < FB_KF_NWORDS; j++) cw[j] = 0;
             const int lo = ta > warm ? ta : warm;
-            for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
+            if (tb > ta) {
                 int32_t win[G + FB_RUN];
-                uint32_t uu[FB_RUN];
-                fb_kf_window<G>(xa, xb, vm, t0, n, win);
-                fb_kf_run_u<G>(win, t0, lo, tb, cd.kind, cd.order, qq, cd.shift, cd.narrow, uu);
-                fb_kf_csa16(cw, uu);
+                fb_kf_history<G>(xa, xb, vm, ta, win);
+                for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
+                    uint32_t uu[FB_RUN];
+                    fb_kf_fetch16<G>(xa, xb, vm, t0, n, win);
+                    fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
+                    fb_kf_csa16(cw, uu);
+                    fb_kf_slide<G>(win);
+                }
             }
+            uint32_t orm_u = 0;
 #pragma unroll
-            for (int j = 0; j < FB_KF_NWORDS; j++) { words[j * U + unit] = cw[j]; orm |= cw[j]; }
+            for (int j = 0; j < FB_KF_NWORDS; j++) { words[j * U + unit] = cw[j]; orm_u |= cw[j]; }
+            orm |= orm_u;
+            if (g.m == 1) {
+                // the unit is a finest partition: its exact minimiser, from the registers
+                const int cnt = g.leaf_len - (unit == 0 ? warm : 0);
+                unsigned long long fmin;
+                int p;
+                if (orm_u < (1u << 24)) {
+                    p = fb_kf_pstart(fb_kf_evalr32(cw, 0), cnt, max_p);
+                    p = fb_kf_walk([&](int pp) { return (unsigned long long)(fb_kf_evalr32(cw, pp) + (uint32_t)cnt * (uint32_t)(pp + 1)); },
+                                   p, max_p, &fmin);
+                } else {
+                    p = fb_kf_pstart(fb_kf_evalr64(cw, 0), cnt, max_p);
+                    p = fb_kf_walk([&](int pp) { return fb_kf_evalr64(cw, pp) + (unsigned long long)cnt * (unsigned long long)(pp + 1); },
+                                   p, max_p, &fmin);
+                }
+                if (fmin + 4ull >= (unsigned long long)FB_RICE_SAT) M->fail = 1; // benign race: every writer stores 1
+                fb_atomic_min_u32(&M->pmin, (uint32_t)p);
+                fb_atomic_max_u32(&M->pmax, (uint32_t)p);
+            }
         }
         if (orm) fb_atomic_or_u32(&M->ormask, orm);
     FB_WPHASE_END
@@ -381,84 +516,70 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
         FB_WPHASE_END
         return;
     }
+    const bool small = M->ormask < (1u << 24);
 
-    // ---- pass 2: exact minimiser of every finest partition (walk on the convex cost)
-    FB_WPHASE(lane)
-        for (int leaf = lane; leaf < g.leaves; leaf += 32) {
-            const int cnt = g.leaf_len - (leaf == 0 ? warm : 0);
-            unsigned long long s0 = 0;
-            for (int k = 0; k < g.m; k++) s0 += fb_kf_eval(words, U, leaf * g.m + k, 0);
-            // starting point ~ log2(mean); any start gives the same result
-            int p = 0;
-            if (s0 > (unsigned long long)cnt && cnt > 0) p = (63 - fb_clz64(s0)) - (31 - fb_clz32((uint32_t)cnt));
-            if (p < 0) p = 0;
-            if (p > max_p) p = max_p;
-            unsigned long long fc = 0;
-            for (int k = 0; k < g.m; k++) fc += fb_kf_eval(words, U, leaf * g.m + k, p);
-            fc += (unsigned long long)cnt * (unsigned long long)(p + 1);
-            bool moved = false;
-            while (p < max_p) {
-                unsigned long long fu = 0;
-                for (int k = 0; k < g.m; k++) fu += fb_kf_eval(words, U, leaf * g.m + k, p + 1);
-                fu += (unsigned long long)cnt * (unsigned long long)(p + 2);
-                if (fu < fc) { fc = fu; p++; moved = true; } else break;
+    // ---- pass 2 (units smaller than a finest partition): minimiser per partition from shared memory
+    if (g.m > 1) {
+        FB_WPHASE(lane)
+            for (int leaf = lane; leaf < g.leaves; leaf += 32) {
+                const int cnt = g.leaf_len - (leaf == 0 ? warm : 0);
+                auto cost = [&](int pp) {
+                    unsigned long long f = (unsigned long long)cnt * (unsigned long long)(pp + 1);
+                    for (int k = 0; k < g.m; k++) f += fb_kf_eval(words, U, leaf * g.m + k, pp, small);
+                    return f;
+                };
+                unsigned long long fmin;
+                int p = fb_kf_pstart(cost(0) - (unsigned long long)cnt, cnt, max_p);
+                p = fb_kf_walk(cost, p, max_p, &fmin);
+                if (fmin + 4ull >= (unsigned long long)FB_RICE_SAT) M->fail = 1;
+                fb_atomic_min_u32(&M->pmin, (uint32_t)p);
+                fb_atomic_max_u32(&M->pmax, (uint32_t)p);
             }
-            if (!moved) {
-                while (p > 0) {
-                    unsigned long long fd = 0;
-                    for (int k = 0; k < g.m; k++) fd += fb_kf_eval(words, U, leaf * g.m + k, p - 1);
-                    fd += (unsigned long long)cnt * (unsigned long long)p;
-                    if (fd <= fc) { fc = fd; p--; } else break;
-                }
-            }
-            if (fc + 4ull >= (unsigned long long)FB_RICE_SAT) M->fail = 1; // benign race: every writer stores 1
-            fb_atomic_min_u32(&M->pmin, (uint32_t)p);
-            fb_atomic_max_u32(&M->pmax, (uint32_t)p);
-        }
-    FB_WPHASE_END
+        FB_WPHASE_END
+    }
     if (M->fail) return;
 
-    // ---- pass 3: partition tree over [pmin, pmax], FB_KF_COLS parameters at a time
+    // ---- pass 3: partition tree over [pmin, pmax], FB_KF_COLS parameters at a time.  One lane per node:
+    // it forms the node's row (leaf: from the counters; inner node: min(a + b - 4, 2^27-1), src/rice.rs:144-152)
+    // and keeps the node's minimum; windows are visited in ascending p, so ties keep the smallest p.
     const int pa0 = (int)M->pmin, pb = (int)M->pmax;
     for (int pa = pa0; pa <= pb; pa += FB_KF_COLS) {
         const int Wc = (pb - pa + 1) < FB_KF_COLS ? (pb - pa + 1) : FB_KF_COLS;
         const bool first = pa == pa0;
-        // leaf tables: min(S + cnt*(p+1) + 4, 2^27-1)   (src/rice.rs:65-105)
         FB_WPHASE(lane)
-            for (int e = lane; e < g.leaves * FB_KF_COLS; e += 32) {
-                const int leaf = e >> 3, j = e & 7;
-                if (j < Wc) {
+            for (int leaf = lane; leaf < g.leaves; leaf += 32) {
+                const int cnt = g.leaf_len - (leaf == 0 ? warm : 0);
+                uint32_t bv = 0xFFFFFFFFu;
+                int bp = pa;
+                for (int j = 0; j < Wc; j++) {
                     const int p = pa + j;
-                    const int cnt = g.leaf_len - (leaf == 0 ? warm : 0);
                     unsigned long long f = 4ull + (unsigned long long)cnt * (unsigned long long)(p + 1);
-                    for (int k = 0; k < g.m; k++) f += fb_kf_eval(words, U, leaf * g.m + k, p);
-                    tbl_a[leaf * FB_KF_ROW + j] = f > FB_RICE_SAT ? FB_RICE_SAT : (uint32_t)f;
+                    for (int k = 0; k < g.m; k++) f += fb_kf_eval(words, U, leaf * g.m + k, p, small);
+                    const uint32_t v = f > FB_RICE_SAT ? FB_RICE_SAT : (uint32_t)f;
+                    tbl_a[leaf * FB_KF_ROW + j] = v;
+                    if (v < bv) { bv = v; bp = p; }
                 }
+                const int idx = g.leaves - 1 + leaf;
+                if (first || bv < best_val[idx]) { best_val[idx] = bv; best_p[idx] = (uint8_t)bp; }
             }
         FB_WPHASE_END
         uint32_t *cur = tbl_a, *nxt = tbl_b;
-        for (int lvl = g.o0; lvl >= 0; lvl--) {
+        for (int lvl = g.o0 - 1; lvl >= 0; lvl--) {
             const int nodes = 1 << lvl;
             FB_WPHASE(lane)
-                // minimiser: smallest (bits, p)  (src/rice.rs:117-141); windows are visited in ascending p
                 for (int node = lane; node < nodes; node += 32) {
-                    const uint32_t *row = cur + node * FB_KF_ROW;
-                    uint32_t bv = row[0];
+                    const uint32_t *ra = cur + (2 * node) * FB_KF_ROW, *rb = ra + FB_KF_ROW;
+                    uint32_t *ro = nxt + node * FB_KF_ROW;
+                    uint32_t bv = 0xFFFFFFFFu;
                     int bp = pa;
-                    for (int j = 1; j < Wc; j++)
-                        if (row[j] < bv) { bv = row[j]; bp = pa + j; }
+                    for (int j = 0; j < Wc; j++) {
+                        uint32_t v = ra[j] + rb[j] - 4u;
+                        v = v < FB_RICE_SAT ? v : FB_RICE_SAT;
+                        ro[j] = v;
+                        if (v < bv) { bv = v; bp = pa + j; }
+                    }
                     const int idx = nodes - 1 + node;
                     if (first || bv < best_val[idx]) { best_val[idx] = bv; best_p[idx] = (uint8_t)bp; }
-                }
-                // merge pairs: min(a + b - 4, 2^27-1)  (src/rice.rs:144-152)
-                if (lvl > 0) {
-                    for (int e = lane; e < (nodes >> 1) * FB_KF_COLS; e += 32) {
-                        const int node = e >> 3, j = e & 7;
-                        if (j < Wc) {
-                            const uint32_t v = cur[(2 * node) * FB_KF_ROW + j] + cur[(2 * node + 1) * FB_KF_ROW + j] - 4u;
-                            nxt[node * FB_KF_ROW + j] = v < FB_RICE_SAT ? v : FB_RICE_SAT;
-                        }
-                    }
                 }
             FB_WPHASE_END
             uint32_t *tmp = cur; cur = nxt; nxt = tmp;
@@ -498,7 +619,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             res->part_order = best;
         }
     FB_WPHASE_END
-    // ---- pass 4c: parameters, bits of every unit, Residual::count_bits
+    // ---- pass 4c: parameters, bits of every unit (for the packer)
     {
         const int best = M->best_level;
         const int nparts = 1 << best;
@@ -509,28 +630,24 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
                 res->params[j] = p;
                 if (p > 14) M->any_gt14 = 1;
             }
-            unsigned long long local = 0;
             for (int unit = lane; unit < U; unit += 32) {
                 const int p = best_p[nparts - 1 + (unit >> ush)];
                 int ta, tb;
                 fb_kf_unit_range(g, unit, &ta, &tb);
                 if (ta < warm) ta = warm;
                 const int cnt = tb > ta ? tb - ta : 0;
-                const unsigned long long b = fb_kf_eval(words, U, unit, p) + (unsigned long long)cnt * (unsigned long long)(p + 1);
-                unit_bits[unit] = (uint32_t)b;
-                local += b;
+                unit_bits[unit] = (uint32_t)(fb_kf_eval(words, U, unit, p, small) + (unsigned long long)cnt * (unsigned long long)(p + 1));
             }
-            xch[2 * lane] = (uint32_t)local;
-            xch[2 * lane + 1] = (uint32_t)(local >> 32);
         FB_WPHASE_END
         FB_WPHASE(lane)
             if (lane == 0) {
-                unsigned long long total = 0;
-                for (int i = 0; i < 32; i++) total += (unsigned long long)xch[2 * i] | ((unsigned long long)xch[2 * i + 1] << 32);
                 const int rice2 = M->any_gt14 ? 1 : 0;
                 res->rice2 = rice2;
-                // src/component/bitrepr.rs:532-544: 2 + 4 + parts*(4|5) + sum q + (n - w) + sum p*len - w*p0
-                res->res_bits = 6ull + (unsigned long long)nparts * (rice2 ? 5ull : 4ull) + total;
+                // src/component/bitrepr.rs:532-544: 2 + 4 + parts*(4|5) + sum q + (n - w) + sum p*len - w*p0.
+                // Every node minimum is S + cnt*(p+1) + 4 (unsaturated, checked above), so the code bits of the
+                // chosen partitioning are the level total minus the 4-bit offsets.
+                res->res_bits = 6ull + (unsigned long long)nparts * (rice2 ? 5ull : 4ull) + lvl_bits[best] -
+                                4ull * (unsigned long long)nparts;
             }
         FB_WPHASE_END
     }
@@ -538,7 +655,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 
 // =====================================================================================================
 // One variant (one warp): fixed_lpc / estimated_qlpc / encode_subframe (src/coding.rs:298-418) on top
-// of K1's analysis.  Writes the decision record `out` (shared memory) and *cand_out (which unit_bits set).
+// of K1's analysis.  Writes the decision record `out` (shared memory) and S->cand[v].
 // =====================================================================================================
 template <int G>
 FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, const FbAnalysis &A, int v,
@@ -547,7 +664,6 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     uint8_t *scratch = smem + L.off_scratch + (uint32_t)v * L.scratch_bytes;
     uint8_t *keep = smem + L.off_keep + (uint32_t)v * L.keep_bytes;
     uint32_t *unit_bits = (uint32_t *)(keep + L.k_unit_bits);
-    uint32_t *xch = (uint32_t *)(keep + L.k_xch);
     FbKfRes *res = (FbKfRes *)(keep + L.k_res);
     FbKfMisc *M = (FbKfMisc *)(scratch + L.s_misc);
     const int n = g.n;
@@ -583,35 +699,38 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     }
     if (n < FB_MIN_PRED_BLOCK) return;
 
-    // fixed candidate (ApproxEnt winner from K1; src/coding.rs:298-331)
+    // candidates: 0 = fixed winner of K1's entropy estimate (src/coding.rs:298-331), 1 = LPC (src/coding.rs:360-381)
     const int kf = J.cfg.use_fixed ? A.fixed_order : -1;
-    unsigned long long fixed_bits = 0;
-    if (kf >= 0) {
+    unsigned long long cbits[2] = {0, 0};
+#if FB_GPU
+#pragma unroll 1
+#endif
+    for (int c = 0; c < 2; c++) {
+        if (c == 0 ? (kf < 0) : !J.cfg.use_lpc) continue;
         FbKfCand cd;
-        cd.kind = 0; cd.order = kf; cd.shift = 0; cd.narrow = true; cd.q = nullptr;
-        fb_kf_search<G>(J, g, xa, xb, vm, cd, scratch, L, unit_bits, xch, &res[0]);
+        cd.kind = c;
+        cd.q = A.qlp;
+        if (c == 0) {
+            cd.order = kf; cd.shift = 0; cd.narrow = true;
+            fb_kf_fixed_coefs(kf, cd.fc);
+        } else {
+            cd.order = A.qlp_order; cd.shift = A.qlp_shift;
+            cd.fc[0] = cd.fc[1] = cd.fc[2] = cd.fc[3] = 0;
+            // src/lpc.rs:361-374: i32 accumulation when max|x| * sum|q| < 2^31 - 1
+            unsigned long long sumabs = 0;
+            for (int j = 0; j < A.qlp_order; j++) sumabs += (unsigned long long)(A.qlp[j] < 0 ? -A.qlp[j] : A.qlp[j]);
+            cd.narrow = (unsigned long long)A.max_abs * sumabs < 0x7FFFFFFFull;
+        }
+        fb_kf_search<G>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), &res[c]);
         if (M->fail) return;
-        fixed_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0].res_bits;
+        cbits[c] = c == 0 ? 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0].res_bits
+                          : 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
+                                (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res[1].res_bits;
     }
+    const unsigned long long fixed_bits = cbits[0], lpc_bits = cbits[1];
     const unsigned long long baseline_bits =
         kf >= 0 ? (fixed_bits < verbatim_bits ? fixed_bits : verbatim_bits) : verbatim_bits;
-
-    // LPC candidate (src/coding.rs:360-381)
-    bool lpc_ok = false;
-    unsigned long long lpc_bits = 0;
-    if (J.cfg.use_lpc) {
-        FbKfCand cd;
-        cd.kind = 1; cd.order = A.qlp_order; cd.shift = A.qlp_shift; cd.q = A.qlp;
-        // src/lpc.rs:361-374: i32 accumulation when max|x| * sum|q| < 2^31 - 1
-        unsigned long long sumabs = 0;
-        for (int j = 0; j < A.qlp_order; j++) sumabs += (unsigned long long)(A.qlp[j] < 0 ? -A.qlp[j] : A.qlp[j]);
-        cd.narrow = (unsigned long long)A.max_abs * sumabs < 0x7FFFFFFFull;
-        fb_kf_search<G>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (L.U_max + 1), xch, &res[1]);
-        if (M->fail) return;
-        lpc_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
-                   (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res[1].res_bits;
-        lpc_ok = lpc_bits < baseline_bits;
-    }
+    const bool lpc_ok = J.cfg.use_lpc && lpc_bits < baseline_bits;
 
     // decision (src/coding.rs:403-416)
     int pick = -1;
@@ -638,13 +757,67 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     FB_WPHASE_END
 }
 
+// ---- MSB-first bit writer with a 64-bit accumulator (src/bitsink.rs semantics) ----------------------
+// A writer owns the bit range [pos_start, pos_end) of the zero-initialised word buffer; only its first and
+// last word can be shared with a neighbour (atomic OR), interior words are stored plainly.
+struct FbBitW {
+    uint32_t *words;
+    uint32_t w_first, w_last, cur_w, fill; // fill < 32: valid bits at the top of acc
+    unsigned long long acc;
+};
+
+FB_DEV void fb_bw_init(FbBitW &r, uint32_t *words, uint32_t pos_start, uint32_t pos_end) {
+    r.words = words;
+    r.w_first = pos_start >> 5;
+    r.w_last = pos_end > pos_start ? ((pos_end - 1) >> 5) : r.w_first;
+    r.cur_w = r.w_first;
+    r.fill = pos_start & 31u;
+    r.acc = 0;
+}
+
+FB_DEV void fb_bw_store(FbBitW &r, uint32_t w) {
+    if (w) {
+        if (r.cur_w == r.w_first || r.cur_w == r.w_last) fb_atomic_or(&r.words[r.cur_w], w);
+        else r.words[r.cur_w] = w;
+    }
+}
+
+// append the k (1..32) low bits of v (v < 2^k)
+FB_DEV void fb_bw_put(FbBitW &r, uint32_t v, uint32_t k) {
+    r.acc |= (unsigned long long)v << (64u - r.fill - k);
+    r.fill += k;
+    if (r.fill >= 32u) {
+        fb_bw_store(r, (uint32_t)(r.acc >> 32));
+        r.acc <<= 32;
+        r.fill -= 32u;
+        r.cur_w++;
+    }
+}
+
+// append q zero bits
+FB_DEV void fb_bw_skip(FbBitW &r, uint32_t q) {
+    const uint32_t total = r.fill + q;
+    if (total >= 32u) {
+        fb_bw_store(r, (uint32_t)(r.acc >> 32));
+        r.acc = 0; // fill < 32, so everything pending was in the high word
+        r.cur_w += total >> 5;
+    }
+    r.fill = total & 31u;
+}
+
+FB_DEV void fb_bw_finish(FbBitW &r) {
+    if (r.fill) fb_bw_store(r, (uint32_t)(r.acc >> 32));
+    r.acc = 0;
+    r.fill = 0;
+}
+
 // =====================================================================================================
-// KF body: one CTA (32 * nvar threads) per frame.
+// KF body: one CTA (32 * nvar threads) per frame.  ktab: CRC tables built by fb_kf_build_ktab.
 // =====================================================================================================
 template <int G>
 FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots, uint32_t *frame_bytes,
-                       fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, uint32_t f, uint8_t *smem,
-                       const FbKfLayout &L) {
+                       fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab, uint32_t f,
+                       uint8_t *smem, const FbKfLayout &L) {
     const int NW = J.nvar;
     const int T = 32 * NW;
     const int n = fb_frame_len(J, f);
@@ -666,7 +839,8 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 *reinterpret_cast<int4 *>(dst + fb_xidx(4 * i)) = v;
             }
         }
-        if (tid == 0) S->frame_fail = 0;
+        for (int i = tid; i < 1024; i += T) S->crc_tab[i] = ktab[i];
+        if (tid == 0) { S->frame_fail = 0; S->crc_acc = 0; S->crc_last = 0; }
     FB_PHASE_END
 
     // ---- analysis: one warp per variant
@@ -693,10 +867,9 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
         return;
     }
 
-    // ---- stereo decision, header, subframe offsets (thread 0); CRC table; clear the word buffer
+    // ---- stereo decision, header, subframe offsets (thread 0)
     const uint32_t max_words = (fb_max_frame_bytes(J.channels, J.bps, J.block_size) + 3u) / 4u + 2u;
     FB_PHASE(tid, T)
-        for (int i = tid; i < 256; i += T) S->crc_tab[i] = fb_crc16_table_entry((uint32_t)i);
         if (tid == 0) {
             int ch_tag = J.channels - 1;
             int sel[FB200_MAX_CHANNELS];
@@ -733,9 +906,7 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             }
             S->data_bytes = (bit + 7u) >> 3;
         }
-    FB_PHASE_END
-    // the scratch of the analysis is dead from here on; the frame words alias it
-    FB_PHASE(tid, T)
+        // the scratch of the analysis is dead from here on; the frame words alias it
         for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
     FB_PHASE_END
 
@@ -785,6 +956,7 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             r.w_first = r.cur_w;
             fb_run_flush(r);
         }
+#define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, (t)))
         if (tid < J.channels) {
             const FbKfSub &D = S->sub[tid];
             const fb200_subframe_info &V = choice[D.variant];
@@ -796,7 +968,6 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             r.w_last = 0xFFFFFFFFu;
             const uint32_t mask = D.bps >= 32 ? 0xFFFFFFFFu : ((1u << D.bps) - 1u);
 #define FB_PUT_ATOMIC(val, nb) do { r.w_first = r.cur_w; fb_run_put(r, (uint32_t)(val), (uint32_t)(nb)); } while (0)
-#define FB_KF_X(t) ((uint32_t)(vm == 0 ? xa[fb_xidx(t)] : (vm == 2 ? fb_mid(xa[fb_xidx(t)], xb[fb_xidx(t)]) : fb_side(xa[fb_xidx(t)], xb[fb_xidx(t)]))))
             if (D.type == FB200_SF_CONSTANT) {
                 FB_PUT_ATOMIC(0x00, 8);
                 FB_PUT_ATOMIC(FB_KF_X(0) & mask, D.bps);
@@ -832,11 +1003,11 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 // Verbatim::write (src/component/bitrepr.rs:463-470): bps bits per sample at fixed positions
                 if (tb <= ta) continue;
                 const uint32_t mask = D.bps >= 32 ? 0xFFFFFFFFu : ((1u << D.bps) - 1u);
-                FbBitRun r;
-                fb_run_init(r, words, D.start_bit + 8u + (uint32_t)ta * (uint32_t)D.bps,
-                            D.start_bit + 8u + (uint32_t)tb * (uint32_t)D.bps);
-                for (int t = ta; t < tb; t++) fb_run_put(r, FB_KF_X(t) & mask, (uint32_t)D.bps);
-                fb_run_flush(r);
+                FbBitW r;
+                fb_bw_init(r, words, D.start_bit + 8u + (uint32_t)ta * (uint32_t)D.bps,
+                           D.start_bit + 8u + (uint32_t)tb * (uint32_t)D.bps);
+                for (int t = ta; t < tb; t++) fb_bw_put(r, FB_KF_X(t) & mask, (uint32_t)D.bps);
+                fb_bw_finish(r);
                 continue;
             }
             // Residual::write (src/component/bitrepr.rs:550-597)
@@ -847,80 +1018,93 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             if (p1 == p0) continue;
             const int ush = g.lgU - D.part_order;
             const uint32_t rp = V.rice_params[unit >> ush];
-            FbBitRun r;
-            fb_run_init(r, words, p0, p1);
-            if ((unit & ((1 << ush) - 1)) == 0) fb_run_put(r, rp, D.rice2 ? 5u : 4u);
+            FbBitW r;
+            fb_bw_init(r, words, p0, p1);
+            if ((unit & ((1 << ush) - 1)) == 0) fb_bw_put(r, rp, D.rice2 ? 5u : 4u);
             const int warm = D.order;
             const int lo = ta > warm ? ta : warm;
-            const int kind = D.type == FB200_SF_LPC ? 1 : 0;
+            FbKfCand cd;
+            cd.kind = D.type == FB200_SF_LPC ? 1 : 0;
+            cd.order = D.order; cd.shift = D.shift; cd.q = V.qlp;
+            fb_kf_fixed_coefs(cd.kind == 0 ? D.order : 0, cd.fc);
             int32_t qq[G];
             unsigned long long sumabs = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) {
-                qq[j] = (kind == 1 && j < D.order) ? (int32_t)V.qlp[j] : 0;
+                qq[j] = (cd.kind == 1 && j < D.order) ? (int32_t)V.qlp[j] : 0;
                 sumabs += (unsigned long long)(qq[j] < 0 ? -qq[j] : qq[j]);
             }
-            const bool narrow = kind == 0 ||
-                                (unsigned long long)ana[(size_t)f * (size_t)J.nvar + (size_t)D.variant].max_abs * sumabs < 0x7FFFFFFFull;
+            cd.narrow = cd.kind == 0 ||
+                        (unsigned long long)ana[(size_t)f * (size_t)J.nvar + (size_t)D.variant].max_abs * sumabs < 0x7FFFFFFFull;
             const uint32_t rmask = (1u << rp) - 1u, rone = 1u << rp;
-            for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
+            if (tb > lo) {
                 int32_t win[G + FB_RUN];
-                uint32_t uu[FB_RUN];
-                fb_kf_window<G>(xa, xb, vm, t0, n, win);
-                fb_kf_run_u<G>(win, t0, lo, tb, kind, D.order, qq, D.shift, narrow, uu);
+                fb_kf_history<G>(xa, xb, vm, ta, win);
+                for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
+                    uint32_t uu[FB_RUN];
+                    fb_kf_fetch16<G>(xa, xb, vm, t0, n, win);
+                    fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
 #pragma unroll
-                for (int i = 0; i < FB_RUN; i++) {
-                    const int t = t0 + i;
-                    if (t >= lo && t < tb) {
-                        fb_run_skip(r, uu[i] >> rp);
-                        fb_run_put(r, (uu[i] & rmask) | rone, rp + 1u);
+                    for (int i = 0; i < FB_RUN; i++) {
+                        const int t = t0 + i;
+                        if (t >= lo && t < tb) {
+                            // q zeros, a one, then the p low bits: one field when it fits in 32 bits
+                            const uint32_t q = uu[i] >> rp, code = (uu[i] & rmask) | rone;
+                            if (q + rp + 1u <= 32u) {
+                                fb_bw_put(r, code, q + rp + 1u);
+                            } else {
+                                fb_bw_skip(r, q);
+                                fb_bw_put(r, code, rp + 1u);
+                            }
+                        }
                     }
+                    fb_kf_slide<G>(win);
                 }
             }
-            fb_run_flush(r);
+            fb_bw_finish(r);
         }
 #undef FB_KF_X
     FB_PHASE_END
 
-    // ---- CRC-16 over data_bytes (Frame::write, src/component/bitrepr.rs:289-320): chunks aligned to the
-    // END of the data (leading zero bytes do not change a CRC with init 0), combined pairwise with
-    // x^(8*Lc*2^k) mod P.  TC = largest power of two <= T threads take part.
-    int TC = 32;
-    while (TC * 2 <= T) TC *= 2;
+    // ---- CRC-16 over data_bytes (Frame::write, src/component/bitrepr.rs:289-320).  Chunks of Lc bytes from
+    // the start of the frame, one per thread, four bytes per step (slicing tables); the chunk CRCs are shifted
+    // to the end of the data with x^(8*Lc*k) (table xp) and one final x^(8*len(last chunk)) (table xb):
+    //   crc = (xor_{i<K-1} crc_i * xp[K-2-i]) * xb[len_last]  xor  crc_{K-1}
     const uint32_t B = S->data_bytes;
-    const uint32_t Lc = (B + (uint32_t)TC - 1u) / (uint32_t)TC;
+    const uint32_t Lc = L.crc_chunk;
+    const uint32_t K = (B + Lc - 1u) / Lc; // >= 1 chunks, K <= T by the choice of Lc
     FB_PHASE(tid, T)
-        if (tid == 0) {
-            uint32_t result = 1, base = 2;
-            uint32_t e = 8u * Lc;
-            while (e) { if (e & 1u) result = fb_crc16_mulmod(result, base); base = fb_crc16_mulmod(base, base); e >>= 1; }
-            S->crc_xpow[0] = result;
-            for (int k = 1; k < 9; k++) S->crc_xpow[k] = fb_crc16_mulmod(S->crc_xpow[k - 1], S->crc_xpow[k - 1]);
-        }
-        if (tid < TC) {
-            long long lo = (long long)B - (long long)(TC - tid) * (long long)Lc;
-            const long long hi = lo + (long long)Lc;
-            if (lo < 0) lo = 0;
+        if ((uint32_t)tid < K) {
+            const uint32_t b0 = (uint32_t)tid * Lc;
+            const uint32_t b1 = b0 + Lc < B ? b0 + Lc : B;
             uint32_t crc = 0;
-            for (long long i = lo; i < hi; i++) {
-                const uint32_t byte = (words[i >> 2] >> (24u - 8u * (uint32_t)(i & 3))) & 0xFFu;
+            uint32_t i = b0;
+            for (; i + 4u <= b1; i += 4u) { // b0 is a multiple of 4: whole big-endian words
+                const uint32_t w = words[i >> 2];
+                crc = S->crc_tab[768 + (((crc >> 8) ^ (w >> 24)) & 0xFFu)] ^ S->crc_tab[512 + ((crc ^ (w >> 16)) & 0xFFu)] ^
+                      S->crc_tab[256 + ((w >> 8) & 0xFFu)] ^ S->crc_tab[w & 0xFFu];
+            }
+            for (; i < b1; i++) {
+                const uint32_t byte = (words[i >> 2] >> (24u - 8u * (i & 3u))) & 0xFFu;
                 crc = ((crc << 8) & 0xFFFFu) ^ S->crc_tab[((crc >> 8) ^ byte) & 0xFFu];
             }
-            S->crc_part[tid] = crc;
+            if ((uint32_t)tid + 1u == K) {
+                S->crc_last = crc;
+            } else {
+                const uint32_t sh = fb_crc16_mulmod(crc, ktab[FB_KTAB_XP + (K - 2u - (uint32_t)tid)]);
+#if FB_GPU
+                if (sh) atomicXor(&S->crc_acc, sh);
+#else
+                S->crc_acc ^= sh;
+#endif
+            }
         }
     FB_PHASE_END
-    for (int k = 0; (1 << k) < TC; k++) {
-        FB_PHASE(tid, T)
-            const int span = 1 << (k + 1);
-            if (tid < TC && (tid % span) == 0) {
-                const uint32_t left = S->crc_part[tid], right = S->crc_part[tid + (1 << k)];
-                S->crc_part[tid] = fb_crc16_mulmod(left, S->crc_xpow[k]) ^ right;
-            }
-        FB_PHASE_END
-    }
     FB_PHASE(tid, T)
         if (tid == 0) {
-            const uint32_t crc = S->crc_part[0];
+            const uint32_t len_last = B - (K - 1u) * Lc;
+            const uint32_t crc = fb_crc16_mulmod(S->crc_acc, ktab[FB_KTAB_XB + len_last]) ^ S->crc_last;
+            // the two CRC bytes follow the (byte-aligned) data, big-endian
             for (int i = 0; i < 2; i++) {
                 const uint32_t pos = B + (uint32_t)i;
                 const uint32_t byte = (crc >> (8 * (1 - i))) & 0xFFu;

@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
 __global__ void __launch_bounds__(256) FB_NAME(fb_kf_frame_g)(FbJob J, const int32_t *xv, const FbAnalysis *ana,
                                                               uint8_t *slots, uint32_t *frame_bytes,
                                                               fb200_frame_info *infos, uint32_t *fb_list,
-                                                              uint32_t *fb_count, FbKfLayout L) {
+                                                              uint32_t *fb_count, const uint32_t *ktab, FbKfLayout L) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_kf_body<FB_INST_G>(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, blockIdx.x, fb_smem, L);
+    fb_kf_body<FB_INST_G>(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
 }
 
 void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
@@ -80,10 +80,10 @@ void FB_NAME(fb_launch_k3_g)(const FbJob &J, const int32_t *xv, const fb200_subf
 }
 
 void FB_NAME(fb_launch_kf_g)(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots, uint32_t *frame_bytes,
-                             fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const FbKfLayout &L,
-                             cudaStream_t st) {
+                             fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,
+                             const FbKfLayout &L, cudaStream_t st) {
     FB_NAME(fb_kf_frame_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xv, ana, slots, frame_bytes, infos, fb_list,
-                                                                      fb_count, L);
+                                                                      fb_count, ktab, L);
 }
 
 cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {

@@ -20,7 +20,7 @@ enum { FB_KERNEL_K2 = 2, FB_KERNEL_K3 = 3, FB_KERNEL_KF = 5 };
                            const uint32_t *count, uint32_t grid, size_t smem, cudaStream_t st);                      \
     void fb_launch_kf_g##G(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots,                  \
                            uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count,    \
-                           const FbKfLayout &L, cudaStream_t st);                                                    \
+                           const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st);                                                    \
     cudaError_t fb_set_smem_g##G(int kernel, int bytes);
 
 FB_DECLARE_LAUNCHERS(4)
@@ -64,8 +64,8 @@ static inline void fb_launch_k3(int ring, const FbJob &J, const int32_t *xv, con
 }
 static inline void fb_launch_kf(int ring, const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots,
                                 uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count,
-                                const FbKfLayout &L, cudaStream_t st) {
-#define FB_CALL(G) fb_launch_kf_g##G(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, L, st)
+                                const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
+#define FB_CALL(G) fb_launch_kf_g##G(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, ktab, L, st)
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }

@@ -92,9 +92,11 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<uint32_t> list(J.n_frames + 1, 0);
         uint32_t count = 0;
         std::vector<uint8_t> smem(KL.total + 64);
+        std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
+        fb_kf_build_ktab(KL.crc_chunk, ktab.data());
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KF(GG) fb_kf_body<GG>(J, B.xv.data(), B.ana.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, f, smem.data(), KL)
+#define EMU_KF(GG) fb_kf_body<GG>(J, B.xv.data(), B.ana.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab.data(), f, smem.data(), KL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KF(4); break;
             case 8: EMU_KF(8); break;
