@@ -58,21 +58,36 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// Device buffers, events and pinned staging of one chunk in flight.  Set 0 also serves the serial path.
+struct ChunkSet {
+    DevBuf pcm, xv, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars;
+    // events: 0 H2D start, 1 H2D end, 2 ingest end, 3 analyze end, 4 rice/fused end, 5 pack/fallback end,
+    //         6 gather end (= chunk done), 7 D2H start, 8 D2H end, 9 H2D end on the copy stream (pipelined path)
+    cudaEvent_t ev[10];
+    int n_ev = 0;
+    uint8_t *pinned = nullptr; // [0, 64): copy of the device scalars; [64, ...): frame sizes of the chunk
+    size_t pinned_cap = 0;
+    bool d2h_pending = false;  // ev[8] has been recorded for a chunk whose D2H time is not accounted yet
+};
+
+#define FB_NSETS 3
+
 struct fb200_ctx {
     fb200_config cfg;
     int channels, bps, sample_rate, block_size, device;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[16];
-    int n_ev = 0;
-    DevBuf pcm, xv, win_full, win_tail, ana, taps, choice, slots, frame_bytes, offsets, out, infos, scalars, fb_list, ktab;
+    cudaStream_t stream = nullptr;   // serial path and compute stream 0
+    cudaStream_t s_k1 = nullptr;     // compute stream 1 (pipelined path: chunks alternate)
+    cudaStream_t s_in = nullptr, s_out = nullptr; // H2D / D2H streams of the pipelined path
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    ChunkSet sets[FB_NSETS];
+    DevBuf win_full, win_tail, ktab;
     int win_tail_n = -1;
-    void *pinned = nullptr; // small pinned staging: err flag, total bytes
-    size_t pinned_cap = 0;
     fb200_timing timing;
     std::string last_error;
     int k2_smem_set = 0, k3_smem_set = 0, kf_smem_set = 0;
     uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
+    uint64_t pipe_chunk_frames = 0; // FB200_CHUNK_FRAMES: frames per chunk of the pipelined host path (0 = default)
     std::mutex mu;
 };
 
@@ -88,7 +103,7 @@ struct fb200_ctx {
 static int fb_reserve(fb200_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return FB200_OK;
     if (b.p) {
-        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FB_CUDA(ctx, cudaDeviceSynchronize());
         FB_CUDA(ctx, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -96,6 +111,19 @@ static int fb_reserve(fb200_ctx *ctx, DevBuf &b, size_t bytes) {
     size_t want = bytes + bytes / 8 + 256;
     FB_CUDA(ctx, cudaMalloc(&b.p, want));
     b.cap = want;
+    return FB200_OK;
+}
+
+static int fb_reserve_pinned(fb200_ctx *ctx, ChunkSet &S, size_t bytes) {
+    if (bytes <= S.pinned_cap) return FB200_OK;
+    if (S.pinned) {
+        FB_CUDA(ctx, cudaDeviceSynchronize());
+        FB_CUDA(ctx, cudaFreeHost(S.pinned));
+        S.pinned = nullptr;
+        S.pinned_cap = 0;
+    }
+    FB_CUDA(ctx, cudaHostAlloc((void **)&S.pinned, bytes + 256, cudaHostAllocDefault));
+    S.pinned_cap = bytes + 256;
     return FB200_OK;
 }
 
@@ -121,7 +149,7 @@ const char *fb200_strerror(int code) {
     }
 }
 
-const char *fb200_version(void) { return "flacenc_b200 0.1.0 (sm_100a)"; }
+const char *fb200_version(void) { return "flacenc_b200 0.2.0 (sm_100a)"; }
 
 const char *fb200_last_error(const fb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
@@ -146,15 +174,24 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
     {
         const char *fg = getenv("FB200_FORCE_GENERIC");
         ctx->force_generic = fg && fg[0] == '1';
+        const char *cf = getenv("FB200_CHUNK_FRAMES");
+        if (cf) ctx->pipe_chunk_frames = strtoull(cf, nullptr, 10);
     }
     bool ok = cudaSetDevice(device) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 16; i++) {
-        ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-        if (ok) ctx->n_ev = i + 1;
+              cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_k1, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+    for (int k = 0; ok && k < FB_NSETS; k++) {
+        ChunkSet &S = ctx->sets[k];
+        for (int i = 0; ok && i < 10; i++) {
+            ok = cudaEventCreate(&S.ev[i]) == cudaSuccess;
+            if (ok) S.n_ev = i + 1;
+        }
+        ok = ok && cudaHostAlloc((void **)&S.pinned, 4096, cudaHostAllocDefault) == cudaSuccess;
+        if (ok) S.pinned_cap = 4096;
     }
-    ctx->pinned_cap = 4096;
-    ok = ok && cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         *err = FB200_ERR_CUDA;
         fb200_destroy(ctx);
@@ -166,14 +203,23 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
 void fb200_destroy(fb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->pcm, &ctx->xv, &ctx->win_full, &ctx->win_tail, &ctx->ana, &ctx->taps, &ctx->choice,
-                      &ctx->slots, &ctx->frame_bytes, &ctx->offsets, &ctx->out, &ctx->infos, &ctx->scalars, &ctx->fb_list, &ctx->ktab};
+    cudaDeviceSynchronize();
+    for (ChunkSet &S : ctx->sets) {
+        DevBuf *bufs[] = {&S.pcm, &S.xv, &S.ana, &S.taps, &S.choice, &S.slots, &S.frame_bytes, &S.offsets, &S.out,
+                          &S.infos, &S.fb_list, &S.scalars};
+        for (DevBuf *b : bufs)
+            if (b->p) cudaFree(b->p);
+        for (int i = 0; i < S.n_ev; i++) cudaEventDestroy(S.ev[i]);
+        if (S.pinned) cudaFreeHost(S.pinned);
+    }
+    DevBuf *bufs[] = {&ctx->win_full, &ctx->win_tail, &ctx->ktab};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
-    for (int i = 0; i < ctx->n_ev; i++) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    cudaStream_t sts[] = {ctx->stream, ctx->s_k1, ctx->s_in, ctx->s_out};
+    for (cudaStream_t st : sts)
+        if (st) cudaStreamDestroy(st);
     delete ctx;
 }
 
@@ -215,6 +261,23 @@ struct EncodeArgs {
     size_t *n_variants = nullptr;
 };
 
+// everything about a call that does not change from chunk to chunk
+struct Plan {
+    int cb = 0, nvar = 0, ring = 0, tail_n = 0;
+    uint64_t bs = 0, total_frames = 0, stride = 0, slot_bytes = 0;
+    uint32_t mb = 0;
+    const float *d_win_tail = nullptr;
+    FbK2Layout L;
+    FbKfLayout KL;
+    size_t k2_smem = 0, k3_smem = 0;
+    bool fused = false;
+};
+
+struct Accum {
+    float ms_h2d = 0, ms_d2h = 0, ms_k[5] = {0, 0, 0, 0, 0};
+    uint64_t launches = 0, fused_frames = 0, fallback = 0;
+};
+
 int fb_upload_window(fb200_ctx *ctx, DevBuf &buf, int n) {
     std::vector<float> w((size_t)n + 64, 0.f);
     fbh_window_weights(ctx->cfg.window_type, ctx->cfg.tukey_alpha, n, w.data());
@@ -222,6 +285,386 @@ int fb_upload_window(fb200_ctx *ctx, DevBuf &buf, int n) {
     if (rc) return rc;
     FB_CUDA(ctx, cudaMemcpyAsync(buf.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `w` dies at scope end
+    return FB200_OK;
+}
+
+// geometry, window tables, CRC tables, shared-memory opt-in
+int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
+    int rc;
+    P.cb = A.container_bytes ? A.container_bytes : 4;
+    P.bs = (uint64_t)ctx->block_size;
+    P.total_frames = (A.n_samples + P.bs - 1) / P.bs;
+    P.nvar = ctx->channels == 2 ? 4 : ctx->channels;
+    P.stride = (uint64_t)((ctx->block_size + 31) & ~31);
+    P.mb = fb_max_frame_bytes(ctx->channels, ctx->bps, ctx->block_size);
+    P.slot_bytes = (P.mb + 15u) & ~15u;
+    P.ring = fb_k1_ring(ctx->cfg.lpc_order);
+    // window tables (src/lpc.rs:217-231: cached per size)
+    if (ctx->win_full.p == nullptr && (rc = fb_upload_window(ctx, ctx->win_full, ctx->block_size))) return rc;
+    P.tail_n = (A.n_samples % P.bs) ? (int)(A.n_samples % P.bs) : ctx->block_size;
+    if (P.tail_n != ctx->block_size && P.tail_n != ctx->win_tail_n) {
+        if ((rc = fb_upload_window(ctx, ctx->win_tail, P.tail_n))) return rc;
+        ctx->win_tail_n = P.tail_n;
+    }
+    P.d_win_tail = (P.tail_n == ctx->block_size) ? (const float *)ctx->win_full.p : (const float *)ctx->win_tail.p;
+
+    FbJob J0 = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, P.cb,
+                            std::min<uint64_t>(A.n_samples, P.bs), (uint32_t)A.first_frame);
+    const int leaves_max = 1 << fb_finest_partition_order(ctx->block_size);
+    const int leaves_tail = 1 << fb_finest_partition_order(P.tail_n);
+    P.L = fb_k2_layout(ctx->block_size, std::max(leaves_max, leaves_tail));
+    P.k2_smem = P.L.total + 3 * sizeof(FbRiceResult);
+    P.k3_smem = fb_k3_smem_bytes(P.mb, ctx->block_size, J0.pack_in_smem);
+    if (P.k2_smem > 227u * 1024u || P.k3_smem > 227u * 1024u) {
+        ctx->last_error = "internal: shared memory budget exceeded";
+        return FB200_ERR_CUDA;
+    }
+    P.fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, P.tail_n, &P.KL);
+    if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
+        std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk));
+        fb_kf_build_ktab(P.KL.crc_chunk, kt.data());
+        if ((rc = fb_reserve(ctx, ctx->ktab, kt.size() * 4u))) return rc;
+        FB_CUDA(ctx, cudaMemcpyAsync(ctx->ktab.p, kt.data(), kt.size() * 4u, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
+        ctx->ktab_chunk = P.KL.crc_chunk;
+    }
+    if (P.fused && (int)P.KL.total > ctx->kf_smem_set) {
+        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, (int)P.KL.total));
+        ctx->kf_smem_set = (int)P.KL.total;
+    }
+    if ((int)P.k2_smem > ctx->k2_smem_set) {
+        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K2, (int)P.k2_smem));
+        ctx->k2_smem_set = (int)P.k2_smem;
+    }
+    if ((int)P.k3_smem > ctx->k3_smem_set) {
+        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K3, (int)P.k3_smem));
+        ctx->k3_smem_set = (int)P.k3_smem;
+    }
+    return FB200_OK;
+}
+
+// device buffers of a set for chunks of up to `frames` frames
+int fb_reserve_set(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet &S, uint64_t frames, uint64_t in_bytes,
+                   uint64_t sizes_frames, uint64_t out_bytes) {
+    int rc;
+    if ((rc = fb_reserve(ctx, S.scalars, 64))) return rc;
+    if ((rc = fb_reserve(ctx, S.frame_bytes, sizes_frames * 4u))) return rc;
+    if ((rc = fb_reserve(ctx, S.offsets, (frames + 1) * 8u))) return rc;
+    if ((rc = fb_reserve(ctx, S.xv, (frames * (uint64_t)P.nvar * P.stride + 64) * 4u))) return rc;
+    if ((rc = fb_reserve(ctx, S.ana, frames * (uint64_t)P.nvar * sizeof(FbAnalysis)))) return rc;
+    if (in_bytes && (rc = fb_reserve(ctx, S.pcm, in_bytes + 16))) return rc;
+    if (A.analyze_only) {
+        if ((rc = fb_reserve(ctx, S.taps, frames * (uint64_t)P.nvar * sizeof(fb200_variant_taps)))) return rc;
+    } else {
+        if ((rc = fb_reserve(ctx, S.choice, frames * (uint64_t)P.nvar * sizeof(fb200_subframe_info)))) return rc;
+        if ((rc = fb_reserve(ctx, S.slots, frames * P.slot_bytes))) return rc;
+        if ((rc = fb_reserve(ctx, S.fb_list, (frames + 1) * 4u))) return rc;
+        if (A.infos && (rc = fb_reserve(ctx, S.infos, frames * sizeof(fb200_frame_info)))) return rc;
+        if (out_bytes && (rc = fb_reserve(ctx, S.out, out_bytes))) return rc;
+    }
+    return FB200_OK;
+}
+
+// Enqueues K0..K4 of one chunk on `st`.  d_pcm: the chunk's interleaved PCM on the device (nullptr: planar frame in
+// S.pcm).  Frame sizes go to d_fb[0..nf), bytes to d_out + offsets starting at *d_total (which advances).
+// Records S.ev[1..6].
+int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet &S, uint64_t f0, uint64_t ns,
+                       const uint8_t *d_pcm, uint32_t *d_fb, uint8_t *d_out, unsigned long long out_cap, cudaStream_t st,
+                       Accum &acc) {
+    FbJob J = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, P.cb, ns,
+                           (uint32_t)(A.first_frame + f0));
+    const uint32_t nvars = J.n_frames * (uint32_t)J.nvar;
+    uint32_t *d_err = (uint32_t *)S.scalars.p;
+    unsigned long long *d_total = (unsigned long long *)((uint8_t *)S.scalars.p + 8);
+    uint32_t *d_fb_count = (uint32_t *)((uint8_t *)S.scalars.p + 16);
+    FB_CUDA(ctx, cudaEventRecord(S.ev[1], st));
+    if (A.planar_host) {
+        fb_k0_ingest_planar<<<(unsigned)((J.tail_n + 255) / 256), 256, 0, st>>>(J, (const int32_t *)S.pcm.p, A.planar_stride,
+                                                                               (int32_t *)S.xv.p, d_err);
+    } else {
+        fb_k0_ingest<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv.p, d_err);
+    }
+    FB_CUDA(ctx, cudaEventRecord(S.ev[2], st));
+    fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
+                 A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
+    FB_CUDA(ctx, cudaEventRecord(S.ev[3], st));
+    acc.launches += 2;
+    if (A.analyze_only) return FB200_OK;
+    fb200_frame_info *d_infos = A.infos ? (fb200_frame_info *)S.infos.p : nullptr;
+    if (P.fused) {
+        // KF: Rice search + frame assembly per frame; frames it cannot reproduce exactly go to the list
+        FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
+        fb_launch_kf(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (uint8_t *)S.slots.p, d_fb, d_infos,
+                     (uint32_t *)S.fb_list.p, d_fb_count, (const uint32_t *)ctx->ktab.p, P.KL, st);
+        FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
+        fb_launch_k2(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
+                     P.L, (const uint32_t *)S.fb_list.p, d_fb_count, 296, P.k2_smem, st);
+        fb_launch_k3(P.ring, J, (const int32_t *)S.xv.p, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
+                     d_fb, d_infos, (const uint32_t *)S.fb_list.p, d_fb_count, 148, P.k3_smem, st);
+        FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
+        acc.fused_frames += J.n_frames;
+        acc.launches += 3;
+    } else {
+        fb_launch_k2(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
+                     P.L, nullptr, nullptr, nvars, P.k2_smem, st);
+        FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
+        fb_launch_k3(P.ring, J, (const int32_t *)S.xv.p, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
+                     d_fb, d_infos, nullptr, nullptr, J.n_frames, P.k3_smem, st);
+        FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
+        acc.launches += 2;
+    }
+    fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
+    fb_k4_gather<<<J.n_frames, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
+                                             (const unsigned long long *)S.offsets.p, d_out, out_cap);
+    acc.launches += 2;
+    FB_CUDA(ctx, cudaGetLastError());
+    // device scalars (error flag, running total, fallback count) for the host
+    FB_CUDA(ctx, cudaMemcpyAsync(S.pinned, S.scalars.p, 24, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(ctx, cudaEventRecord(S.ev[6], st));
+    return FB200_OK;
+}
+
+// kernel times of a finished chunk (S.ev[6] has completed)
+int fb_harvest_kernel_times(fb200_ctx *ctx, ChunkSet &S, bool analyze_only, Accum &acc) {
+    float t;
+    const int last = analyze_only ? 2 : 5;
+    for (int k = 0; k < last; k++) {
+        FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[1 + k], S.ev[2 + k]));
+        acc.ms_k[k] += t;
+    }
+    return FB200_OK;
+}
+
+void fb_store_timing(fb200_ctx *ctx, const Accum &acc, float total_ms, uint64_t in_bytes, uint64_t out_bytes) {
+    fb200_timing &T = ctx->timing;
+    T.h2d_ms = acc.ms_h2d;
+    T.k_ingest_ms = acc.ms_k[0];
+    T.k_analyze_ms = acc.ms_k[1];
+    T.k_rice_ms = acc.ms_k[2];
+    T.k_pack_ms = acc.ms_k[3];
+    T.k_gather_ms = acc.ms_k[4];
+    T.kernels_ms = acc.ms_k[0] + acc.ms_k[1] + acc.ms_k[2] + acc.ms_k[3] + acc.ms_k[4];
+    T.d2h_ms = acc.ms_d2h;
+    T.total_ms = total_ms;
+    T.launches = acc.launches;
+    T.in_bytes = in_bytes;
+    T.out_bytes = out_bytes;
+    T.fused_frames = acc.fused_frames - acc.fallback;
+    T.fallback_frames = acc.fallback;
+}
+
+// ---- serial path: device-resident input/output, single planar frames, analysis taps, small host batches.
+// Chunks run back to back on one stream; the output offsets continue across chunks on the device.
+int fb_encode_serial(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P) {
+    ChunkSet &S = ctx->sets[0];
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // chunking: bound the working set (planar variants + slots) to ~2 GiB per pass
+    const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + P.slot_bytes + 4096u;
+    uint64_t chunk_frames = std::max<uint64_t>(64, (2048ull << 20) / per_frame);
+    chunk_frames = std::min<uint64_t>(chunk_frames, P.total_frames);
+    const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
+    uint64_t in_chunk = 0;
+    if (A.pcm_host) in_chunk = std::min(chunk_frames * P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb, in_bytes_total);
+    else if (A.planar_host) in_chunk = (uint64_t)ctx->channels * (uint64_t)A.planar_stride * 4u;
+    if ((rc = fb_reserve_set(ctx, P, A, S, chunk_frames, in_chunk, P.total_frames,
+                             (A.out_host && !A.analyze_only) ? std::max<size_t>(A.out_cap, 16) : 0)))
+        return rc;
+    uint8_t *d_out = A.out_dev ? A.out_dev : (uint8_t *)S.out.p;
+    FB_CUDA(ctx, cudaMemsetAsync(S.scalars.p, 0, 64, st));
+    Accum acc;
+    FB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, st));
+    for (uint64_t f0 = 0; f0 < P.total_frames; f0 += chunk_frames) {
+        const uint64_t nf = std::min(chunk_frames, P.total_frames - f0);
+        const uint64_t s0 = f0 * P.bs;
+        const uint64_t ns = std::min(A.n_samples - s0, nf * P.bs);
+        FB_CUDA(ctx, cudaEventRecord(S.ev[0], st));
+        const uint8_t *d_pcm = nullptr;
+        if (A.pcm_host) {
+            const uint64_t off = s0 * (uint64_t)ctx->channels * (uint64_t)P.cb;
+            const uint64_t len = ns * (uint64_t)ctx->channels * (uint64_t)P.cb;
+            FB_CUDA(ctx, cudaMemcpyAsync(S.pcm.p, (const uint8_t *)A.pcm_host + off, len, cudaMemcpyHostToDevice, st));
+            d_pcm = (const uint8_t *)S.pcm.p;
+        } else if (A.pcm_dev) {
+            d_pcm = (const uint8_t *)A.pcm_dev + s0 * (uint64_t)ctx->channels * (uint64_t)P.cb;
+        } else {
+            FB_CUDA(ctx, cudaMemcpyAsync(S.pcm.p, A.planar_host, in_chunk, cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = fb_enqueue_kernels(ctx, P, A, S, f0, ns, d_pcm, (uint32_t *)S.frame_bytes.p + f0, d_out,
+                                     (unsigned long long)A.out_cap, st, acc)))
+            return rc;
+        if (A.analyze_only) {
+            FB_CUDA(ctx, cudaMemcpyAsync(A.taps + f0 * (uint64_t)P.nvar, S.taps.p,
+                                         (size_t)(nf * (uint64_t)P.nvar) * sizeof(fb200_variant_taps),
+                                         cudaMemcpyDeviceToHost, st));
+            FB_CUDA(ctx, cudaStreamSynchronize(st));
+            if ((rc = fb_harvest_kernel_times(ctx, S, true, acc))) return rc;
+            continue;
+        }
+        if (A.infos)
+            FB_CUDA(ctx, cudaMemcpyAsync(A.infos + f0, S.infos.p, (size_t)nf * sizeof(fb200_frame_info),
+                                         cudaMemcpyDeviceToHost, st));
+        // per-chunk timings need the events to have completed; chunks are serial on one stream
+        FB_CUDA(ctx, cudaEventSynchronize(S.ev[6]));
+        float t;
+        FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[0], S.ev[1]));
+        acc.ms_h2d += t;
+        if ((rc = fb_harvest_kernel_times(ctx, S, false, acc))) return rc;
+        acc.fallback += *(const uint32_t *)(S.pinned + 16);
+    }
+    if (A.analyze_only) return FB200_OK;
+
+    FB_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t err_flag = *(const uint32_t *)S.pinned;
+    const unsigned long long total = *(const unsigned long long *)(S.pinned + 8);
+    if (err_flag) {
+        ctx->last_error = "input sample out of the range of bits_per_sample";
+        return FB200_ERR_CONFIG; // VerifyError (src/source.rs:262-275)
+    }
+    if (A.out_len) *A.out_len = (size_t)total;
+    if (total > A.out_cap) {
+        ctx->last_error = "output capacity too small";
+        return FB200_ERR_CAPACITY;
+    }
+    FB_CUDA(ctx, cudaEventRecord(S.ev[7], st));
+    if (A.frame_sizes)
+        FB_CUDA(ctx, cudaMemcpyAsync(A.frame_sizes, S.frame_bytes.p, P.total_frames * 4u, cudaMemcpyDeviceToHost, st));
+    if (A.out_host) FB_CUDA(ctx, cudaMemcpyAsync(A.out_host, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(ctx, cudaEventRecord(S.ev[8], st));
+    FB_CUDA(ctx, cudaEventRecord(ctx->ev_end, st));
+    FB_CUDA(ctx, cudaStreamSynchronize(st));
+    float t_total = 0;
+    FB_CUDA(ctx, cudaEventElapsedTime(&acc.ms_d2h, S.ev[7], S.ev[8]));
+    FB_CUDA(ctx, cudaEventElapsedTime(&t_total, ctx->ev_begin, ctx->ev_end));
+    fb_store_timing(ctx, acc, t_total, in_bytes_total, total);
+    return FB200_OK;
+}
+
+// ---- pipelined path: host PCM in, host frame bytes out.  The batch is cut into chunks; chunk c's H2D copy
+// (stream s_in), kernels (compute streams, alternating so the latency-bound analysis kernel of one chunk overlaps
+// the fused kernel of the previous one) and D2H copy (stream s_out) overlap with those of its neighbours.
+// FB_NSETS buffer sets rotate; a set is reused once its D2H copy has been enqueued and is waited for by event.
+int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint64_t chunk_frames) {
+    int rc;
+    const uint64_t nchunks = (P.total_frames + chunk_frames - 1) / chunk_frames;
+    const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
+    const uint64_t in_chunk = std::min(chunk_frames * P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb, in_bytes_total);
+    for (ChunkSet &S : ctx->sets) {
+        if ((rc = fb_reserve_set(ctx, P, A, S, chunk_frames, in_chunk, chunk_frames, chunk_frames * (uint64_t)P.mb + 16)))
+            return rc;
+        if ((rc = fb_reserve_pinned(ctx, S, 64 + chunk_frames * 4u))) return rc;
+        S.d2h_pending = false;
+    }
+    Accum acc;
+    unsigned long long host_off = 0;
+    int result = FB200_OK;
+    FB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->s_in));
+
+    auto chunk_range = [&](uint64_t c, uint64_t &f0, uint64_t &nf, uint64_t &s0, uint64_t &ns) {
+        f0 = c * chunk_frames;
+        nf = std::min(chunk_frames, P.total_frames - f0);
+        s0 = f0 * P.bs;
+        ns = std::min(A.n_samples - s0, nf * P.bs);
+    };
+    auto enqueue = [&](uint64_t c) -> int {
+        ChunkSet &S = ctx->sets[c % FB_NSETS];
+        uint64_t f0, nf, s0, ns;
+        chunk_range(c, f0, nf, s0, ns);
+        if (S.d2h_pending) {
+            // the set's previous chunk: its D2H must have drained before the buffers are overwritten
+            FB_CUDA(ctx, cudaEventSynchronize(S.ev[8]));
+            float t;
+            FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
+            acc.ms_d2h += t;
+            S.d2h_pending = false;
+        }
+        const uint64_t off = s0 * (uint64_t)ctx->channels * (uint64_t)P.cb;
+        const uint64_t len = ns * (uint64_t)ctx->channels * (uint64_t)P.cb;
+        FB_CUDA(ctx, cudaEventRecord(S.ev[0], ctx->s_in));
+        FB_CUDA(ctx, cudaMemcpyAsync(S.pcm.p, (const uint8_t *)A.pcm_host + off, len, cudaMemcpyHostToDevice, ctx->s_in));
+        cudaStream_t sk = (c & 1) ? ctx->s_k1 : ctx->stream;
+        FB_CUDA(ctx, cudaEventRecord(S.ev[9], ctx->s_in));
+        FB_CUDA(ctx, cudaStreamWaitEvent(sk, S.ev[9], 0));
+        FB_CUDA(ctx, cudaMemsetAsync(S.scalars.p, 0, 64, sk));
+        return fb_enqueue_kernels(ctx, P, A, S, f0, ns, (const uint8_t *)S.pcm.p, (uint32_t *)S.frame_bytes.p,
+                                  (uint8_t *)S.out.p, (unsigned long long)S.out.cap, sk, acc);
+    };
+    auto finish = [&](uint64_t c) -> int {
+        ChunkSet &S = ctx->sets[c % FB_NSETS];
+        uint64_t f0, nf, s0, ns;
+        chunk_range(c, f0, nf, s0, ns);
+        FB_CUDA(ctx, cudaEventSynchronize(S.ev[6]));
+        float t;
+        FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[0], S.ev[9]));
+        acc.ms_h2d += t;
+        int rc2;
+        if ((rc2 = fb_harvest_kernel_times(ctx, S, false, acc))) return rc2;
+        const uint32_t err_flag = *(const uint32_t *)S.pinned;
+        const unsigned long long total = *(const unsigned long long *)(S.pinned + 8);
+        acc.fallback += *(const uint32_t *)(S.pinned + 16);
+        if (err_flag && result == FB200_OK) {
+            ctx->last_error = "input sample out of the range of bits_per_sample";
+            result = FB200_ERR_CONFIG; // VerifyError (src/source.rs:262-275)
+        }
+        if (host_off + total > A.out_cap && result == FB200_OK) {
+            ctx->last_error = "output capacity too small";
+            result = FB200_ERR_CAPACITY;
+        }
+        cudaStream_t sk = (c & 1) ? ctx->s_k1 : ctx->stream;
+        (void)sk;
+        FB_CUDA(ctx, cudaEventRecord(S.ev[7], ctx->s_out));
+        if (result == FB200_OK) {
+            if (A.out_host && total)
+                FB_CUDA(ctx, cudaMemcpyAsync(A.out_host + host_off, S.out.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->s_out));
+            if (A.frame_sizes) {
+                // via pinned staging so the copy stays asynchronous; handed over after the final synchronize
+                FB_CUDA(ctx, cudaMemcpyAsync(S.pinned + 64, S.frame_bytes.p, (size_t)nf * 4u, cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+            if (A.infos)
+                FB_CUDA(ctx, cudaMemcpyAsync(A.infos + f0, S.infos.p, (size_t)nf * sizeof(fb200_frame_info),
+                                             cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        FB_CUDA(ctx, cudaEventRecord(S.ev[8], ctx->s_out));
+        S.d2h_pending = true;
+        host_off += total;
+        return FB200_OK;
+    };
+    // frame sizes staged in a set's pinned area must be copied out before the set is reused
+    auto collect_sizes = [&](uint64_t c) -> int {
+        if (!A.frame_sizes || result != FB200_OK) return FB200_OK;
+        ChunkSet &S = ctx->sets[c % FB_NSETS];
+        uint64_t f0, nf, s0, ns;
+        chunk_range(c, f0, nf, s0, ns);
+        FB_CUDA(ctx, cudaEventSynchronize(S.ev[8]));
+        memcpy(A.frame_sizes + f0, S.pinned + 64, (size_t)nf * 4u);
+        return FB200_OK;
+    };
+
+    const uint64_t ahead = FB_NSETS - 1;
+    for (uint64_t c = 0; c < nchunks + ahead; c++) {
+        if (c >= FB_NSETS && (rc = collect_sizes(c - FB_NSETS))) return rc; // before chunk c reuses that set
+        if (c < nchunks && (rc = enqueue(c))) return rc;
+        if (c >= ahead && (rc = finish(c - ahead))) return rc;
+    }
+    for (uint64_t c = nchunks > FB_NSETS ? nchunks - FB_NSETS : 0; c < nchunks; c++)
+        if ((rc = collect_sizes(c))) return rc;
+    FB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->s_out));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_k1));
+    for (ChunkSet &S : ctx->sets) {
+        if (S.d2h_pending) {
+            float t;
+            FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
+            acc.ms_d2h += t;
+            S.d2h_pending = false;
+        }
+    }
+    if (A.out_len) *A.out_len = (size_t)host_off;
+    if (result != FB200_OK) return result;
+    float t_total = 0;
+    FB_CUDA(ctx, cudaEventElapsedTime(&t_total, ctx->ev_begin, ctx->ev_end));
+    fb_store_timing(ctx, acc, t_total, in_bytes_total, host_off);
     return FB200_OK;
 }
 
@@ -252,232 +695,18 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
         return FB200_ERR_CONFIG;
     }
     if (A.analyze_only && (uint64_t)A.taps_cap < total_frames * (uint64_t)nvar) return FB200_ERR_CAPACITY;
-
-    // chunking: bound the working set (planar variants + slots) to ~2 GiB per pass
-    const uint64_t stride = (uint64_t)((ctx->block_size + 31) & ~31);
-    const uint32_t mb = fb_max_frame_bytes(ctx->channels, ctx->bps, ctx->block_size);
-    const uint64_t per_frame = (uint64_t)nvar * stride * 4u + ((mb + 15u) & ~15u) + 4096u;
-    uint64_t chunk_frames = std::max<uint64_t>(64, (2048ull << 20) / per_frame);
-    chunk_frames = std::min<uint64_t>(chunk_frames, total_frames);
-
-    // device scalars: [0] err flag (u32), [8] running total bytes (u64), [16] fallback-list length (u32)
-    int rc;
-    if ((rc = fb_reserve(ctx, ctx->scalars, 64))) return rc;
-    FB_CUDA(ctx, cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->stream));
-    uint32_t *d_err = (uint32_t *)ctx->scalars.p;
-    unsigned long long *d_total = (unsigned long long *)((uint8_t *)ctx->scalars.p + 8);
-    uint32_t *d_fb_count = (uint32_t *)((uint8_t *)ctx->scalars.p + 16);
-
-    if ((rc = fb_reserve(ctx, ctx->frame_bytes, total_frames * 4u))) return rc;
-    if ((rc = fb_reserve(ctx, ctx->offsets, (chunk_frames + 1) * 8u))) return rc;
-    if ((rc = fb_reserve(ctx, ctx->xv, (chunk_frames * (uint64_t)nvar * stride + 64) * 4u))) return rc;
-    if ((rc = fb_reserve(ctx, ctx->ana, chunk_frames * (uint64_t)nvar * sizeof(FbAnalysis)))) return rc;
-    if (A.analyze_only) {
-        if ((rc = fb_reserve(ctx, ctx->taps, chunk_frames * (uint64_t)nvar * sizeof(fb200_variant_taps)))) return rc;
-    } else {
-        if ((rc = fb_reserve(ctx, ctx->choice, chunk_frames * (uint64_t)nvar * sizeof(fb200_subframe_info)))) return rc;
-        if ((rc = fb_reserve(ctx, ctx->slots, chunk_frames * (uint64_t)((mb + 15u) & ~15u)))) return rc;
-        if ((rc = fb_reserve(ctx, ctx->fb_list, (chunk_frames + 1) * 4u))) return rc;
-        if (A.infos && (rc = fb_reserve(ctx, ctx->infos, chunk_frames * sizeof(fb200_frame_info)))) return rc;
-        if (A.out_host && (rc = fb_reserve(ctx, ctx->out, A.out_cap ? A.out_cap : 16))) return rc;
+    Plan P;
+    int rc = fb_make_plan(ctx, A, P);
+    if (rc) return rc;
+    // host batches of more than one chunk are pipelined; the chunk is sized so that the per-variant analysis
+    // kernel still has a few thousand threads and the copies of neighbouring chunks overlap the kernels
+    if (A.pcm_host && !A.analyze_only) {
+        uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 6144;
+        const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + 2 * P.slot_bytes + 4096u;
+        chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(64, (1024ull << 20) / per_frame));
+        if (total_frames > chunk + chunk / 2) return fb_encode_pipelined(ctx, A, P, chunk);
     }
-    uint8_t *d_out = A.out_dev ? A.out_dev : (uint8_t *)ctx->out.p;
-
-    // window tables (src/lpc.rs:217-231: cached per size)
-    if (ctx->win_full.p == nullptr && (rc = fb_upload_window(ctx, ctx->win_full, ctx->block_size))) return rc;
-    const int tail_n = (A.n_samples % bs) ? (int)(A.n_samples % bs) : ctx->block_size;
-    if (tail_n != ctx->block_size && tail_n != ctx->win_tail_n) {
-        if ((rc = fb_upload_window(ctx, ctx->win_tail, tail_n))) return rc;
-        ctx->win_tail_n = tail_n;
-    }
-    const float *d_win_tail = (tail_n == ctx->block_size) ? (const float *)ctx->win_full.p : (const float *)ctx->win_tail.p;
-
-    // host input staging area on the device
-    const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)cb;
-    if (A.pcm_host) {
-        uint64_t chunk_in = chunk_frames * bs * (uint64_t)ctx->channels * (uint64_t)cb;
-        if ((rc = fb_reserve(ctx, ctx->pcm, std::min(chunk_in, in_bytes_total) + 16))) return rc;
-    } else if (A.planar_host) {
-        if ((rc = fb_reserve(ctx, ctx->pcm, (uint64_t)ctx->channels * (uint64_t)A.planar_stride * 4u + 16))) return rc;
-    }
-
-    // opt-in to large dynamic shared memory once
-    FbJob J0 = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, cb ? cb : 4,
-                            std::min<uint64_t>(A.n_samples, chunk_frames * bs), (uint32_t)A.first_frame);
-    const int leaves_max = 1 << fb_finest_partition_order(ctx->block_size); // tail leaves <= block leaves? not always:
-    int leaves_tail = 1 << fb_finest_partition_order(tail_n);
-    const FbK2Layout L = fb_k2_layout(ctx->block_size, std::max(leaves_max, leaves_tail));
-    const size_t k2_smem = L.total + 3 * sizeof(FbRiceResult);
-    const size_t k3_smem = fb_k3_smem_bytes(mb, ctx->block_size, J0.pack_in_smem);
-    if (k2_smem > 227u * 1024u || k3_smem > 227u * 1024u) {
-        ctx->last_error = "internal: shared memory budget exceeded";
-        return FB200_ERR_CUDA;
-    }
-    const int ring = fb_k1_ring(ctx->cfg.lpc_order);
-    FbKfLayout KL;
-    const bool fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, tail_n, &KL);
-    if (fused && ctx->ktab_chunk != KL.crc_chunk) {
-        std::vector<uint32_t> kt(fb_kf_ktab_words(KL.crc_chunk));
-        fb_kf_build_ktab(KL.crc_chunk, kt.data());
-        if ((rc = fb_reserve(ctx, ctx->ktab, kt.size() * 4u))) return rc;
-        FB_CUDA(ctx, cudaMemcpyAsync(ctx->ktab.p, kt.data(), kt.size() * 4u, cudaMemcpyHostToDevice, ctx->stream));
-        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
-        ctx->ktab_chunk = KL.crc_chunk;
-    }
-    if (fused && (int)KL.total > ctx->kf_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_KF, (int)KL.total));
-        ctx->kf_smem_set = (int)KL.total;
-    }
-    if ((int)k2_smem > ctx->k2_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_K2, (int)k2_smem));
-        ctx->k2_smem_set = (int)k2_smem;
-    }
-    if ((int)k3_smem > ctx->k3_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(ring, FB_KERNEL_K3, (int)k3_smem));
-        ctx->k3_smem_set = (int)k3_smem;
-    }
-
-    cudaStream_t st = ctx->stream;
-    float ms_h2d = 0, ms_k[5] = {0, 0, 0, 0, 0};
-    uint64_t launches = 0, n_chunks = 0, fused_frames = 0;
-    uint32_t *h_fb_counts = (uint32_t *)((uint8_t *)ctx->pinned + 64); // per-chunk fallback counts
-    const uint64_t max_counts = (ctx->pinned_cap - 64) / 4;
-    FB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st)); // start of the call
-
-    for (uint64_t f0 = 0; f0 < total_frames; f0 += chunk_frames) {
-        const uint64_t nf = std::min(chunk_frames, total_frames - f0);
-        const uint64_t s0 = f0 * bs;
-        const uint64_t ns = std::min(A.n_samples - s0, nf * bs);
-        FbJob J = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, cb ? cb : 4, ns,
-                               (uint32_t)(A.first_frame + f0));
-        const uint32_t nvars = J.n_frames * (uint32_t)J.nvar;
-        uint32_t *d_fb = (uint32_t *)ctx->frame_bytes.p + f0;
-
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-        const uint8_t *d_pcm = nullptr;
-        if (A.pcm_host) {
-            const uint64_t off = s0 * (uint64_t)ctx->channels * (uint64_t)cb;
-            const uint64_t len = ns * (uint64_t)ctx->channels * (uint64_t)cb;
-            FB_CUDA(ctx, cudaMemcpyAsync(ctx->pcm.p, (const uint8_t *)A.pcm_host + off, len, cudaMemcpyHostToDevice, st));
-            d_pcm = (const uint8_t *)ctx->pcm.p;
-        } else if (A.pcm_dev) {
-            d_pcm = (const uint8_t *)A.pcm_dev + s0 * (uint64_t)ctx->channels * (uint64_t)cb;
-        } else {
-            FB_CUDA(ctx, cudaMemcpyAsync(ctx->pcm.p, A.planar_host,
-                                         (uint64_t)ctx->channels * (uint64_t)A.planar_stride * 4u,
-                                         cudaMemcpyHostToDevice, st));
-        }
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-        // K0
-        if (A.planar_host) {
-            fb_k0_ingest_planar<<<(unsigned)((J.tail_n + 255) / 256), 256, 0, st>>>(
-                J, (const int32_t *)ctx->pcm.p, A.planar_stride, (int32_t *)ctx->xv.p, d_err);
-        } else {
-            fb_k0_ingest<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)ctx->xv.p, d_err);
-        }
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-        // K1
-        fb_launch_k1(ring, J, (const int32_t *)ctx->xv.p, (const float *)ctx->win_full.p, d_win_tail,
-                     (FbAnalysis *)ctx->ana.p, A.analyze_only ? (fb200_variant_taps *)ctx->taps.p : nullptr, nvars, st);
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-        launches += 2;
-        if (A.analyze_only) {
-            FB_CUDA(ctx, cudaMemcpyAsync(A.taps + f0 * (uint64_t)nvar, ctx->taps.p,
-                                         (size_t)nvars * sizeof(fb200_variant_taps), cudaMemcpyDeviceToHost, st));
-            FB_CUDA(ctx, cudaStreamSynchronize(st));
-            continue;
-        }
-        fb200_frame_info *d_infos = A.infos ? (fb200_frame_info *)ctx->infos.p : nullptr;
-        if (fused) {
-            // KF: Rice search + frame assembly per frame; frames it cannot reproduce exactly go to the list
-            FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
-            fb_launch_kf(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p, (uint8_t *)ctx->slots.p, d_fb,
-                         d_infos, (uint32_t *)ctx->fb_list.p, d_fb_count, (const uint32_t *)ctx->ktab.p, KL, st);
-            FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-            fb_launch_k2(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
-                         (fb200_subframe_info *)ctx->choice.p, L, (const uint32_t *)ctx->fb_list.p, d_fb_count, 296,
-                         k2_smem, st);
-            fb_launch_k3(ring, J, (const int32_t *)ctx->xv.p, (const fb200_subframe_info *)ctx->choice.p,
-                         (uint8_t *)ctx->slots.p, d_fb, d_infos, (const uint32_t *)ctx->fb_list.p, d_fb_count, 148,
-                         k3_smem, st);
-            FB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
-            if (n_chunks < max_counts)
-                FB_CUDA(ctx, cudaMemcpyAsync(&h_fb_counts[n_chunks], d_fb_count, 4, cudaMemcpyDeviceToHost, st));
-            n_chunks++;
-            fused_frames += J.n_frames;
-            launches += 3;
-        } else {
-            fb_launch_k2(ring, J, (const int32_t *)ctx->xv.p, (const FbAnalysis *)ctx->ana.p,
-                         (fb200_subframe_info *)ctx->choice.p, L, nullptr, nullptr, nvars, k2_smem, st);
-            FB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-            fb_launch_k3(ring, J, (const int32_t *)ctx->xv.p, (const fb200_subframe_info *)ctx->choice.p,
-                         (uint8_t *)ctx->slots.p, d_fb, d_infos, nullptr, nullptr, J.n_frames, k3_smem, st);
-            FB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
-        }
-        // K4
-        fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)ctx->offsets.p, J.n_frames, d_total);
-        fb_k4_gather<<<J.n_frames, 256, 0, st>>>((const uint8_t *)ctx->slots.p, J.slot_bytes, d_fb,
-                                                 (const unsigned long long *)ctx->offsets.p, d_out,
-                                                 (unsigned long long)A.out_cap);
-        FB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
-        launches += fused ? 2 : 4;
-        FB_CUDA(ctx, cudaGetLastError());
-        if (A.infos) {
-            FB_CUDA(ctx, cudaMemcpyAsync(A.infos + f0, ctx->infos.p, (size_t)J.n_frames * sizeof(fb200_frame_info),
-                                         cudaMemcpyDeviceToHost, st));
-        }
-        // per-chunk timings need the events to have completed; chunks are serial on one stream
-        FB_CUDA(ctx, cudaEventSynchronize(ctx->ev[7]));
-        float t;
-        FB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); ms_h2d += t;
-        for (int k = 0; k < 5; k++) {
-            FB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev[2 + k], ctx->ev[3 + k]));
-            ms_k[k] += t;
-        }
-    }
-    if (A.analyze_only) return FB200_OK;
-
-    // results: error flag + total, sizes, bytes
-    FB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
-    FB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->scalars.p, 16, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint32_t err_flag = *(const uint32_t *)ctx->pinned;
-    const unsigned long long total = *(const unsigned long long *)((const uint8_t *)ctx->pinned + 8);
-    if (err_flag) {
-        ctx->last_error = "input sample out of the range of bits_per_sample";
-        return FB200_ERR_CONFIG; // VerifyError (src/source.rs:262-275)
-    }
-    if (A.out_len) *A.out_len = (size_t)total;
-    if (total > A.out_cap) {
-        ctx->last_error = "output capacity too small";
-        return FB200_ERR_CAPACITY;
-    }
-    if (A.frame_sizes)
-        FB_CUDA(ctx, cudaMemcpyAsync(A.frame_sizes, ctx->frame_bytes.p, total_frames * 4u, cudaMemcpyDeviceToHost, st));
-    if (A.out_host) FB_CUDA(ctx, cudaMemcpyAsync(A.out_host, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(ctx, cudaEventRecord(ctx->ev[9], st));
-    FB_CUDA(ctx, cudaStreamSynchronize(st));
-
-    float t_d2h = 0, t_total = 0;
-    FB_CUDA(ctx, cudaEventElapsedTime(&t_d2h, ctx->ev[8], ctx->ev[9]));
-    FB_CUDA(ctx, cudaEventElapsedTime(&t_total, ctx->ev[0], ctx->ev[9]));
-    ctx->timing.h2d_ms = ms_h2d;
-    ctx->timing.k_ingest_ms = ms_k[0];
-    ctx->timing.k_analyze_ms = ms_k[1];
-    ctx->timing.k_rice_ms = ms_k[2];
-    ctx->timing.k_pack_ms = ms_k[3];
-    ctx->timing.k_gather_ms = ms_k[4];
-    ctx->timing.kernels_ms = ms_k[0] + ms_k[1] + ms_k[2] + ms_k[3] + ms_k[4];
-    ctx->timing.d2h_ms = t_d2h;
-    ctx->timing.total_ms = t_total;
-    ctx->timing.launches = launches;
-    uint64_t fallback = 0;
-    for (uint64_t i = 0; i < n_chunks && i < max_counts; i++) fallback += h_fb_counts[i];
-    ctx->timing.fused_frames = fused_frames - fallback;
-    ctx->timing.fallback_frames = fallback;
-    ctx->timing.in_bytes = in_bytes_total;
-    ctx->timing.out_bytes = total;
-    return FB200_OK;
+    return fb_encode_serial(ctx, A, P);
 }
 
 } // namespace

@@ -1313,13 +1313,29 @@ FB_DEV void fb_k4_scan_body(const uint32_t *frame_bytes, unsigned long long *off
     FB_PHASE_END
 }
 
-// copies frame f from its slot to out + offsets[f]; `tid`/`T` index the bytes
+// copies frame f from its (16-byte aligned) slot to out + offsets[f]: bytes up to the first 4-byte aligned
+// destination address, then whole destination words assembled from two source words, then the tail bytes
 FB_DEV void fb_k4_gather_thread(const uint8_t *slots, uint32_t slot_bytes, const uint32_t *frame_bytes,
                                 const unsigned long long *offsets, uint8_t *out, unsigned long long out_cap,
                                 uint32_t f, int tid, int T) {
     const uint8_t *src = slots + (size_t)f * (size_t)slot_bytes;
-    unsigned long long o = offsets[f];
-    uint32_t len = frame_bytes[f];
+    const unsigned long long o = offsets[f];
+    const uint32_t len = frame_bytes[f];
     if (o + len > out_cap) return; // capacity error is reported by the host from offsets[n_frames]
-    for (uint32_t i = (uint32_t)tid; i < len; i += (uint32_t)T) out[o + i] = src[i];
+    uint8_t *dst = out + o;
+    uint32_t head = (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u);
+    if (head > len) head = len;
+    const uint32_t nw = (len - head) >> 2;
+    if ((uint32_t)tid < head) dst[tid] = src[tid];
+    const uint32_t *srcw = (const uint32_t *)src;
+    uint32_t *dstw = (uint32_t *)(dst + head);
+    const uint32_t sh = (head & 3u) * 8u;
+    for (uint32_t k = (uint32_t)tid; k < nw; k += (uint32_t)T) {
+        const uint32_t wi = (head >> 2) + k;
+        uint32_t v = srcw[wi];
+        if (sh) v = (v >> sh) | (srcw[wi + 1] << (32u - sh)); // wi + 1 still holds frame bytes when sh != 0
+        dstw[k] = v;
+    }
+    const uint32_t done = head + 4u * nw;
+    if ((uint32_t)tid < len - done) dst[done + (uint32_t)tid] = src[done + (uint32_t)tid];
 }

@@ -196,6 +196,42 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
         assert (t.fused_frames, t.fallback_frames) == (0, 0)  # BitCount selection: generic kernels only
 
 
+def test_pipelined_host_path_matches_oracle(monkeypatch):
+    """Host batches longer than 1.5 chunks go through the H2D / kernels / D2H pipeline (three rotating buffer
+    sets, two compute streams).  With 5-frame chunks a 38-frame batch exercises set reuse several times."""
+    monkeypatch.setenv("FB200_CHUNK_FRAMES", "5")
+    vcfg = Encoder().into_verified()
+    n = 4096 * 37 + 1000
+    x = sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=9)
+    ref, ref_sizes = O.encode_frames(O.default_config(), x, 2, 16, 44100, 4096, first_frame_number=7)
+    with Context(vcfg, 2, 16, 44100, 4096) as ctx:
+        for _ in range(2):  # second call reuses the sets
+            got, sizes, infos = ctx.encode_interleaved(pack_pcm(x, 2), 2, n, 7, want_infos=True)
+            assert list(sizes) == list(ref_sizes)
+            assert got.tobytes() == ref
+            assert [infos[i].frame_number for i in range(38)] == list(range(7, 45))
+            assert [infos[i].frame_bytes for i in range(38)] == list(ref_sizes)
+            t = ctx.timing()
+            assert t.fused_frames == 38 and t.launches == 8 * 7
+        # an out-of-range sample in a late chunk is still a VerifyError
+        bad = x.copy()
+        bad[4096 * 30 + 5, 1] = 40000
+        with pytest.raises(VerifyError):
+            ctx.encode_interleaved(pack_pcm(bad, 4), 4, n)
+        # and the context stays usable afterwards
+        got, sizes, _ = ctx.encode_interleaved(pack_pcm(x, 2), 2, n, 7)
+        assert got.tobytes() == ref
+        # capacity error
+        small = np.empty(len(ref) - 10, np.uint8)
+        nf, olen = C.c_size_t(0), C.c_size_t(0)
+        buf = pack_pcm(x, 2)
+        rc = _ffi.lib().fb200_encode_interleaved(ctx._h, buf.ctypes.data, 2, n, 7, small.ctypes.data, len(small), None,
+                                                  None, C.byref(nf), C.byref(olen))
+        assert rc == _ffi.ERR_CAPACITY
+    out, nf = O.decode_frames(ref, 2, 16)
+    assert nf == 38 and np.array_equal(out, x)
+
+
 def test_fused_geometry_odd_block_sizes():
     rng = np.random.default_rng(11)
     for n in (64, 66, 127, 128, 341 * 8, 3136, 98 * 32, 5000, 4100, 8192, 9216, 12345, 16383):
