@@ -21,15 +21,30 @@
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fb_k0_ingest(FbJob J, const uint8_t *pcm, int32_t *xv, uint32_t *err_flag) {
-    uint64_t s = (uint64_t)blockIdx.x * 256u + threadIdx.x;
-    if (s < J.n_samples) fb_k0_sample(J, pcm, xv, err_flag, s);
+__global__ void __launch_bounds__(256) fb_k0_ingest(FbJob J, const uint8_t *pcm, int32_t *xt, uint32_t *err_flag,
+                                                    uint64_t n_items) {
+    const uint64_t idx = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (idx >= n_items) return;
+    uint32_t f;
+    int t4;
+    fb_k0_item(idx, J.stride / 4, &f, &t4);
+    if (f < J.n_frames && t4 < J.stride / 4) fb_k0_quad(J, pcm, xt, err_flag, f, t4);
 }
 
-__global__ void __launch_bounds__(256) fb_k0_ingest_planar(FbJob J, const int32_t *src, int src_stride, int32_t *xv,
+__global__ void __launch_bounds__(256) fb_k0_ingest_planar(FbJob J, const int32_t *src, int src_stride, int32_t *xt,
                                                            uint32_t *err_flag) {
-    int t = (int)(blockIdx.x * 256u + threadIdx.x);
-    if (t < J.tail_n) fb_k0_planar_sample(J, src, src_stride, xv, err_flag, t);
+    const int t4 = (int)(blockIdx.x * 256u + threadIdx.x);
+    if (t4 < J.stride / 4) fb_k0_planar_quad(J, src, src_stride, xt, err_flag, t4);
+}
+
+// K0b: plain rows by variant for the frames the generic kernels run on (list == nullptr: every frame, one CTA each)
+__global__ void __launch_bounds__(256) fb_k0b_expand(FbJob J, const int32_t *xc, int32_t *xv4, const uint32_t *list,
+                                                     const uint32_t *count) {
+    const uint32_t total = list ? *count : J.n_frames;
+    for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
+        const uint32_t f = list ? list[i] : i;
+        for (int t4 = (int)threadIdx.x; t4 < J.stride / 4; t4 += 256) fb_k0b_expand4(J, xc, xv4, f, t4);
+    }
 }
 
 // offsets[i] = *total + exclusive prefix; *total advances by the chunk's bytes (single CTA)
@@ -60,7 +75,7 @@ struct DevBuf {
 
 // Device buffers, events and pinned staging of one chunk in flight.  Set 0 also serves the serial path.
 struct ChunkSet {
-    DevBuf pcm, xv, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars;
+    DevBuf pcm, xv, xv4, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars;
     // events: 0 H2D start, 1 H2D end, 2 ingest end, 3 analyze end, 4 rice/fused end, 5 pack/fallback end,
     //         6 gather end (= chunk done), 7 D2H start, 8 D2H end, 9 H2D end on the copy stream (pipelined path)
     cudaEvent_t ev[10];
@@ -205,7 +220,7 @@ void fb200_destroy(fb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (ChunkSet &S : ctx->sets) {
-        DevBuf *bufs[] = {&S.pcm, &S.xv, &S.ana, &S.taps, &S.choice, &S.slots, &S.frame_bytes, &S.offsets, &S.out,
+        DevBuf *bufs[] = {&S.pcm, &S.xv, &S.xv4, &S.ana, &S.taps, &S.choice, &S.slots, &S.frame_bytes, &S.offsets, &S.out,
                           &S.infos, &S.fb_list, &S.scalars};
         for (DevBuf *b : bufs)
             if (b->p) cudaFree(b->p);
@@ -350,7 +365,8 @@ int fb_reserve_set(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet 
     if ((rc = fb_reserve(ctx, S.scalars, 64))) return rc;
     if ((rc = fb_reserve(ctx, S.frame_bytes, sizes_frames * 4u))) return rc;
     if ((rc = fb_reserve(ctx, S.offsets, (frames + 1) * 8u))) return rc;
-    if ((rc = fb_reserve(ctx, S.xv, (frames * (uint64_t)P.nvar * P.stride + 64) * 4u))) return rc;
+    if ((rc = fb_reserve(ctx, S.xv, (fb_xt_words((int)P.stride, frames * (uint64_t)ctx->channels) + 64) * 4u))) return rc;
+    if (!A.analyze_only && (rc = fb_reserve(ctx, S.xv4, (frames * (uint64_t)P.nvar * P.stride + 64) * 4u))) return rc;
     if ((rc = fb_reserve(ctx, S.ana, frames * (uint64_t)P.nvar * sizeof(FbAnalysis)))) return rc;
     if (in_bytes && (rc = fb_reserve(ctx, S.pcm, in_bytes + 16))) return rc;
     if (A.analyze_only) {
@@ -379,10 +395,12 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     uint32_t *d_fb_count = (uint32_t *)((uint8_t *)S.scalars.p + 16);
     FB_CUDA(ctx, cudaEventRecord(S.ev[1], st));
     if (A.planar_host) {
-        fb_k0_ingest_planar<<<(unsigned)((J.tail_n + 255) / 256), 256, 0, st>>>(J, (const int32_t *)S.pcm.p, A.planar_stride,
-                                                                               (int32_t *)S.xv.p, d_err);
+        fb_k0_ingest_planar<<<(unsigned)((J.stride / 4 + 255) / 256), 256, 0, st>>>(J, (const int32_t *)S.pcm.p,
+                                                                                   A.planar_stride, (int32_t *)S.xv.p, d_err);
     } else {
-        fb_k0_ingest<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv.p, d_err);
+        // items: ceil(frames / 16) frame groups x ceil(quads / 2) quad pairs x 32 lanes
+        const uint64_t n_items = (uint64_t)((J.n_frames + 15u) / 16u) * (uint64_t)((J.stride / 4 + 1) / 2) * 32u;
+        fb_k0_ingest<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv.p, d_err, n_items);
     }
     FB_CUDA(ctx, cudaEventRecord(S.ev[2], st));
     fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
@@ -391,27 +409,32 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     acc.launches += 2;
     if (A.analyze_only) return FB200_OK;
     fb200_frame_info *d_infos = A.infos ? (fb200_frame_info *)S.infos.p : nullptr;
+    // plain rows by variant for the generic kernels (K0b)
+    const int32_t *xg = (const int32_t *)S.xv4.p;
     if (P.fused) {
         // KF: Rice search + frame assembly per frame; frames it cannot reproduce exactly go to the list
         FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
         fb_launch_kf(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (uint8_t *)S.slots.p, d_fb, d_infos,
                      (uint32_t *)S.fb_list.p, d_fb_count, (const uint32_t *)ctx->ktab.p, P.KL, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
-        fb_launch_k2(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
+        fb_k0b_expand<<<148, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, (const uint32_t *)S.fb_list.p,
+                                           d_fb_count);
+        fb_launch_k2(P.ring, J, xg, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
                      P.L, (const uint32_t *)S.fb_list.p, d_fb_count, 296, P.k2_smem, st);
-        fb_launch_k3(P.ring, J, (const int32_t *)S.xv.p, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
+        fb_launch_k3(P.ring, J, xg, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
                      d_fb, d_infos, (const uint32_t *)S.fb_list.p, d_fb_count, 148, P.k3_smem, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
         acc.fused_frames += J.n_frames;
-        acc.launches += 3;
+        acc.launches += 4;
     } else {
-        fb_launch_k2(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
+        fb_k0b_expand<<<J.n_frames, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, nullptr, nullptr);
+        fb_launch_k2(P.ring, J, xg, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
                      P.L, nullptr, nullptr, nvars, P.k2_smem, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
-        fb_launch_k3(P.ring, J, (const int32_t *)S.xv.p, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
+        fb_launch_k3(P.ring, J, xg, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
                      d_fb, d_infos, nullptr, nullptr, J.n_frames, P.k3_smem, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
-        acc.launches += 2;
+        acc.launches += 3;
     }
     fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
     fb_k4_gather<<<J.n_frames, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,

@@ -25,6 +25,8 @@
 #define FB_DEV inline
 #include <math.h>
 struct int4 { int32_t x, y, z, w; };
+static inline int32_t min(int32_t a, int32_t b) { return a < b ? a : b; }
+static inline int32_t max(int32_t a, int32_t b) { return a > b ? a : b; }
 struct float4 { float x, y, z, w; };
 #endif
 
@@ -43,16 +45,19 @@ struct float4 { float x, y, z, w; };
 #define FB_SYNC() ((void)0)
 #endif
 
-// Warp-0 regions: a stretch of work done by the first warp only, split into warp-synchronous
-// sub-phases (FB_WPHASE ... FB_WPHASE_END, lanes 0..31).  The other warps wait at FB_WARP0_END.
+// ---- warp-scope phase macros ---------------------------------------------------------------------
+// FB_WARPS_BEGIN(w, NW) ... FB_WARPS_END : every warp of the CTA runs the enclosed code independently
+// (the emulation runs the warps one after the other); inside, FB_WPHASE(lane) ... FB_WPHASE_END is a
+// region between two warp barriers.  Values that steer warp-uniform control flow are read from shared
+// memory between phases, under the same rule as the CTA-scope macros.
 #if FB_GPU
-#define FB_WARP0_BEGIN if (threadIdx.x < 32) {
-#define FB_WARP0_END } __syncthreads();
+#define FB_WARPS_BEGIN(w, NW) { const int w = (int)(threadIdx.x >> 5); (void)w;
+#define FB_WARPS_END } __syncthreads();
 #define FB_WPHASE(lane) { const int lane = (int)(threadIdx.x & 31u); (void)lane;
 #define FB_WPHASE_END } __syncwarp();
 #else
-#define FB_WARP0_BEGIN {
-#define FB_WARP0_END }
+#define FB_WARPS_BEGIN(w, NW) for (int w = 0; w < (NW); ++w) {
+#define FB_WARPS_END }
 #define FB_WPHASE(lane) for (int lane = 0; lane < 32; ++lane) {
 #define FB_WPHASE_END }
 #endif
@@ -121,6 +126,11 @@ FB_DEV int64_t fb_mad_wide(int32_t a, int32_t b, int64_t c) {
     return c + (int64_t)a * (int64_t)b;
 #endif
 }
+
+// M = (L + R) >> 1 (arithmetic), S = L - R (src/coding.rs:476-484); unsigned adds so that stale padding
+// words (whose results are masked) cannot overflow a signed int
+FB_HD int32_t fb_mid(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b) >> 1; }
+FB_HD int32_t fb_side(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
 // src/rice.rs:169-171 encode_signbit: (|v| << 1) - (v < 0)
 FB_HD uint32_t fb_zigzag(int32_t v) { return ((uint32_t)v << 1) ^ (uint32_t)(v >> 31); }

@@ -37,19 +37,17 @@
 #define FB_KF_NWORDS 7     // bit-sliced counter words per unit (counts <= 127)
 #define FB_KF_UNIT_MAX 112 // samples per unit (7 runs of 16)
 
-// ---- warp-scope phase macros (see fb_common.h for the CTA-scope ones) --------------------------
-// FB_WARPS_BEGIN(w, NW) ... FB_WARPS_END : every warp of the CTA runs the enclosed code independently
-// (the emulation runs the warps one after the other); inside, FB_WPHASE(lane) ... FB_WPHASE_END is a
-// region between two warp barriers.  Values that steer warp-uniform control flow are read from shared
-// memory between phases, under the same rule as the CTA-scope macros.
+// 16-byte global -> shared copy that does not pass through registers (LDGSTS), so a thread keeps all the copies of
+// its staging loop in flight at once
 #if FB_GPU
-#define FB_WARPS_BEGIN(w, NW) { const int w = (int)(threadIdx.x >> 5); (void)w;
-#define FB_WARPS_END } __syncthreads();
-#define FB_WSYNC() __syncwarp()
+FB_DEV void fb_copy16_async(int32_t *dst_smem, const int32_t *src_global) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_global) : "memory");
+}
+FB_DEV void fb_copy_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 #else
-#define FB_WARPS_BEGIN(w, NW) for (int w = 0; w < (NW); ++w) {
-#define FB_WARPS_END }
-#define FB_WSYNC() ((void)0)
+FB_DEV void fb_copy16_async(int32_t *dst, const int32_t *src) { memcpy(dst, src, 16); }
+FB_DEV void fb_copy_async_wait() {}
 #endif
 
 #if FB_GPU
@@ -308,11 +306,6 @@ FB_DEV int fb_kf_pstart(unsigned long long s0, int cnt, int max_p) {
     if (p < 0) p = 0;
     return p > max_p ? max_p : p;
 }
-
-// M = (L + R) >> 1 (arithmetic), S = L - R (src/coding.rs:476-484); unsigned adds so that stale padding
-// words (whose results are masked) cannot overflow a signed int
-FB_HD int32_t fb_mid(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b) >> 1; }
-FB_HD int32_t fb_side(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
 // ---- residual runs out of the staged planes ------------------------------------------------------
 // vm: 0 = plane xa as is, 2 = mid, 3 = side.  A run's window is win[i] = x[t0 - G + i], i < G + FB_RUN:
@@ -828,19 +821,19 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     uint32_t *words = (uint32_t *)(smem + L.off_scratch);
     uint8_t *slot = slots + (size_t)f * (size_t)J.slot_bytes;
 
-    // ---- stage the independent channels (coalesced 16-byte loads; rows are padded to a multiple of 32)
+    // ---- stage the independent channels from the row-interleaved store xt (16-byte loads)
     FB_PHASE(tid, T)
         const int n4 = (n + 3) >> 2;
-        for (int c = 0; c < J.channels; c++) {
-            const int32_t *src = xv + ((size_t)f * (size_t)J.nvar + (size_t)c) * (size_t)J.stride;
-            int32_t *dst = xs + (size_t)c * L.x_stride;
-            for (int i = tid; i < n4; i += T) {
-                const int4 v = *reinterpret_cast<const int4 *>(src + 4 * i);
-                *reinterpret_cast<int4 *>(dst + fb_xidx(4 * i)) = v;
+        // quad i of every channel together: the rows of one frame are adjacent in xt (one 32-byte sector for stereo)
+        for (int i = tid; i < n4; i += T) {
+            for (int c = 0; c < J.channels; c++) {
+                const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
+                fb_copy16_async(xs + (size_t)c * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
             }
         }
         for (int i = tid; i < 1024; i += T) S->crc_tab[i] = ktab[i];
         if (tid == 0) { S->frame_fail = 0; S->crc_acc = 0; S->crc_last = 0; }
+        fb_copy_async_wait();
     FB_PHASE_END
 
     // ---- analysis: one warp per variant

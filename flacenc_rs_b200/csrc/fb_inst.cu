@@ -9,12 +9,13 @@
 #define FB_CAT(a, b) FB_CAT2(a, b)
 #define FB_NAME(base) FB_CAT(base, FB_INST_G)
 
+// analysis: one thread per channel variant (fb_kernels.cuh)
 #define FB_K1_THREADS 128
-__global__ void __launch_bounds__(FB_K1_THREADS) FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xv, const float *win_full,
+__global__ void __launch_bounds__(FB_K1_THREADS) FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt, const float *win_full,
                                                                           const float *win_tail, FbAnalysis *ana,
                                                                           fb200_variant_taps *taps, uint32_t n_variants) {
-    uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
-    if (gv < n_variants) fb_k1_thread<FB_INST_G>(J, xv, win_full, win_tail, ana, taps, gv);
+    const uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
+    if (gv < n_variants) fb_k1_thread<FB_INST_G>(J, xt, win_full, win_tail, ana, taps, gv);
 }
 
 // generic Rice search: one CTA per channel variant.  list == nullptr: variant blockIdx.x; else the variants of the

@@ -30,7 +30,7 @@ static unsigned long long fb_emu_mode_count[4] = {0, 0, 0, 0};
 // K0: ingest.  Mirrors Fill::fill_le_bytes / fill_interleaved + deinterleave
 // (src/source.rs:278-299, src/arrayutils.rs:248-264,345-364), FrameBuf::verify_samples
 // (src/source.rs:262-275) and the M/S synthesis of try_stereo_coding (src/coding.rs:476-484).
-// xv layout: [frame][variant][stride] int32.
+// Output: the row-interleaved planar store xt (below); M and S are formed on the fly by the consumers.
 // =================================================================================================
 FB_DEV int32_t fb_load_sample(const uint8_t *pcm, uint64_t idx, int container_bytes) {
     if (container_bytes == 1) {
@@ -48,55 +48,147 @@ FB_DEV int32_t fb_load_sample(const uint8_t *pcm, uint64_t idx, int container_by
     }
 }
 
-// one inter-channel sample `s` (global index within the batch)
-FB_DEV void fb_k0_sample(const FbJob &J, const uint8_t *pcm, int32_t *xv, uint32_t *err_flag, uint64_t s) {
-    uint32_t f = (uint32_t)(s / (uint64_t)J.block_size);
-    int t = (int)(s - (uint64_t)f * (uint64_t)J.block_size);
-    int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
-    int32_t *dst = xv + (size_t)f * (size_t)J.nvar * (size_t)J.stride + t;
+// ---- planar sample store "xt" ------------------------------------------------------------------------
+// Rows are numbered row = frame * channels + channel and stored interleaved in units of 32 rows at a granularity
+// of FB_XT_CH samples:  word offset of sample t of row r =
+//     (((r / 32) * (stride / CH) + t / CH) * 32 + r % 32) * CH + t % CH.
+// The analysis kernel walks 32 rows in lockstep (lane = variant): its warp-wide 16-byte loads of "the next four
+// samples of my row" fall into one 32 * CH * 4-byte block that the following CH / 4 - 1 loads reuse, while a frame's
+// own samples still come in runs of CH * 4 bytes per row (adjacent rows = the channels of the frame) for the
+// per-frame kernel.
+#define FB_XT_CH 4
+FB_HD size_t fb_xt_off(int stride, uint32_t row, int t) {
+    return ((((size_t)(row >> 5) * (size_t)(stride / FB_XT_CH) + (size_t)(t / FB_XT_CH)) << 5) + (size_t)(row & 31u)) * FB_XT_CH +
+           (size_t)(t % FB_XT_CH);
+}
+// offset of the quad at t (multiple of 4) relative to the row base fb_xt_off(stride, row, 0)
+FB_HD size_t fb_xt_quad(int t) { return (size_t)(t / FB_XT_CH) * (32u * FB_XT_CH) + (size_t)(t % FB_XT_CH); }
+FB_HD size_t fb_xt_words(int stride, uint64_t rows) { return (size_t)((rows + 31u) >> 5) * 32u * (size_t)stride; }
+
+// K0 work item: four consecutive samples (t = 4*t4 ..) of every channel of frame f.  Samples at or beyond the
+// frame's length are stored as zeros.  src/source.rs:262-275 range check -> err_flag.
+FB_DEV void fb_k0_quad(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t *err_flag, uint32_t f, int t4) {
+    const int n = fb_frame_len(J, f);
+    const int t = 4 * t4;
+    const int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
+    const uint64_t s = (uint64_t)f * (uint64_t)J.block_size + (uint64_t)t; // inter-channel sample index in the batch
     bool bad = false;
-    if (J.channels == 2) {
-        int32_t l, r;
-        if (J.container_bytes == 2) {
-            // one aligned 32-bit load per stereo sample
-            uint32_t w = ((const uint32_t *)pcm)[s];
-            l = (int32_t)(int16_t)(w & 0xFFFFu);
-            r = (int32_t)(int16_t)(w >> 16);
-        } else {
-            l = fb_load_sample(pcm, s * 2, J.container_bytes);
-            r = fb_load_sample(pcm, s * 2 + 1, J.container_bytes);
-        }
-        bad = (l < lo) | (l > hi) | (r < lo) | (r > hi);
-        dst[0] = l;
-        dst[(size_t)J.stride] = r;
-        dst[2 * (size_t)J.stride] = (l + r) >> 1; // M
-        dst[3 * (size_t)J.stride] = l - r;        // S
+    if (J.channels == 2 && J.container_bytes == 2 && t + 4 <= n && (((uintptr_t)pcm + s * 4u) & 15u) == 0) {
+        // 16-bit stereo: four (L, R) pairs in one 16-byte load
+        const int4 w = *reinterpret_cast<const int4 *>(pcm + s * 4u);
+        int4 l, r;
+        l.x = (int32_t)(int16_t)((uint32_t)w.x & 0xFFFFu); r.x = w.x >> 16;
+        l.y = (int32_t)(int16_t)((uint32_t)w.y & 0xFFFFu); r.y = w.y >> 16;
+        l.z = (int32_t)(int16_t)((uint32_t)w.z & 0xFFFFu); r.z = w.z >> 16;
+        l.w = (int32_t)(int16_t)((uint32_t)w.w & 0xFFFFu); r.w = w.w >> 16;
+        const int32_t mn = min(min(min(l.x, l.y), min(l.z, l.w)), min(min(r.x, r.y), min(r.z, r.w)));
+        const int32_t mx = max(max(max(l.x, l.y), max(l.z, l.w)), max(max(r.x, r.y), max(r.z, r.w)));
+        bad = (mn < lo) | (mx > hi);
+        *reinterpret_cast<int4 *>(xt + fb_xt_off(J.stride, f * 2u, t)) = l;
+        *reinterpret_cast<int4 *>(xt + fb_xt_off(J.stride, f * 2u + 1u, t)) = r;
     } else {
         for (int c = 0; c < J.channels; c++) {
-            int32_t v = fb_load_sample(pcm, s * (uint64_t)J.channels + (uint64_t)c, J.container_bytes);
-            bad |= (v < lo) | (v > hi);
-            dst[(size_t)c * (size_t)J.stride] = v;
+            int32_t q[4];
+            for (int i = 0; i < 4; i++) {
+                int32_t v = 0;
+                if (t + i < n) {
+                    v = fb_load_sample(pcm, (s + (uint64_t)i) * (uint64_t)J.channels + (uint64_t)c, J.container_bytes);
+                    bad |= (v < lo) | (v > hi);
+                }
+                q[i] = v;
+            }
+            int4 o;
+            o.x = q[0]; o.y = q[1]; o.z = q[2]; o.w = q[3];
+            *reinterpret_cast<int4 *>(xt + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, t)) = o;
         }
     }
     if (bad) fb_atomic_or(err_flag, 1u);
 }
 
-// same for a planar FrameBuf input (fb200_encode_planar_frame): src[ch * src_stride + t]
-FB_DEV void fb_k0_planar_sample(const FbJob &J, const int32_t *src, int src_stride, int32_t *xv,
-                                uint32_t *err_flag, int t) {
-    int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
+// same for a planar FrameBuf input (fb200_encode_planar_frame): src[ch * src_stride + t], one frame (f = 0)
+FB_DEV void fb_k0_planar_quad(const FbJob &J, const int32_t *src, int src_stride, int32_t *xt, uint32_t *err_flag, int t4) {
+    const int n = J.tail_n, t = 4 * t4;
+    const int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
     bool bad = false;
     for (int c = 0; c < J.channels; c++) {
-        int32_t v = src[(size_t)c * (size_t)src_stride + t];
-        bad |= (v < lo) | (v > hi);
-        xv[(size_t)c * (size_t)J.stride + t] = v;
-    }
-    if (J.channels == 2) {
-        int32_t l = src[t], r = src[(size_t)src_stride + t];
-        xv[2 * (size_t)J.stride + t] = (l + r) >> 1;
-        xv[3 * (size_t)J.stride + t] = l - r;
+        int32_t q[4];
+        for (int i = 0; i < 4; i++) {
+            int32_t v = 0;
+            if (t + i < n) {
+                v = src[(size_t)c * (size_t)src_stride + (size_t)(t + i)];
+                bad |= (v < lo) | (v > hi);
+            }
+            q[i] = v;
+        }
+        int4 o;
+        o.x = q[0]; o.y = q[1]; o.z = q[2]; o.w = q[3];
+        *reinterpret_cast<int4 *>(xt + fb_xt_off(J.stride, (uint32_t)c, t)) = o;
     }
     if (bad) fb_atomic_or(err_flag, 1u);
+}
+
+// mapping of a K0 thread to its work item: 16 consecutive frames x 2 quads per warp, so both the PCM reads
+// (2 adjacent quads = full 32-byte sectors per frame) and the xt writes (16 frames = adjacent rows) use whole sectors
+FB_HD void fb_k0_item(uint64_t idx, int quads_per_frame, uint32_t *f, int *t4) {
+    const uint64_t warp = idx >> 5;
+    const uint32_t lane = (uint32_t)(idx & 31u);
+    const uint64_t pairs = (uint64_t)((quads_per_frame + 1) >> 1);
+    const uint64_t fg = warp / pairs, tp = warp - fg * pairs;
+    *f = (uint32_t)(fg * 16u + (lane & 15u));
+    *t4 = (int)(tp * 2u + (lane >> 4));
+}
+
+// The planar samples of a variant: rows of xt.  The stereo variants M and S are not stored; every consumer
+// forms sample = (a + m * b) >> sh from the two channel rows with (m, sh) = (0, 0) for a plain channel (pb == pa),
+// (1, 1) for M = (L + R) >> 1 and (-1, 0) for S = L - R (src/coding.rs:476-484) -- one code path for all lanes.
+struct FbVarRows {
+    const int32_t *pa, *pb; // row bases (sample 0); four samples at t (multiple of 4) are at p + fb_xt_quad(t)
+    int32_t m, sh;
+};
+
+FB_HD FbVarRows fb_variant_rows(const FbJob &J, const int32_t *xt, uint32_t f, int v) {
+    FbVarRows r;
+    if (J.channels == 2 && v >= 2) {
+        r.pa = xt + fb_xt_off(J.stride, f * 2u, 0);
+        r.pb = xt + fb_xt_off(J.stride, f * 2u + 1u, 0);
+        r.m = v == 2 ? 1 : -1;
+        r.sh = v == 2 ? 1 : 0;
+    } else {
+        r.pa = xt + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)v, 0);
+        r.pb = r.pa;
+        r.m = 0;
+        r.sh = 0;
+    }
+    return r;
+}
+
+FB_HD int32_t fb_mix(int32_t a, int32_t b, int32_t m, int32_t sh) {
+    return (int32_t)((uint32_t)a + (uint32_t)m * (uint32_t)b) >> sh;
+}
+
+// four samples t..t+3 of a variant (t a multiple of 4)
+FB_DEV void fb_rows_load4(const FbVarRows &r, int t, int32_t *dst) {
+    const size_t o = fb_xt_quad(t);
+    const int4 a = *reinterpret_cast<const int4 *>(r.pa + o);
+    const int4 b = *reinterpret_cast<const int4 *>(r.pb + o);
+    dst[0] = fb_mix(a.x, b.x, r.m, r.sh);
+    dst[1] = fb_mix(a.y, b.y, r.m, r.sh);
+    dst[2] = fb_mix(a.z, b.z, r.m, r.sh);
+    dst[3] = fb_mix(a.w, b.w, r.m, r.sh);
+}
+
+// K0b: the generic kernels K2/K3 index plain rows by variant, xv4[(frame * nvar + v) * stride + t] (for stereo
+// with the M and S rows, src/coding.rs:476-484).  That copy is produced from xt only for the frames those kernels
+// run on.
+FB_DEV void fb_k0b_expand4(const FbJob &J, const int32_t *xt, int32_t *xv4, uint32_t f, int t4) {
+    for (int v = 0; v < J.nvar; v++) {
+        const FbVarRows rows = fb_variant_rows(J, xt, f, v);
+        int32_t q[4];
+        fb_rows_load4(rows, 4 * t4, q);
+        int4 o;
+        o.x = q[0]; o.y = q[1]; o.z = q[2]; o.w = q[3];
+        *reinterpret_cast<int4 *>(xv4 + ((size_t)f * (size_t)J.nvar + (size_t)v) * (size_t)J.stride + 4 * (size_t)t4) = o;
+    }
 }
 
 // =================================================================================================
@@ -110,8 +202,9 @@ FB_DEV void fb_k0_planar_sample(const FbJob &J, const int32_t *src, int src_stri
 //     FMAs starting at t = lpc_order for every lag (src/lpc.rs:533-548)
 //   * symmetric_levinson_recursion::<f64> (src/lpc.rs:633-705), quantize_parameters (:234-302)
 // R = ring size = lpc_order rounded up to a multiple of 4; lags 0..R are accumulated, lags above
-// lpc_order are ignored.  Independent variants give the parallelism (32 per warp), the R+1
-// independent FMA chains per thread give the ILP.
+// lpc_order are ignored.  Independent variants give the parallelism (32 per warp, and a warp's 16-byte
+// loads of "the next four samples of my row" fall in one 512-byte block of the row-interleaved store),
+// the R+1 independent FMA chains per thread give the ILP.
 // =================================================================================================
 
 // src/lpc.rs:633-705
@@ -186,9 +279,89 @@ FB_DEV int fb_quantize(const double *coefs, int n, int precision, int16_t *q, in
     return order;
 }
 
+// Sequential state of one variant's pass (registers of one thread).
 template <int R>
-FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, const float *win,
-                          FbAnalysis *out, fb200_variant_taps *taps) {
+struct FbK1State {
+    float s0, s1, s2, s3, s4;       // running f32 sums of |e_k| of the current estimate partition
+    int32_t pe0, pe1, pe2, pe3;     // previous e_0..e_3 (zero history)
+    int32_t xmin, xmax;
+    int part, pend, psize, n, P;
+    double acc[R + 1];              // autocorrelation lags 0..R
+    double ring[R];                 // y[t-1] .. y[t-R]
+};
+
+// R samples starting at t0 (a multiple of R).  GUARDED: samples may lie beyond n, t may be below P, an estimate
+// partition may end at any sample.  Otherwise all R samples are valid, t0 >= P and partitions end on multiples of 4.
+template <int R, bool GUARDED>
+FB_DEV void fb_k1_group(FbK1State<R> &S, const FbVarRows &rows, const float *win, int t0, bool do_ent, bool do_lpc,
+                        float (*psum)[5]) {
+    int32_t xs[R];
+    float ws[R];
+#pragma unroll
+    for (int i = 0; i < R; i += 4) {
+        fb_rows_load4(rows, t0 + i, xs + i);
+        const float4 v = *reinterpret_cast<const float4 *>(win + t0 + i);
+        ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
+    }
+#pragma unroll
+    for (int s = 0; s < R; s++) {
+        const int t = t0 + s;
+        if (GUARDED && t >= S.n) break;
+        const int32_t xt = xs[s];
+        S.xmin = xt < S.xmin ? xt : S.xmin;
+        S.xmax = xt > S.xmax ? xt : S.xmax;
+        if (do_ent) {
+            // zero-history differences, wrapping i32 (src/coding.rs:188-195)
+            const int32_t e0 = xt;
+            const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)S.pe0);
+            const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)S.pe1);
+            const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)S.pe2);
+            const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)S.pe3);
+            S.pe0 = e0; S.pe1 = e1; S.pe2 = e2; S.pe3 = e3;
+            S.s0 = FB_FADD((float)(e0 < 0 ? -e0 : e0), S.s0);
+            S.s1 = FB_FADD((float)(e1 < 0 ? -e1 : e1), S.s1);
+            S.s2 = FB_FADD((float)(e2 < 0 ? -e2 : e2), S.s2);
+            S.s3 = FB_FADD((float)(e3 < 0 ? -e3 : e3), S.s3);
+            S.s4 = FB_FADD((float)(e4 < 0 ? -e4 : e4), S.s4);
+            if ((GUARDED || (s & 3) == 3) && t + 1 == S.pend) {
+                psum[S.part][0] = S.s0; psum[S.part][1] = S.s1; psum[S.part][2] = S.s2;
+                psum[S.part][3] = S.s3; psum[S.part][4] = S.s4;
+                S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
+                S.part++;
+                S.pend = (S.pend + S.psize < S.n) ? S.pend + S.psize : S.n;
+            }
+        }
+        if (do_lpc) {
+            const double y = (double)FB_FMUL((float)xt, ws[s]);
+            if (!GUARDED || t >= S.P) {
+                S.acc[0] = FB_FMA(y, y, S.acc[0]);
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    // logical y[t-1-j] lives in ring[(s-1-j) mod R]; static after unrolling
+                    S.acc[j + 1] = FB_FMA(S.ring[(s - 1 - j + 2 * R) % R], y, S.acc[j + 1]);
+                }
+            }
+            S.ring[s] = y; // overwrites y[t-R]
+        }
+    }
+}
+
+// R must equal fb_k1_ring(J.cfg.lpc_order); one kernel instantiation per R keeps the register
+// allocation of the common small orders independent of the order-24 case.
+FB_HD int fb_k1_ring(int lpc_order) { return (lpc_order + 3) & ~3; }
+
+template <int R>
+FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail,
+                         FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t gv) {
+    const uint32_t f = gv / (uint32_t)J.nvar;
+    const int v = (int)(gv - f * (uint32_t)J.nvar);
+    const int n = fb_frame_len(J, f);
+    const int bps_v = fb_variant_bps(J, v);
+    const FbVarRows rows = fb_variant_rows(J, xt, f, v);
+    const float *win = (n == J.block_size) ? win_full : win_tail;
+    FbAnalysis *out = ana + gv;
+    fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
+
     const int P = J.cfg.lpc_order;
     const bool too_short = n < FB_MIN_PRED_BLOCK;
     const bool do_ent = !too_short && J.cfg.use_fixed && J.cfg.fixed_order_sel == 1;
@@ -198,85 +371,38 @@ FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, co
     const int psize = (n + parts - 1) / parts;
 
     float psum[FB_MAX_ENT_PARTS][5]; // per-partition sequential f32 sums of |e_k|
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
-    int32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
-    int part = 0, pend = psize < n ? psize : n;
-    bool allsame = true;
-    const int32_t x0 = x[0];
-    int32_t xmin = x0, xmax = x0;
-
-    double acc[R + 1];
-    double ring[R];
+    FbK1State<R> S;
+    S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
+    S.pe0 = S.pe1 = S.pe2 = S.pe3 = 0;
+    S.part = 0;
+    S.psize = psize;
+    S.pend = psize < n ? psize : n;
+    S.n = n;
+    S.P = P;
 #pragma unroll
-    for (int i = 0; i <= R; i++) acc[i] = 0.0;
+    for (int i = 0; i <= R; i++) S.acc[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < R; i++) ring[i] = 0.0;
-
-    for (int t0 = 0; t0 < n; t0 += R) {
-        int32_t xs[R];
-#pragma unroll
-        for (int i = 0; i < R; i += 4) {
-            // stride is a multiple of 32 samples and t0 a multiple of 4: aligned 16-byte loads
-            const int4 v = *reinterpret_cast<const int4 *>(x + t0 + i);
-            xs[i] = v.x; xs[i + 1] = v.y; xs[i + 2] = v.z; xs[i + 3] = v.w;
-        }
-        float ws[R];
-        if (do_lpc) {
-#pragma unroll
-            for (int i = 0; i < R; i += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(win + t0 + i);
-                ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < R; s++) {
-            const int t = t0 + s;
-            if (t < n) {
-                const int32_t xt = xs[s];
-                allsame = allsame && (xt == x0);
-                xmin = xt < xmin ? xt : xmin;
-                xmax = xt > xmax ? xt : xmax;
-                if (do_ent) {
-                    // zero-history differences, wrapping i32 (src/coding.rs:188-195)
-                    const int32_t e0 = xt;
-                    const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)pe0);
-                    const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)pe1);
-                    const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)pe2);
-                    const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)pe3);
-                    pe0 = e0; pe1 = e1; pe2 = e2; pe3 = e3;
-                    s0 = FB_FADD((float)(e0 < 0 ? -e0 : e0), s0);
-                    s1 = FB_FADD((float)(e1 < 0 ? -e1 : e1), s1);
-                    s2 = FB_FADD((float)(e2 < 0 ? -e2 : e2), s2);
-                    s3 = FB_FADD((float)(e3 < 0 ? -e3 : e3), s3);
-                    s4 = FB_FADD((float)(e4 < 0 ? -e4 : e4), s4);
-                    if (t + 1 == pend) {
-                        psum[part][0] = s0; psum[part][1] = s1; psum[part][2] = s2;
-                        psum[part][3] = s3; psum[part][4] = s4;
-                        s0 = s1 = s2 = s3 = s4 = 0.f;
-                        part++;
-                        pend = (pend + psize < n) ? pend + psize : n;
-                    }
-                }
-                if (do_lpc) {
-                    const double y = (double)FB_FMUL((float)xt, ws[s]);
-                    if (t >= P) {
-                        acc[0] = FB_FMA(y, y, acc[0]);
-#pragma unroll
-                        for (int j = 0; j < R; j++) {
-                            // logical y[t-1-j] lives in ring[(s-1-j) mod R]; static after unrolling
-                            acc[j + 1] = FB_FMA(ring[(s - 1 - j + 2 * R) % R], y, acc[j + 1]);
-                        }
-                    }
-                    ring[s] = y; // overwrites y[t-R]
-                }
-            }
-        }
+    for (int i = 0; i < R; i++) S.ring[i] = 0.0;
+    {
+        int32_t q[4];
+        fb_rows_load4(rows, 0, q);
+        S.xmin = S.xmax = q[0];
     }
+    // first group guarded (t < lpc_order), then whole groups without per-sample checks when the estimate
+    // partitions end on multiples of 4, then the guarded remainder
+    const bool fast_ok = (psize & 3) == 0;
+    int t0 = 0;
+    fb_k1_group<R, true>(S, rows, win, 0, do_ent, do_lpc, psum);
+    t0 = R;
+    if (fast_ok)
+        for (; t0 + R <= n; t0 += R) fb_k1_group<R, false>(S, rows, win, t0, do_ent, do_lpc, psum);
+    for (; t0 < n; t0 += R) fb_k1_group<R, true>(S, rows, win, t0, do_ent, do_lpc, psum);
 
+    const bool allsame = S.xmin == S.xmax; // src/arrayutils.rs:382-389
     out->is_constant = allsame ? 1 : 0;
     {
-        const uint32_t a = xmin < 0 ? (uint32_t)(-(int64_t)xmin) : (uint32_t)xmin;
-        const uint32_t b = xmax < 0 ? (uint32_t)(-(int64_t)xmax) : (uint32_t)xmax;
+        const uint32_t a = S.xmin < 0 ? (uint32_t)(-(int64_t)S.xmin) : (uint32_t)S.xmin;
+        const uint32_t b = S.xmax < 0 ? (uint32_t)(-(int64_t)S.xmax) : (uint32_t)S.xmax;
         out->max_abs = a > b ? a : b;
         out->pad = 0;
     }
@@ -322,7 +448,7 @@ FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, co
         double corr[FB200_MAX_LPC_ORDER + 1];
 #pragma unroll
         for (int i = 0; i <= R; i++)
-            if (i <= FB200_MAX_LPC_ORDER) corr[i] = acc[i];
+            if (i <= FB200_MAX_LPC_ORDER) corr[i] = S.acc[i];
         double lpc[FB200_MAX_LPC_ORDER];
         fb_levinson(corr, corr + 1, P, lpc);
         int16_t q[32];
@@ -341,33 +467,16 @@ FB_DEV void fb_k1_variant(const FbJob &J, const int32_t *x, int n, int bps_v, co
     }
 }
 
-// R must equal fb_k1_ring(J.cfg.lpc_order); one kernel instantiation per R keeps the register
-// allocation of the common small orders independent of the order-24 case.
-FB_HD int fb_k1_ring(int lpc_order) { return (lpc_order + 3) & ~3; }
-
-template <int R>
-FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
-                         FbAnalysis *ana, fb200_variant_taps *taps, uint32_t gv) {
-    uint32_t f = gv / (uint32_t)J.nvar;
-    int v = (int)(gv - f * (uint32_t)J.nvar);
-    int n = fb_frame_len(J, f);
-    const int32_t *x = xv + (size_t)gv * (size_t)J.stride;
-    const float *win = (n == J.block_size) ? win_full : win_tail;
-    int bps_v = fb_variant_bps(J, v);
-    fb200_variant_taps *tp = taps ? taps + gv : nullptr;
-    fb_k1_variant<R>(J, x, n, bps_v, win, ana + gv, tp);
-}
-
 #if !FB_GPU
-inline void fb_k1_dispatch(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
+inline void fb_k1_dispatch(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail,
                            FbAnalysis *ana, fb200_variant_taps *taps, uint32_t gv) {
     switch (fb_k1_ring(J.cfg.lpc_order)) {
-    case 4: fb_k1_thread<4>(J, xv, win_full, win_tail, ana, taps, gv); break;
-    case 8: fb_k1_thread<8>(J, xv, win_full, win_tail, ana, taps, gv); break;
-    case 12: fb_k1_thread<12>(J, xv, win_full, win_tail, ana, taps, gv); break;
-    case 16: fb_k1_thread<16>(J, xv, win_full, win_tail, ana, taps, gv); break;
-    case 20: fb_k1_thread<20>(J, xv, win_full, win_tail, ana, taps, gv); break;
-    default: fb_k1_thread<24>(J, xv, win_full, win_tail, ana, taps, gv); break;
+    case 4: fb_k1_thread<4>(J, xt, win_full, win_tail, ana, taps, gv); break;
+    case 8: fb_k1_thread<8>(J, xt, win_full, win_tail, ana, taps, gv); break;
+    case 12: fb_k1_thread<12>(J, xt, win_full, win_tail, ana, taps, gv); break;
+    case 16: fb_k1_thread<16>(J, xt, win_full, win_tail, ana, taps, gv); break;
+    case 20: fb_k1_thread<20>(J, xt, win_full, win_tail, ana, taps, gv); break;
+    default: fb_k1_thread<24>(J, xt, win_full, win_tail, ana, taps, gv); break;
     }
 }
 #endif

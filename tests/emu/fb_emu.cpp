@@ -36,7 +36,7 @@ int fbemu_frame_header(int n, int ch_tag, int bps, int rate, uint32_t number, ui
 }
 
 struct EmuBuffers {
-    std::vector<int32_t> xv;
+    std::vector<int32_t> xv, xv4;
     std::vector<float> win_full, win_tail;
     std::vector<FbAnalysis> ana;
     std::vector<fb200_variant_taps> taps;
@@ -60,7 +60,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     if (J.n_frames == 0) return FB200_OK;
     if ((uint64_t)first_frame + J.n_frames > (1ull << 31)) return FB200_ERR_CONFIG;
     const size_t nvars = (size_t)J.n_frames * J.nvar;
-    B.xv.assign(nvars * J.stride + 64, 0x55555555); // poison: padding must never influence results
+    B.xv.assign(fb_xt_words(J.stride, (uint64_t)J.n_frames * J.channels) + 64, 0x55555555); // poison: padding must never influence results
     B.win_full.assign(J.block_size + 64, 0.f);
     B.win_tail.assign(J.tail_n + 64, 0.f);
     fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.block_size, B.win_full.data());
@@ -72,9 +72,15 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
 
     // K0
     if (planar) {
-        for (int t = 0; t < J.tail_n; t++) fb_k0_planar_sample(J, planar, planar_stride, B.xv.data(), &err_flag, t);
+        for (int t4 = 0; t4 < J.stride / 4; t4++) fb_k0_planar_quad(J, planar, planar_stride, B.xv.data(), &err_flag, t4);
     } else {
-        for (uint64_t s = 0; s < n_samples; s++) fb_k0_sample(J, (const uint8_t *)pcm, B.xv.data(), &err_flag, s);
+        const uint64_t n_items = (uint64_t)((J.n_frames + 15u) / 16u) * (uint64_t)((J.stride / 4 + 1) / 2) * 32u;
+        for (uint64_t idx = 0; idx < n_items; idx++) {
+            uint32_t f;
+            int t4;
+            fb_k0_item(idx, J.stride / 4, &f, &t4);
+            if (f < J.n_frames && t4 < J.stride / 4) fb_k0_quad(J, (const uint8_t *)pcm, B.xv.data(), &err_flag, f, t4);
+        }
     }
     if (err_flag) return FB200_ERR_CONFIG;
     // K1
@@ -113,6 +119,11 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     } else {
         for (uint32_t f = 0; f < J.n_frames; f++) todo.push_back(f);
     }
+    // K0b: rows by variant for the generic kernels
+    B.xv4.assign(nvars * J.stride + 64, 0x55555555);
+    for (uint32_t f : todo)
+        for (int t4 = 0; t4 < J.stride / 4; t4++) fb_k0b_expand4(J, B.xv.data(), B.xv4.data(), f, t4);
+    const int32_t *xg = B.xv4.data();
     // K2
     {
         int nmax = J.block_size;
@@ -122,12 +133,12 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
           for (uint32_t gv = f * J.nvar; gv < (f + 1) * (uint32_t)J.nvar; gv++) {
             memset(smem.data(), 0xAB, smem.size());
             switch (fb_k1_ring(J.cfg.lpc_order)) {
-            case 4: fb_k2_body<4>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
-            case 8: fb_k2_body<8>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
-            case 12: fb_k2_body<12>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
-            case 16: fb_k2_body<16>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
-            case 20: fb_k2_body<20>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
-            default: fb_k2_body<24>(J, B.xv.data(), B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 4: fb_k2_body<4>(J, xg, B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 8: fb_k2_body<8>(J, xg, B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 12: fb_k2_body<12>(J, xg, B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 16: fb_k2_body<16>(J, xg, B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            case 20: fb_k2_body<20>(J, xg, B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
+            default: fb_k2_body<24>(J, xg, B.ana.data(), B.choice.data(), gv, smem.data(), L); break;
             }
           }
     }
@@ -137,7 +148,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<uint8_t> smem(fb_k3_smem_bytes(mb, J.block_size, J.pack_in_smem) + 64);
         for (uint32_t f : todo) {
             memset(smem.data(), 0xEF, smem.size());
-#define EMU_K3(GG) fb_k3_body<GG>(J, B.xv.data(), B.choice.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), f, smem.data())
+#define EMU_K3(GG) fb_k3_body<GG>(J, xg, B.choice.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), f, smem.data())
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_K3(4); break;
             case 8: EMU_K3(8); break;

@@ -212,7 +212,7 @@ def test_pipelined_host_path_matches_oracle(monkeypatch):
             assert [infos[i].frame_number for i in range(38)] == list(range(7, 45))
             assert [infos[i].frame_bytes for i in range(38)] == list(ref_sizes)
             t = ctx.timing()
-            assert t.fused_frames == 38 and t.launches == 8 * 7
+            assert t.fused_frames == 38 and t.launches == 8 * 8
         # an out-of-range sample in a late chunk is still a VerifyError
         bad = x.copy()
         bad[4096 * 30 + 5, 1] = 40000

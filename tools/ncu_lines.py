@@ -48,7 +48,7 @@ def main():
                 lines_of[off] = (cur, m.group(2))
         if lines_of:
             break
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True,
                          text=True).stdout.splitlines()
     rows = list(csv.reader(raw))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
