@@ -262,7 +262,12 @@ FB_DEV uint32_t fb_kf_evalr32(const uint32_t *cw, int p) {
     for (int j = 0; j < FB_KF_NWORDS; j++) s += (cw[j] >> p) << j;
     return s;
 }
-FB_DEV unsigned long long fb_kf_eval64(const uint32_t *words, int U, int unit, int p) {
+#if FB_GPU
+static __device__ __noinline__
+#else
+inline
+#endif
+unsigned long long fb_kf_eval64(const uint32_t *words, int U, int unit, int p) {
     unsigned long long s = 0;
 #pragma unroll
     for (int j = 0; j < FB_KF_NWORDS; j++) s += (unsigned long long)(words[j * U + unit] >> p) << j;
@@ -283,17 +288,29 @@ FB_DEV unsigned long long fb_kf_eval(const uint32_t *words, int U, int unit, int
 // like PrcBitTable::minimizer (src/rice.rs:117-141).
 template <class F>
 FB_DEV int fb_kf_walk(F f, int p, int max_p, unsigned long long *fmin) {
-    unsigned long long fc = f(p);
+    // one evaluation site: first the start, then upwards, then (if the first step up failed) downwards
+    unsigned long long fc = 0;
+    int q = p, dir = 0; // dir 0: evaluating the start, +1: trying p + 1, -1: trying p - 1
     bool moved = false;
-    while (p < max_p) {
-        const unsigned long long fu = f(p + 1);
-        if (fu < fc) { fc = fu; p++; moved = true; } else break;
-    }
-    if (!moved) {
-        while (p > 0) {
-            const unsigned long long fd = f(p - 1);
-            if (fd <= fc) { fc = fd; p--; } else break;
+    for (;;) {
+        const unsigned long long fq = f(q);
+        if (dir == 0) {
+            fc = fq;
+            dir = 1;
+        } else if (dir > 0) {
+            if (fq < fc) { fc = fq; p = q; moved = true; }
+            else if (moved) break;
+            else dir = -1;
+        } else {
+            if (fq <= fc) { fc = fq; p = q; }
+            else break;
         }
+        if (dir > 0 && p >= max_p) {
+            if (moved) break;
+            dir = -1;
+        }
+        if (dir < 0 && p <= 0) break;
+        q = p + dir;
     }
     *fmin = fc;
     return p;
@@ -335,35 +352,22 @@ FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) 
     return vm == 2 ? fb_mid(a, xb[o]) : fb_side(a, xb[o]);
 }
 
-// win[0..G) = x[ta - G .. ta), zeros before the start of the frame
+// win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4)
 template <int G>
 FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, int32_t *win) {
-    if ((ta & 3) == 0) {
 #pragma unroll
-        for (int i = 0; i < G; i += 4) {
-            const int t = ta - G + i;
-            if (t >= 0) fb_kf_load4(xa, xb, vm, t, win + i);
-            else { win[i] = 0; win[i + 1] = 0; win[i + 2] = 0; win[i + 3] = 0; }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < G; i++) {
-            const int t = ta - G + i;
-            win[i] = t >= 0 ? fb_kf_load1(xa, xb, vm, t) : 0;
-        }
+    for (int i = 0; i < G; i += 4) {
+        const int t = ta - G + i;
+        if (t >= 0) fb_kf_load4(xa, xb, vm, t, win + i);
+        else { win[i] = 0; win[i + 1] = 0; win[i + 2] = 0; win[i + 3] = 0; }
     }
 }
 
-// win[G..G+16) = x[t0 .. t0+16); samples at t >= n are don't-cares (their results are masked)
+// win[G..G+16) = x[t0 .. t0+16) (t0 a multiple of 4); samples at t >= n are don't-cares (their results are masked)
 template <int G>
-FB_DEV void fb_kf_fetch16(const int32_t *xa, const int32_t *xb, int vm, int t0, int n, int32_t *win) {
-    if ((t0 & 3) == 0) {
+FB_DEV void fb_kf_fetch16(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
 #pragma unroll
-        for (int i = 0; i < FB_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
-    } else {
-#pragma unroll
-        for (int i = 0; i < FB_RUN; i++) win[G + i] = (t0 + i < n) ? fb_kf_load1(xa, xb, vm, t0 + i) : 0;
-    }
+    for (int i = 0; i < FB_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
 }
 
 template <int G>
@@ -470,7 +474,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
                 fb_kf_history<G>(xa, xb, vm, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
                     uint32_t uu[FB_RUN];
-                    fb_kf_fetch16<G>(xa, xb, vm, t0, n, win);
+                    fb_kf_fetch16<G>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
                     fb_kf_csa16(cw, uu);
                     fb_kf_slide<G>(win);
@@ -821,6 +825,22 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     uint32_t *words = (uint32_t *)(smem + L.off_scratch);
     uint8_t *slot = slots + (size_t)f * (size_t)J.slot_bytes;
 
+    // units must start on multiples of 4 samples (16-byte window loads): frames whose finest partitions are not a
+    // multiple of 4 long (odd tail frames, odd block sizes) are left to the generic kernels
+    if ((g.leaf_len & 3) != 0) {
+        FB_PHASE(tid, T)
+            if (tid == 0) {
+#if FB_GPU
+                const uint32_t slot_i = atomicAdd(fb_count, 1u);
+#else
+                const uint32_t slot_i = (*fb_count)++;
+#endif
+                fb_list[slot_i] = f;
+            }
+        FB_PHASE_END
+        return;
+    }
+
     // ---- stage the independent channels from the row-interleaved store xt (16-byte loads)
     FB_PHASE(tid, T)
         const int n4 = (n + 3) >> 2;
@@ -1035,7 +1055,7 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 fb_kf_history<G>(xa, xb, vm, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
                     uint32_t uu[FB_RUN];
-                    fb_kf_fetch16<G>(xa, xb, vm, t0, n, win);
+                    fb_kf_fetch16<G>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
 #pragma unroll
                     for (int i = 0; i < FB_RUN; i++) {
@@ -1043,12 +1063,9 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                         if (t >= lo && t < tb) {
                             // q zeros, a one, then the p low bits: one field when it fits in 32 bits
                             const uint32_t q = uu[i] >> rp, code = (uu[i] & rmask) | rone;
-                            if (q + rp + 1u <= 32u) {
-                                fb_bw_put(r, code, q + rp + 1u);
-                            } else {
-                                fb_bw_skip(r, q);
-                                fb_bw_put(r, code, rp + 1u);
-                            }
+                            uint32_t len = q + rp + 1u;
+                            if (len > 32u) { fb_bw_skip(r, q); len = rp + 1u; }
+                            fb_bw_put(r, code, len);
                         }
                     }
                     fb_kf_slide<G>(win);

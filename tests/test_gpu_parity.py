@@ -175,13 +175,17 @@ def test_pathological_residuals():
 
 
 def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
-    """Default config: every frame is encoded by the fused per-frame kernel.  A residual >= 2^26 (zigzag >= 2^27)
-    or a saturated table minimum hands the frame to the generic kernels; results stay byte-identical."""
+    """Default config: every full frame is encoded by the fused per-frame kernel.  A tail frame whose finest Rice
+    partitions are not a multiple of 4 samples (2728 = 8 x 341), a residual >= 2^26 (zigzag >= 2^27) or a saturated
+    table minimum hands the frame to the generic kernels; results stay byte-identical."""
     vcfg = Encoder().into_verified()
     n = 4096 * 5 + 2728
     x = sigen.noisy_sine_pcm(n, 2, 16, 44100)
     with Context(vcfg, 2, 16, 44100, 4096) as ctx:
         ctx.encode_interleaved(pack_pcm(x, 2), 2, n)
+        t = ctx.timing()
+        assert (t.fused_frames, t.fallback_frames) == (5, 1)
+        ctx.encode_interleaved(pack_pcm(x[: 4096 * 5 + 2048], 2), 2, 4096 * 5 + 2048)
         t = ctx.timing()
         assert (t.fused_frames, t.fallback_frames) == (6, 0)
     y = crafted_huge_residual_stereo()
@@ -212,7 +216,7 @@ def test_pipelined_host_path_matches_oracle(monkeypatch):
             assert [infos[i].frame_number for i in range(38)] == list(range(7, 45))
             assert [infos[i].frame_bytes for i in range(38)] == list(ref_sizes)
             t = ctx.timing()
-            assert t.fused_frames == 38 and t.launches == 8 * 8
+            assert (t.fused_frames, t.fallback_frames) == (37, 1) and t.launches == 8 * 8  # tail 1000 = 8 x 125
         # an out-of-range sample in a late chunk is still a VerifyError
         bad = x.copy()
         bad[4096 * 30 + 5, 1] = 40000
