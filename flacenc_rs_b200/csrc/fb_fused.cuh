@@ -32,6 +32,7 @@
 
 #include "fb_kernels.cuh"
 
+#define FB_KF_RUN 16       // samples per residual run (register window of G + FB_KF_RUN samples)
 #define FB_KF_COLS 8       // Rice parameters evaluated per tree pass
 #define FB_KF_ROW 9        // row stride of the tree tables (one pad word: conflict-free column reads)
 #define FB_KF_NWORDS 7     // bit-sliced counter words per unit (counts <= 127)
@@ -222,10 +223,11 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
 #define FB_CSA(h, l, a, b, c) do { const uint32_t a__ = (a), b__ = (b), c__ = (c); const uint32_t x__ = a__ ^ b__; \
                                    (h) = (a__ & b__) | (x__ & c__); (l) = x__ ^ c__; } while (0)
 
-// adds 16 values into the counter words cw[0..6] (weights 1, 2, 4, 8, 16, 32, 64)
-FB_DEV void fb_kf_csa16(uint32_t *cw, const uint32_t *d) {
-    uint32_t twoA, twoB, fourA, fourB, eightA, eightB, sixteen;
-    uint32_t ones = cw[0], twos = cw[1], fours = cw[2], eights = cw[3];
+// adds FB_KF_RUN (8 or 16) values into the counter words cw[0..6] (weights 1, 2, 4, 8, 16, 32, 64);
+// counts stay <= 127 by construction (units of at most 112 samples)
+FB_DEV void fb_kf_csa_run(uint32_t *cw, const uint32_t *d) {
+    uint32_t twoA, twoB, fourA, fourB, eightA;
+    uint32_t ones = cw[0], twos = cw[1], fours = cw[2];
     FB_CSA(twoA, ones, ones, d[0], d[1]);
     FB_CSA(twoB, ones, ones, d[2], d[3]);
     FB_CSA(fourA, twos, twos, twoA, twoB);
@@ -233,6 +235,8 @@ FB_DEV void fb_kf_csa16(uint32_t *cw, const uint32_t *d) {
     FB_CSA(twoB, ones, ones, d[6], d[7]);
     FB_CSA(fourB, twos, twos, twoA, twoB);
     FB_CSA(eightA, fours, fours, fourA, fourB);
+#if FB_KF_RUN == 16
+    uint32_t eightB, sixteen, eights = cw[3];
     FB_CSA(twoA, ones, ones, d[8], d[9]);
     FB_CSA(twoB, ones, ones, d[10], d[11]);
     FB_CSA(fourA, twos, twos, twoA, twoB);
@@ -241,9 +245,14 @@ FB_DEV void fb_kf_csa16(uint32_t *cw, const uint32_t *d) {
     FB_CSA(fourB, twos, twos, twoA, twoB);
     FB_CSA(eightB, fours, fours, fourA, fourB);
     FB_CSA(sixteen, eights, eights, eightA, eightB);
-    cw[0] = ones; cw[1] = twos; cw[2] = fours; cw[3] = eights;
-    // ripple the carry into the 16/32/64 words (half adders); counts stay <= 127 by construction
+    cw[3] = eights;
     uint32_t c = cw[4] & sixteen; cw[4] ^= sixteen;
+#else
+    // ripple the carry of weight 8 into the 8/16/32/64 words (half adders)
+    uint32_t c0 = cw[3] & eightA; cw[3] ^= eightA;
+    uint32_t c = cw[4] & c0; cw[4] ^= c0;
+#endif
+    cw[0] = ones; cw[1] = twos; cw[2] = fours;
     uint32_t c2 = cw[5] & c;      cw[5] ^= c;
     cw[6] ^= c2;
 }
@@ -325,7 +334,7 @@ FB_DEV int fb_kf_pstart(unsigned long long s0, int cnt, int max_p) {
 }
 
 // ---- residual runs out of the staged planes ------------------------------------------------------
-// vm: 0 = plane xa as is, 2 = mid, 3 = side.  A run's window is win[i] = x[t0 - G + i], i < G + FB_RUN:
+// vm: 0 = plane xa as is, 2 = mid, 3 = side.  A run's window is win[i] = x[t0 - G + i], i < G + FB_KF_RUN:
 // the G history samples are loaded once per unit and then slide in registers, the 16 new samples come
 // from 16-byte shared-memory loads (scalar loads when the unit is not 4-aligned).
 
@@ -363,17 +372,17 @@ FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, 
     }
 }
 
-// win[G..G+16) = x[t0 .. t0+16) (t0 a multiple of 4); samples at t >= n are don't-cares (their results are masked)
+// win[G..G+RUN) = x[t0 .. t0+RUN) (t0 a multiple of 4); samples at t >= n are don't-cares (their results are masked)
 template <int G>
-FB_DEV void fb_kf_fetch16(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
+FB_DEV void fb_kf_fetch_run(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
 #pragma unroll
-    for (int i = 0; i < FB_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
+    for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
 }
 
 template <int G>
 FB_DEV void fb_kf_slide(int32_t *win) {
 #pragma unroll
-    for (int i = 0; i < G; i++) win[i] = win[i + FB_RUN];
+    for (int i = 0; i < G; i++) win[i] = win[i + FB_KF_RUN];
 }
 
 // description of one residual candidate of a variant
@@ -399,12 +408,13 @@ template <int G>
 FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCand &cd, const int32_t *qq, uint32_t *u) {
     // bit i of vmask: sample t0 + i lies in [lo, hi)
     const int a = lo - t0, b = hi - t0;
-    const uint32_t m_hi = b >= FB_RUN ? 0xFFFFu : (b <= 0 ? 0u : ((1u << b) - 1u));
-    const uint32_t m_lo = a <= 0 ? 0u : (a >= FB_RUN ? 0xFFFFu : ((1u << a) - 1u));
+    const uint32_t full = (1u << FB_KF_RUN) - 1u;
+    const uint32_t m_hi = b >= FB_KF_RUN ? full : (b <= 0 ? 0u : ((1u << b) - 1u));
+    const uint32_t m_lo = a <= 0 ? 0u : (a >= FB_KF_RUN ? full : ((1u << a) - 1u));
     const uint32_t vmask = m_hi & ~m_lo;
     if (cd.kind == 0) {
 #pragma unroll
-        for (int i = 0; i < FB_RUN; i++) {
+        for (int i = 0; i < FB_KF_RUN; i++) {
             const uint32_t e = (uint32_t)win[G + i] + (uint32_t)cd.fc[0] * (uint32_t)win[G + i - 1] +
                                (uint32_t)cd.fc[1] * (uint32_t)win[G + i - 2] + (uint32_t)cd.fc[2] * (uint32_t)win[G + i - 3] +
                                (uint32_t)cd.fc[3] * (uint32_t)win[G + i - 4];
@@ -412,7 +422,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
         }
     } else if (cd.narrow) {
 #pragma unroll
-        for (int i = 0; i < FB_RUN; i++) {
+        for (int i = 0; i < FB_KF_RUN; i++) {
             uint32_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) acc += (uint32_t)qq[j] * (uint32_t)win[G + i - 1 - j];
@@ -420,16 +430,16 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < FB_RUN; i++) {
+        for (int i = 0; i < FB_KF_RUN; i++) {
             int64_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) acc = fb_mad_wide(qq[j], win[G + i - 1 - j], acc);
             u[i] = fb_zigzag((int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> cd.shift)));
         }
     }
-    if (vmask != 0xFFFFu) {
+    if (vmask != full) {
 #pragma unroll
-        for (int i = 0; i < FB_RUN; i++) u[i] = ((vmask >> i) & 1u) ? u[i] : 0u;
+        for (int i = 0; i < FB_KF_RUN; i++) u[i] = ((vmask >> i) & 1u) ? u[i] : 0u;
     }
 }
 
@@ -470,13 +480,13 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             for (int j = 0; j < FB_KF_NWORDS; j++) cw[j] = 0;
             const int lo = ta > warm ? ta : warm;
             if (tb > ta) {
-                int32_t win[G + FB_RUN];
+                int32_t win[G + FB_KF_RUN];
                 fb_kf_history<G>(xa, xb, vm, ta, win);
-                for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
-                    uint32_t uu[FB_RUN];
-                    fb_kf_fetch16<G>(xa, xb, vm, t0, win);
+                for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
+                    uint32_t uu[FB_KF_RUN];
+                    fb_kf_fetch_run<G>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
-                    fb_kf_csa16(cw, uu);
+                    fb_kf_csa_run(cw, uu);
                     fb_kf_slide<G>(win);
                 }
             }
@@ -1051,14 +1061,14 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                         (unsigned long long)ana[(size_t)f * (size_t)J.nvar + (size_t)D.variant].max_abs * sumabs < 0x7FFFFFFFull;
             const uint32_t rmask = (1u << rp) - 1u, rone = 1u << rp;
             if (tb > lo) {
-                int32_t win[G + FB_RUN];
+                int32_t win[G + FB_KF_RUN];
                 fb_kf_history<G>(xa, xb, vm, ta, win);
-                for (int t0 = ta; t0 < tb; t0 += FB_RUN) {
-                    uint32_t uu[FB_RUN];
-                    fb_kf_fetch16<G>(xa, xb, vm, t0, win);
+                for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
+                    uint32_t uu[FB_KF_RUN];
+                    fb_kf_fetch_run<G>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
 #pragma unroll
-                    for (int i = 0; i < FB_RUN; i++) {
+                    for (int i = 0; i < FB_KF_RUN; i++) {
                         const int t = t0 + i;
                         if (t >= lo && t < tb) {
                             // q zeros, a one, then the p low bits: one field when it fits in 32 bits
