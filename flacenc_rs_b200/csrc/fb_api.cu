@@ -6,12 +6,15 @@
 // returns FB200_ERR_CUDA.  Reference citations are relative to /root/reference/.
 #include <cuda_runtime.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
+#include <array>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "fb_host.h"
@@ -569,7 +572,26 @@ int fb_encode_serial(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P) {
 // FB_NSETS buffer sets rotate; a set is reused once its D2H copy has been enqueued and is waited for by event.
 int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint64_t chunk_frames) {
     int rc;
-    const uint64_t nchunks = (P.total_frames + chunk_frames - 1) / chunk_frames;
+    // chunk schedule: the H2D stream is the bottleneck, so what matters at the end is how much work is left once the
+    // last copy has landed.  One short final chunk (a quarter of the nominal size) keeps that tail small; more than
+    // one does not pay, because every chunk costs about a millisecond of kernel latency.  The frames before it are
+    // spread evenly over chunks of at most the nominal size.
+    std::vector<std::pair<uint64_t, uint64_t>> chunks; // (first frame, frames)
+    {
+        const uint64_t last = std::max<uint64_t>(1, std::min<uint64_t>(chunk_frames / 4, P.total_frames / 2));
+        const uint64_t body = P.total_frames - last;
+        const uint64_t nb = (body + chunk_frames - 1) / chunk_frames;
+        uint64_t f = 0;
+        for (uint64_t i = 0; i < nb; i++) {
+            const uint64_t take = body / nb + (i < body % nb ? 1 : 0);
+            chunks.push_back({f, take});
+            f += take;
+        }
+        chunks.push_back({f, last});
+        chunk_frames = 0;
+        for (auto &c : chunks) chunk_frames = std::max(chunk_frames, c.second);
+    }
+    const uint64_t nchunks = chunks.size();
     const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
     const uint64_t in_chunk = std::min(chunk_frames * P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb, in_bytes_total);
     for (ChunkSet &S : ctx->sets) {
@@ -581,11 +603,20 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
     Accum acc;
     unsigned long long host_off = 0;
     int result = FB200_OK;
+    // FB200_TRACE=1: device timeline per chunk (ms since the start of the call) on stderr
+    const bool trace = getenv("FB200_TRACE") != nullptr;
+    std::vector<std::array<float, 6>> tr(trace ? nchunks : 0);
+    std::vector<uint64_t> set_chunk(FB_NSETS, 0); // chunk whose D2H events a set currently holds
+    auto trace_d2h = [&](ChunkSet &S, uint64_t c) {
+        if (!trace) return;
+        cudaEventElapsedTime(&tr[c][4], ctx->ev_begin, S.ev[7]);
+        cudaEventElapsedTime(&tr[c][5], ctx->ev_begin, S.ev[8]);
+    };
     FB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->s_in));
 
     auto chunk_range = [&](uint64_t c, uint64_t &f0, uint64_t &nf, uint64_t &s0, uint64_t &ns) {
-        f0 = c * chunk_frames;
-        nf = std::min(chunk_frames, P.total_frames - f0);
+        f0 = chunks[c].first;
+        nf = chunks[c].second;
         s0 = f0 * P.bs;
         ns = std::min(A.n_samples - s0, nf * P.bs);
     };
@@ -599,6 +630,7 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
             float t;
             FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
             acc.ms_d2h += t;
+            trace_d2h(S, set_chunk[c % FB_NSETS]);
             S.d2h_pending = false;
         }
         const uint64_t off = s0 * (uint64_t)ctx->channels * (uint64_t)P.cb;
@@ -649,6 +681,11 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
         }
         FB_CUDA(ctx, cudaEventRecord(S.ev[8], ctx->s_out));
         S.d2h_pending = true;
+        set_chunk[c % FB_NSETS] = c;
+        if (trace) {
+            const int idx[4] = {0, 9, 1, 6};
+            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&tr[c][i], ctx->ev_begin, S.ev[idx[i]]);
+        }
         host_off += total;
         return FB200_OK;
     };
@@ -675,16 +712,24 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_k1));
-    for (ChunkSet &S : ctx->sets) {
+    for (int k = 0; k < FB_NSETS; k++) {
+        ChunkSet &S = ctx->sets[k];
         if (S.d2h_pending) {
             float t;
             FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
             acc.ms_d2h += t;
+            trace_d2h(S, set_chunk[(size_t)k]);
             S.d2h_pending = false;
         }
     }
     if (A.out_len) *A.out_len = (size_t)host_off;
     if (result != FB200_OK) return result;
+    if (trace) {
+        for (uint64_t c = 0; c < nchunks; c++)
+            fprintf(stderr, "fb200 trace: chunk %llu frames %llu  h2d %.3f-%.3f  kernels %.3f-%.3f  d2h %.3f-%.3f\n",
+                    (unsigned long long)c, (unsigned long long)chunks[c].second, tr[c][0], tr[c][1], tr[c][2], tr[c][3],
+                    tr[c][4], tr[c][5]);
+    }
     float t_total = 0;
     FB_CUDA(ctx, cudaEventElapsedTime(&t_total, ctx->ev_begin, ctx->ev_end));
     fb_store_timing(ctx, acc, t_total, in_bytes_total, host_off);
@@ -724,7 +769,7 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     // host batches of more than one chunk are pipelined; the chunk is sized so that the per-variant analysis
     // kernel still has a few thousand threads and the copies of neighbouring chunks overlap the kernels
     if (A.pcm_host && !A.analyze_only) {
-        uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 6144;
+        uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 4864;
         const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + 2 * P.slot_bytes + 4096u;
         chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(64, (1024ull << 20) / per_frame));
         if (total_frames > chunk + chunk / 2) return fb_encode_pipelined(ctx, A, P, chunk);
