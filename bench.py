@@ -111,6 +111,21 @@ def cpu_port_throughput(pcm: np.ndarray, threads: int, target_seconds: float):
     return passes * len(sample) / total_s, frames, total_s, nbytes, passes
 
 
+MODEL_OPS_PER_SAMPLE = 250.0  # minimal integer/FP lane-ops per inter-channel sample (stereo, default config)
+NCU_KF = {  # dominant kernel (fused encode), `ncu --set full` of round 1 (profiles/r1_kf_ncu_summary.md)
+    "dram_bytes_per_frame": 44100.0, "issue_active_pct": 41.0, "warp_inst_per_frame": 65500.0}
+
+
+def issue_roofline(value: float, clocks: dict) -> dict:
+    sm_mhz = float(clocks.get("sm_mhz") or 1965.0)
+    peak = 148 * 4 * 32 * sm_mhz * 1e6  # SMs x schedulers x lanes x clock: lane-ops/s of one issue slot per scheduler
+    return {"bound": "issue", "model_ops_per_sample": MODEL_OPS_PER_SAMPLE, "peak_lane_ops_per_s": peak,
+            "peak_samples_per_s": peak / MODEL_OPS_PER_SAMPLE, "frac": value * MODEL_OPS_PER_SAMPLE / peak,
+            "ncu_dominant_kernel": NCU_KF,
+            "note": "frac = value x 250 ops / (148 SM x 4 x 32 lanes x SM clock), per GPU at N=1; ncu numbers are from the "
+                    "committed capture, not this run"}
+
+
 def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
@@ -233,18 +248,21 @@ def main() -> None:
         fused_frames, fallback_frames = t.fused_frames, t.fallback_frames
     barrier()
     wall_dev = time.perf_counter() - w0
-    clocks = sampler.stop()
 
-    # ---- timed: end to end with host buffers (e2e)
+    # ---- timed: end to end with host buffers (e2e): the library's own CUDA events bracket every H2D copy, kernel and
+    # D2H copy of the call; the wall clock around the loop is reported next to it
     barrier()
     e2e_ms = 0.0
     h2d_ms = d2h_ms = 0.0
+    w1 = time.perf_counter()
     for _ in range(args.steps):
         out_len_h, t = step_host()
         e2e_ms += t.total_ms
         h2d_ms += t.h2d_ms
         d2h_ms += t.d2h_ms
     barrier()
+    wall_e2e = time.perf_counter() - w1
+    clocks = sampler.stop()
     assert out_len_h == out_len
 
     # max over ranks of the device time; aggregate = all ranks' samples / that time
@@ -289,13 +307,19 @@ def main() -> None:
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": dom, "peak_kind": peak_kind,
+                         "traffic": NCU_KF["dram_bytes_per_frame"] * n_frames if dom == "encode" else None,
+                         "traffic_note": "dram bytes read+written by the dominant kernel per step, from the committed ncu "
+                                         "capture (bytes per frame x frames of this step)",
+                         "kernel": dom, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_step": alg_bytes,
                          "whole_step_achieved_gbs": whole, "whole_step_frac": whole / peak,
-                         "note": "compute/issue-bound path (~700 integer/FP ops per inter-channel sample): the HBM "
-                                 "fraction is low by construction, see DESIGN.md"},
+                         "note": "the path is instruction-issue bound (hundreds of integer/FP ops per 6.2 algorithmic bytes): "
+                                 "the HBM fraction is low by construction, see issue_roofline and DESIGN.md"},
+            # instruction-issue bound of the analysis (the binding resource): minimal op model of the
+            # reference algorithm vs the INT32/FP32 lane-op rate of the part at the sampled SM clock
+            "issue_roofline": issue_roofline(value, clocks),
             "clocks": clocks,
-            "wall_s_device_loop": wall_dev,
+            "wall_s_device_loop": wall_dev, "wall_s_e2e_loop": wall_e2e,
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Writes profiles/<tag>_ncu_summary.md from gpurun_out/prof_<tag>.ncu-rep and gpurun_out/launches_<tag>.csv."""
+import csv
+import subprocess
+import sys
+from collections import defaultdict
+
+tag = sys.argv[1]
+rep = f"gpurun_out/prof_{tag}.ncu-rep"
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()
+rows = list(csv.reader(raw))
+hdr, units = rows[0], rows[1]
+want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+body = rows[2:]
+names = [r[hdr.index("Kernel Name")].split("(")[0] for r in body]
+out = [f"# {tag}: `ncu --set full --clock-control none` of the two heaviest kernels\n\n",
+       f"Command: `bash tools/gpu_profile.sh {tag}` (bench.py --seconds 600: 6460 frames of the C2 workload; one launch of each "
+       "kernel, cold cache, serialised -- compare shares, not absolutes).  The .ncu-rep stays in gpurun_out/ (scratch).\n\n",
+       "| metric | " + " | ".join(names) + " |\n", "|---|" + "---|" * len(names) + "\n"]
+for k in want:
+    if k in hdr:
+        i = hdr.index(k)
+        out.append(f"| {k} [{units[i]}] | " + " | ".join(r[i] for r in body) + " |\n")
+# launch list
+try:
+    lr = list(csv.reader(open(f"gpurun_out/launches_{tag}.csv")))
+    hi = next(i for i, r in enumerate(lr) if r and r[0] == "ID")
+    h = lr[hi]
+    kn, mv = h.index("Kernel Name"), h.index("Metric Value")
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in lr[hi + 1:]:
+        if len(r) > mv:
+            name = r[kn].split("(")[0]
+            agg[name][0] += 1
+            agg[name][1] += float(r[mv].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    unit = lr[hi + 1][h.index("Metric Unit")]
+    out.append(f"\n## Launch list (`--metrics gpu__time_duration.sum`, first 80 launches of the same command)\n\n"
+               f"| kernel | launches | total [{unit}] | share |\n|---|---|---|---|\n")
+    for name, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| {name} | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f} % |\n")
+except Exception as e:  # noqa: BLE001
+    out.append(f"\n(launch list unavailable: {e})\n")
+open(f"profiles/{tag}_ncu_summary.md", "w").write("".join(out))
+print("".join(out))
