@@ -80,8 +80,9 @@ struct DevBuf {
 struct ChunkSet {
     DevBuf pcm, xv, xv4, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars;
     // events: 0 H2D start, 1 H2D end, 2 ingest end, 3 analyze end, 4 rice/fused end, 5 pack/fallback end,
-    //         6 gather end (= chunk done), 7 D2H start, 8 D2H end, 9 H2D end on the copy stream (pipelined path)
-    cudaEvent_t ev[10];
+    //         6 gather end (= chunk done), 7 D2H start, 8 D2H end, 9 H2D end on the copy stream (pipelined path),
+    //         10 start of the back half (fused kernel onwards) on its stream
+    cudaEvent_t ev[11];
     int n_ev = 0;
     uint8_t *pinned = nullptr; // [0, 64): copy of the device scalars; [64, ...): frame sizes of the chunk
     size_t pinned_cap = 0;
@@ -203,7 +204,7 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
               cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
     for (int k = 0; ok && k < FB_NSETS; k++) {
         ChunkSet &S = ctx->sets[k];
-        for (int i = 0; ok && i < 10; i++) {
+        for (int i = 0; ok && i < 11; i++) {
             ok = cudaEventCreate(&S.ev[i]) == cudaSuccess;
             if (ok) S.n_ev = i + 1;
         }
@@ -389,12 +390,14 @@ int fb_reserve_set(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet 
 // Records S.ev[1..6].
 int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet &S, uint64_t f0, uint64_t ns,
                        const uint8_t *d_pcm, uint32_t *d_fb, uint8_t *d_out, unsigned long long out_cap, cudaStream_t st,
-                       Accum &acc) {
+                       Accum &acc, cudaStream_t st_back = nullptr, unsigned long long *d_total_shared = nullptr) {
+    // front half (ingest, analysis) on `st`; back half (fused kernel .. gather) on `st_back` when given, so the
+    // analysis of the next chunk can overlap the fused kernel of this one
     FbJob J = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, P.cb, ns,
                            (uint32_t)(A.first_frame + f0));
     const uint32_t nvars = J.n_frames * (uint32_t)J.nvar;
     uint32_t *d_err = (uint32_t *)S.scalars.p;
-    unsigned long long *d_total = (unsigned long long *)((uint8_t *)S.scalars.p + 8);
+    unsigned long long *d_total = d_total_shared ? d_total_shared : (unsigned long long *)((uint8_t *)S.scalars.p + 8);
     uint32_t *d_fb_count = (uint32_t *)((uint8_t *)S.scalars.p + 16);
     FB_CUDA(ctx, cudaEventRecord(S.ev[1], st));
     if (A.planar_host) {
@@ -411,6 +414,11 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     FB_CUDA(ctx, cudaEventRecord(S.ev[3], st));
     acc.launches += 2;
     if (A.analyze_only) return FB200_OK;
+    if (st_back && st_back != st) {
+        FB_CUDA(ctx, cudaStreamWaitEvent(st_back, S.ev[3], 0));
+        st = st_back;
+    }
+    FB_CUDA(ctx, cudaEventRecord(S.ev[10], st));
     fb200_frame_info *d_infos = A.infos ? (fb200_frame_info *)S.infos.p : nullptr;
     // plain rows by variant for the generic kernels (K0b)
     const int32_t *xg = (const int32_t *)S.xv4.p;
@@ -455,7 +463,7 @@ int fb_harvest_kernel_times(fb200_ctx *ctx, ChunkSet &S, bool analyze_only, Accu
     float t;
     const int last = analyze_only ? 2 : 5;
     for (int k = 0; k < last; k++) {
-        FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[1 + k], S.ev[2 + k]));
+        FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[k == 2 ? 10 : 1 + k], S.ev[2 + k]));
         acc.ms_k[k] += t;
     }
     return FB200_OK;
