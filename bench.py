@@ -230,9 +230,9 @@ def main() -> None:
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    # "encode" = the fused per-frame kernel (Rice search + frame assembly); "fallback" = the generic kernels over
-    # the frames it handed back (normally none)
-    dev_ms, kern = 0.0, {"ingest": 0.0, "analyze": 0.0, "encode": 0.0, "fallback": 0.0, "gather": 0.0}
+    # "plan" = KA (Rice search, decisions, frame plan), "pack" = KP (bit packing + CRC + store at the final offset),
+    # "fallback+scan" = the generic kernels over the frames KA handed back (normally a tail frame) + the size scan
+    dev_ms, kern = 0.0, {"ingest": 0.0, "analyze": 0.0, "plan": 0.0, "pack": 0.0, "fallback+scan": 0.0}
     fused_frames = fallback_frames = 0
     launches = 0
     w0 = time.perf_counter()
@@ -241,9 +241,9 @@ def main() -> None:
         dev_ms += t.total_ms
         kern["ingest"] += t.k_ingest_ms
         kern["analyze"] += t.k_analyze_ms
-        kern["encode"] += t.k_rice_ms
-        kern["fallback"] += t.k_pack_ms
-        kern["gather"] += t.k_gather_ms
+        kern["plan"] += t.k_rice_ms
+        kern["pack"] += t.k_pack_ms
+        kern["fallback+scan"] += t.k_gather_ms
         launches += t.launches
         fused_frames, fallback_frames = t.fused_frames, t.fallback_frames
     barrier()
@@ -307,7 +307,7 @@ def main() -> None:
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_KF["dram_bytes_per_frame"] * n_frames if dom == "encode" else None,
+                         "traffic": NCU_KF["dram_bytes_per_frame"] * n_frames if dom == "plan" else None,
                          "traffic_note": "dram bytes read+written by the dominant kernel per step, from the committed ncu "
                                          "capture (bytes per frame x frames of this step)",
                          "kernel": dom, "peak_kind": peak_kind,

@@ -62,6 +62,15 @@ __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *fram
     if (threadIdx.x == 0) *total = offsets[n_frames];
 }
 
+// gather of the frames on the fused path's fallback list only (everything else is stored in place by KP)
+__global__ void __launch_bounds__(256) fb_k4_gather_list(const uint8_t *slots, uint32_t slot_bytes, const uint32_t *frame_bytes,
+                                                         const unsigned long long *offsets, uint8_t *out,
+                                                         unsigned long long out_cap, const uint32_t *list, const uint32_t *count) {
+    const uint32_t total = *count;
+    for (uint32_t i = blockIdx.x; i < total; i += gridDim.x)
+        fb_k4_gather_thread(slots, slot_bytes, frame_bytes, offsets, out, out_cap, list[i], (int)threadIdx.x, 256);
+}
+
 __global__ void __launch_bounds__(256) fb_k4_gather(const uint8_t *slots, uint32_t slot_bytes, const uint32_t *frame_bytes,
                                                     const unsigned long long *offsets, uint8_t *out,
                                                     unsigned long long out_cap) {
@@ -78,7 +87,7 @@ struct DevBuf {
 
 // Device buffers, events and pinned staging of one chunk in flight.  Set 0 also serves the serial path.
 struct ChunkSet {
-    DevBuf pcm, xv, xv4, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars;
+    DevBuf pcm, xv, xv4, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars, plan, psubs, poffs;
     // events: 0 H2D start, 1 H2D end, 2 ingest end, 3 analyze end, 4 rice/fused end, 5 pack/fallback end,
     //         6 gather end (= chunk done), 7 D2H start, 8 D2H end, 9 H2D end on the copy stream (pipelined path),
     //         10 start of the back half (fused kernel onwards) on its stream
@@ -225,7 +234,7 @@ void fb200_destroy(fb200_ctx *ctx) {
     cudaDeviceSynchronize();
     for (ChunkSet &S : ctx->sets) {
         DevBuf *bufs[] = {&S.pcm, &S.xv, &S.xv4, &S.ana, &S.taps, &S.choice, &S.slots, &S.frame_bytes, &S.offsets, &S.out,
-                          &S.infos, &S.fb_list, &S.scalars};
+                          &S.infos, &S.fb_list, &S.scalars, &S.plan, &S.psubs, &S.poffs};
         for (DevBuf *b : bufs)
             if (b->p) cudaFree(b->p);
         for (int i = 0; i < S.n_ev; i++) cudaEventDestroy(S.ev[i]);
@@ -293,6 +302,8 @@ struct Plan {
 };
 
 struct Accum {
+    bool fused = false; // ms_k[2..4]: fused = plan kernel | fallback kernels + scan | pack kernel (+ list gather);
+                        //             generic = Rice search | assembly | scan + gather
     float ms_h2d = 0, ms_d2h = 0, ms_k[5] = {0, 0, 0, 0, 0};
     uint64_t launches = 0, fused_frames = 0, fallback = 0;
 };
@@ -339,6 +350,8 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         return FB200_ERR_CUDA;
     }
     P.fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, P.tail_n, &P.KL);
+    if (getenv("FB200_KF_SMEM_PAD")) P.KL.total += (uint32_t)atoi(getenv("FB200_KF_SMEM_PAD")); // occupancy experiments
+    if (getenv("FB200_KF_DEBUG_STOP")) P.KL.debug_stop = (uint32_t)atoi(getenv("FB200_KF_DEBUG_STOP"));
     if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
         std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk));
         fb_kf_build_ktab(P.KL.crc_chunk, kt.data());
@@ -379,6 +392,11 @@ int fb_reserve_set(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet 
         if ((rc = fb_reserve(ctx, S.choice, frames * (uint64_t)P.nvar * sizeof(fb200_subframe_info)))) return rc;
         if ((rc = fb_reserve(ctx, S.slots, frames * P.slot_bytes))) return rc;
         if ((rc = fb_reserve(ctx, S.fb_list, (frames + 1) * 4u))) return rc;
+        if (P.fused) {
+            if ((rc = fb_reserve(ctx, S.plan, frames * sizeof(FbKfPlan)))) return rc;
+            if ((rc = fb_reserve(ctx, S.psubs, frames * (uint64_t)ctx->channels * sizeof(fb200_subframe_info)))) return rc;
+            if ((rc = fb_reserve(ctx, S.poffs, frames * (uint64_t)ctx->channels * (P.KL.U_max + 1) * 4u))) return rc;
+        }
         if (A.infos && (rc = fb_reserve(ctx, S.infos, frames * sizeof(fb200_frame_info)))) return rc;
         if (out_bytes && (rc = fb_reserve(ctx, S.out, out_bytes))) return rc;
     }
@@ -423,10 +441,13 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     // plain rows by variant for the generic kernels (K0b)
     const int32_t *xg = (const int32_t *)S.xv4.p;
     if (P.fused) {
-        // KF: Rice search + frame assembly per frame; frames it cannot reproduce exactly go to the list
+        // KA: analysis + plan + frame sizes; frames it cannot reproduce exactly go to the list and are encoded into
+        // their slots by the generic kernels.  Then the scan of all frame sizes, KP packs every planned frame
+        // straight to its final offset, and the listed frames are gathered from their slots.
         FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
-        fb_launch_kf(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, (uint8_t *)S.slots.p, d_fb, d_infos,
-                     (uint32_t *)S.fb_list.p, d_fb_count, (const uint32_t *)ctx->ktab.p, P.KL, st);
+        fb_launch_ka(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, S.plan.p,
+                     (fb200_subframe_info *)S.psubs.p, (uint32_t *)S.poffs.p, d_fb, d_infos, (uint32_t *)S.fb_list.p,
+                     d_fb_count, P.KL, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
         fb_k0b_expand<<<148, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, (const uint32_t *)S.fb_list.p,
                                            d_fb_count);
@@ -434,9 +455,17 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
                      P.L, (const uint32_t *)S.fb_list.p, d_fb_count, 296, P.k2_smem, st);
         fb_launch_k3(P.ring, J, xg, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
                      d_fb, d_infos, (const uint32_t *)S.fb_list.p, d_fb_count, 148, P.k3_smem, st);
+        fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
+        fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, S.plan.p, (const fb200_subframe_info *)S.psubs.p,
+                     (const uint32_t *)S.poffs.p, (const unsigned long long *)S.offsets.p, d_out, out_cap,
+                     (const uint32_t *)ctx->ktab.p, P.KL, st);
+        fb_k4_gather_list<<<148, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
+                                               (const unsigned long long *)S.offsets.p, d_out, out_cap,
+                                               (const uint32_t *)S.fb_list.p, d_fb_count);
         acc.fused_frames += J.n_frames;
-        acc.launches += 4;
+        acc.fused = true;
+        acc.launches += 7;
     } else {
         fb_k0b_expand<<<J.n_frames, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, nullptr, nullptr);
         fb_launch_k2(P.ring, J, xg, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
@@ -445,12 +474,11 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         fb_launch_k3(P.ring, J, xg, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
                      d_fb, d_infos, nullptr, nullptr, J.n_frames, P.k3_smem, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
-        acc.launches += 3;
+        fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
+        fb_k4_gather<<<J.n_frames, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
+                                                 (const unsigned long long *)S.offsets.p, d_out, out_cap);
+        acc.launches += 5;
     }
-    fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
-    fb_k4_gather<<<J.n_frames, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
-                                             (const unsigned long long *)S.offsets.p, d_out, out_cap);
-    acc.launches += 2;
     FB_CUDA(ctx, cudaGetLastError());
     // device scalars (error flag, running total, fallback count) for the host
     FB_CUDA(ctx, cudaMemcpyAsync(S.pinned, S.scalars.p, 24, cudaMemcpyDeviceToHost, st));
@@ -475,8 +503,8 @@ void fb_store_timing(fb200_ctx *ctx, const Accum &acc, float total_ms, uint64_t 
     T.k_ingest_ms = acc.ms_k[0];
     T.k_analyze_ms = acc.ms_k[1];
     T.k_rice_ms = acc.ms_k[2];
-    T.k_pack_ms = acc.ms_k[3];
-    T.k_gather_ms = acc.ms_k[4];
+    T.k_pack_ms = acc.fused ? acc.ms_k[4] : acc.ms_k[3];
+    T.k_gather_ms = acc.fused ? acc.ms_k[3] : acc.ms_k[4];
     T.kernels_ms = acc.ms_k[0] + acc.ms_k[1] + acc.ms_k[2] + acc.ms_k[3] + acc.ms_k[4];
     T.d2h_ms = acc.ms_d2h;
     T.total_ms = total_ms;

@@ -25,6 +25,7 @@
 #define FB_DEV inline
 #include <math.h>
 struct int4 { int32_t x, y, z, w; };
+struct int2 { int32_t x, y; };
 static inline int32_t min(int32_t a, int32_t b) { return a < b ? a : b; }
 static inline int32_t max(int32_t a, int32_t b) { return a > b ? a : b; }
 struct float4 { float x, y, z, w; };

@@ -145,6 +145,7 @@ struct FbKfLayout {
     uint32_t words_bytes; // bytes of the frame word buffer
     uint32_t U_max, leaves_max;
     uint32_t crc_chunk;   // Lc
+    uint32_t debug_stop;  // experiments only: 1 = return after the analysis phase
     uint32_t total;
 };
 
@@ -187,6 +188,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.U_max = U;
     L.leaves_max = leaves;
     L.crc_chunk = fb_kf_crc_chunk(channels, bps, block_size, 32 * nvar);
+    L.debug_stop = 0;
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
     uint32_t o = 0;
     L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
@@ -819,12 +821,49 @@ FB_DEV void fb_bw_finish(FbBitW &r) {
 }
 
 // =====================================================================================================
-// KF body: one CTA (32 * nvar threads) per frame.  ktab: CRC tables built by fb_kf_build_ktab.
+// The fused path is two kernels, each one CTA (32 * nvar threads) per frame, so that all warps resident on an SM
+// run the same (smaller) code -- a single kernel with every phase inlined thrashed the instruction caches:
+//   KA  stage the channels, analyse every variant (one warp each), subframe + stereo decisions, frame header,
+//       bit offsets of all units; writes the frame's PLAN (header, subframe records, unit offsets) and its size
+//   KP  (after the scan of the frame sizes) stage the channels again, pack the frame from the plan into shared
+//       memory, CRC-16, and store it at its final offset of the output stream (no per-frame slot, no gather)
+// Frames KA cannot reproduce exactly are appended to the fallback list (plan state 1) and skipped by KP.
 // =====================================================================================================
+struct FbKfPlan {               // global, one per frame; the leading part mirrors FbKfFrame
+    FbKfSub sub[FB200_MAX_CHANNELS];
+    uint8_t header[16];
+    int32_t header_len, ch_tag;
+    uint32_t data_bytes;
+    uint32_t state;             // 0: planned by KA, 1: left to the generic kernels
+};
+
 template <int G>
-FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots, uint32_t *frame_bytes,
-                       fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab, uint32_t f,
-                       uint8_t *smem, const FbKfLayout &L) {
+FB_DEV void fb_kf_stage(const FbJob &J, const int32_t *xv, uint32_t f, int n, int32_t *xs, const FbKfLayout &L, int tid, int T) {
+    // quad i of every channel together: the rows of one frame are adjacent in xt (one 32-byte sector for stereo)
+    const int n4 = (n + 3) >> 2;
+    for (int i = tid; i < n4; i += T) {
+        for (int c = 0; c < J.channels; c++) {
+            const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
+            fb_copy16_async(xs + (size_t)c * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
+        }
+    }
+}
+
+FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *plan, uint32_t f) {
+#if FB_GPU
+    const uint32_t slot_i = atomicAdd(fb_count, 1u);
+#else
+    const uint32_t slot_i = (*fb_count)++;
+#endif
+    fb_list[slot_i] = f;
+    plan[f].state = 1;
+}
+
+// ---- KA: analysis and plan.  psubs: [frame][channels] chosen subframe records; poffs: [frame][channels][U_max+1]
+template <int G>
+FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *psubs,
+                       uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
+                       uint32_t *fb_count, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
     const int NW = J.nvar;
     const int T = 32 * NW;
     const int n = fb_frame_len(J, f);
@@ -832,37 +871,20 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     int32_t *xs = (int32_t *)(smem + L.off_x);
     fb200_subframe_info *choice = (fb200_subframe_info *)(smem + L.off_choice);
     FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
-    uint32_t *words = (uint32_t *)(smem + L.off_scratch);
-    uint8_t *slot = slots + (size_t)f * (size_t)J.slot_bytes;
 
     // units must start on multiples of 4 samples (16-byte window loads): frames whose finest partitions are not a
     // multiple of 4 long (odd tail frames, odd block sizes) are left to the generic kernels
     if ((g.leaf_len & 3) != 0) {
         FB_PHASE(tid, T)
-            if (tid == 0) {
-#if FB_GPU
-                const uint32_t slot_i = atomicAdd(fb_count, 1u);
-#else
-                const uint32_t slot_i = (*fb_count)++;
-#endif
-                fb_list[slot_i] = f;
-            }
+            if (tid == 0) fb_kf_to_fallback(fb_list, fb_count, plan, f);
         FB_PHASE_END
         return;
     }
 
-    // ---- stage the independent channels from the row-interleaved store xt (16-byte loads)
+    // ---- stage the independent channels from the row-interleaved store xt (16-byte asynchronous copies)
     FB_PHASE(tid, T)
-        const int n4 = (n + 3) >> 2;
-        // quad i of every channel together: the rows of one frame are adjacent in xt (one 32-byte sector for stereo)
-        for (int i = tid; i < n4; i += T) {
-            for (int c = 0; c < J.channels; c++) {
-                const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
-                fb_copy16_async(xs + (size_t)c * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
-            }
-        }
-        for (int i = tid; i < 1024; i += T) S->crc_tab[i] = ktab[i];
-        if (tid == 0) { S->frame_fail = 0; S->crc_acc = 0; S->crc_last = 0; }
+        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T);
+        if (tid == 0) S->frame_fail = 0;
         fb_copy_async_wait();
     FB_PHASE_END
 
@@ -872,26 +894,20 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
         const FbKfMisc *M = (const FbKfMisc *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_misc);
         FB_WPHASE(lane)
             if (lane == 0 && M->fail) S->frame_fail = 1; // benign race between warps
+            if (lane == 0) choice[w].reserved = (int32_t)ana[(size_t)f * (size_t)J.nvar + (size_t)w].max_abs;
         FB_WPHASE_END
     FB_WARPS_END
 
+    if (L.debug_stop == 1) return;
     if (S->frame_fail) {
         // not reproducible here: hand the frame to the literal kernels
         FB_PHASE(tid, T)
-            if (tid == 0) {
-#if FB_GPU
-                const uint32_t slot_i = atomicAdd(fb_count, 1u);
-#else
-                const uint32_t slot_i = (*fb_count)++;
-#endif
-                fb_list[slot_i] = f;
-            }
+            if (tid == 0) fb_kf_to_fallback(fb_list, fb_count, plan, f);
         FB_PHASE_END
         return;
     }
 
     // ---- stereo decision, header, subframe offsets (thread 0)
-    const uint32_t max_words = (fb_max_frame_bytes(J.channels, J.bps, J.block_size) + 3u) / 4u + 2u;
     FB_PHASE(tid, T)
         if (tid == 0) {
             int ch_tag = J.channels - 1;
@@ -929,8 +945,6 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             }
             S->data_bytes = (bit + 7u) >> 3;
         }
-        // the scratch of the analysis is dead from here on; the frame words alias it
-        for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
     FB_PHASE_END
 
     // ---- bit offsets of the units of every coded subframe: exclusive scan incl. the parameter fields
@@ -966,6 +980,88 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
         }
     FB_WARPS_END
 
+    // ---- the plan: header + subframe geometry, the chosen subframe records, the unit offsets, the frame size
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            S->frame_fail = 0; // doubles as plan state 0
+            frame_bytes[f] = S->data_bytes + 2u;
+        }
+        {
+            // FbKfPlan mirrors the head of FbKfFrame up to and including frame_fail (= state)
+            const uint32_t *src = (const uint32_t *)S;
+            uint32_t *dst = (uint32_t *)&plan[f];
+            for (int i = tid; i < (int)(sizeof(FbKfPlan) / 4); i += T) dst[i] = src[i];
+        }
+        for (int c = 0; c < J.channels; c++) {
+            const FbKfSub &D = S->sub[c];
+            const uint32_t *src = (const uint32_t *)&choice[D.variant];
+            uint32_t *dst = (uint32_t *)&psubs[(size_t)f * (size_t)J.channels + (size_t)c];
+            for (int i = tid; i < (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = src[i];
+            if (D.type == FB200_SF_FIXED || D.type == FB200_SF_LPC) {
+                const uint32_t *ub = (const uint32_t *)(smem + L.off_keep + (uint32_t)D.variant * L.keep_bytes + L.k_unit_bits) +
+                                     (size_t)D.cand * (L.U_max + 1);
+                uint32_t *po = poffs + ((size_t)f * (size_t)J.channels + (size_t)c) * (L.U_max + 1);
+                for (int i = tid; i <= g.U; i += T) po[i] = ub[i];
+            }
+        }
+        if (infos) {
+            fb200_frame_info &I = infos[f];
+            if (tid == 0) {
+                I.channel_assignment = S->ch_tag;
+                I.block_size = n;
+                I.frame_number = J.first_frame_number + f;
+                I.frame_bytes = S->data_bytes + 2u;
+            }
+            for (int c = 0; c < J.channels; c++) {
+                const uint32_t *src = (const uint32_t *)&choice[S->sub[c].variant];
+                uint32_t *dst = (uint32_t *)&I.sub[c];
+                // word 7 is `reserved`: the block size, like the generic kernels (internally it carries max |x|)
+                for (int i = tid; i < (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = i == 7 ? (uint32_t)n : src[i];
+            }
+        }
+    FB_PHASE_END
+}
+
+// ---- KP: pack a planned frame and store it at out + offsets[f]
+template <int G>
+FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, const fb200_subframe_info *psubs,
+                       const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out, unsigned long long out_cap,
+                       const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
+    const int NW = J.nvar;
+    const int T = 32 * NW;
+    if (plan[f].state != 0) return; // the generic kernels own this frame
+    const int n = fb_frame_len(J, f);
+    const FbKfGeom g = fb_kf_geom(n);
+    int32_t *xs = (int32_t *)(smem + L.off_x);
+    FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
+    fb200_subframe_info *psub = (fb200_subframe_info *)(smem + L.off_choice);   // [channels]
+    uint32_t *poff = (uint32_t *)(smem + L.off_keep);                           // [channels][U_max + 1]
+    uint32_t *words = (uint32_t *)(smem + L.off_scratch);
+    const uint32_t max_words = (fb_max_frame_bytes(J.channels, J.bps, J.block_size) + 3u) / 4u + 2u;
+
+    // ---- stage the channels, the plan, the CRC tables; clear the word buffer
+    FB_PHASE(tid, T)
+        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T);
+        {
+            const uint32_t *src = (const uint32_t *)&plan[f];
+            uint32_t *dst = (uint32_t *)S;
+            for (int i = tid; i < (int)(sizeof(FbKfPlan) / 4); i += T) dst[i] = src[i];
+        }
+        {
+            const uint32_t *src = (const uint32_t *)&psubs[(size_t)f * (size_t)J.channels];
+            uint32_t *dst = (uint32_t *)psub;
+            for (int i = tid; i < J.channels * (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = src[i];
+        }
+        {
+            const uint32_t *src = poffs + (size_t)f * (size_t)J.channels * (L.U_max + 1);
+            for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) poff[i] = src[i];
+        }
+        for (int i = tid; i < 1024; i += T) S->crc_tab[i] = ktab[i];
+        for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
+        if (tid == 0) { S->crc_acc = 0; S->crc_last = 0; }
+        fb_copy_async_wait();
+    FB_PHASE_END
+
     // ---- frame header, subframe heads, and the samples of every unit
     FB_PHASE(tid, T)
         if (tid == 0) {
@@ -982,7 +1078,7 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
 #define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, (t)))
         if (tid < J.channels) {
             const FbKfSub &D = S->sub[tid];
-            const fb200_subframe_info &V = choice[D.variant];
+            const fb200_subframe_info &V = psub[tid];
             int vm = 0;
             const int32_t *xa = xs + (size_t)D.variant * L.x_stride, *xb = xa;
             if (J.channels == 2 && D.variant >= 2) { vm = D.variant; xa = xs; xb = xs + L.x_stride; }
@@ -1034,9 +1130,8 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 continue;
             }
             // Residual::write (src/component/bitrepr.rs:550-597)
-            const fb200_subframe_info &V = choice[D.variant];
-            const uint32_t *ub = (const uint32_t *)(smem + L.off_keep + (uint32_t)D.variant * L.keep_bytes + L.k_unit_bits) +
-                                 (size_t)D.cand * (L.U_max + 1);
+            const fb200_subframe_info &V = psub[c];
+            const uint32_t *ub = poff + (size_t)c * (L.U_max + 1);
             const uint32_t p0 = D.code_bit + ub[unit], p1 = D.code_bit + ub[unit + 1];
             if (p1 == p0) continue;
             const int ush = g.lgU - D.part_order;
@@ -1058,7 +1153,7 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 sumabs += (unsigned long long)(qq[j] < 0 ? -qq[j] : qq[j]);
             }
             cd.narrow = cd.kind == 0 ||
-                        (unsigned long long)ana[(size_t)f * (size_t)J.nvar + (size_t)D.variant].max_abs * sumabs < 0x7FFFFFFFull;
+                        (unsigned long long)(uint32_t)V.reserved * sumabs < 0x7FFFFFFFull; // reserved: max |x| of the variant
             const uint32_t rmask = (1u << rp) - 1u, rone = 1u << rp;
             if (tb > lo) {
                 int32_t win[G + FB_KF_RUN];
@@ -1130,31 +1225,31 @@ FB_DEV void fb_kf_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 const uint32_t byte = (crc >> (8 * (1 - i))) & 0xFFu;
                 fb_atomic_or(&words[pos >> 2], byte << (24u - 8u * (pos & 3u)));
             }
-            frame_bytes[f] = B + 2u;
-            if (infos) {
-                fb200_frame_info &I = infos[f];
-                I.channel_assignment = S->ch_tag;
-                I.block_size = n;
-                I.frame_number = J.first_frame_number + f;
-                I.frame_bytes = B + 2u;
-            }
-        }
-        if (infos) {
-            fb200_frame_info &I = infos[f];
-            for (int c = 0; c < J.channels; c++) {
-                const uint8_t *src = (const uint8_t *)&choice[S->sub[c].variant];
-                uint8_t *dst = (uint8_t *)&I.sub[c];
-                for (int i = tid; i < (int)sizeof(fb200_subframe_info); i += T) dst[i] = src[i];
-            }
         }
     FB_PHASE_END
-    // ---- store: big-endian words -> bytes of the slot
+    // ---- store: the frame's bytes (big-endian words in shared memory) at out + offsets[f].  Head bytes up to the first
+    // 4-byte aligned destination address, whole words assembled from two shared-memory words, tail bytes.
     FB_PHASE(tid, T)
-        const uint32_t nwords = (B + 2u + 3u) / 4u;
-        uint32_t *dstw = (uint32_t *)slot;
-        for (uint32_t w = (uint32_t)tid; w < nwords; w += (uint32_t)T) {
-            const uint32_t v = words[w];
-            dstw[w] = ((v & 0xFFu) << 24) | ((v & 0xFF00u) << 8) | ((v >> 8) & 0xFF00u) | (v >> 24);
+        const uint32_t len = B + 2u;
+        const unsigned long long o = offsets[f];
+        if (o + len <= out_cap) { // a capacity error is reported by the host from the total
+            uint8_t *dst = out + o;
+            uint32_t head = (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u);
+            if (head > len) head = len;
+            const uint32_t nw = (len - head) >> 2;
+            if ((uint32_t)tid < head) dst[tid] = (uint8_t)(words[0] >> (24u - 8u * (uint32_t)tid));
+            uint32_t *dstw = (uint32_t *)(dst + head);
+            const uint32_t sh = head * 8u; // head <= 3: stream word k starts at byte head + 4k
+            for (uint32_t k = (uint32_t)tid; k < nw; k += (uint32_t)T) {
+                uint32_t v = words[k];
+                if (sh) v = (v << sh) | (words[k + 1] >> (32u - sh));
+                dstw[k] = ((v & 0xFFu) << 24) | ((v & 0xFF00u) << 8) | ((v >> 8) & 0xFF00u) | (v >> 24);
+            }
+            const uint32_t done = head + 4u * nw;
+            if ((uint32_t)tid < len - done) {
+                const uint32_t p = done + (uint32_t)tid;
+                dst[p] = (uint8_t)(words[p >> 2] >> (24u - 8u * (p & 3u)));
+            }
         }
     FB_PHASE_END
 }

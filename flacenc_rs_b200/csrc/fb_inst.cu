@@ -53,13 +53,21 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
     }
 }
 
-// fused per-frame kernel (fb_fused.cuh): one CTA of 32 * nvar threads per frame
-__global__ void __launch_bounds__(256) FB_NAME(fb_kf_frame_g)(FbJob J, const int32_t *xv, const FbAnalysis *ana,
-                                                              uint8_t *slots, uint32_t *frame_bytes,
-                                                              fb200_frame_info *infos, uint32_t *fb_list,
-                                                              uint32_t *fb_count, const uint32_t *ktab, FbKfLayout L) {
+// fused path (fb_fused.cuh), one CTA of 32 * nvar threads per frame: KA = analysis + plan, KP = pack + store
+__global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int32_t *xt, const FbAnalysis *ana, FbKfPlan *plan,
+                                                             fb200_subframe_info *psubs, uint32_t *poffs,
+                                                             uint32_t *frame_bytes, fb200_frame_info *infos,
+                                                             uint32_t *fb_list, uint32_t *fb_count, FbKfLayout L) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_kf_body<FB_INST_G>(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
+    fb_ka_body<FB_INST_G>(J, xt, ana, plan, psubs, poffs, frame_bytes, infos, fb_list, fb_count, blockIdx.x, fb_smem, L);
+}
+
+__global__ void __launch_bounds__(256) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const FbKfPlan *plan,
+                                                             const fb200_subframe_info *psubs, const uint32_t *poffs,
+                                                             const unsigned long long *offsets, uint8_t *out,
+                                                             unsigned long long out_cap, const uint32_t *ktab, FbKfLayout L) {
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    fb_kp_body<FB_INST_G>(J, xt, plan, psubs, poffs, offsets, out, out_cap, ktab, blockIdx.x, fb_smem, L);
 }
 
 void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
@@ -80,11 +88,18 @@ void FB_NAME(fb_launch_k3_g)(const FbJob &J, const int32_t *xv, const fb200_subf
     FB_NAME(fb_k3_pack_g)<<<grid, FB_K3_THREADS, smem, st>>>(J, xv, choice, slots, frame_bytes, infos, list, count);
 }
 
-void FB_NAME(fb_launch_kf_g)(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots, uint32_t *frame_bytes,
-                             fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,
-                             const FbKfLayout &L, cudaStream_t st) {
-    FB_NAME(fb_kf_frame_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xv, ana, slots, frame_bytes, infos, fb_list,
-                                                                      fb_count, ktab, L);
+void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan, fb200_subframe_info *psubs,
+                             uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
+                             uint32_t *fb_count, const FbKfLayout &L, cudaStream_t st) {
+    FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, ana, (FbKfPlan *)plan, psubs, poffs, frame_bytes,
+                                                                     infos, fb_list, fb_count, L);
+}
+
+void FB_NAME(fb_launch_kp_g)(const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,
+                             const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,
+                             unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
+    FB_NAME(fb_kp_pack_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, (const FbKfPlan *)plan, psubs, poffs, offsets, out,
+                                                                     out_cap, ktab, L);
 }
 
 cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {
@@ -93,8 +108,11 @@ cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {
         return cudaFuncSetAttribute(FB_NAME(fb_k2_rice_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     case FB_KERNEL_K3:
         return cudaFuncSetAttribute(FB_NAME(fb_k3_pack_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    case FB_KERNEL_KF:
-        return cudaFuncSetAttribute(FB_NAME(fb_kf_frame_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case FB_KERNEL_KF: {
+        cudaError_t e = cudaFuncSetAttribute(FB_NAME(fb_ka_plan_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(FB_NAME(fb_kp_pack_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    }
     default:
         return cudaErrorInvalidValue;
     }

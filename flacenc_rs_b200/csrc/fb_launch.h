@@ -18,9 +18,13 @@ enum { FB_KERNEL_K2 = 2, FB_KERNEL_K3 = 3, FB_KERNEL_KF = 5 };
     void fb_launch_k3_g##G(const FbJob &J, const int32_t *xv, const fb200_subframe_info *choice, uint8_t *slots,      \
                            uint32_t *frame_bytes, fb200_frame_info *infos, const uint32_t *list,                     \
                            const uint32_t *count, uint32_t grid, size_t smem, cudaStream_t st);                      \
-    void fb_launch_kf_g##G(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots,                  \
-                           uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count,    \
-                           const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st);                                                    \
+    void fb_launch_ka_g##G(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan,                     \
+                           fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes,                      \
+                           fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const FbKfLayout &L,     \
+                           cudaStream_t st);                                                                        \
+    void fb_launch_kp_g##G(const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,    \
+                           const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,                  \
+                           unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st); \
     cudaError_t fb_set_smem_g##G(int kernel, int bytes);
 
 FB_DECLARE_LAUNCHERS(4)
@@ -62,10 +66,17 @@ static inline void fb_launch_k3(int ring, const FbJob &J, const int32_t *xv, con
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }
-static inline void fb_launch_kf(int ring, const FbJob &J, const int32_t *xv, const FbAnalysis *ana, uint8_t *slots,
-                                uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count,
-                                const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-#define FB_CALL(G) fb_launch_kf_g##G(J, xv, ana, slots, frame_bytes, infos, fb_list, fb_count, ktab, L, st)
+static inline void fb_launch_ka(int ring, const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan,
+                                fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos,
+                                uint32_t *fb_list, uint32_t *fb_count, const FbKfLayout &L, cudaStream_t st) {
+#define FB_CALL(G) fb_launch_ka_g##G(J, xt, ana, plan, psubs, poffs, frame_bytes, infos, fb_list, fb_count, L, st)
+    FB_FOR_G(ring, FB_CALL)
+#undef FB_CALL
+}
+static inline void fb_launch_kp(int ring, const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,
+                                const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,
+                                unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
+#define FB_CALL(G) fb_launch_kp_g##G(J, xt, plan, psubs, poffs, offsets, out, out_cap, ktab, L, st)
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }

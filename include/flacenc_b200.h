@@ -107,8 +107,9 @@ typedef struct fb200_ctx fb200_ctx;
 /* Timing of the last encode call on a context, in milliseconds (CUDA events on the context's stream). */
 typedef struct fb200_timing {
     float h2d_ms, kernels_ms, d2h_ms, total_ms;
-    /* k_rice_ms: fused kernel (Rice search + assembly) or generic Rice search; k_pack_ms: generic assembly
-     * (all frames, or only the fused kernel's fallback list) */
+    /* fused path: k_rice_ms = analysis/plan kernel, k_pack_ms = pack kernel (+ gather of listed frames),
+     * k_gather_ms = generic kernels over the fallback list + scan of the frame sizes;
+     * generic path: k_rice_ms = Rice search, k_pack_ms = frame assembly, k_gather_ms = scan + gather */
     float k_ingest_ms, k_analyze_ms, k_rice_ms, k_pack_ms, k_gather_ms;
     uint64_t launches;            /* kernels launched by the call */
     uint64_t in_bytes, out_bytes; /* PCM bytes consumed / frame bytes produced */

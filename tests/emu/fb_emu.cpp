@@ -45,6 +45,7 @@ struct EmuBuffers {
     std::vector<uint32_t> frame_bytes;
     std::vector<unsigned long long> offsets;
     std::vector<fb200_frame_info> infos;
+    std::vector<uint8_t> stream; // contiguous frame bytes (offsets[n_frames] of them)
 };
 
 static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *planar, int planar_stride,
@@ -94,24 +95,29 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     std::vector<uint32_t> todo;
     FbKfLayout KL;
     const bool fused = !fb_emu_force_generic && fbh_fused_ok(J, J.tail_n, &KL);
+    std::vector<FbKfPlan> plan;
+    std::vector<fb200_subframe_info> psubs;
+    std::vector<uint32_t> poffs;
     if (fused) {
         std::vector<uint32_t> list(J.n_frames + 1, 0);
         uint32_t count = 0;
         std::vector<uint8_t> smem(KL.total + 64);
-        std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
-        fb_kf_build_ktab(KL.crc_chunk, ktab.data());
+        plan.resize(J.n_frames);
+        memset(plan.data(), 0xEE, plan.size() * sizeof(FbKfPlan));
+        psubs.resize((size_t)J.n_frames * J.channels);
+        poffs.assign((size_t)J.n_frames * J.channels * (KL.U_max + 1), 0xDDDDDDDDu);
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KF(GG) fb_kf_body<GG>(J, B.xv.data(), B.ana.data(), B.slots.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab.data(), f, smem.data(), KL)
+#define EMU_KA(GG) fb_ka_body<GG>(J, B.xv.data(), B.ana.data(), plan.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, f, smem.data(), KL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
-            case 4: EMU_KF(4); break;
-            case 8: EMU_KF(8); break;
-            case 12: EMU_KF(12); break;
-            case 16: EMU_KF(16); break;
-            case 20: EMU_KF(20); break;
-            default: EMU_KF(24); break;
+            case 4: EMU_KA(4); break;
+            case 8: EMU_KA(8); break;
+            case 12: EMU_KA(12); break;
+            case 16: EMU_KA(16); break;
+            case 20: EMU_KA(20); break;
+            default: EMU_KA(24); break;
             }
-#undef EMU_KF
+#undef EMU_KA
         }
         todo.assign(list.begin(), list.begin() + count);
         fb_emu_fused_frames += J.n_frames - count;
@@ -166,6 +172,31 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<unsigned long long> partials(FB_K4_THREADS);
         fb_k4_scan_body(B.frame_bytes.data(), B.offsets.data(), J.n_frames, partials.data());
     }
+    // the output stream: KP packs the planned frames in place; the others are gathered from their slots
+    const unsigned long long total = B.offsets[J.n_frames];
+    B.stream.assign((size_t)total + 16, 0x77);
+    if (fused) {
+        std::vector<uint8_t> smem(KL.total + 64);
+        std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
+        fb_kf_build_ktab(KL.crc_chunk, ktab.data());
+        for (uint32_t f = 0; f < J.n_frames; f++) {
+            memset(smem.data(), 0xAB, smem.size());
+#define EMU_KP(GG) fb_kp_body<GG>(J, B.xv.data(), plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KL)
+            switch (fb_k1_ring(J.cfg.lpc_order)) {
+            case 4: EMU_KP(4); break;
+            case 8: EMU_KP(8); break;
+            case 12: EMU_KP(12); break;
+            case 16: EMU_KP(16); break;
+            case 20: EMU_KP(20); break;
+            default: EMU_KP(24); break;
+            }
+#undef EMU_KP
+        }
+    }
+    for (uint32_t f : todo)
+        for (int tid = 0; tid < 256; tid++)
+            fb_k4_gather_thread(B.slots.data(), J.slot_bytes, B.frame_bytes.data(), B.offsets.data(), B.stream.data(), total, f,
+                                tid, 256);
     return FB200_OK;
 }
 
@@ -187,10 +218,7 @@ int fbemu_encode_interleaved(const fb200_config *cfg, const void *pcm, int conta
     unsigned long long total = B.offsets[J.n_frames];
     if (out_len) *out_len = (size_t)total;
     if (total > out_cap) return FB200_ERR_CAPACITY;
-    for (uint32_t f = 0; f < J.n_frames; f++)
-        for (int tid = 0; tid < 256; tid++)
-            fb_k4_gather_thread(B.slots.data(), J.slot_bytes, B.frame_bytes.data(), B.offsets.data(), out, out_cap, f,
-                                tid, 256);
+    memcpy(out, B.stream.data(), (size_t)total);
     if (frame_sizes) memcpy(frame_sizes, B.frame_bytes.data(), sizeof(uint32_t) * J.n_frames);
     if (infos) memcpy(infos, B.infos.data(), sizeof(fb200_frame_info) * J.n_frames);
     return FB200_OK;
@@ -209,7 +237,7 @@ int fbemu_encode_planar_frame(const fb200_config *cfg, const int32_t *planar, in
     unsigned long long total = B.offsets[1];
     if (out_len) *out_len = (size_t)total;
     if (total > out_cap) return FB200_ERR_CAPACITY;
-    memcpy(out, B.slots.data(), (size_t)total);
+    memcpy(out, B.stream.data(), (size_t)total);
     if (info) *info = B.infos[0];
     return FB200_OK;
 }
