@@ -296,7 +296,7 @@ struct Plan {
     uint32_t mb = 0;
     const float *d_win_tail = nullptr;
     FbK2Layout L;
-    FbKfLayout KL;
+    FbKfLayout KL, KPL; // shared-memory layouts of the plan kernel and of the pack kernel
     size_t k2_smem = 0, k3_smem = 0;
     bool fused = false;
 };
@@ -350,6 +350,8 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         return FB200_ERR_CUDA;
     }
     P.fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, P.tail_n, &P.KL);
+    P.KPL = fb_kp_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n);
+    if (getenv("FB200_KP_X32")) P.KPL = P.KL; // experiments: pack kernel on the plan kernel's int32 layout
     if (getenv("FB200_KF_SMEM_PAD")) P.KL.total += (uint32_t)atoi(getenv("FB200_KF_SMEM_PAD")); // occupancy experiments
     if (getenv("FB200_KF_DEBUG_STOP")) P.KL.debug_stop = (uint32_t)atoi(getenv("FB200_KF_DEBUG_STOP"));
     if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
@@ -459,7 +461,7 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
         fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, S.plan.p, (const fb200_subframe_info *)S.psubs.p,
                      (const uint32_t *)S.poffs.p, (const unsigned long long *)S.offsets.p, d_out, out_cap,
-                     (const uint32_t *)ctx->ktab.p, P.KL, st);
+                     (const uint32_t *)ctx->ktab.p, P.KPL, st);
         fb_k4_gather_list<<<148, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
                                                (const unsigned long long *)S.offsets.p, d_out, out_cap,
                                                (const uint32_t *)S.fb_list.p, d_fb_count);

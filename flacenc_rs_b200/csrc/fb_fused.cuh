@@ -100,6 +100,10 @@ FB_HD void fb_kf_unit_range(const FbKfGeom &g, int u, int *t0, int *t1) {
 // index of sample t in a staged plane: 4 pad words per 64 samples keep 16-byte loads of lanes that are
 // 64 samples apart on different banks
 FB_HD int fb_xidx(int t) { return t + ((t >> 6) << 2); }
+// A kernel may stage streams of at most 16 bits per sample as int16 (half the shared memory, more CTAs per SM);
+// fb_xidx is then a halfword index (8 pad bytes per 64 samples keep the 8-byte loads conflict-free).  The flag
+// travels in bit 2 of the variant mode `vm`.
+#define FB_VM_X16 4
 
 // ---- CRC-16 tables (poly 0x8005, init 0, MSB first; src/component/bitrepr.rs:40,270-271) ------------
 // Built on the host once per context and read by the kernel:
@@ -132,7 +136,8 @@ inline void fb_kf_build_ktab(uint32_t Lc, uint32_t *t) {
 
 // ---- shared-memory layout (bytes), identical on host and device ---------------------------------
 struct FbKfLayout {
-    uint32_t x_stride;   // words per staged plane
+    uint32_t x_stride;   // 32-bit words per staged plane
+    uint32_t x16;        // planes hold int16 samples
     uint32_t off_x;      // channels planes
     uint32_t off_keep;   // per warp: unit_bits[2][U+1], xch[64], results
     uint32_t keep_bytes;
@@ -175,7 +180,6 @@ struct FbKfFrame {
     uint32_t frame_fail;
     int32_t  cand[FB200_MAX_CHANNELS]; // per variant: result set of the chosen coding (0 fixed, 1 lpc)
     uint32_t crc_acc, crc_last;
-    uint32_t crc_tab[1024];
 };
 
 FB_HD uint32_t fb_align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -189,6 +193,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.leaves_max = leaves;
     L.crc_chunk = fb_kf_crc_chunk(channels, bps, block_size, 32 * nvar);
     L.debug_stop = 0;
+    L.x16 = 0;
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
     uint32_t o = 0;
     L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
@@ -216,6 +221,22 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.words_bytes = fb_align16(((fb_max_frame_bytes(channels, bps, block_size) + 3u) & ~3u) + 16u);
     const uint32_t scratch_total = (uint32_t)nvar * s;
     L.off_scratch = o;  o += scratch_total > L.words_bytes ? scratch_total : L.words_bytes;
+    L.total = o;
+    return L;
+}
+
+// Shared memory of the pack kernel KP: planes (int16 when the stream has at most 16 bits per sample), the frame's
+// plan, the chosen subframe records, the unit offsets and the frame's word buffer.  Returned in the same struct.
+FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, int tail_n) {
+    FbKfLayout L = fb_kf_layout(channels, nvar, bps, block_size, tail_n);
+    L.x16 = bps <= 16 ? 1u : 0u;
+    if (L.x16) L.x_stride = ((L.x_stride + 1u) / 2u + 3u) & ~3u;
+    uint32_t o = 0;
+    L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
+    L.off_keep = o;     o += fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u);   // unit offsets
+    L.off_choice = o;   o += fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info));
+    L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
+    L.off_scratch = o;  o += L.words_bytes;                                            // frame words
     L.total = o;
     return L;
 }
@@ -343,24 +364,43 @@ FB_DEV int fb_kf_pstart(unsigned long long s0, int cnt, int max_p) {
 // four samples t..t+3 (t a multiple of 4, inside the plane incl. its slack)
 FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
     const int o = fb_xidx(t);
-    const int4 a = *reinterpret_cast<const int4 *>(xa + o);
-    if (vm < 2) {
-        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
-    } else {
-        const int4 b = *reinterpret_cast<const int4 *>(xb + o);
-        if (vm == 2) {
-            dst[0] = fb_mid(a.x, b.x); dst[1] = fb_mid(a.y, b.y); dst[2] = fb_mid(a.z, b.z); dst[3] = fb_mid(a.w, b.w);
-        } else {
-            dst[0] = fb_side(a.x, b.x); dst[1] = fb_side(a.y, b.y); dst[2] = fb_side(a.z, b.z); dst[3] = fb_side(a.w, b.w);
+    int32_t a[4], b[4];
+    if (vm & FB_VM_X16) {
+        const int2 wa = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xa) + o);
+        a[0] = (int32_t)(int16_t)(uint32_t)wa.x; a[1] = wa.x >> 16; a[2] = (int32_t)(int16_t)(uint32_t)wa.y; a[3] = wa.y >> 16;
+        if (vm & 2) {
+            const int2 wb = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xb) + o);
+            b[0] = (int32_t)(int16_t)(uint32_t)wb.x; b[1] = wb.x >> 16; b[2] = (int32_t)(int16_t)(uint32_t)wb.y; b[3] = wb.y >> 16;
         }
+    } else {
+        const int4 wa = *reinterpret_cast<const int4 *>(xa + o);
+        a[0] = wa.x; a[1] = wa.y; a[2] = wa.z; a[3] = wa.w;
+        if (vm & 2) {
+            const int4 wb = *reinterpret_cast<const int4 *>(xb + o);
+            b[0] = wb.x; b[1] = wb.y; b[2] = wb.z; b[3] = wb.w;
+        }
+    }
+    if (!(vm & 2)) {
+        dst[0] = a[0]; dst[1] = a[1]; dst[2] = a[2]; dst[3] = a[3];
+    } else if ((vm & 3) == 2) {
+        dst[0] = fb_mid(a[0], b[0]); dst[1] = fb_mid(a[1], b[1]); dst[2] = fb_mid(a[2], b[2]); dst[3] = fb_mid(a[3], b[3]);
+    } else {
+        dst[0] = fb_side(a[0], b[0]); dst[1] = fb_side(a[1], b[1]); dst[2] = fb_side(a[2], b[2]); dst[3] = fb_side(a[3], b[3]);
     }
 }
 
 FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
     const int o = fb_xidx(t);
-    const int32_t a = xa[o];
-    if (vm < 2) return a;
-    return vm == 2 ? fb_mid(a, xb[o]) : fb_side(a, xb[o]);
+    int32_t a, b = 0;
+    if (vm & FB_VM_X16) {
+        a = reinterpret_cast<const int16_t *>(xa)[o];
+        if (vm & 2) b = reinterpret_cast<const int16_t *>(xb)[o];
+    } else {
+        a = xa[o];
+        if (vm & 2) b = xb[o];
+    }
+    if (!(vm & 2)) return a;
+    return (vm & 3) == 2 ? fb_mid(a, b) : fb_side(a, b);
 }
 
 // win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4)
@@ -679,9 +719,9 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     const int bps_v = fb_variant_bps(J, v);
     const unsigned long long verbatim_bits = 8ull + (unsigned long long)n * (unsigned long long)bps_v;
     // sample planes of this variant
-    int vm = 0;
+    int vm = L.x16 ? FB_VM_X16 : 0;
     const int32_t *xa = xs + (size_t)v * L.x_stride, *xb = xa;
-    if (J.channels == 2 && v >= 2) { vm = v; xa = xs; xb = xs + L.x_stride; }
+    if (J.channels == 2 && v >= 2) { vm |= v; xa = xs; xb = xs + L.x_stride; }
 
     FB_WPHASE(lane)
         if (lane == 0) {
@@ -766,6 +806,16 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     FB_WPHASE_END
 }
 
+// ORs the k (1..32) low bits of v (v < 2^k) into the MSB-first bit stream at bit position pos.  The buffer is
+// zero-initialised and every bit is written once, so concurrent writers only ever share words, never bits.
+FB_DEV void fb_or_bits(uint32_t *words, uint32_t pos, uint32_t v, uint32_t k) {
+    const uint32_t o = pos & 31u;
+    const unsigned long long w = (unsigned long long)v << (64u - o - k);
+    fb_atomic_or(&words[pos >> 5], (uint32_t)(w >> 32));
+    const uint32_t lo = (uint32_t)w;
+    if (lo) fb_atomic_or(&words[(pos >> 5) + 1u], lo);
+}
+
 // ---- MSB-first bit writer with a 64-bit accumulator (src/bitsink.rs semantics) ----------------------
 // A writer owns the bit range [pos_start, pos_end) of the zero-initialised word buffer; only its first and
 // last word can be shared with a neighbour (atomic OR), interior words are stored plainly.
@@ -841,10 +891,24 @@ template <int G>
 FB_DEV void fb_kf_stage(const FbJob &J, const int32_t *xv, uint32_t f, int n, int32_t *xs, const FbKfLayout &L, int tid, int T) {
     // quad i of every channel together: the rows of one frame are adjacent in xt (one 32-byte sector for stereo)
     const int n4 = (n + 3) >> 2;
-    for (int i = tid; i < n4; i += T) {
-        for (int c = 0; c < J.channels; c++) {
-            const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
-            fb_copy16_async(xs + (size_t)c * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
+    if (L.x16) {
+#pragma unroll 4
+        for (int i = tid; i < n4; i += T) {
+            for (int c = 0; c < J.channels; c++) {
+                const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
+                const int4 v = *reinterpret_cast<const int4 *>(src + fb_xt_quad(4 * i));
+                int2 w;
+                w.x = (int32_t)(((uint32_t)v.x & 0xFFFFu) | ((uint32_t)v.y << 16));
+                w.y = (int32_t)(((uint32_t)v.z & 0xFFFFu) | ((uint32_t)v.w << 16));
+                *reinterpret_cast<int2 *>(reinterpret_cast<int16_t *>(xs + (size_t)c * L.x_stride) + fb_xidx(4 * i)) = w;
+            }
+        }
+    } else {
+        for (int i = tid; i < n4; i += T) {
+            for (int c = 0; c < J.channels; c++) {
+                const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
+                fb_copy16_async(xs + (size_t)c * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
+            }
         }
     }
 }
@@ -1056,7 +1120,6 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             const uint32_t *src = poffs + (size_t)f * (size_t)J.channels * (L.U_max + 1);
             for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) poff[i] = src[i];
         }
-        for (int i = tid; i < 1024; i += T) S->crc_tab[i] = ktab[i];
         for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
         if (tid == 0) { S->crc_acc = 0; S->crc_last = 0; }
         fb_copy_async_wait();
@@ -1079,9 +1142,9 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
         if (tid < J.channels) {
             const FbKfSub &D = S->sub[tid];
             const fb200_subframe_info &V = psub[tid];
-            int vm = 0;
+            int vm = L.x16 ? FB_VM_X16 : 0;
             const int32_t *xa = xs + (size_t)D.variant * L.x_stride, *xb = xa;
-            if (J.channels == 2 && D.variant >= 2) { vm = D.variant; xa = xs; xb = xs + L.x_stride; }
+            if (J.channels == 2 && D.variant >= 2) { vm |= D.variant; xa = xs; xb = xs + L.x_stride; }
             FbBitRun r;
             fb_run_init(r, words, D.start_bit, D.start_bit + 1);
             r.w_last = 0xFFFFFFFFu;
@@ -1115,9 +1178,9 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             if (D.type == FB200_SF_CONSTANT) continue;
             int ta, tb;
             fb_kf_unit_range(g, unit, &ta, &tb);
-            int vm = 0;
+            int vm = L.x16 ? FB_VM_X16 : 0;
             const int32_t *xa = xs + (size_t)D.variant * L.x_stride, *xb = xa;
-            if (J.channels == 2 && D.variant >= 2) { vm = D.variant; xa = xs; xb = xs + L.x_stride; }
+            if (J.channels == 2 && D.variant >= 2) { vm |= D.variant; xa = xs; xb = xs + L.x_stride; }
             if (D.type == FB200_SF_VERBATIM) {
                 // Verbatim::write (src/component/bitrepr.rs:463-470): bps bits per sample at fixed positions
                 if (tb <= ta) continue;
@@ -1136,9 +1199,15 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             if (p1 == p0) continue;
             const int ush = g.lgU - D.part_order;
             const uint32_t rp = V.rice_params[unit >> ush];
-            FbBitW r;
-            fb_bw_init(r, words, p0, p1);
-            if ((unit & ((1 << ush) - 1)) == 0) fb_bw_put(r, rp, D.rice2 ? 5u : 4u);
+            // Every code is OR-ed into the zero-initialised word buffer on its own: the q leading zeros need no
+            // write, the (p + 1)-bit tail "1 rrr" lands at bit position pos + q, and pos advances by q + p + 1.
+            // Only the running position is sequential; the writes of a run are independent of one another.
+            uint32_t pos = p0;
+            if ((unit & ((1 << ush) - 1)) == 0) {
+                const uint32_t pbits = D.rice2 ? 5u : 4u;
+                fb_or_bits(words, pos, rp, pbits);
+                pos += pbits;
+            }
             const int warm = D.order;
             const int lo = ta > warm ? ta : warm;
             FbKfCand cd;
@@ -1166,17 +1235,14 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
                     for (int i = 0; i < FB_KF_RUN; i++) {
                         const int t = t0 + i;
                         if (t >= lo && t < tb) {
-                            // q zeros, a one, then the p low bits: one field when it fits in 32 bits
-                            const uint32_t q = uu[i] >> rp, code = (uu[i] & rmask) | rone;
-                            uint32_t len = q + rp + 1u;
-                            if (len > 32u) { fb_bw_skip(r, q); len = rp + 1u; }
-                            fb_bw_put(r, code, len);
+                            const uint32_t q = uu[i] >> rp;
+                            fb_or_bits(words, pos + q, (uu[i] & rmask) | rone, rp + 1u);
+                            pos += q + rp + 1u;
                         }
                     }
                     fb_kf_slide<G>(win);
                 }
             }
-            fb_bw_finish(r);
         }
 #undef FB_KF_X
     FB_PHASE_END
@@ -1196,12 +1262,12 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             uint32_t i = b0;
             for (; i + 4u <= b1; i += 4u) { // b0 is a multiple of 4: whole big-endian words
                 const uint32_t w = words[i >> 2];
-                crc = S->crc_tab[768 + (((crc >> 8) ^ (w >> 24)) & 0xFFu)] ^ S->crc_tab[512 + ((crc ^ (w >> 16)) & 0xFFu)] ^
-                      S->crc_tab[256 + ((w >> 8) & 0xFFu)] ^ S->crc_tab[w & 0xFFu];
+                crc = ktab[768 + (((crc >> 8) ^ (w >> 24)) & 0xFFu)] ^ ktab[512 + ((crc ^ (w >> 16)) & 0xFFu)] ^
+                      ktab[256 + ((w >> 8) & 0xFFu)] ^ ktab[w & 0xFFu];
             }
             for (; i < b1; i++) {
                 const uint32_t byte = (words[i >> 2] >> (24u - 8u * (i & 3u))) & 0xFFu;
-                crc = ((crc << 8) & 0xFFFFu) ^ S->crc_tab[((crc >> 8) ^ byte) & 0xFFu];
+                crc = ((crc << 8) & 0xFFFFu) ^ ktab[((crc >> 8) ^ byte) & 0xFFu];
             }
             if ((uint32_t)tid + 1u == K) {
                 S->crc_last = crc;

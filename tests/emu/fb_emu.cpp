@@ -176,12 +176,13 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     const unsigned long long total = B.offsets[J.n_frames];
     B.stream.assign((size_t)total + 16, 0x77);
     if (fused) {
-        std::vector<uint8_t> smem(KL.total + 64);
+        const FbKfLayout KPL = fb_kp_layout(J.channels, J.nvar, J.bps, J.block_size, J.tail_n);
+        std::vector<uint8_t> smem(KPL.total + 64);
         std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
         fb_kf_build_ktab(KL.crc_chunk, ktab.data());
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KP(GG) fb_kp_body<GG>(J, B.xv.data(), plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KL)
+#define EMU_KP(GG) fb_kp_body<GG>(J, B.xv.data(), plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KP(4); break;
             case 8: EMU_KP(8); break;
