@@ -280,7 +280,8 @@ FB_HD uint8_t fb_crc8(const uint8_t *d, int len) {
 }
 
 // Fixed-blocking frame header incl. CRC-8; returns the number of bytes (<= 16).
-FB_HD int fb_frame_header(int n, int ch_tag, int bps, int sample_rate, uint32_t frame_number, uint8_t *out) {
+FB_HD int fb_frame_header(int n, int ch_tag, int bps, int sample_rate, uint32_t frame_number, uint8_t *out,
+                           const uint32_t *crc8_tab = nullptr) {
     int bs_bits, sr_bits;
     uint32_t bs_extra, sr_extra;
     int bs_tag = fb_block_size_tag(n, &bs_bits, &bs_extra);
@@ -306,7 +307,14 @@ FB_HD int fb_frame_header(int n, int ch_tag, int bps, int sample_rate, uint32_t 
     if (bs_bits == 16) { out[k++] = (uint8_t)(bs_extra >> 8); out[k++] = (uint8_t)bs_extra; }
     if (sr_bits == 8) out[k++] = (uint8_t)sr_extra;
     if (sr_bits == 16) { out[k++] = (uint8_t)(sr_extra >> 8); out[k++] = (uint8_t)sr_extra; }
-    out[k] = fb_crc8(out, k);
+    if (crc8_tab) {
+        // table form of the same CRC-8 (256 entries built on the host)
+        uint32_t crc = 0;
+        for (int i = 0; i < k; i++) crc = crc8_tab[(crc ^ out[i]) & 0xFFu];
+        out[k] = (uint8_t)crc;
+    } else {
+        out[k] = fb_crc8(out, k);
+    }
     return k + 1;
 }
 

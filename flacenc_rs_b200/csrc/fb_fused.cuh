@@ -109,9 +109,11 @@ FB_HD int fb_xidx(int t) { return t + ((t >> 6) << 2); }
 // Built on the host once per context and read by the kernel:
 //   [0, 1024)            slicing-by-4 tables: T[k][b] = CRC of byte b followed by k zero bytes
 //   [1024, 1280)         xp[j] = x^(8 * Lc * j) mod P, j < 256   (Lc = bytes per CRC chunk, see fb_kf_crc_chunk)
-//   [1280, 1280 + Lc+4)  xb[i] = x^(8 * i) mod P, i <= Lc
+//   [1280, 1536)         CRC-8 (poly 0x07, init 0) byte table for the frame header
+//   [1536, 1536 + Lc+4)  xb[i] = x^(8 * i) mod P, i <= Lc
 #define FB_KTAB_XP 1024
-#define FB_KTAB_XB 1280
+#define FB_KTAB_C8 1280
+#define FB_KTAB_XB 1536
 FB_HD uint32_t fb_kf_crc_chunk(int channels, int bps, int block_size, int threads) {
     const uint32_t mb = fb_max_frame_bytes(channels, bps, block_size);
     return ((mb + (uint32_t)threads - 1u) / (uint32_t)threads + 3u) & ~3u;
@@ -125,6 +127,10 @@ inline void fb_kf_build_ktab(uint32_t Lc, uint32_t *t) {
             c = ((c << 8) & 0xFFFFu) ^ fb_crc16_table_entry((c >> 8) & 0xFFu);
             t[k * 256 + b] = c;
         }
+    }
+    for (uint32_t b = 0; b < 256; b++) {
+        const uint8_t one = (uint8_t)b;
+        t[FB_KTAB_C8 + b] = fb_crc8(&one, 1);
     }
     // x^(8*i): start from 1 and multiply by x^8 (= 0x100 reduced: as a 16-bit polynomial x^8 is 0x0100)
     uint32_t v = 1;
@@ -927,7 +933,7 @@ FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *p
 template <int G>
 FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *psubs,
                        uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
-                       uint32_t *fb_count, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
+                       uint32_t *fb_count, const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
     const int NW = J.nvar;
     const int T = 32 * NW;
     const int n = fb_frame_len(J, f);
@@ -989,7 +995,8 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 else if (ch_tag == 10) { sel[0] = 2; sel[1] = 3; }
             }
             S->ch_tag = ch_tag;
-            S->header_len = fb_frame_header(n, ch_tag, J.bps, J.sample_rate, J.first_frame_number + f, S->header);
+            S->header_len = fb_frame_header(n, ch_tag, J.bps, J.sample_rate, J.first_frame_number + f, S->header,
+                                            ktab + FB_KTAB_C8);
             uint32_t bit = (uint32_t)S->header_len * 8u;
             for (int c = 0; c < J.channels; c++) {
                 const fb200_subframe_info &V = choice[sel[c]];
@@ -1011,79 +1018,71 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
         }
     FB_PHASE_END
 
-    // ---- bit offsets of the units of every coded subframe: exclusive scan incl. the parameter fields
-    // (warp c scans subframe c; channels <= nvar)
+    // ---- the plan, in one warp-parallel block: warp c scans the unit bits of subframe c (exclusive scan incl. the
+    // parameter fields) straight into the global unit offsets and copies the subframe's record; all warps share the
+    // copies of the frame plan and of the optional info record
     FB_WARPS_BEGIN(w, NW)
-        if (w < J.channels && (S->sub[w].type == FB200_SF_FIXED || S->sub[w].type == FB200_SF_LPC)) {
+        if (w < J.channels) {
             const FbKfSub &D = S->sub[w];
-            uint8_t *keep = smem + L.off_keep + (uint32_t)D.variant * L.keep_bytes;
-            uint32_t *ub = (uint32_t *)(keep + L.k_unit_bits) + (size_t)D.cand * (L.U_max + 1);
-            uint32_t *xch = (uint32_t *)(smem + L.off_keep + (uint32_t)w * L.keep_bytes + L.k_xch);
-            const int per = g.U >> 5;
-            const int ush = g.lgU - D.part_order;
-            const uint32_t pbits = D.rice2 ? 5u : 4u;
-            FB_WPHASE(lane)
-                uint32_t s = 0;
-                for (int i = 0; i < per; i++) {
-                    const int unit = lane * per + i;
-                    s += ub[unit] + (((unit & ((1 << ush) - 1)) == 0) ? pbits : 0u);
-                }
-                xch[lane] = s;
-            FB_WPHASE_END
-            FB_WPHASE(lane)
-                uint32_t s = 0;
-                for (int i = 0; i < lane; i++) s += xch[i];
-                for (int i = 0; i < per; i++) {
-                    const int unit = lane * per + i;
-                    const uint32_t b = ub[unit] + (((unit & ((1 << ush) - 1)) == 0) ? pbits : 0u);
-                    ub[unit] = s;
-                    s += b;
-                }
-                if (lane == 31) ub[g.U] = s;
-            FB_WPHASE_END
-        }
-    FB_WARPS_END
-
-    // ---- the plan: header + subframe geometry, the chosen subframe records, the unit offsets, the frame size
-    FB_PHASE(tid, T)
-        if (tid == 0) {
-            S->frame_fail = 0; // doubles as plan state 0
-            frame_bytes[f] = S->data_bytes + 2u;
-        }
-        {
-            // FbKfPlan mirrors the head of FbKfFrame up to and including frame_fail (= state)
-            const uint32_t *src = (const uint32_t *)S;
-            uint32_t *dst = (uint32_t *)&plan[f];
-            for (int i = tid; i < (int)(sizeof(FbKfPlan) / 4); i += T) dst[i] = src[i];
-        }
-        for (int c = 0; c < J.channels; c++) {
-            const FbKfSub &D = S->sub[c];
-            const uint32_t *src = (const uint32_t *)&choice[D.variant];
-            uint32_t *dst = (uint32_t *)&psubs[(size_t)f * (size_t)J.channels + (size_t)c];
-            for (int i = tid; i < (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = src[i];
             if (D.type == FB200_SF_FIXED || D.type == FB200_SF_LPC) {
-                const uint32_t *ub = (const uint32_t *)(smem + L.off_keep + (uint32_t)D.variant * L.keep_bytes + L.k_unit_bits) +
-                                     (size_t)D.cand * (L.U_max + 1);
-                uint32_t *po = poffs + ((size_t)f * (size_t)J.channels + (size_t)c) * (L.U_max + 1);
-                for (int i = tid; i <= g.U; i += T) po[i] = ub[i];
+                uint8_t *keep = smem + L.off_keep + (uint32_t)D.variant * L.keep_bytes;
+                const uint32_t *ub = (const uint32_t *)(keep + L.k_unit_bits) + (size_t)D.cand * (L.U_max + 1);
+                uint32_t *xch = (uint32_t *)(smem + L.off_keep + (uint32_t)w * L.keep_bytes + L.k_xch);
+                uint32_t *po = poffs + ((size_t)f * (size_t)J.channels + (size_t)w) * (L.U_max + 1);
+                const int per = g.U >> 5;
+                const int ush = g.lgU - D.part_order;
+                const uint32_t pbits = D.rice2 ? 5u : 4u;
+                FB_WPHASE(lane)
+                    uint32_t s = 0;
+                    for (int i = 0; i < per; i++) {
+                        const int unit = lane * per + i;
+                        s += ub[unit] + (((unit & ((1 << ush) - 1)) == 0) ? pbits : 0u);
+                    }
+                    xch[lane] = s;
+                FB_WPHASE_END
+                FB_WPHASE(lane)
+                    uint32_t s = 0;
+                    for (int i = 0; i < lane; i++) s += xch[i];
+                    for (int i = 0; i < per; i++) {
+                        const int unit = lane * per + i;
+                        po[unit] = s;
+                        s += ub[unit] + (((unit & ((1 << ush) - 1)) == 0) ? pbits : 0u);
+                    }
+                    if (lane == 31) po[g.U] = s;
+                FB_WPHASE_END
             }
+            FB_WPHASE(lane)
+                const uint32_t *src = (const uint32_t *)&choice[D.variant];
+                uint32_t *dst = (uint32_t *)&psubs[(size_t)f * (size_t)J.channels + (size_t)w];
+                for (int i = lane; i < (int)(sizeof(fb200_subframe_info) / 4); i += 32) dst[i] = src[i];
+            FB_WPHASE_END
         }
-        if (infos) {
-            fb200_frame_info &I = infos[f];
-            if (tid == 0) {
-                I.channel_assignment = S->ch_tag;
-                I.block_size = n;
-                I.frame_number = J.first_frame_number + f;
-                I.frame_bytes = S->data_bytes + 2u;
+        FB_WPHASE(lane)
+            const int tid = w * 32 + lane;
+            if (tid == 0) frame_bytes[f] = S->data_bytes + 2u;
+            {
+                // FbKfPlan mirrors the head of FbKfFrame up to and including frame_fail (= state 0 here)
+                const uint32_t *src = (const uint32_t *)S;
+                uint32_t *dst = (uint32_t *)&plan[f];
+                for (int i = tid; i < (int)(sizeof(FbKfPlan) / 4); i += T) dst[i] = src[i];
             }
-            for (int c = 0; c < J.channels; c++) {
-                const uint32_t *src = (const uint32_t *)&choice[S->sub[c].variant];
-                uint32_t *dst = (uint32_t *)&I.sub[c];
-                // word 7 is `reserved`: the block size, like the generic kernels (internally it carries max |x|)
-                for (int i = tid; i < (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = i == 7 ? (uint32_t)n : src[i];
+            if (infos) {
+                fb200_frame_info &I = infos[f];
+                if (tid == 0) {
+                    I.channel_assignment = S->ch_tag;
+                    I.block_size = n;
+                    I.frame_number = J.first_frame_number + f;
+                    I.frame_bytes = S->data_bytes + 2u;
+                }
+                for (int c = 0; c < J.channels; c++) {
+                    const uint32_t *src = (const uint32_t *)&choice[S->sub[c].variant];
+                    uint32_t *dst = (uint32_t *)&I.sub[c];
+                    // word 7 is `reserved`: the block size, like the generic kernels (internally it carries max |x|)
+                    for (int i = tid; i < (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = i == 7 ? (uint32_t)n : src[i];
+                }
             }
-        }
-    FB_PHASE_END
+        FB_WPHASE_END
+    FB_WARPS_END
 }
 
 // ---- KP: pack a planned frame and store it at out + offsets[f]

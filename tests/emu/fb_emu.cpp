@@ -102,13 +102,15 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<uint32_t> list(J.n_frames + 1, 0);
         uint32_t count = 0;
         std::vector<uint8_t> smem(KL.total + 64);
+        std::vector<uint32_t> ktab_a(fb_kf_ktab_words(KL.crc_chunk));
+        fb_kf_build_ktab(KL.crc_chunk, ktab_a.data());
         plan.resize(J.n_frames);
         memset(plan.data(), 0xEE, plan.size() * sizeof(FbKfPlan));
         psubs.resize((size_t)J.n_frames * J.channels);
         poffs.assign((size_t)J.n_frames * J.channels * (KL.U_max + 1), 0xDDDDDDDDu);
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KA(GG) fb_ka_body<GG>(J, B.xv.data(), B.ana.data(), plan.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, f, smem.data(), KL)
+#define EMU_KA(GG) fb_ka_body<GG>(J, B.xv.data(), B.ana.data(), plan.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KA(4); break;
             case 8: EMU_KA(8); break;
