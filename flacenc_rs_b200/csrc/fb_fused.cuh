@@ -190,7 +190,7 @@ struct FbKfFrame {
 
 FB_HD uint32_t fb_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
-FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, int tail_n) {
+FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, int tail_n, bool x16 = false) {
     FbKfLayout L;
     const FbKfGeom ga = fb_kf_geom(block_size), gb = fb_kf_geom(tail_n);
     const uint32_t U = (uint32_t)(ga.U > gb.U ? ga.U : gb.U);
@@ -199,8 +199,9 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.leaves_max = leaves;
     L.crc_chunk = fb_kf_crc_chunk(channels, bps, block_size, 32 * nvar);
     L.debug_stop = 0;
-    L.x16 = 0;
+    L.x16 = (x16 && bps <= 16) ? 1u : 0u;
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
+    if (L.x16) L.x_stride = ((L.x_stride + 1u) / 2u + 3u) & ~3u;
     uint32_t o = 0;
     L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
     // kept per warp
@@ -234,9 +235,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
 // Shared memory of the pack kernel KP: planes (int16 when the stream has at most 16 bits per sample), the frame's
 // plan, the chosen subframe records, the unit offsets and the frame's word buffer.  Returned in the same struct.
 FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, int tail_n) {
-    FbKfLayout L = fb_kf_layout(channels, nvar, bps, block_size, tail_n);
-    L.x16 = bps <= 16 ? 1u : 0u;
-    if (L.x16) L.x_stride = ((L.x_stride + 1u) / 2u + 3u) & ~3u;
+    FbKfLayout L = fb_kf_layout(channels, nvar, bps, block_size, tail_n, true);
     uint32_t o = 0;
     L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
     L.off_keep = o;     o += fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u);   // unit offsets

@@ -279,70 +279,97 @@ FB_DEV int fb_quantize(const double *coefs, int n, int precision, int16_t *q, in
     return order;
 }
 
-// Sequential state of one variant's pass (registers of one thread).
-template <int R>
-struct FbK1State {
+// K1 makes two sequential passes over a variant, each with straight-line inner bodies (no per-sample branches, so
+// the unrolled samples share one register-renamed schedule):
+//   pass E  min/max (-> constant, max |x|) and the fixed-predictor entropy estimate, 8 samples per group
+//   pass A  windowing and the autocorrelation lags, R samples per group
+
+// ---- pass E state: registers of one thread
+struct FbK1Ent {
     float s0, s1, s2, s3, s4;       // running f32 sums of |e_k| of the current estimate partition
     int32_t pe0, pe1, pe2, pe3;     // previous e_0..e_3 (zero history)
     int32_t xmin, xmax;
-    int part, pend, psize, n, P;
-    double acc[R + 1];              // autocorrelation lags 0..R
-    double ring[R];                 // y[t-1] .. y[t-R]
+    int part, pend, psize, n;
 };
 
-// R samples starting at t0 (a multiple of R).  GUARDED: samples may lie beyond n, t may be below P, an estimate
-// partition may end at any sample.  Otherwise all R samples are valid, t0 >= P and partitions end on multiples of 4.
-template <int R, bool GUARDED>
-FB_DEV void fb_k1_group(FbK1State<R> &S, const FbVarRows &rows, const float *win, int t0, bool do_ent, bool do_lpc,
-                        float (*psum)[5]) {
-    int32_t xs[R];
-    float ws[R];
+FB_DEV void fb_k1_ent_close(FbK1Ent &S, float (*psum)[5]) {
+    psum[S.part][0] = S.s0; psum[S.part][1] = S.s1; psum[S.part][2] = S.s2;
+    psum[S.part][3] = S.s3; psum[S.part][4] = S.s4;
+    S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
+    S.part++;
+    S.pend = (S.pend + S.psize < S.n) ? S.pend + S.psize : S.n;
+}
+
+// 8 samples starting at t0.  GUARDED: samples may lie beyond n and a partition may end at any sample; otherwise all
+// 8 are valid and a partition can only end with the group.  zero-history differences, wrapping i32
+// (src/coding.rs:188-195); |e| is taken on the float (the conversion is symmetric; |e| < 2^31 always).
+FB_DEV void fb_k1_ent_load(const FbVarRows &rows, int t0, int32_t *xs) {
+    fb_rows_load4(rows, t0, xs);
+    fb_rows_load4(rows, t0 + 4, xs + 4);
+}
+
+template <bool GUARDED, bool DO_ENT>
+FB_DEV void fb_k1_ent_group(FbK1Ent &S, const int32_t *xs, int t0, float (*psum)[5]) {
 #pragma unroll
-    for (int i = 0; i < R; i += 4) {
-        fb_rows_load4(rows, t0 + i, xs + i);
-        const float4 v = *reinterpret_cast<const float4 *>(win + t0 + i);
-        ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
-    }
-#pragma unroll
-    for (int s = 0; s < R; s++) {
+    for (int s = 0; s < 8; s++) {
         const int t = t0 + s;
         if (GUARDED && t >= S.n) break;
         const int32_t xt = xs[s];
         S.xmin = xt < S.xmin ? xt : S.xmin;
         S.xmax = xt > S.xmax ? xt : S.xmax;
-        if (do_ent) {
-            // zero-history differences, wrapping i32 (src/coding.rs:188-195)
+        if (DO_ENT) {
             const int32_t e0 = xt;
             const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)S.pe0);
             const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)S.pe1);
             const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)S.pe2);
             const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)S.pe3);
             S.pe0 = e0; S.pe1 = e1; S.pe2 = e2; S.pe3 = e3;
-            S.s0 = FB_FADD((float)(e0 < 0 ? -e0 : e0), S.s0);
-            S.s1 = FB_FADD((float)(e1 < 0 ? -e1 : e1), S.s1);
-            S.s2 = FB_FADD((float)(e2 < 0 ? -e2 : e2), S.s2);
-            S.s3 = FB_FADD((float)(e3 < 0 ? -e3 : e3), S.s3);
-            S.s4 = FB_FADD((float)(e4 < 0 ? -e4 : e4), S.s4);
-            if ((GUARDED || (s & 3) == 3) && t + 1 == S.pend) {
-                psum[S.part][0] = S.s0; psum[S.part][1] = S.s1; psum[S.part][2] = S.s2;
-                psum[S.part][3] = S.s3; psum[S.part][4] = S.s4;
-                S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
-                S.part++;
-                S.pend = (S.pend + S.psize < S.n) ? S.pend + S.psize : S.n;
-            }
+            S.s0 = FB_FADD(fabsf((float)e0), S.s0);
+            S.s1 = FB_FADD(fabsf((float)e1), S.s1);
+            S.s2 = FB_FADD(fabsf((float)e2), S.s2);
+            S.s3 = FB_FADD(fabsf((float)e3), S.s3);
+            S.s4 = FB_FADD(fabsf((float)e4), S.s4);
+            if (GUARDED && t + 1 == S.pend) fb_k1_ent_close(S, psum);
         }
-        if (do_lpc) {
-            const double y = (double)FB_FMUL((float)xt, ws[s]);
-            if (!GUARDED || t >= S.P) {
-                S.acc[0] = FB_FMA(y, y, S.acc[0]);
+    }
+    if (DO_ENT && !GUARDED && t0 + 8 == S.pend) fb_k1_ent_close(S, psum);
+}
+
+// ---- pass A state
+template <int R>
+struct FbK1Acc {
+    double acc[R + 1];              // autocorrelation lags 0..R
+    double ring[R];                 // y[t-1] .. y[t-R]
+};
+
+// R samples starting at t0 (a multiple of R).  y[t] = (f32)x[t] * w[t] (src/lpc.rs:739-756); r[lag] += y[t-lag] * y[t]
+// as sequential f64 FMAs starting at t = lpc_order for every lag (src/lpc.rs:533-548).
+template <int R>
+FB_DEV void fb_k1_acc_load(const FbVarRows &rows, const float *win, int t0, int32_t *xs, float *ws) {
 #pragma unroll
-                for (int j = 0; j < R; j++) {
-                    // logical y[t-1-j] lives in ring[(s-1-j) mod R]; static after unrolling
-                    S.acc[j + 1] = FB_FMA(S.ring[(s - 1 - j + 2 * R) % R], y, S.acc[j + 1]);
-                }
+    for (int i = 0; i < R; i += 4) {
+        fb_rows_load4(rows, t0 + i, xs + i);
+        const float4 v = *reinterpret_cast<const float4 *>(win + t0 + i);
+        ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
+    }
+}
+
+template <int R, bool GUARDED>
+FB_DEV void fb_k1_acc_group(FbK1Acc<R> &S, const int32_t *xs, const float *ws, int t0, int n, int P) {
+#pragma unroll
+    for (int s = 0; s < R; s++) {
+        const int t = t0 + s;
+        if (GUARDED && t >= n) break;
+        const double y = (double)FB_FMUL((float)xs[s], ws[s]);
+        if (!GUARDED || t >= P) {
+            S.acc[0] = FB_FMA(y, y, S.acc[0]);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                // logical y[t-1-j] lives in ring[(s-1-j) mod R]; static after unrolling
+                S.acc[j + 1] = FB_FMA(S.ring[(s - 1 - j + 2 * R) % R], y, S.acc[j + 1]);
             }
-            S.ring[s] = y; // overwrites y[t-R]
         }
+        S.ring[s] = y; // overwrites y[t-R]
     }
 }
 
@@ -371,32 +398,47 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
     const int psize = (n + parts - 1) / parts;
 
     float psum[FB_MAX_ENT_PARTS][5]; // per-partition sequential f32 sums of |e_k|
-    FbK1State<R> S;
+    FbK1Ent S;
     S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
     S.pe0 = S.pe1 = S.pe2 = S.pe3 = 0;
     S.part = 0;
     S.psize = psize;
     S.pend = psize < n ? psize : n;
     S.n = n;
-    S.P = P;
-#pragma unroll
-    for (int i = 0; i <= R; i++) S.acc[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < R; i++) S.ring[i] = 0.0;
     {
         int32_t q[4];
         fb_rows_load4(rows, 0, q);
         S.xmin = S.xmax = q[0];
     }
-    // first group guarded (t < lpc_order), then whole groups without per-sample checks when the estimate
-    // partitions end on multiples of 4, then the guarded remainder
-    const bool fast_ok = (psize & 3) == 0;
-    int t0 = 0;
-    fb_k1_group<R, true>(S, rows, win, 0, do_ent, do_lpc, psum);
-    t0 = R;
-    if (fast_ok)
-        for (; t0 + R <= n; t0 += R) fb_k1_group<R, false>(S, rows, win, t0, do_ent, do_lpc, psum);
-    for (; t0 < n; t0 += R) fb_k1_group<R, true>(S, rows, win, t0, do_ent, do_lpc, psum);
+    // ---- pass E: whole groups without per-sample checks when the estimate partitions end on multiples of 8
+    // (prefetching the next group into a second register buffer was measured slower: it costs occupancy)
+    {
+        int32_t xs[8];
+        int t0 = 0;
+        if (do_ent) {
+            if ((psize & 7) == 0)
+                for (; t0 + 8 <= n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<false, true>(S, xs, t0, psum); }
+            for (; t0 < n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<true, true>(S, xs, t0, psum); }
+        } else {
+            for (; t0 + 8 <= n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<false, false>(S, xs, t0, psum); }
+            for (; t0 < n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<true, false>(S, xs, t0, psum); }
+        }
+    }
+    // ---- pass A: first group guarded (t < lpc_order), whole groups, guarded remainder
+    FbK1Acc<R> A;
+#pragma unroll
+    for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) A.ring[i] = 0.0;
+    if (do_lpc) {
+        int32_t xs[R];
+        float ws[R];
+        int t0 = R;
+        fb_k1_acc_load<R>(rows, win, 0, xs, ws);
+        fb_k1_acc_group<R, true>(A, xs, ws, 0, n, P);
+        for (; t0 + R <= n; t0 += R) { fb_k1_acc_load<R>(rows, win, t0, xs, ws); fb_k1_acc_group<R, false>(A, xs, ws, t0, n, P); }
+        for (; t0 < n; t0 += R) { fb_k1_acc_load<R>(rows, win, t0, xs, ws); fb_k1_acc_group<R, true>(A, xs, ws, t0, n, P); }
+    }
 
     const bool allsame = S.xmin == S.xmax; // src/arrayutils.rs:382-389
     out->is_constant = allsame ? 1 : 0;
@@ -448,7 +490,7 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
         double corr[FB200_MAX_LPC_ORDER + 1];
 #pragma unroll
         for (int i = 0; i <= R; i++)
-            if (i <= FB200_MAX_LPC_ORDER) corr[i] = S.acc[i];
+            if (i <= FB200_MAX_LPC_ORDER) corr[i] = A.acc[i];
         double lpc[FB200_MAX_LPC_ORDER];
         fb_levinson(corr, corr + 1, P, lpc);
         int16_t q[32];
