@@ -166,6 +166,18 @@ FB_HD int32_t fb_mix(int32_t a, int32_t b, int32_t m, int32_t sh) {
     return (int32_t)((uint32_t)a + (uint32_t)m * (uint32_t)b) >> sh;
 }
 
+// software prefetch of the quad at t into L1 (no registers are tied up; the later load hits the cache).
+// Below ~20 K variants per launch the analysis kernel has too few warps per SM to hide DRAM latency otherwise.
+FB_DEV void fb_rows_prefetch4(const FbVarRows &r, int t) {
+#if FB_GPU
+    const size_t o = fb_xt_quad(t);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(r.pa + o));
+    if (r.pb != r.pa) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.pb + o));
+#else
+    (void)r; (void)t;
+#endif
+}
+
 // four samples t..t+3 of a variant (t a multiple of 4)
 FB_DEV void fb_rows_load4(const FbVarRows &r, int t, int32_t *dst) {
     const size_t o = fb_xt_quad(t);
@@ -283,6 +295,8 @@ FB_DEV int fb_quantize(const double *coefs, int n, int precision, int16_t *q, in
 // the unrolled samples share one register-renamed schedule):
 //   pass E  min/max (-> constant, max |x|) and the fixed-predictor entropy estimate, 8 samples per group
 //   pass A  windowing and the autocorrelation lags, R samples per group
+
+#define FB_K1_AHEAD 48 // software prefetch distance in samples (a multiple of 4)
 
 // ---- pass E state: registers of one thread
 struct FbK1Ent {
@@ -417,7 +431,11 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
         int t0 = 0;
         if (do_ent) {
             if ((psize & 7) == 0)
-                for (; t0 + 8 <= n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<false, true>(S, xs, t0, psum); }
+                for (; t0 + 8 <= n; t0 += 8) {
+                    if (t0 + FB_K1_AHEAD + 8 <= J.stride) { fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD); fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD + 4); }
+                    fb_k1_ent_load(rows, t0, xs);
+                    fb_k1_ent_group<false, true>(S, xs, t0, psum);
+                }
             for (; t0 < n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<true, true>(S, xs, t0, psum); }
         } else {
             for (; t0 + 8 <= n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<false, false>(S, xs, t0, psum); }
@@ -436,7 +454,14 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
         int t0 = R;
         fb_k1_acc_load<R>(rows, win, 0, xs, ws);
         fb_k1_acc_group<R, true>(A, xs, ws, 0, n, P);
-        for (; t0 + R <= n; t0 += R) { fb_k1_acc_load<R>(rows, win, t0, xs, ws); fb_k1_acc_group<R, false>(A, xs, ws, t0, n, P); }
+        for (; t0 + R <= n; t0 += R) {
+            if (t0 + FB_K1_AHEAD + R <= J.stride) {
+#pragma unroll
+                for (int i = 0; i < R; i += 4) fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD + i);
+            }
+            fb_k1_acc_load<R>(rows, win, t0, xs, ws);
+            fb_k1_acc_group<R, false>(A, xs, ws, t0, n, P);
+        }
         for (; t0 < n; t0 += R) { fb_k1_acc_load<R>(rows, win, t0, xs, ws); fb_k1_acc_group<R, true>(A, xs, ws, t0, n, P); }
     }
 
