@@ -349,11 +349,8 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         ctx->last_error = "internal: shared memory budget exceeded";
         return FB200_ERR_CUDA;
     }
-    P.fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, P.tail_n, &P.KL, getenv("FB200_KA_X16") != nullptr);
+    P.fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, P.tail_n, &P.KL);
     P.KPL = fb_kp_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n);
-    if (getenv("FB200_KP_X32")) P.KPL = P.KL; // experiments: pack kernel on the plan kernel's int32 layout
-    if (getenv("FB200_KF_SMEM_PAD")) P.KL.total += (uint32_t)atoi(getenv("FB200_KF_SMEM_PAD")); // occupancy experiments
-    if (getenv("FB200_KF_DEBUG_STOP")) P.KL.debug_stop = (uint32_t)atoi(getenv("FB200_KF_DEBUG_STOP"));
     if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
         std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk));
         fb_kf_build_ktab(P.KL.crc_chunk, kt.data());

@@ -156,7 +156,7 @@ struct FbKfLayout {
     uint32_t words_bytes; // bytes of the frame word buffer
     uint32_t U_max, leaves_max;
     uint32_t crc_chunk;   // Lc
-    uint32_t debug_stop;  // experiments only: 1 = return after the analysis phase
+    uint32_t off_crc_tab; // pack kernel: the four CRC-16 slicing tables (4 KiB)
     uint32_t total;
 };
 
@@ -198,7 +198,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.U_max = U;
     L.leaves_max = leaves;
     L.crc_chunk = fb_kf_crc_chunk(channels, bps, block_size, 32 * nvar);
-    L.debug_stop = 0;
+    L.off_crc_tab = 0;
     L.x16 = (x16 && bps <= 16) ? 1u : 0u;
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
     if (L.x16) L.x_stride = ((L.x_stride + 1u) / 2u + 3u) & ~3u;
@@ -241,6 +241,7 @@ FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, i
     L.off_keep = o;     o += fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u);   // unit offsets
     L.off_choice = o;   o += fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info));
     L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
+    L.off_crc_tab = o;  o += 4096u;
     L.off_scratch = o;  o += L.words_bytes;                                            // frame words
     L.total = o;
     return L;
@@ -967,7 +968,6 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
         FB_WPHASE_END
     FB_WARPS_END
 
-    if (L.debug_stop == 1) return;
     if (S->frame_fail) {
         // not reproducible here: hand the frame to the literal kernels
         FB_PHASE(tid, T)
@@ -1099,6 +1099,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
     fb200_subframe_info *psub = (fb200_subframe_info *)(smem + L.off_choice);   // [channels]
     uint32_t *poff = (uint32_t *)(smem + L.off_keep);                           // [channels][U_max + 1]
     uint32_t *words = (uint32_t *)(smem + L.off_scratch);
+    uint32_t *crc_tab = (uint32_t *)(smem + L.off_crc_tab);
     const uint32_t max_words = (fb_max_frame_bytes(J.channels, J.bps, J.block_size) + 3u) / 4u + 2u;
 
     // ---- stage the channels, the plan, the CRC tables; clear the word buffer
@@ -1118,6 +1119,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             const uint32_t *src = poffs + (size_t)f * (size_t)J.channels * (L.U_max + 1);
             for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) poff[i] = src[i];
         }
+        for (int i = tid; i < 1024; i += T) crc_tab[i] = ktab[i];
         for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
         if (tid == 0) { S->crc_acc = 0; S->crc_last = 0; }
         fb_copy_async_wait();
@@ -1260,12 +1262,12 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             uint32_t i = b0;
             for (; i + 4u <= b1; i += 4u) { // b0 is a multiple of 4: whole big-endian words
                 const uint32_t w = words[i >> 2];
-                crc = ktab[768 + (((crc >> 8) ^ (w >> 24)) & 0xFFu)] ^ ktab[512 + ((crc ^ (w >> 16)) & 0xFFu)] ^
-                      ktab[256 + ((w >> 8) & 0xFFu)] ^ ktab[w & 0xFFu];
+                crc = crc_tab[768 + (((crc >> 8) ^ (w >> 24)) & 0xFFu)] ^ crc_tab[512 + ((crc ^ (w >> 16)) & 0xFFu)] ^
+                      crc_tab[256 + ((w >> 8) & 0xFFu)] ^ crc_tab[w & 0xFFu];
             }
             for (; i < b1; i++) {
                 const uint32_t byte = (words[i >> 2] >> (24u - 8u * (i & 3u))) & 0xFFu;
-                crc = ((crc << 8) & 0xFFFFu) ^ ktab[((crc >> 8) ^ byte) & 0xFFu];
+                crc = ((crc << 8) & 0xFFFFu) ^ crc_tab[((crc >> 8) ^ byte) & 0xFFu];
             }
             if ((uint32_t)tid + 1u == K) {
                 S->crc_last = crc;
