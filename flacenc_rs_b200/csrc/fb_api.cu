@@ -359,9 +359,10 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
         ctx->ktab_chunk = P.KL.crc_chunk;
     }
-    if (P.fused && (int)P.KL.total > ctx->kf_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, (int)P.KL.total));
-        ctx->kf_smem_set = (int)P.KL.total;
+    const int kf_smem = (int)std::max(P.KL.total, P.KPL.total); // plan kernel and pack kernel
+    if (P.fused && kf_smem > ctx->kf_smem_set) {
+        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, kf_smem));
+        ctx->kf_smem_set = kf_smem;
     }
     if ((int)P.k2_smem > ctx->k2_smem_set) {
         FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K2, (int)P.k2_smem));

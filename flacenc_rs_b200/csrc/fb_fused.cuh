@@ -37,6 +37,7 @@
 #define FB_KF_ROW 9        // row stride of the tree tables (one pad word: conflict-free column reads)
 #define FB_KF_NWORDS 7     // bit-sliced counter words per unit (counts <= 127)
 #define FB_KF_UNIT_MAX 112 // samples per unit (7 runs of 16)
+#define FB_KF_SMEM_LIMIT (225u * 1024u) // dynamic shared memory one CTA may ask for (227 KiB on sm_100a, minus slack)
 
 // 16-byte global -> shared copy that does not pass through registers (LDGSTS), so a thread keeps all the copies of
 // its staging loop in flight at once
@@ -157,6 +158,7 @@ struct FbKfLayout {
     uint32_t U_max, leaves_max;
     uint32_t crc_chunk;   // Lc
     uint32_t off_crc_tab; // pack kernel: the four CRC-16 slicing tables (4 KiB)
+    uint32_t group_ch;    // pack kernel: channels staged at a time (all of them unless the frame is too large)
     uint32_t total;
 };
 
@@ -199,6 +201,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.leaves_max = leaves;
     L.crc_chunk = fb_kf_crc_chunk(channels, bps, block_size, 32 * nvar);
     L.off_crc_tab = 0;
+    L.group_ch = (uint32_t)channels;
     L.x16 = (x16 && bps <= 16) ? 1u : 0u;
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
     if (L.x16) L.x_stride = ((L.x_stride + 1u) / 2u + 3u) & ~3u;
@@ -226,8 +229,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.s_misc = s;       s += fb_align16((uint32_t)sizeof(FbKfMisc));
     L.scratch_bytes = s;
     L.words_bytes = fb_align16(((fb_max_frame_bytes(channels, bps, block_size) + 3u) & ~3u) + 16u);
-    const uint32_t scratch_total = (uint32_t)nvar * s;
-    L.off_scratch = o;  o += scratch_total > L.words_bytes ? scratch_total : L.words_bytes;
+    L.off_scratch = o;  o += (uint32_t)nvar * s; // (the pack kernel's layout puts the frame words here instead)
     L.total = o;
     return L;
 }
@@ -236,8 +238,18 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
 // plan, the chosen subframe records, the unit offsets and the frame's word buffer.  Returned in the same struct.
 FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, int tail_n) {
     FbKfLayout L = fb_kf_layout(channels, nvar, bps, block_size, tail_n, true);
+    // everything but the planes, then as many planes as fit next to it (channels other than a stereo pair are
+    // independent, so they can be staged and packed group by group)
+    const uint32_t fixed = fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u) +
+                           fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info)) +
+                           fb_align16((uint32_t)sizeof(FbKfFrame)) + 4096u + L.words_bytes;
+    const uint32_t plane = L.x_stride * 4u;
+    uint32_t gc = (uint32_t)channels;
+    while (gc > 1u && fixed + fb_align16(gc * plane) > FB_KF_SMEM_LIMIT) gc--;
+    if (channels == 2) gc = 2; // M and S need both planes
+    L.group_ch = gc;
     uint32_t o = 0;
-    L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
+    L.off_x = o;        o += fb_align16(gc * L.x_stride * 4u);
     L.off_keep = o;     o += fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u);   // unit offsets
     L.off_choice = o;   o += fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info));
     L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
@@ -893,27 +905,29 @@ struct FbKfPlan {               // global, one per frame; the leading part mirro
     uint32_t state;             // 0: planned by KA, 1: left to the generic kernels
 };
 
+// stages channels [c0, c1) of frame f into planes 0 .. c1-c0-1
 template <int G>
-FB_DEV void fb_kf_stage(const FbJob &J, const int32_t *xv, uint32_t f, int n, int32_t *xs, const FbKfLayout &L, int tid, int T) {
+FB_DEV void fb_kf_stage(const FbJob &J, const int32_t *xv, uint32_t f, int n, int32_t *xs, const FbKfLayout &L, int tid, int T,
+                        int c0, int c1) {
     // quad i of every channel together: the rows of one frame are adjacent in xt (one 32-byte sector for stereo)
     const int n4 = (n + 3) >> 2;
     if (L.x16) {
 #pragma unroll 4
         for (int i = tid; i < n4; i += T) {
-            for (int c = 0; c < J.channels; c++) {
+            for (int c = c0; c < c1; c++) {
                 const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
                 const int4 v = *reinterpret_cast<const int4 *>(src + fb_xt_quad(4 * i));
                 int2 w;
                 w.x = (int32_t)(((uint32_t)v.x & 0xFFFFu) | ((uint32_t)v.y << 16));
                 w.y = (int32_t)(((uint32_t)v.z & 0xFFFFu) | ((uint32_t)v.w << 16));
-                *reinterpret_cast<int2 *>(reinterpret_cast<int16_t *>(xs + (size_t)c * L.x_stride) + fb_xidx(4 * i)) = w;
+                *reinterpret_cast<int2 *>(reinterpret_cast<int16_t *>(xs + (size_t)(c - c0) * L.x_stride) + fb_xidx(4 * i)) = w;
             }
         }
     } else {
         for (int i = tid; i < n4; i += T) {
-            for (int c = 0; c < J.channels; c++) {
+            for (int c = c0; c < c1; c++) {
                 const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
-                fb_copy16_async(xs + (size_t)c * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
+                fb_copy16_async(xs + (size_t)(c - c0) * L.x_stride + fb_xidx(4 * i), src + fb_xt_quad(4 * i));
             }
         }
     }
@@ -953,7 +967,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
 
     // ---- stage the independent channels from the row-interleaved store xt (16-byte asynchronous copies)
     FB_PHASE(tid, T)
-        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T);
+        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, J.channels);
         if (tid == 0) S->frame_fail = 0;
         fb_copy_async_wait();
     FB_PHASE_END
@@ -1102,9 +1116,10 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
     uint32_t *crc_tab = (uint32_t *)(smem + L.off_crc_tab);
     const uint32_t max_words = (fb_max_frame_bytes(J.channels, J.bps, J.block_size) + 3u) / 4u + 2u;
 
-    // ---- stage the channels, the plan, the CRC tables; clear the word buffer
+    // ---- the plan, the CRC tables; clear the word buffer; stage the first group of channels
+    const int GC = (int)L.group_ch;
     FB_PHASE(tid, T)
-        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T);
+        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, GC < J.channels ? GC : J.channels);
         {
             const uint32_t *src = (const uint32_t *)&plan[f];
             uint32_t *dst = (uint32_t *)S;
@@ -1125,9 +1140,17 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
         fb_copy_async_wait();
     FB_PHASE_END
 
-    // ---- frame header, subframe heads, and the samples of every unit
+    // ---- frame header, subframe heads, and the samples of every unit -- per group of staged channels
+    for (int c0 = 0; c0 < J.channels; c0 += GC) {
+    const int c1 = c0 + GC < J.channels ? c0 + GC : J.channels;
+    if (c0 > 0) {
+        FB_PHASE(tid, T)
+            fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, c0, c1);
+            fb_copy_async_wait();
+        FB_PHASE_END
+    }
     FB_PHASE(tid, T)
-        if (tid == 0) {
+        if (tid == 0 && c0 == 0) {
             FbBitRun r;
             fb_run_init(r, words, 0, 1);
             r.w_last = 0xFFFFFFFFu;
@@ -1139,11 +1162,11 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             fb_run_flush(r);
         }
 #define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, (t)))
-        if (tid < J.channels) {
-            const FbKfSub &D = S->sub[tid];
-            const fb200_subframe_info &V = psub[tid];
+        if (tid < c1 - c0) {
+            const FbKfSub &D = S->sub[c0 + tid];
+            const fb200_subframe_info &V = psub[c0 + tid];
             int vm = L.x16 ? FB_VM_X16 : 0;
-            const int32_t *xa = xs + (size_t)D.variant * L.x_stride, *xb = xa;
+            const int32_t *xa = xs + (size_t)(D.variant - c0) * L.x_stride, *xb = xa;
             if (J.channels == 2 && D.variant >= 2) { vm |= D.variant; xa = xs; xb = xs + L.x_stride; }
             FbBitRun r;
             fb_run_init(r, words, D.start_bit, D.start_bit + 1);
@@ -1172,14 +1195,14 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             r.w_first = r.cur_w;
             fb_run_flush(r);
         }
-        for (int item = tid; item < J.channels * g.U; item += T) {
-            const int c = item >> g.lgU, unit = item & (g.U - 1);
+        for (int item = tid; item < (c1 - c0) * g.U; item += T) {
+            const int c = c0 + (item >> g.lgU), unit = item & (g.U - 1);
             const FbKfSub &D = S->sub[c];
             if (D.type == FB200_SF_CONSTANT) continue;
             int ta, tb;
             fb_kf_unit_range(g, unit, &ta, &tb);
             int vm = L.x16 ? FB_VM_X16 : 0;
-            const int32_t *xa = xs + (size_t)D.variant * L.x_stride, *xb = xa;
+            const int32_t *xa = xs + (size_t)(D.variant - c0) * L.x_stride, *xb = xa;
             if (J.channels == 2 && D.variant >= 2) { vm |= D.variant; xa = xs; xb = xs + L.x_stride; }
             if (D.type == FB200_SF_VERBATIM) {
                 // Verbatim::write (src/component/bitrepr.rs:463-470): bps bits per sample at fixed positions
@@ -1246,6 +1269,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
         }
 #undef FB_KF_X
     FB_PHASE_END
+    } // channel groups
 
     // ---- CRC-16 over data_bytes (Frame::write, src/component/bitrepr.rs:289-320).  Chunks of Lc bytes from
     // the start of the frame, one per thread, four bytes per step (slicing tables); the chunk CRCs are shifted

@@ -122,10 +122,12 @@ inline int fbh_leaves_max(const FbJob &J) {
 // The fused per-frame kernel (fb_fused.cuh) serves a batch when the fixed order comes from K1's entropy
 // estimate (OrderSel::ApproxEnt, the default; BitCount needs one Rice search per order and stays on the
 // generic kernels) and the frame's working set fits in shared memory.
-#define FB_KF_SMEM_LIMIT (200u * 1024u)
 inline bool fbh_fused_ok(const FbJob &J, int tail_n_call, FbKfLayout *Lout, bool x16 = false) {
     if (J.cfg.use_fixed && J.cfg.fixed_order_sel != 1) return false;
     FbKfLayout L = fb_kf_layout(J.channels, J.nvar, J.bps, J.block_size, tail_n_call, x16);
     if (Lout) *Lout = L;
-    return L.total <= FB_KF_SMEM_LIMIT;
+    if (L.total > FB_KF_SMEM_LIMIT) return false;
+    // the pack kernel stages channels in groups; it needs room for at least one plane (both planes for stereo)
+    const FbKfLayout LP = fb_kp_layout(J.channels, J.nvar, J.bps, J.block_size, tail_n_call);
+    return LP.total <= FB_KF_SMEM_LIMIT;
 }

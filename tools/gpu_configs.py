@@ -59,8 +59,8 @@ for name, ch, bps, rate, block, secs, kw in CASES:
             olen, _ = ctx.encode_device(d_in.data_ptr(), cb, n, d_out.data_ptr(), cap, 0, sizes)
             t = ctx.timing()
             ms.append(t.total_ms)
-        kern = {"ingest": t.k_ingest_ms, "analyze": t.k_analyze_ms, "encode": t.k_rice_ms, "fallback": t.k_pack_ms,
-                "gather": t.k_gather_ms}
+        kern = {"ingest": t.k_ingest_ms, "analyze": t.k_analyze_ms, "plan": t.k_rice_ms, "pack": t.k_pack_ms,
+                "fallback+scan": t.k_gather_ms}
         fused, fb = t.fused_frames, t.fallback_frames
         got, hs, _ = ctx.encode_interleaved(h_in.numpy(), cb, n, 0, out=h_out.numpy())
         e2e = []
