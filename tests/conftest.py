@@ -54,3 +54,60 @@ def crafted_huge_residual_stereo(order: int = 24) -> np.ndarray:
             s[len(s) - 2 - j] = 8388607 if q[j] > 0 else -8388607
         s[len(s) - 1] = -8388607
     return np.stack([s, -s], axis=1)
+
+
+def random_case(rng):
+    """One seeded fuzz case: (signal, channels, bps, rate, block size, first frame number, oracle-style config kwargs)."""
+    channels = int(rng.choice([1, 2, 2, 2, 3, 4, 6, 8]))
+    bps = int(rng.choice([8, 12, 16, 16, 20, 24]))
+    block = int(rng.choice([64, 96, 128, 192, 256, 500, 576, 1024, 1152, 2048, 2304, 4096, 4608, 1000, 3136]))
+    frames = int(rng.integers(1, 4))
+    n = block * (frames - 1) + int(rng.integers(1, block + 1))
+    kind = int(rng.integers(0, 6))
+    t = np.arange(n)
+    full = (1 << (bps - 1)) - 1
+    chans = []
+    for c in range(channels):
+        if kind == 0:      # tone + noise
+            x = 0.6 * np.sin(t * (0.01 + 0.02 * rng.random()) + c) + 0.05 * rng.standard_normal(n)
+        elif kind == 1:    # random walk
+            x = np.cumsum(rng.standard_normal(n)) / 40.0
+        elif kind == 2:    # loud / quiet halves
+            x = np.where(t < n // 2, 0.8 * rng.uniform(-1, 1, n), 0.002 * rng.uniform(-1, 1, n))
+        elif kind == 3:    # sparse impulses on silence
+            x = np.zeros(n)
+            x[rng.integers(0, n, max(1, n // 200))] = rng.uniform(-1, 1, max(1, n // 200))
+        elif kind == 4:    # full-scale white noise (verbatim territory)
+            x = rng.uniform(-1, 1, n)
+        else:              # decaying chirp
+            x = np.exp(-t / (n / 3.0)) * np.sin(t * t * 1e-5 + c)
+        chans.append(np.clip(np.round(x * full), -full - 1, full).astype(np.int32))
+    if channels == 2 and rng.random() < 0.3:
+        chans[1] = chans[0] + rng.integers(-2, 3, n).astype(np.int32)  # near-identical channels: side-channel wins
+        chans[1] = np.clip(chans[1], -full - 1, full)
+    cfg = {}
+    if rng.random() < 0.5:
+        cfg["lpc_order"] = int(rng.integers(1, 25))
+    if rng.random() < 0.3:
+        cfg["quant_precision"] = int(rng.integers(2, 16))
+    if rng.random() < 0.2:
+        cfg["window_type"] = 0
+    if rng.random() < 0.2:
+        cfg["tukey_alpha"] = float(rng.choice([0.0, 0.1, 0.5, 1.0]))
+    if rng.random() < 0.2:
+        cfg["prc_max_parameter"] = int(rng.choice([2, 7, 14, 20, 30]))
+    if rng.random() < 0.15:
+        cfg["fixed_max_order"] = int(rng.integers(0, 5))
+    if rng.random() < 0.15:
+        cfg["approx_ent_partitions"] = int(rng.choice([1, 4, 8, 32, 64]))
+    if rng.random() < 0.1:
+        cfg["use_lpc"] = 0
+    if rng.random() < 0.1:
+        cfg["use_fixed"] = 0
+    if rng.random() < 0.1:
+        cfg["fixed_order_sel"] = 0
+    rate = int(rng.choice([8000, 22050, 44100, 48000, 96000, 12345]))
+    first = int(rng.choice([0, 1, 127, 128, 70000, (1 << 31) - 10]))
+    return np.stack(chans, axis=1), channels, bps, rate, block, first, cfg
+
+

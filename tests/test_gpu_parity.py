@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm
+from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case
 from flacenc_rs_b200 import _ffi, sigen
 from flacenc_rs_b200.config import Encoder, Fixed, OrderSel, Qlpc, StereoCoding, SubFrameCoding, Window, Prc
 from flacenc_rs_b200.encoder import (Context, StreamInfo, encode_fixed_size_frame, encode_with_fixed_block_size)
@@ -253,6 +253,14 @@ def test_fused_geometry_odd_block_sizes():
     for n in (64, 66, 127, 128, 341 * 8, 3136, 98 * 32, 5000, 4100, 8192, 9216, 12345, 16383):
         x = (rng.normal(0, 300, n + 17).cumsum() % 20000 - 10000).astype(np.int32)
         _compare(x, 1, 16, 44100, n)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_randomised_formats_signals_and_configs(seed):
+    """the seeded fuzz of tests/test_kernel_logic_emu.py against the real kernels (both device paths)"""
+    rng = np.random.default_rng(1000 + seed)
+    x, channels, bps, rate, block, first, cfg = random_case(rng)
+    _compare(x, channels, bps, rate, block, first_frame=first, **cfg)
 
 
 def test_first_frame_number_and_utf8_lengths():

@@ -4,7 +4,7 @@ The same comparisons run against the real kernels in tests/test_gpu_parity.py (-
 import numpy as np
 import pytest
 
-from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm
+from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case
 from flacenc_rs_b200 import sigen
 from oracle import oracle as O
 from emu import emu as E
@@ -266,3 +266,12 @@ def test_float_tier_taps_match_oracle():
             bps_v = 17 if v == 3 else 16
             est = [O.estimate_entropy(e5[k], k, 16) + bps_v * k for k in range(5)]
             assert list(tp.fixed_est_bits) == est
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_randomised_formats_signals_and_configs(seed):
+    """seeded fuzz over channel counts, sample sizes, block sizes (incl. odd tails), signal classes and encoder options:
+    the kernel bodies (fused and generic paths) must reproduce the oracle's frame bytes, which must decode losslessly"""
+    rng = np.random.default_rng(1000 + seed)
+    x, channels, bps, rate, block, first, cfg = random_case(rng)
+    _compare(x, channels, bps, rate, block, first_frame=first, **cfg)
