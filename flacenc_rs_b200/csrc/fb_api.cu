@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) fb_k0_ingest(FbJob J, const uint8_t *pcm,
     uint32_t f;
     int t4;
     fb_k0_item(idx, J.stride / 4, &f, &t4);
-    if (f < J.n_frames && t4 < J.stride / 4) fb_k0_quad(J, pcm, xt, err_flag, f, t4);
+    if (f < J.n_frames && t4 < J.stride / 4) fb_k0_quad_any(J, pcm, xt, err_flag, f, t4);
 }
 
 __global__ void __launch_bounds__(256) fb_k0_ingest_planar(FbJob J, const int32_t *src, int src_stride, int32_t *xt,

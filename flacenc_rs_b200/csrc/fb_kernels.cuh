@@ -105,6 +105,58 @@ FB_DEV void fb_k0_quad(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t
     if (bad) fb_atomic_or(err_flag, 1u);
 }
 
+// K0 fast path for packed 24-bit samples (container 3): the 12 * CH bytes of a quad are read as 3 * CH aligned words
+// and the samples cut out with compile-time shifts.  Requires a 4-byte aligned PCM base and a whole quad inside the
+// frame; everything else takes fb_k0_quad.
+template <int CH>
+FB_DEV void fb_k0_quad_p24(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t *err_flag, uint32_t f, int t4) {
+    const int t = 4 * t4;
+    const int32_t lo = -(int32_t)(1u << (J.bps - 1)), hi = (int32_t)((1u << (J.bps - 1)) - 1u);
+    const uint64_t s = (uint64_t)f * (uint64_t)J.block_size + (uint64_t)t;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + s * (uint64_t)(3 * CH));
+    uint32_t w[3 * CH + 1];
+#pragma unroll
+    for (int i = 0; i < 3 * CH; i++) w[i] = src[i];
+    w[3 * CH] = 0;
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        int32_t q[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int b = (i * CH + c) * 3; // byte offset inside the quad, compile-time
+            const int wi = b >> 2, sh = (b & 3) * 8;
+            const uint32_t v = sh == 0 ? w[wi] : ((w[wi] >> sh) | (w[wi + 1] << (32 - sh)));
+            q[i] = (int32_t)(v << 8) >> 8; // sign-extend 24 bits (src/source.rs:280-286)
+            bad |= (q[i] < lo) | (q[i] > hi);
+        }
+        int4 o;
+        o.x = q[0]; o.y = q[1]; o.z = q[2]; o.w = q[3];
+        *reinterpret_cast<int4 *>(xt + fb_xt_off(J.stride, f * (uint32_t)CH + (uint32_t)c, t)) = o;
+    }
+    if (bad) fb_atomic_or(err_flag, 1u);
+}
+
+FB_DEV bool fb_k0_p24_ok(const FbJob &J, const uint8_t *pcm, uint32_t f, int t4) {
+    return J.container_bytes == 3 && 4 * t4 + 4 <= fb_frame_len(J, f) && (((uintptr_t)pcm) & 3u) == 0;
+}
+
+FB_DEV void fb_k0_quad_any(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t *err_flag, uint32_t f, int t4) {
+    if (fb_k0_p24_ok(J, pcm, f, t4)) {
+        switch (J.channels) {
+        case 1: fb_k0_quad_p24<1>(J, pcm, xt, err_flag, f, t4); return;
+        case 2: fb_k0_quad_p24<2>(J, pcm, xt, err_flag, f, t4); return;
+        case 3: fb_k0_quad_p24<3>(J, pcm, xt, err_flag, f, t4); return;
+        case 4: fb_k0_quad_p24<4>(J, pcm, xt, err_flag, f, t4); return;
+        case 5: fb_k0_quad_p24<5>(J, pcm, xt, err_flag, f, t4); return;
+        case 6: fb_k0_quad_p24<6>(J, pcm, xt, err_flag, f, t4); return;
+        case 7: fb_k0_quad_p24<7>(J, pcm, xt, err_flag, f, t4); return;
+        default: fb_k0_quad_p24<8>(J, pcm, xt, err_flag, f, t4); return;
+        }
+    }
+    fb_k0_quad(J, pcm, xt, err_flag, f, t4);
+}
+
 // same for a planar FrameBuf input (fb200_encode_planar_frame): src[ch * src_stride + t], one frame (f = 0)
 FB_DEV void fb_k0_planar_quad(const FbJob &J, const int32_t *src, int src_stride, int32_t *xt, uint32_t *err_flag, int t4) {
     const int n = J.tail_n, t = 4 * t4;

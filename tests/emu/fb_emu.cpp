@@ -80,7 +80,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
             uint32_t f;
             int t4;
             fb_k0_item(idx, J.stride / 4, &f, &t4);
-            if (f < J.n_frames && t4 < J.stride / 4) fb_k0_quad(J, (const uint8_t *)pcm, B.xv.data(), &err_flag, f, t4);
+            if (f < J.n_frames && t4 < J.stride / 4) fb_k0_quad_any(J, (const uint8_t *)pcm, B.xv.data(), &err_flag, f, t4);
         }
     }
     if (err_flag) return FB200_ERR_CONFIG;
