@@ -1,6 +1,7 @@
-// fb_fused.cuh -- KF: the fused per-frame kernel (Rice search of every channel variant + frame assembly).
+// fb_fused.cuh -- the fused path: per-frame plan kernel KA (Rice search of every channel variant, decisions, frame
+// plan) and per-frame pack kernel KP (bit packing, CRC-16, store at the final stream offset).
 //
-// One CTA per frame, one warp per channel variant (L, R, M, S for stereo).  The frame's independent
+// KA: one CTA per frame, one warp per channel variant (L, R, M, S for stereo).  The frame's independent
 // channels are staged once in shared memory (M and S are formed on the fly: src/coding.rs:476-484);
 // everything else runs out of shared memory and registers:
 //
@@ -21,13 +22,14 @@
 //     pass 4  partition order, parameters, exact Residual::count_bits (src/component/bitrepr.rs:532-544)
 //             and the bit length of every unit (again from the counters)
 //   subframe decision (src/coding.rs:384-418); then per frame: stereo decision (src/coding.rs:454-527),
-//   header + CRC-8, bit offsets of all units by a scan, packing (one thread per unit; residuals are
-//   recomputed from the staged samples), CRC-16, store.
+//   header + CRC-8, bit offsets of all units by a warp scan; the plan and the frame size go to global memory.
+// KP (after the scan of the frame sizes): stages the channels again, every thread packs one unit (residuals
+//   recomputed, every code OR-ed on its own into the zeroed word buffer), CRC-16, store at out + offsets[f].
 //
-// Whatever this kernel cannot reproduce exactly -- a residual >= 2^27 (the reference's 16-sample chunked
-// saturating accumulation matters, src/rice.rs:75-98) or a saturated table minimum -- is not guessed: the
-// frame is appended to a fallback list and redone by the generic K2/K3 kernels (fb_kernels.cuh), which
-// replay the reference literally.  Results are byte-identical either way.
+// Whatever KA cannot reproduce exactly -- a residual >= 2^26 (the reference's 16-sample chunked saturating
+// accumulation matters, src/rice.rs:75-98), a saturated table minimum, finest partitions that are not a multiple
+// of 4 samples -- is not guessed: the frame is appended to a fallback list and redone by the generic K2/K3
+// kernels (fb_kernels.cuh), which replay the reference literally.  Results are byte-identical either way.
 #pragma once
 
 #include "fb_kernels.cuh"

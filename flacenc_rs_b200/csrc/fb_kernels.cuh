@@ -1,15 +1,18 @@
 // fb_kernels.cuh -- kernel bodies of the B200 FLAC frame-encode pipeline.
 //
-//   K0 ingest   : interleaved packed PCM -> planar int32 channel variants (L,R,M,S for stereo),
-//                 range check                                   [thread per inter-channel sample]
+//   K0 ingest   : interleaved packed PCM -> row-interleaved planar int32 channel rows, range check
+//                                                               [thread per (frame, 4 samples)]
 //   K1 analyze  : constant detection, fixed-predictor entropy estimate, windowed autocorrelation
 //                 (sequential f64 FMA, bit-identical to the scalar reference), Levinson-Durbin,
 //                 qlp quantisation                              [thread per channel variant]
-//   K2 rice     : residual of the fixed winner and of the LPC candidate, partitioned Rice search,
-//                 exact bit counts, per-variant subframe decision [CTA per channel variant]
+//   fused path  : fb_fused.cuh (plan kernel KA, pack kernel KP) -- the default for eligible batches
+//   generic path, for the frames KA hands back and for batches that are not eligible:
+//   K0b expand  : plain rows per variant (with M and S)
+//   K2 rice     : residual of the fixed winner and of the LPC candidate, partitioned Rice search by literal
+//                 table replay, exact bit counts, per-variant subframe decision [CTA per channel variant]
 //   K3 pack     : stereo decision, frame header + CRC-8, bit packing from a prefix scan of code
-//                 lengths, CRC-16                               [CTA per frame]
-//   K4 gather   : exclusive scan of frame sizes, compaction into one contiguous byte stream
+//                 lengths, CRC-16, into a per-frame slot          [CTA per frame]
+//   K4          : exclusive scan of frame sizes; gather of slots into the contiguous byte stream
 //
 // Every body is written as barrier-delimited phases (FB_PHASE ... FB_PHASE_END) so the same source
 // also runs under the CPU emulation used by the logic tests (see fb_common.h).
