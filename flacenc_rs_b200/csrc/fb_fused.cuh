@@ -381,46 +381,44 @@ FB_DEV int fb_kf_pstart(unsigned long long s0, int cnt, int max_p) {
 // the G history samples are loaded once per unit and then slide in registers, the 16 new samples come
 // from 16-byte shared-memory loads (scalar loads when the unit is not 4-aligned).
 
+// Variant mode `vm`: bits 0-1 = 0 plain channel (xb == xa), 2 mid, 3 side; bit 2 = int16 planes.  Every sample is
+// formed as (a + m * b) >> sh with (m, sh) = (0, 0), (1, 1), (-1, 0): one branch-free path for all variants
+// (src/coding.rs:476-484 for M and S).
+FB_DEV void fb_vm_mix(int vm, int32_t *m, int32_t *sh) {
+    const int k = vm & 3;
+    *m = k == 2 ? 1 : (k == 3 ? -1 : 0);
+    *sh = k == 2 ? 1 : 0;
+}
+
 // four samples t..t+3 (t a multiple of 4, inside the plane incl. its slack)
 FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
     const int o = fb_xidx(t);
-    int32_t a[4], b[4];
+    int32_t m, sh;
+    fb_vm_mix(vm, &m, &sh);
     if (vm & FB_VM_X16) {
         const int2 wa = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xa) + o);
-        a[0] = (int32_t)(int16_t)(uint32_t)wa.x; a[1] = wa.x >> 16; a[2] = (int32_t)(int16_t)(uint32_t)wa.y; a[3] = wa.y >> 16;
-        if (vm & 2) {
-            const int2 wb = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xb) + o);
-            b[0] = (int32_t)(int16_t)(uint32_t)wb.x; b[1] = wb.x >> 16; b[2] = (int32_t)(int16_t)(uint32_t)wb.y; b[3] = wb.y >> 16;
-        }
+        const int2 wb = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xb) + o);
+        dst[0] = fb_mix((int32_t)(int16_t)(uint32_t)wa.x, (int32_t)(int16_t)(uint32_t)wb.x, m, sh);
+        dst[1] = fb_mix(wa.x >> 16, wb.x >> 16, m, sh);
+        dst[2] = fb_mix((int32_t)(int16_t)(uint32_t)wa.y, (int32_t)(int16_t)(uint32_t)wb.y, m, sh);
+        dst[3] = fb_mix(wa.y >> 16, wb.y >> 16, m, sh);
     } else {
         const int4 wa = *reinterpret_cast<const int4 *>(xa + o);
-        a[0] = wa.x; a[1] = wa.y; a[2] = wa.z; a[3] = wa.w;
-        if (vm & 2) {
-            const int4 wb = *reinterpret_cast<const int4 *>(xb + o);
-            b[0] = wb.x; b[1] = wb.y; b[2] = wb.z; b[3] = wb.w;
-        }
-    }
-    if (!(vm & 2)) {
-        dst[0] = a[0]; dst[1] = a[1]; dst[2] = a[2]; dst[3] = a[3];
-    } else if ((vm & 3) == 2) {
-        dst[0] = fb_mid(a[0], b[0]); dst[1] = fb_mid(a[1], b[1]); dst[2] = fb_mid(a[2], b[2]); dst[3] = fb_mid(a[3], b[3]);
-    } else {
-        dst[0] = fb_side(a[0], b[0]); dst[1] = fb_side(a[1], b[1]); dst[2] = fb_side(a[2], b[2]); dst[3] = fb_side(a[3], b[3]);
+        const int4 wb = *reinterpret_cast<const int4 *>(xb + o);
+        dst[0] = fb_mix(wa.x, wb.x, m, sh);
+        dst[1] = fb_mix(wa.y, wb.y, m, sh);
+        dst[2] = fb_mix(wa.z, wb.z, m, sh);
+        dst[3] = fb_mix(wa.w, wb.w, m, sh);
     }
 }
 
 FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
     const int o = fb_xidx(t);
-    int32_t a, b = 0;
-    if (vm & FB_VM_X16) {
-        a = reinterpret_cast<const int16_t *>(xa)[o];
-        if (vm & 2) b = reinterpret_cast<const int16_t *>(xb)[o];
-    } else {
-        a = xa[o];
-        if (vm & 2) b = xb[o];
-    }
-    if (!(vm & 2)) return a;
-    return (vm & 3) == 2 ? fb_mid(a, b) : fb_side(a, b);
+    int32_t m, sh;
+    fb_vm_mix(vm, &m, &sh);
+    if (vm & FB_VM_X16)
+        return fb_mix(reinterpret_cast<const int16_t *>(xa)[o], reinterpret_cast<const int16_t *>(xb)[o], m, sh);
+    return fb_mix(xa[o], xb[o], m, sh);
 }
 
 // win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4)
