@@ -390,9 +390,8 @@ FB_DEV void fb_vm_mix(int vm, int32_t *m, int32_t *sh) {
     *sh = k == 2 ? 1 : 0;
 }
 
-// four samples t..t+3 (t a multiple of 4, inside the plane incl. its slack)
-FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
-    const int o = fb_xidx(t);
+// four samples at plane offset o = fb_xidx(t) (t a multiple of 4, inside the plane incl. its slack)
+FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, int o, int32_t *dst) {
     int32_t m, sh;
     fb_vm_mix(vm, &m, &sh);
     if (vm & FB_VM_X16) {
@@ -410,6 +409,10 @@ FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int
         dst[2] = fb_mix(wa.z, wb.z, m, sh);
         dst[3] = fb_mix(wa.w, wb.w, m, sh);
     }
+}
+
+FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
+    fb_kf_load4_at(xa, xb, vm, fb_xidx(t), dst);
 }
 
 FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
@@ -435,8 +438,15 @@ FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, 
 // win[G..G+RUN) = x[t0 .. t0+RUN) (t0 a multiple of 4); samples at t >= n are don't-cares (their results are masked)
 template <int G>
 FB_DEV void fb_kf_fetch_run(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
+    if ((t0 & 15) == 0) {
+        // a run that starts on a multiple of 16 lies inside one 64-sample block of the padded plane: one index
+        const int o = fb_xidx(t0);
 #pragma unroll
-    for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
+        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4_at(xa, xb, vm, o + i, win + G + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
+    }
 }
 
 template <int G>
