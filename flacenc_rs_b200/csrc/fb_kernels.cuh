@@ -423,7 +423,8 @@ FB_DEV void fb_k1_acc_load(const FbVarRows &rows, const float *win, int t0, int3
     }
 }
 
-template <int R, bool GUARDED>
+// SKIP = R - lpc_order (0..3): the lags above lpc_order are not accumulated at all.
+template <int R, bool GUARDED, int SKIP>
 FB_DEV void fb_k1_acc_group(FbK1Acc<R> &S, const int32_t *xs, const float *ws, int t0, int n, int P) {
 #pragma unroll
     for (int s = 0; s < R; s++) {
@@ -433,12 +434,33 @@ FB_DEV void fb_k1_acc_group(FbK1Acc<R> &S, const int32_t *xs, const float *ws, i
         if (!GUARDED || t >= P) {
             S.acc[0] = FB_FMA(y, y, S.acc[0]);
 #pragma unroll
-            for (int j = 0; j < R; j++) {
+            for (int j = 0; j < R - SKIP; j++) {
                 // logical y[t-1-j] lives in ring[(s-1-j) mod R]; static after unrolling
                 S.acc[j + 1] = FB_FMA(S.ring[(s - 1 - j + 2 * R) % R], y, S.acc[j + 1]);
             }
         }
         S.ring[s] = y; // overwrites y[t-R]
+    }
+}
+
+template <int R, int SKIP>
+FB_DEV void fb_k1_pass_a(const FbJob &J, FbK1Acc<R> &A, const FbVarRows &rows, const float *win, int n, int P) {
+    int32_t xs[R];
+    float ws[R];
+    int t0 = R;
+    fb_k1_acc_load<R>(rows, win, 0, xs, ws);
+    fb_k1_acc_group<R, true, SKIP>(A, xs, ws, 0, n, P);
+    for (; t0 + R <= n; t0 += R) {
+        if (t0 + FB_K1_AHEAD + R <= J.stride) {
+#pragma unroll
+            for (int i = 0; i < R; i += 4) fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD + i);
+        }
+        fb_k1_acc_load<R>(rows, win, t0, xs, ws);
+        fb_k1_acc_group<R, false, SKIP>(A, xs, ws, t0, n, P);
+    }
+    for (; t0 < n; t0 += R) {
+        fb_k1_acc_load<R>(rows, win, t0, xs, ws);
+        fb_k1_acc_group<R, true, SKIP>(A, xs, ws, t0, n, P);
     }
 }
 
@@ -504,20 +526,12 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
 #pragma unroll
     for (int i = 0; i < R; i++) A.ring[i] = 0.0;
     if (do_lpc) {
-        int32_t xs[R];
-        float ws[R];
-        int t0 = R;
-        fb_k1_acc_load<R>(rows, win, 0, xs, ws);
-        fb_k1_acc_group<R, true>(A, xs, ws, 0, n, P);
-        for (; t0 + R <= n; t0 += R) {
-            if (t0 + FB_K1_AHEAD + R <= J.stride) {
-#pragma unroll
-                for (int i = 0; i < R; i += 4) fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD + i);
-            }
-            fb_k1_acc_load<R>(rows, win, t0, xs, ws);
-            fb_k1_acc_group<R, false>(A, xs, ws, t0, n, P);
+        switch (R - P) {
+        case 0: fb_k1_pass_a<R, 0>(J, A, rows, win, n, P); break;
+        case 1: fb_k1_pass_a<R, 1>(J, A, rows, win, n, P); break;
+        case 2: fb_k1_pass_a<R, 2>(J, A, rows, win, n, P); break;
+        default: fb_k1_pass_a<R, 3>(J, A, rows, win, n, P); break;
         }
-        for (; t0 < n; t0 += R) { fb_k1_acc_load<R>(rows, win, t0, xs, ws); fb_k1_acc_group<R, true>(A, xs, ws, t0, n, P); }
     }
 
     const bool allsame = S.xmin == S.xmax; // src/arrayutils.rs:382-389
