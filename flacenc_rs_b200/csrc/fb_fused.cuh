@@ -490,6 +490,15 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
                                (uint32_t)cd.fc[3] * (uint32_t)win[G + i - 4];
             u[i] = fb_zigzag((int32_t)e);
         }
+    } else if (cd.narrow && G >= 8 && cd.order <= G - 2) {
+        // the common orders (e.g. 10 with G = 12) leave the last two taps zero: skip them
+#pragma unroll
+        for (int i = 0; i < FB_KF_RUN; i++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < G - 2; j++) acc += (uint32_t)qq[j] * (uint32_t)win[G + i - 1 - j];
+            u[i] = fb_zigzag((int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> cd.shift)));
+        }
     } else if (cd.narrow) {
 #pragma unroll
         for (int i = 0; i < FB_KF_RUN; i++) {
