@@ -321,6 +321,21 @@ def main() -> None:
             "clocks": clocks,
             "wall_s_device_loop": wall_dev, "wall_s_e2e_loop": wall_e2e,
         }
+        if not args.no_cpu_baseline and world == 1:
+            # informational: the whole-stream API (fLaC + STREAMINFO + frames) with pageable buffers; its MD5 of the
+            # PCM is sequential host work (src/source.rs:406-429) that runs on its own thread next to the GPU work and
+            # bounds this call -- reported separately, not part of the frame path measured above
+            from flacenc_rs_b200.encoder import encode_with_fixed_block_size
+            from flacenc_rs_b200.source import MemSource
+            ns = min(n, 600 * RATE)
+            src = MemSource.from_samples(pcm_i32[:ns], CHANNELS, BPS, RATE)
+            t0 = time.perf_counter()
+            stream = encode_with_fixed_block_size(Encoder().into_verified(), src, BLOCK, devices=[local_rank])
+            dt = time.perf_counter() - t0
+            line["stream_api"] = {"value": ns / dt, "unit": "samples/s", "seconds_of_audio": ns / RATE, "wall_s": dt,
+                                  "stream_bytes": len(stream),
+                                  "note": "encode_with_fixed_block_size on pageable host memory incl. sample packing in "
+                                          "Python, MD5 and STREAMINFO; MD5-bound (one host core)"}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, frames, secs, _, passes = cpu_port_throughput(pcm_i32[: min(n, 1200 * RATE)], threads, target_seconds=12.0)

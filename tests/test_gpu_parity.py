@@ -363,6 +363,22 @@ def test_encode_with_fixed_block_size_stream():
     assert len(e) == 42
 
 
+def test_stream_sharded_over_devices():
+    """fb200_encode_stream with a device list: contiguous frame ranges per device (one host thread + context each, no
+    collective), concatenated in order; min/max frame size merged.  With one visible GPU the list repeats device 0,
+    which still exercises the sharding arithmetic (3 shards of a 29-frame stream, short tail)."""
+    ndev = _ffi.lib().fb200_device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    n = 1024 * 28 + 300
+    signal = sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=21)
+    src = MemSource.from_samples(signal, 2, 16, 44100)
+    stream = encode_with_fixed_block_size(Encoder().into_verified(), src, 1024, devices=devices)
+    ref = O.encode_stream(O.default_config(), signal, 2, 16, 44100, 1024)
+    assert stream.write() == ref
+    out, info = O.decode_stream(stream.write())
+    assert np.array_equal(out, signal) and info.total_samples == n
+
+
 def test_device_resident_api_matches_host_api():
     """fb200_encode_device (HBM in, HBM out) returns the same bytes as the host-buffer call"""
     import torch
