@@ -9,13 +9,12 @@
 #define FB_CAT(a, b) FB_CAT2(a, b)
 #define FB_NAME(base) FB_CAT(base, FB_INST_G)
 
-// analysis: one thread per channel variant (fb_kernels.cuh)
-#define FB_K1_THREADS 128
+// analysis: one thread per channel variant, rows staged per warp (fb_kernels.cuh)
 __global__ void __launch_bounds__(FB_K1_THREADS) FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt, const float *win_full,
                                                                           const float *win_tail, FbAnalysis *ana,
                                                                           fb200_variant_taps *taps, uint32_t n_variants) {
-    const uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
-    if (gv < n_variants) fb_k1_thread<FB_INST_G>(J, xt, win_full, win_tail, ana, taps, gv);
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    fb_k1_warp<FB_INST_G>(J, xt, win_full, win_tail, ana, taps, n_variants, fb_smem);
 }
 
 // generic Rice search: one CTA per channel variant.  list == nullptr: variant blockIdx.x; else the variants of the
@@ -74,7 +73,10 @@ __global__ void __launch_bounds__(256) FB_NAME(fb_kp_pack_g)(FbJob J, const int3
 void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
                              FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
     const unsigned grid = (nvars + FB_K1_THREADS - 1) / FB_K1_THREADS;
-    FB_NAME(fb_k1_analyze_g)<<<grid, FB_K1_THREADS, 0, st>>>(J, xv, win_full, win_tail, ana, taps, nvars);
+    const uint32_t smem = fb_k1_smem_bytes(J.channels, J.nvar);
+    if (smem > 48u * 1024u)
+        cudaFuncSetAttribute(FB_NAME(fb_k1_analyze_g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    FB_NAME(fb_k1_analyze_g)<<<grid, FB_K1_THREADS, smem, st>>>(J, xv, win_full, win_tail, ana, taps, nvars);
 }
 
 void FB_NAME(fb_launch_k2_g)(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, fb200_subframe_info *choice,

@@ -350,35 +350,85 @@ FB_DEV int fb_quantize(const double *coefs, int n, int precision, int16_t *q, in
 // the unrolled samples share one register-renamed schedule):
 //   pass E  min/max (-> constant, max |x|) and the fixed-predictor entropy estimate, 8 samples per group
 //   pass A  windowing and the autocorrelation lags, R samples per group
-
-#define FB_K1_AHEAD 48 // software prefetch distance in samples (a multiple of 4)
+// On the GPU a warp (32 variants = a contiguous range of xt rows) stages the rows it walks in a shared-memory ring
+// with cp.async several groups ahead, so neither pass ever waits for DRAM; the arithmetic below is shared with the
+// plain per-thread driver that the CPU emulation uses.
 
 // ---- pass E state: registers of one thread
 struct FbK1Ent {
     float s0, s1, s2, s3, s4;       // running f32 sums of |e_k| of the current estimate partition
     int32_t pe0, pe1, pe2, pe3;     // previous e_0..e_3 (zero history)
     int32_t xmin, xmax;
-    int part, pend, psize, n;
+    int pstart, pend, psize, n;
+    unsigned long long b0, b1, b2, b3, b4; // estimated bits per order, summed over the closed partitions
 };
 
-FB_DEV void fb_k1_ent_close(FbK1Ent &S, float (*psum)[5]) {
-    psum[S.part][0] = S.s0; psum[S.part][1] = S.s1; psum[S.part][2] = S.s2;
-    psum[S.part][3] = S.s3; psum[S.part][4] = S.s4;
+FB_DEV void fb_k1_ent_init(FbK1Ent &S, int n, int psize, int32_t first) {
     S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
-    S.part++;
-    S.pend = (S.pend + S.psize < S.n) ? S.pend + S.psize : S.n;
+    S.pe0 = S.pe1 = S.pe2 = S.pe3 = 0;
+    S.pstart = 0;
+    S.psize = psize;
+    S.pend = psize < n ? psize : n;
+    S.n = n;
+    S.b0 = S.b1 = S.b2 = S.b3 = S.b4 = 0;
+    S.xmin = S.xmax = first;
+}
+
+// bits of one partition [end - len, end) for order k (src/coding.rs:209-223): the first k samples of the frame are
+// not counted, the sum still includes them
+FB_DEV unsigned long long fb_k1_part_bits(float sum, int k, int end, int len) {
+    if (end < k) return 0;
+    const int cnt = (end - k) < len ? (end - k) : len;
+    return fb_entropy_partition_bits(sum, cnt);
+}
+
+// a partition ends: its five estimates are independent chains (evaluated side by side), then the sums restart
+FB_DEV void fb_k1_ent_close(FbK1Ent &S) {
+    const int end = S.pend, len = end - S.pstart;
+    if (len > 0) {
+        S.b0 += fb_k1_part_bits(S.s0, 0, end, len);
+        S.b1 += fb_k1_part_bits(S.s1, 1, end, len);
+        S.b2 += fb_k1_part_bits(S.s2, 2, end, len);
+        S.b3 += fb_k1_part_bits(S.s3, 3, end, len);
+        S.b4 += fb_k1_part_bits(S.s4, 4, end, len);
+    }
+    S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
+    S.pstart = end;
+    S.pend = (end + S.psize < S.n) ? end + S.psize : S.n;
+}
+
+// the same, out of line, for the per-sample checks of the guarded groups (keeps the tail code small)
+struct FbK1Bits5 { unsigned long long b[5]; };
+#if FB_GPU
+static __device__ __noinline__
+#else
+static inline
+#endif
+FbK1Bits5 fb_k1_part_bits5(float s0, float s1, float s2, float s3, float s4, int end, int len) {
+    FbK1Bits5 r;
+    r.b[0] = fb_k1_part_bits(s0, 0, end, len);
+    r.b[1] = fb_k1_part_bits(s1, 1, end, len);
+    r.b[2] = fb_k1_part_bits(s2, 2, end, len);
+    r.b[3] = fb_k1_part_bits(s3, 3, end, len);
+    r.b[4] = fb_k1_part_bits(s4, 4, end, len);
+    return r;
+}
+FB_DEV void fb_k1_ent_close_tail(FbK1Ent &S) {
+    const int end = S.pend, len = end - S.pstart;
+    if (len > 0) {
+        const FbK1Bits5 r = fb_k1_part_bits5(S.s0, S.s1, S.s2, S.s3, S.s4, end, len);
+        S.b0 += r.b[0]; S.b1 += r.b[1]; S.b2 += r.b[2]; S.b3 += r.b[3]; S.b4 += r.b[4];
+    }
+    S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
+    S.pstart = end;
+    S.pend = (end + S.psize < S.n) ? end + S.psize : S.n;
 }
 
 // 8 samples starting at t0.  GUARDED: samples may lie beyond n and a partition may end at any sample; otherwise all
 // 8 are valid and a partition can only end with the group.  zero-history differences, wrapping i32
 // (src/coding.rs:188-195); |e| is taken on the float (the conversion is symmetric; |e| < 2^31 always).
-FB_DEV void fb_k1_ent_load(const FbVarRows &rows, int t0, int32_t *xs) {
-    fb_rows_load4(rows, t0, xs);
-    fb_rows_load4(rows, t0 + 4, xs + 4);
-}
-
 template <bool GUARDED, bool DO_ENT>
-FB_DEV void fb_k1_ent_group(FbK1Ent &S, const int32_t *xs, int t0, float (*psum)[5]) {
+FB_DEV void fb_k1_ent_group(FbK1Ent &S, const int32_t *xs, int t0) {
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         const int t = t0 + s;
@@ -398,10 +448,10 @@ FB_DEV void fb_k1_ent_group(FbK1Ent &S, const int32_t *xs, int t0, float (*psum)
             S.s2 = FB_FADD(fabsf((float)e2), S.s2);
             S.s3 = FB_FADD(fabsf((float)e3), S.s3);
             S.s4 = FB_FADD(fabsf((float)e4), S.s4);
-            if (GUARDED && t + 1 == S.pend) fb_k1_ent_close(S, psum);
+            if (GUARDED && t + 1 == S.pend) fb_k1_ent_close_tail(S);
         }
     }
-    if (DO_ENT && !GUARDED && t0 + 8 == S.pend) fb_k1_ent_close(S, psum);
+    if (DO_ENT && !GUARDED && t0 + 8 == S.pend) fb_k1_ent_close(S);
 }
 
 // ---- pass A state
@@ -413,16 +463,6 @@ struct FbK1Acc {
 
 // R samples starting at t0 (a multiple of R).  y[t] = (f32)x[t] * w[t] (src/lpc.rs:739-756); r[lag] += y[t-lag] * y[t]
 // as sequential f64 FMAs starting at t = lpc_order for every lag (src/lpc.rs:533-548).
-template <int R>
-FB_DEV void fb_k1_acc_load(const FbVarRows &rows, const float *win, int t0, int32_t *xs, float *ws) {
-#pragma unroll
-    for (int i = 0; i < R; i += 4) {
-        fb_rows_load4(rows, t0 + i, xs + i);
-        const float4 v = *reinterpret_cast<const float4 *>(win + t0 + i);
-        ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
-    }
-}
-
 // SKIP = R - lpc_order (0..3): the lags above lpc_order are not accumulated at all.
 template <int R, bool GUARDED, int SKIP>
 FB_DEV void fb_k1_acc_group(FbK1Acc<R> &S, const int32_t *xs, const float *ws, int t0, int n, int P) {
@@ -443,24 +483,15 @@ FB_DEV void fb_k1_acc_group(FbK1Acc<R> &S, const int32_t *xs, const float *ws, i
     }
 }
 
-template <int R, int SKIP>
-FB_DEV void fb_k1_pass_a(const FbJob &J, FbK1Acc<R> &A, const FbVarRows &rows, const float *win, int n, int P) {
-    int32_t xs[R];
-    float ws[R];
-    int t0 = R;
-    fb_k1_acc_load<R>(rows, win, 0, xs, ws);
-    fb_k1_acc_group<R, true, SKIP>(A, xs, ws, 0, n, P);
-    for (; t0 + R <= n; t0 += R) {
-        if (t0 + FB_K1_AHEAD + R <= J.stride) {
+// window weights of the R samples at t0; GUARDED: nothing is read at or beyond n (the tables end shortly after n)
+template <int R, bool GUARDED>
+FB_DEV void fb_k1_win_load(const float *win, int t0, int n, float *ws) {
 #pragma unroll
-            for (int i = 0; i < R; i += 4) fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD + i);
-        }
-        fb_k1_acc_load<R>(rows, win, t0, xs, ws);
-        fb_k1_acc_group<R, false, SKIP>(A, xs, ws, t0, n, P);
-    }
-    for (; t0 < n; t0 += R) {
-        fb_k1_acc_load<R>(rows, win, t0, xs, ws);
-        fb_k1_acc_group<R, true, SKIP>(A, xs, ws, t0, n, P);
+    for (int i = 0; i < R; i += 4) {
+        float4 v;
+        v.x = v.y = v.z = v.w = 0.f;
+        if (!GUARDED || t0 + i < n) v = *reinterpret_cast<const float4 *>(win + t0 + i);
+        ws[i] = v.x; ws[i + 1] = v.y; ws[i + 2] = v.z; ws[i + 3] = v.w;
     }
 }
 
@@ -468,72 +499,29 @@ FB_DEV void fb_k1_pass_a(const FbJob &J, FbK1Acc<R> &A, const FbVarRows &rows, c
 // allocation of the common small orders independent of the order-24 case.
 FB_HD int fb_k1_ring(int lpc_order) { return (lpc_order + 3) & ~3; }
 
-template <int R>
-FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail,
-                         FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t gv) {
-    const uint32_t f = gv / (uint32_t)J.nvar;
-    const int v = (int)(gv - f * (uint32_t)J.nvar);
-    const int n = fb_frame_len(J, f);
-    const int bps_v = fb_variant_bps(J, v);
-    const FbVarRows rows = fb_variant_rows(J, xt, f, v);
-    const float *win = (n == J.block_size) ? win_full : win_tail;
-    FbAnalysis *out = ana + gv;
-    fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
+// ---- what a variant's analysis needs besides the samples
+struct FbK1Var {
+    int n, bps_v, P, psize;
+    bool do_ent, do_lpc;
+    const float *win;
+};
 
-    const int P = J.cfg.lpc_order;
-    const bool too_short = n < FB_MIN_PRED_BLOCK;
-    const bool do_ent = !too_short && J.cfg.use_fixed && J.cfg.fixed_order_sel == 1;
-    const bool do_lpc = !too_short && J.cfg.use_lpc;
-    const int n_orders = (J.cfg.fixed_max_order < 4 ? J.cfg.fixed_max_order : 4) + 1;
+FB_DEV FbK1Var fb_k1_var(const FbJob &J, uint32_t f, int v, const float *win_full, const float *win_tail) {
+    FbK1Var V;
+    V.n = fb_frame_len(J, f);
+    V.bps_v = fb_variant_bps(J, v);
+    V.P = J.cfg.lpc_order;
+    const bool too_short = V.n < FB_MIN_PRED_BLOCK;
+    V.do_ent = !too_short && J.cfg.use_fixed && J.cfg.fixed_order_sel == 1;
+    V.do_lpc = !too_short && J.cfg.use_lpc;
     const int parts = J.cfg.approx_ent_partitions;
-    const int psize = (n + parts - 1) / parts;
+    V.psize = (V.n + parts - 1) / parts;
+    V.win = (V.n == J.block_size) ? win_full : win_tail;
+    return V;
+}
 
-    float psum[FB_MAX_ENT_PARTS][5]; // per-partition sequential f32 sums of |e_k|
-    FbK1Ent S;
-    S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
-    S.pe0 = S.pe1 = S.pe2 = S.pe3 = 0;
-    S.part = 0;
-    S.psize = psize;
-    S.pend = psize < n ? psize : n;
-    S.n = n;
-    {
-        int32_t q[4];
-        fb_rows_load4(rows, 0, q);
-        S.xmin = S.xmax = q[0];
-    }
-    // ---- pass E: whole groups without per-sample checks when the estimate partitions end on multiples of 8
-    // (prefetching the next group into a second register buffer was measured slower: it costs occupancy)
-    {
-        int32_t xs[8];
-        int t0 = 0;
-        if (do_ent) {
-            if ((psize & 7) == 0)
-                for (; t0 + 8 <= n; t0 += 8) {
-                    if (t0 + FB_K1_AHEAD + 8 <= J.stride) { fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD); fb_rows_prefetch4(rows, t0 + FB_K1_AHEAD + 4); }
-                    fb_k1_ent_load(rows, t0, xs);
-                    fb_k1_ent_group<false, true>(S, xs, t0, psum);
-                }
-            for (; t0 < n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<true, true>(S, xs, t0, psum); }
-        } else {
-            for (; t0 + 8 <= n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<false, false>(S, xs, t0, psum); }
-            for (; t0 < n; t0 += 8) { fb_k1_ent_load(rows, t0, xs); fb_k1_ent_group<true, false>(S, xs, t0, psum); }
-        }
-    }
-    // ---- pass A: first group guarded (t < lpc_order), whole groups, guarded remainder
-    FbK1Acc<R> A;
-#pragma unroll
-    for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < R; i++) A.ring[i] = 0.0;
-    if (do_lpc) {
-        switch (R - P) {
-        case 0: fb_k1_pass_a<R, 0>(J, A, rows, win, n, P); break;
-        case 1: fb_k1_pass_a<R, 1>(J, A, rows, win, n, P); break;
-        case 2: fb_k1_pass_a<R, 2>(J, A, rows, win, n, P); break;
-        default: fb_k1_pass_a<R, 3>(J, A, rows, win, n, P); break;
-        }
-    }
-
+// results of pass E: constant flag, max |x|, ApproxEnt order (src/coding.rs:264-285, :396-401)
+FB_DEV void fb_k1_finish_ent(const FbJob &J, const FbK1Var &V, const FbK1Ent &S, FbAnalysis *out, fb200_variant_taps *taps) {
     const bool allsame = S.xmin == S.xmax; // src/arrayutils.rs:382-389
     out->is_constant = allsame ? 1 : 0;
     {
@@ -543,65 +531,366 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
         out->pad = 0;
     }
     out->fixed_order = -1;
-    out->qlp_order = 0;
-    out->qlp_shift = 0;
     for (int k = 0; k < 5; k++) out->fixed_est[k] = 0;
-    for (int i = 0; i < 32; i++) out->qlp[i] = 0;
     if (taps) {
         memset(taps, 0, sizeof(*taps));
         taps->is_constant = allsame ? 1 : 0;
         taps->fixed_order = -1;
     }
-
-    if (do_ent) {
+    if (V.do_ent) {
         // estimate_entropy per order + bits_per_sample * order; first minimum wins; accepted only
-        // if below the verbatim size (src/coding.rs:264-285, :396-401)
-        const uint64_t verbatim_bits = 8 + (uint64_t)n * (uint64_t)bps_v;
+        // if below the verbatim size
+        const int n_orders = (J.cfg.fixed_max_order < 4 ? J.cfg.fixed_max_order : 4) + 1;
+        const uint64_t verbatim_bits = 8 + (uint64_t)V.n * (uint64_t)V.bps_v;
+        const unsigned long long est[5] = {S.b0, S.b1, S.b2, S.b3, S.b4};
         int best = -1;
         uint64_t best_bits = 0;
-        for (int k = 0; k < n_orders; k++) {
-            uint64_t bits = 0;
-            int offset = 0;
-            for (int p = 0; p < parts; p++) {
-                int end = offset + psize < n ? offset + psize : n;
-                int len = end - offset;
-                if (len > 0 && end >= k) {
-                    int cnt = (end - k) < len ? (end - k) : len;
-                    bits += fb_entropy_partition_bits(psum[p][k], cnt);
-                }
-                offset = end;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            if (k < n_orders) {
+                const uint64_t bits = est[k] + (uint64_t)V.bps_v * (uint64_t)k;
+                out->fixed_est[k] = bits;
+                if (taps) taps->fixed_est_bits[k] = bits;
+                if (best < 0 || bits < best_bits) { best = k; best_bits = bits; }
             }
-            bits += (uint64_t)bps_v * (uint64_t)k;
-            out->fixed_est[k] = bits;
-            if (taps) taps->fixed_est_bits[k] = bits;
-            if (best < 0 || bits < best_bits) { best = k; best_bits = bits; }
         }
         if (best >= 0 && best_bits < verbatim_bits) out->fixed_order = best;
         if (taps) taps->fixed_order = out->fixed_order;
     }
+}
 
-    if (do_lpc) {
-        double corr[FB200_MAX_LPC_ORDER + 1];
+// results of pass A: Levinson, quantiser
+template <int R>
+FB_DEV void fb_k1_finish_lpc(const FbJob &J, const FbK1Var &V, const FbK1Acc<R> &A, FbAnalysis *out, fb200_variant_taps *taps) {
+    out->qlp_order = 0;
+    out->qlp_shift = 0;
+    if (!V.do_lpc) {
+        for (int i = 0; i < 32; i++) out->qlp[i] = 0;
+        return;
+    }
+    double corr[FB200_MAX_LPC_ORDER + 1];
 #pragma unroll
-        for (int i = 0; i <= R; i++)
-            if (i <= FB200_MAX_LPC_ORDER) corr[i] = A.acc[i];
-        double lpc[FB200_MAX_LPC_ORDER];
-        fb_levinson(corr, corr + 1, P, lpc);
-        int16_t q[32];
-        int shift;
-        int order = fb_quantize(lpc, P, J.cfg.quant_precision, q, &shift);
-        out->qlp_order = order;
-        out->qlp_shift = shift;
-        for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
-        if (taps) {
-            for (int i = 0; i <= P; i++) taps->autocorr[i] = corr[i];
-            for (int i = 0; i < P; i++) taps->lpc[i] = lpc[i];
-            for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
-            taps->qlp_order = order;
-            taps->qlp_shift = shift;
+    for (int i = 0; i <= R; i++)
+        if (i <= FB200_MAX_LPC_ORDER) corr[i] = A.acc[i];
+    double lpc[FB200_MAX_LPC_ORDER];
+    fb_levinson(corr, corr + 1, V.P, lpc);
+    int16_t q[32];
+    int shift;
+    int order = fb_quantize(lpc, V.P, J.cfg.quant_precision, q, &shift);
+    out->qlp_order = order;
+    out->qlp_shift = shift;
+    for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
+    if (taps) {
+        for (int i = 0; i <= V.P; i++) taps->autocorr[i] = corr[i];
+        for (int i = 0; i < V.P; i++) taps->lpc[i] = lpc[i];
+        for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
+        taps->qlp_order = order;
+        taps->qlp_shift = shift;
+    }
+}
+
+template <int R, int SKIP>
+FB_DEV void fb_k1_pass_a(FbK1Acc<R> &A, const FbVarRows &rows, const FbK1Var &V) {
+    int32_t xs[R];
+    float ws[R];
+    const int n = V.n;
+    for (int t0 = 0; t0 < n; t0 += R) {
+        const bool fast = t0 > 0 && t0 + R <= n;
+#pragma unroll
+        for (int i = 0; i < R; i += 4) fb_rows_load4(rows, t0 + i, xs + i);
+        if (fast) {
+            fb_k1_win_load<R, false>(V.win, t0, n, ws);
+            fb_k1_acc_group<R, false, SKIP>(A, xs, ws, t0, n, V.P);
+        } else {
+            fb_k1_win_load<R, true>(V.win, t0, n, ws);
+            fb_k1_acc_group<R, true, SKIP>(A, xs, ws, t0, n, V.P);
         }
     }
 }
+
+// plain driver: one thread walks its variant straight from xt (CPU emulation; the GPU kernel is fb_k1_warp below)
+template <int R>
+FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail,
+                         FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t gv) {
+    const uint32_t f = gv / (uint32_t)J.nvar;
+    const int v = (int)(gv - f * (uint32_t)J.nvar);
+    const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
+    const FbVarRows rows = fb_variant_rows(J, xt, f, v);
+    FbAnalysis *out = ana + gv;
+    fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
+    const int n = V.n;
+
+    FbK1Ent S;
+    {
+        int32_t q[4];
+        fb_rows_load4(rows, 0, q);
+        fb_k1_ent_init(S, n, V.psize, q[0]);
+    }
+    {
+        int32_t xs[8];
+        const bool whole = (V.psize & 7) == 0;
+        for (int t0 = 0; t0 < n; t0 += 8) {
+            fb_rows_load4(rows, t0, xs);
+            fb_rows_load4(rows, t0 + 4, xs + 4);
+            const bool fast = t0 + 8 <= n && (whole || !V.do_ent);
+            if (V.do_ent) {
+                if (fast) fb_k1_ent_group<false, true>(S, xs, t0);
+                else fb_k1_ent_group<true, true>(S, xs, t0);
+            } else {
+                if (fast) fb_k1_ent_group<false, false>(S, xs, t0);
+                else fb_k1_ent_group<true, false>(S, xs, t0);
+            }
+        }
+    }
+    fb_k1_finish_ent(J, V, S, out, taps);
+
+    FbK1Acc<R> A;
+#pragma unroll
+    for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) A.ring[i] = 0.0;
+    if (V.do_lpc) {
+        switch (R - V.P) {
+        case 0: fb_k1_pass_a<R, 0>(A, rows, V); break;
+        case 1: fb_k1_pass_a<R, 1>(A, rows, V); break;
+        case 2: fb_k1_pass_a<R, 2>(A, rows, V); break;
+        default: fb_k1_pass_a<R, 3>(A, rows, V); break;
+        }
+    }
+    fb_k1_finish_lpc<R>(J, V, A, out, taps);
+}
+
+// rows of xt that the 32 variants of one warp can span, rounded to the staging pitch (16, 32 or 48 rows)
+FB_HD int fb_k1_pitch_rows(int channels, int nvar) {
+    const int frames = (32 % nvar == 0) ? 32 / nvar : (32 + nvar - 1) / nvar + 1;
+    const int rows = frames * channels;
+    return rows <= 16 ? 16 : (rows <= 32 ? 32 : 48);
+}
+#define FB_K1_THREADS 128
+#define FB_K1_NQ 32 // quads of every staged row in a warp's ring (128 samples)
+FB_HD uint32_t fb_k1_smem_bytes(int channels, int nvar) {
+    return (uint32_t)(FB_K1_THREADS / 32) * FB_K1_NQ * (uint32_t)fb_k1_pitch_rows(channels, nvar) * 16u;
+}
+
+#if FB_GPU
+// ---- GPU driver: a warp stages the xt rows of its 32 variants in a shared-memory ring (cp.async, NG - 1 groups
+// ahead) and every lane then walks its variant out of the ring.  A "quad" is four samples of every staged row: in xt
+// the quads of up to 32 consecutive rows are contiguous, and they keep that order in the ring, so the copy is
+// 16 bytes per lane and the reads of the lanes (16 bytes each from row a and row b) are conflict free.
+struct FbK1Stage {
+    uint32_t ring;          // shared-space address of the warp's ring
+    uint32_t pitch;         // bytes per staged quad
+    // copy role: this lane copies quads qsub, qsub + qstep, ... of every group, 16 bytes of one row (two rows when
+    // more than 32 rows are staged); lanes without a row have cp_quads = 0
+    const int32_t *g0;      // global address of (row, quad qsub)
+    uint32_t d0;            // byte offset of (row, quad qsub) inside a group slot
+    uint32_t g1_off;        // second row: word offset from g0 (0: none), staged 512 bytes further
+    int qsub, qstep;
+    int cp_quads;           // quads stored per row (0: nothing to copy)
+    // read role
+    uint32_t ra, rb;        // byte offsets of this lane's a / b row inside a staged quad
+    int32_t m, sh;          // sample = (a + m * b) >> sh
+};
+
+template <int N>
+FB_DEV void fb_k1_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+FB_DEV void fb_k1_cp16(uint32_t dst, const int32_t *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// copies the QC quads starting at quad q0 to the chunk slot at shared address `slot_addr`; always commits one
+// cp.async group.  The common case (16-row pitch, whole chunk inside the rows) is a straight run of copies at constant
+// offsets.
+template <int QC>
+FB_DEV void fb_k1_stage_issue(const FbK1Stage &T, uint32_t slot_addr, int q0) {
+    const int32_t *src = T.g0 + (size_t)q0 * (32u * FB_XT_CH);
+    const uint32_t dst = slot_addr + T.d0;
+    if (q0 + QC <= T.cp_quads) { // warp-uniform unless some lanes have no row at all
+        if (T.qstep == 2) {
+#pragma unroll
+            for (int k = 0; k < QC / 2; k++) fb_k1_cp16(dst + (uint32_t)k * 512u, src + (size_t)k * (2u * 32u * FB_XT_CH));
+            if ((QC & 1) && T.qsub == 0) fb_k1_cp16(dst + (uint32_t)(QC / 2) * 512u, src + (size_t)(QC / 2) * (2u * 32u * FB_XT_CH));
+        } else {
+#pragma unroll
+            for (int k = 0; k < QC; k++) {
+                fb_k1_cp16(dst + (uint32_t)k * T.pitch, src + (size_t)k * (32u * FB_XT_CH));
+                if (T.g1_off) fb_k1_cp16(dst + (uint32_t)k * T.pitch + 512u, src + (size_t)k * (32u * FB_XT_CH) + T.g1_off);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = T.qsub; i < QC; i += T.qstep) {
+            if (q0 + i < T.cp_quads) {
+                const int k = i - T.qsub;
+                fb_k1_cp16(dst + (uint32_t)k * T.pitch, src + (size_t)k * (32u * FB_XT_CH));
+                if (T.g1_off) fb_k1_cp16(dst + (uint32_t)k * T.pitch + 512u, src + (size_t)k * (32u * FB_XT_CH) + T.g1_off);
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// the lane's 4 * QG samples of the group slot at shared address `slot_addr`
+template <int QG>
+FB_DEV void fb_k1_stage_read(const FbK1Stage &T, uint32_t slot_addr, int32_t *xs) {
+#pragma unroll
+    for (int i = 0; i < QG; i++) {
+        const uint32_t base = slot_addr + (uint32_t)i * T.pitch;
+        int4 a, b;
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(base + T.ra));
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(base + T.rb));
+        xs[4 * i + 0] = fb_mix(a.x, b.x, T.m, T.sh);
+        xs[4 * i + 1] = fb_mix(a.y, b.y, T.m, T.sh);
+        xs[4 * i + 2] = fb_mix(a.z, b.z, T.m, T.sh);
+        xs[4 * i + 3] = fb_mix(a.w, b.w, T.m, T.sh);
+    }
+}
+
+// One pass of the warp over its rows in groups of 4 * QG samples, staged in chunks of GC groups.  body(g, xs) gets
+// group g's samples of this lane.  NC chunk slots: NC - 1 copies in flight while one chunk is read.
+template <int QG, int GC, typename Body>
+FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
+    constexpr int QC = QG * GC;
+    constexpr int NC = FB_K1_NQ / QC;
+    constexpr int D = NC - 1;
+    static_assert(NC >= 2, "ring too small");
+    const uint32_t group_bytes = (uint32_t)QG * T.pitch, slot_bytes = (uint32_t)GC * group_bytes;
+    const uint32_t ring_end = T.ring + (uint32_t)NC * slot_bytes;
+#pragma unroll 1
+    for (int c = 0; c < D; c++) fb_k1_stage_issue<QC>(T, T.ring + (uint32_t)c * slot_bytes, c * QC);
+    uint32_t slot_r = T.ring, slot_w = T.ring + (uint32_t)D * slot_bytes;
+    int q_w = D * QC;
+#pragma unroll 1
+    for (int g0 = 0; g0 < groups; g0 += GC) {
+        fb_k1_cp_wait<D - 1>(); // this chunk has landed (this lane's copies) ...
+        __syncwarp();           // ... and everybody's; all lanes are also done reading the previous chunk
+        fb_k1_stage_issue<QC>(T, slot_w, q_w);
+        q_w += QC;
+        slot_w += slot_bytes;
+        slot_w = slot_w == ring_end ? T.ring : slot_w;
+#pragma unroll 1
+        for (int gi = 0; gi < GC; gi++) {
+            if (g0 + gi >= groups) break;
+            int32_t xs[4 * QG];
+            fb_k1_stage_read<QG>(T, slot_r + (uint32_t)gi * group_bytes, xs);
+            body(g0 + gi, xs);
+        }
+        slot_r += slot_bytes;
+        slot_r = slot_r == ring_end ? T.ring : slot_r;
+    }
+    fb_k1_cp_wait<0>();
+    __syncwarp(); // the ring may be refilled by the next pass
+}
+
+template <int R, int SKIP>
+FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &V, int n_w, bool uniform) {
+    fb_k1_stream<R / 4, (R <= 8 ? 4 : (R <= 16 ? 2 : 1))>(T, (n_w + R - 1) / R, [&](int g, const int32_t *xs) {
+        const int t0 = g * R;
+        float ws[R];
+        if (uniform && g > 0 && t0 + R <= n_w) {
+            fb_k1_win_load<R, false>(V.win, t0, V.n, ws);
+            fb_k1_acc_group<R, false, SKIP>(A, xs, ws, t0, V.n, V.P);
+        } else {
+            fb_k1_win_load<R, true>(V.win, t0, V.n, ws);
+            fb_k1_acc_group<R, true, SKIP>(A, xs, ws, t0, V.n, V.P);
+        }
+    });
+}
+
+template <int R>
+FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail, FbAnalysis *ana,
+                       fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
+    const uint32_t gv0 = gv - lane;
+    if (gv0 >= n_variants) return; // the whole warp has nothing to do
+    const bool valid = gv < n_variants;
+    const uint32_t gve = valid ? gv : n_variants - 1u; // surplus lanes shadow the last variant (they still copy)
+    const uint32_t nvar = (uint32_t)J.nvar, ch = (uint32_t)J.channels;
+    const uint32_t f = gve / nvar;
+    const int v = (int)(gve - f * nvar);
+    const uint32_t gvl = gv0 + 31u < n_variants ? gv0 + 31u : n_variants - 1u;
+    const uint32_t f_lo = gv0 / nvar, f_hi = gvl / nvar;
+    const uint32_t rlo = f_lo * ch;
+    const uint32_t NR = (f_hi - f_lo + 1u) * ch;
+    const int n_w = fb_frame_len(J, f_lo);               // frames of a batch only get shorter at its end
+    const bool uniform = fb_frame_len(J, f_hi) == n_w;   // all lanes walk frames of one length
+    const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
+    FbAnalysis *out = ana + gve;
+    fb200_variant_taps *taps = taps_all ? taps_all + gve : nullptr;
+
+    FbK1Stage T;
+    {
+        const uint32_t prow = (uint32_t)fb_k1_pitch_rows(J.channels, J.nvar);
+        T.pitch = prow * 16u;
+        T.ring = (uint32_t)__cvta_generic_to_shared(smem) + warp * (uint32_t)FB_K1_NQ * T.pitch;
+        uint32_t row_a, row_b;
+        if (ch == 2u && v >= 2) {
+            row_a = f * 2u; row_b = row_a + 1u;
+            T.m = v == 2 ? 1 : -1;
+            T.sh = v == 2 ? 1 : 0;
+        } else {
+            row_a = row_b = f * ch + (uint32_t)v;
+            T.m = 0; T.sh = 0;
+        }
+        T.ra = (row_a - rlo) * 16u;
+        T.rb = (row_b - rlo) * 16u;
+        uint32_t ri = lane;
+        T.qsub = 0;
+        T.qstep = 1;
+        if (prow == 16u) { ri = lane & 15u; T.qsub = (int)(lane >> 4); T.qstep = 2; }
+        const uint32_t rc = ri < NR ? ri : 0u; // lanes beyond the rows copy nothing
+        T.g0 = xt + fb_xt_off(J.stride, rlo + rc, 0) + (size_t)T.qsub * (32u * FB_XT_CH);
+        T.d0 = ri * 16u + (uint32_t)T.qsub * T.pitch;
+        T.cp_quads = ri < NR ? J.stride / FB_XT_CH : 0;
+        // more than 32 rows: lane ri also copies row ri + 32, which lies one 32-row unit further in xt; the lanes
+        // whose second row does not exist get offset 0 and skip it
+        T.g1_off = 0;
+        if (prow > 32u) {
+            const uint32_t r2 = ri + 32u < NR ? ri + 32u : rc;
+            T.g1_off = (uint32_t)(fb_xt_off(J.stride, rlo + r2, 0) - fb_xt_off(J.stride, rlo + rc, 0));
+        }
+    }
+
+    // ---- pass E
+    {
+        FbK1Ent S;
+        fb_k1_ent_init(S, V.n, V.psize, 0);
+        S.xmin = 2147483647;
+        S.xmax = -2147483647 - 1;
+        const bool ent_w = J.cfg.use_fixed && J.cfg.fixed_order_sel == 1 && n_w >= FB_MIN_PRED_BLOCK;
+        const bool whole = uniform && (!ent_w || (V.psize & 7) == 0);
+        if (ent_w)
+            fb_k1_stream<2, 4>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
+                if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, true>(S, xs, g * 8);
+                else fb_k1_ent_group<true, true>(S, xs, g * 8);
+            });
+        else
+            fb_k1_stream<2, 4>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
+                if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, false>(S, xs, g * 8);
+                else fb_k1_ent_group<true, false>(S, xs, g * 8);
+            });
+        if (valid) fb_k1_finish_ent(J, V, S, out, taps);
+    }
+
+    // ---- pass A
+    FbK1Acc<R> A;
+#pragma unroll
+    for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) A.ring[i] = 0.0;
+    if (J.cfg.use_lpc && n_w >= FB_MIN_PRED_BLOCK) {
+        switch (R - V.P) {
+        case 0: fb_k1_warp_pass_a<R, 0>(T, A, V, n_w, uniform); break;
+        case 1: fb_k1_warp_pass_a<R, 1>(T, A, V, n_w, uniform); break;
+        case 2: fb_k1_warp_pass_a<R, 2>(T, A, V, n_w, uniform); break;
+        default: fb_k1_warp_pass_a<R, 3>(T, A, V, n_w, uniform); break;
+        }
+    }
+    if (valid) fb_k1_finish_lpc<R>(J, V, A, out, taps);
+}
+#endif
 
 #if !FB_GPU
 inline void fb_k1_dispatch(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail,

@@ -30,7 +30,7 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 body = rows[2:]
 names = [r[hdr.index("Kernel Name")].split("(")[0] for r in body]
 out = [f"# {tag}: `ncu --set full --clock-control none` of the two heaviest kernels\n\n",
-       f"Command: `bash tools/gpu_profile.sh {tag}` (bench.py --seconds 600: 6460 frames of the C2 workload; one launch of each "
+       f"Command: `bash tools/gpu_profile.sh {tag}` (bench.py default workload: 38760 frames of C2; one launch of each "
        "kernel, cold cache, serialised -- compare shares, not absolutes).  The .ncu-rep stays in gpurun_out/ (scratch).\n\n",
        "| metric | " + " | ".join(names) + " |\n", "|---|" + "---|" * len(names) + "\n"]
 for k in want:
