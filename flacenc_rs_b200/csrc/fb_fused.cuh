@@ -48,9 +48,19 @@ FB_DEV void fb_copy16_async(int32_t *dst_smem, const int32_t *src_global) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_global) : "memory");
 }
+FB_DEV void fb_copy8_async(void *dst_smem, const void *src_global) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+}
+FB_DEV void fb_copy4_async(void *dst_smem, const void *src_global) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_global) : "memory");
+}
 FB_DEV void fb_copy_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 #else
 FB_DEV void fb_copy16_async(int32_t *dst, const int32_t *src) { memcpy(dst, src, 16); }
+FB_DEV void fb_copy8_async(void *dst, const void *src) { memcpy(dst, src, 8); }
+FB_DEV void fb_copy4_async(void *dst, const void *src) { memcpy(dst, src, 4); }
 FB_DEV void fb_copy_async_wait() {}
 #endif
 
@@ -931,7 +941,7 @@ FB_DEV void fb_kf_stage(const FbJob &J, const int32_t *xv, uint32_t f, int n, in
     // quad i of every channel together: the rows of one frame are adjacent in xt (one 32-byte sector for stereo)
     const int n4 = (n + 3) >> 2;
     if (L.x16) {
-#pragma unroll 4
+#pragma unroll 8
         for (int i = tid; i < n4; i += T) {
             for (int c = c0; c < c1; c++) {
                 const int32_t *src = xv + fb_xt_off(J.stride, f * (uint32_t)J.channels + (uint32_t)c, 0);
@@ -1137,25 +1147,27 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
 
     // ---- the plan, the CRC tables; clear the word buffer; stage the first group of channels
     const int GC = (int)L.group_ch;
+    static_assert(sizeof(FbKfPlan) % 16 == 0 && sizeof(fb200_subframe_info) % 8 == 0, "async copy granularity");
     FB_PHASE(tid, T)
-        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, GC < J.channels ? GC : J.channels);
+        // the small records fly (cp.async) while the planes are staged through registers
         {
-            const uint32_t *src = (const uint32_t *)&plan[f];
-            uint32_t *dst = (uint32_t *)S;
-            for (int i = tid; i < (int)(sizeof(FbKfPlan) / 4); i += T) dst[i] = src[i];
+            const int32_t *src = (const int32_t *)&plan[f];
+            int32_t *dst = (int32_t *)S;
+            for (int i = tid; i < (int)(sizeof(FbKfPlan) / 16); i += T) fb_copy16_async(dst + 4 * i, src + 4 * i);
         }
         {
-            const uint32_t *src = (const uint32_t *)&psubs[(size_t)f * (size_t)J.channels];
-            uint32_t *dst = (uint32_t *)psub;
-            for (int i = tid; i < J.channels * (int)(sizeof(fb200_subframe_info) / 4); i += T) dst[i] = src[i];
+            const uint64_t *src = (const uint64_t *)&psubs[(size_t)f * (size_t)J.channels];
+            uint64_t *dst = (uint64_t *)psub;
+            for (int i = tid; i < J.channels * (int)(sizeof(fb200_subframe_info) / 8); i += T) fb_copy8_async(dst + i, src + i);
         }
         {
             const uint32_t *src = poffs + (size_t)f * (size_t)J.channels * (L.U_max + 1);
-            for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) poff[i] = src[i];
+            for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) fb_copy4_async(poff + i, src + i);
         }
-        for (int i = tid; i < 1024; i += T) crc_tab[i] = ktab[i];
+        for (int i = tid; i < 256; i += T) fb_copy16_async((int32_t *)crc_tab + 4 * i, (const int32_t *)ktab + 4 * i);
+        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, GC < J.channels ? GC : J.channels);
         for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
-        if (tid == 0) { S->crc_acc = 0; S->crc_last = 0; }
+        if (tid == 0) { S->crc_acc = 0; S->crc_last = 0; } // (beyond the part of S that the plan copy fills)
         fb_copy_async_wait();
     FB_PHASE_END
 
