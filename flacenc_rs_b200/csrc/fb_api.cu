@@ -446,7 +446,7 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         // straight to its final offset, and the listed frames are gathered from their slots.
         FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
         fb_launch_ka(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, S.plan.p,
-                     (fb200_subframe_info *)S.psubs.p, (uint32_t *)S.poffs.p, d_fb, d_infos, (uint32_t *)S.fb_list.p,
+                     (fb200_subframe_info *)S.choice.p, (fb200_subframe_info *)S.psubs.p, (uint32_t *)S.poffs.p, d_fb, d_infos, (uint32_t *)S.fb_list.p,
                      d_fb_count, (const uint32_t *)ctx->ktab.p, P.KL, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
         fb_k0b_expand<<<148, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, (const uint32_t *)S.fb_list.p,

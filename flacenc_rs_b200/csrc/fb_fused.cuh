@@ -35,8 +35,8 @@
 #include "fb_kernels.cuh"
 
 #define FB_KF_RUN 16       // samples per residual run (register window of G + FB_KF_RUN samples)
-#define FB_KF_COLS 8       // Rice parameters evaluated per tree pass
-#define FB_KF_ROW 9        // row stride of the tree tables (one pad word: conflict-free column reads)
+#define FB_KF_COLS 4       // Rice parameters evaluated per tree pass
+#define FB_KF_ROW 5        // row stride of the tree tables (one pad word: conflict-free column reads)
 #define FB_KF_NWORDS 7     // bit-sliced counter words per unit (counts <= 127)
 #define FB_KF_UNIT_MAX 112 // samples per unit (7 runs of 16)
 #define FB_KF_SMEM_LIMIT (225u * 1024u) // dynamic shared memory one CTA may ask for (227 KiB on sm_100a, minus slack)
@@ -158,10 +158,10 @@ struct FbKfLayout {
     uint32_t x_stride;   // 32-bit words per staged plane
     uint32_t x16;        // planes hold int16 samples
     uint32_t off_x;      // channels planes
-    uint32_t off_keep;   // per warp: unit_bits[2][U+1], xch[64], results
+    uint32_t off_keep;   // per warp: unit_bits[2][U+1], results of both candidates
     uint32_t keep_bytes;
-    uint32_t k_unit_bits, k_xch, k_res;
-    uint32_t off_choice; // nvar x fb200_subframe_info
+    uint32_t k_unit_bits, k_res, res_stride;
+    uint32_t off_choice; // pack kernel: channels x fb200_subframe_info
     uint32_t off_frame;  // FbKfFrame
     uint32_t off_scratch; // per warp scratch, aliased by the frame words during packing
     uint32_t scratch_bytes;
@@ -222,17 +222,21 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     // kept per warp
     uint32_t k = 0;
     L.k_unit_bits = k;  k += fb_align16(2u * (U + 1u) * 4u);
-    L.k_xch = k;        k += 64u * 8u;
-    L.k_res = k;        k += fb_align16(2u * (uint32_t)sizeof(FbKfRes));
+    L.res_stride = fb_align16((uint32_t)offsetof(FbKfRes, params) + leaves); // params[] holds at most `leaves` entries
+    L.k_res = k;        k += 2u * L.res_stride;
     L.keep_bytes = k;
     L.off_keep = o;     o += (uint32_t)nvar * k;
-    L.off_choice = o;   o += fb_align16((uint32_t)nvar * (uint32_t)sizeof(fb200_subframe_info));
+    L.off_choice = 0;   // (the plan kernel keeps the variants' records in global memory)
     L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
     // scratch per warp
     uint32_t s = 0;
     L.s_words = s;      s += fb_align16(FB_KF_NWORDS * U * 4u);
     uint32_t ta = leaves * FB_KF_ROW * 4u;
-    if (ta < 16u * 32u * 4u) ta = 16u * 32u * 4u; // also the level-sum exchange (16 levels x 32 lanes)
+    {
+        uint32_t levels = 1; // also the level-sum exchange (levels x 32 lanes) and the offset scan's 32 words
+        while ((1u << (levels - 1u)) < leaves) levels++;
+        if (ta < levels * 32u * 4u) ta = levels * 32u * 4u;
+    }
     L.s_tbl_a = s;      s += fb_align16(ta);
     L.s_tbl_b = s;      s += fb_align16((leaves / 2u + 1u) * FB_KF_ROW * 4u);
     L.s_best_val = s;   s += fb_align16(2u * leaves * 4u);
@@ -683,7 +687,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
     }
 
     // ---- pass 4a: totals per level (lane partials -> exchange -> one lane per level)
-    uint32_t *lx = tbl_a; // 16 x 32 exchange words
+    uint32_t *lx = tbl_a; // (o0 + 1) x 32 exchange words
     FB_WPHASE(lane)
         for (int lvl = 0; lvl <= g.o0; lvl++) {
             const int nodes = 1 << lvl;
@@ -760,7 +764,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     uint8_t *scratch = smem + L.off_scratch + (uint32_t)v * L.scratch_bytes;
     uint8_t *keep = smem + L.off_keep + (uint32_t)v * L.keep_bytes;
     uint32_t *unit_bits = (uint32_t *)(keep + L.k_unit_bits);
-    FbKfRes *res = (FbKfRes *)(keep + L.k_res);
+    FbKfRes *res[2] = {(FbKfRes *)(keep + L.k_res), (FbKfRes *)(keep + L.k_res + L.res_stride)};
     FbKfMisc *M = (FbKfMisc *)(scratch + L.s_misc);
     const int n = g.n;
     const int bps_v = fb_variant_bps(J, v);
@@ -817,11 +821,11 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             for (int j = 0; j < A.qlp_order; j++) sumabs += (unsigned long long)(A.qlp[j] < 0 ? -A.qlp[j] : A.qlp[j]);
             cd.narrow = (unsigned long long)A.max_abs * sumabs < 0x7FFFFFFFull;
         }
-        fb_kf_search<G>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), &res[c]);
+        fb_kf_search<G>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), res[c]);
         if (M->fail) return;
-        cbits[c] = c == 0 ? 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0].res_bits
+        cbits[c] = c == 0 ? 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0]->res_bits
                           : 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
-                                (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res[1].res_bits;
+                                (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res[1]->res_bits;
     }
     const unsigned long long fixed_bits = cbits[0], lpc_bits = cbits[1];
     const unsigned long long baseline_bits =
@@ -836,7 +840,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     if (pick == 0 && !(fixed_bits < verbatim_bits)) pick = -1;
     if (pick < 0) return;
 
-    const FbKfRes *R = &res[pick];
+    const FbKfRes *R = res[pick];
     FB_WPHASE(lane)
         if (lane == 0) {
             out->type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED;
@@ -974,15 +978,17 @@ FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *p
 
 // ---- KA: analysis and plan.  psubs: [frame][channels] chosen subframe records; poffs: [frame][channels][U_max+1]
 template <int G>
-FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *psubs,
-                       uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
+FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *vsubs,
+                       fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                        uint32_t *fb_count, const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
     const int NW = J.nvar;
     const int T = 32 * NW;
     const int n = fb_frame_len(J, f);
     const FbKfGeom g = fb_kf_geom(n);
     int32_t *xs = (int32_t *)(smem + L.off_x);
-    fb200_subframe_info *choice = (fb200_subframe_info *)(smem + L.off_choice);
+    // decision records of the frame's variants: global memory (written and re-read by this CTA only, so they stay in
+    // L2; shared memory is what limits the CTAs per SM)
+    fb200_subframe_info *choice = vsubs + (size_t)f * (size_t)J.nvar;
     FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
 
     // units must start on multiples of 4 samples (16-byte window loads): frames whose finest partitions are not a
@@ -1069,7 +1075,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             if (D.type == FB200_SF_FIXED || D.type == FB200_SF_LPC) {
                 uint8_t *keep = smem + L.off_keep + (uint32_t)D.variant * L.keep_bytes;
                 const uint32_t *ub = (const uint32_t *)(keep + L.k_unit_bits) + (size_t)D.cand * (L.U_max + 1);
-                uint32_t *xch = (uint32_t *)(smem + L.off_keep + (uint32_t)w * L.keep_bytes + L.k_xch);
+                uint32_t *xch = (uint32_t *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_tbl_a); // free again
                 uint32_t *po = poffs + ((size_t)f * (size_t)J.channels + (size_t)w) * (L.U_max + 1);
                 const int per = g.U >> 5;
                 const int ush = g.lgU - D.part_order;

@@ -54,12 +54,12 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
 
 // fused path (fb_fused.cuh), one CTA of 32 * nvar threads per frame: KA = analysis + plan, KP = pack + store
 __global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int32_t *xt, const FbAnalysis *ana, FbKfPlan *plan,
-                                                             fb200_subframe_info *psubs, uint32_t *poffs,
+                                                             fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,
                                                              uint32_t *frame_bytes, fb200_frame_info *infos,
                                                              uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,
                                                              FbKfLayout L) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_ka_body<FB_INST_G>(J, xt, ana, plan, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
+    fb_ka_body<FB_INST_G>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
 }
 
 __global__ void __launch_bounds__(256) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const FbKfPlan *plan,
@@ -91,10 +91,11 @@ void FB_NAME(fb_launch_k3_g)(const FbJob &J, const int32_t *xv, const fb200_subf
     FB_NAME(fb_k3_pack_g)<<<grid, FB_K3_THREADS, smem, st>>>(J, xv, choice, slots, frame_bytes, infos, list, count);
 }
 
-void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan, fb200_subframe_info *psubs,
+void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan, fb200_subframe_info *vsubs,
+                             fb200_subframe_info *psubs,
                              uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                              uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-    FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, ana, (FbKfPlan *)plan, psubs, poffs, frame_bytes,
+    FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, ana, (FbKfPlan *)plan, vsubs, psubs, poffs, frame_bytes,
                                                                      infos, fb_list, fb_count, ktab, L);
 }
 

@@ -19,7 +19,8 @@ enum { FB_KERNEL_K2 = 2, FB_KERNEL_K3 = 3, FB_KERNEL_KF = 5 };
                            uint32_t *frame_bytes, fb200_frame_info *infos, const uint32_t *list,                     \
                            const uint32_t *count, uint32_t grid, size_t smem, cudaStream_t st);                      \
     void fb_launch_ka_g##G(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan,                     \
-                           fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes,                      \
+                           fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,                 \
+                           uint32_t *frame_bytes,                                                                   \
                            fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,    \
                            const FbKfLayout &L, cudaStream_t st);                                                   \
     void fb_launch_kp_g##G(const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,    \
@@ -67,10 +68,10 @@ static inline void fb_launch_k3(int ring, const FbJob &J, const int32_t *xv, con
 #undef FB_CALL
 }
 static inline void fb_launch_ka(int ring, const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan,
-                                fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos,
+                                fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos,
                                 uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L,
                                 cudaStream_t st) {
-#define FB_CALL(G) fb_launch_ka_g##G(J, xt, ana, plan, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, L, st)
+#define FB_CALL(G) fb_launch_ka_g##G(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, L, st)
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }

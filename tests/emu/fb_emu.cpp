@@ -110,7 +110,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         poffs.assign((size_t)J.n_frames * J.channels * (KL.U_max + 1), 0xDDDDDDDDu);
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KA(GG) fb_ka_body<GG>(J, B.xv.data(), B.ana.data(), plan.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL)
+#define EMU_KA(GG) fb_ka_body<GG>(J, B.xv.data(), B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KA(4); break;
             case 8: EMU_KA(8); break;
