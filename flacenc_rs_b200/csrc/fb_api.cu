@@ -114,6 +114,7 @@ struct fb200_ctx {
     std::string last_error;
     int k2_smem_set = 0, k3_smem_set = 0, kf_smem_set = 0;
     uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
+    bool no_pairs = false;      // FB200_KP_PAIRS=0: the pack kernel always stages planes (tests exercise both)
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
     uint64_t pipe_chunk_frames = 0; // FB200_CHUNK_FRAMES: frames per chunk of the pipelined host path (0 = default)
     std::mutex mu;
@@ -202,6 +203,8 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
     {
         const char *fg = getenv("FB200_FORCE_GENERIC");
         ctx->force_generic = fg && fg[0] == '1';
+        const char *kp = getenv("FB200_KP_PAIRS");
+        ctx->no_pairs = kp && kp[0] == '0';
         const char *cf = getenv("FB200_CHUNK_FRAMES");
         if (cf) ctx->pipe_chunk_frames = strtoull(cf, nullptr, 10);
     }
@@ -296,7 +299,8 @@ struct Plan {
     uint32_t mb = 0;
     const float *d_win_tail = nullptr;
     FbK2Layout L;
-    FbKfLayout KL, KPL; // shared-memory layouts of the plan kernel and of the pack kernel
+    FbKfLayout KL, KPL, KPLp; // shared-memory layouts of the plan kernel and of the pack kernel (planes / PCM pairs)
+    bool kp_pairs = false;    // 16-bit stereo in a 2-byte container: the pack kernel may stage the PCM itself
     size_t k2_smem = 0, k3_smem = 0;
     bool fused = false;
 };
@@ -351,6 +355,8 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
     }
     P.fused = !A.analyze_only && !ctx->force_generic && fbh_fused_ok(J0, P.tail_n, &P.KL);
     P.KPL = fb_kp_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n);
+    P.kp_pairs = !ctx->no_pairs && fb_kp_pairs_format(ctx->channels, ctx->bps, P.cb) && A.planar_host == nullptr;
+    P.KPLp = fb_kp_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n, P.kp_pairs);
     if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
         std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk));
         fb_kf_build_ktab(P.KL.crc_chunk, kt.data());
@@ -359,7 +365,7 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
         ctx->ktab_chunk = P.KL.crc_chunk;
     }
-    const int kf_smem = (int)std::max(P.KL.total, P.KPL.total); // plan kernel and pack kernel
+    const int kf_smem = (int)std::max(P.KL.total, std::max(P.KPL.total, P.KPLp.total)); // plan kernel and pack kernel
     if (P.fused && kf_smem > ctx->kf_smem_set) {
         FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, kf_smem));
         ctx->kf_smem_set = kf_smem;
@@ -457,9 +463,11 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
                      d_fb, d_infos, (const uint32_t *)S.fb_list.p, d_fb_count, 148, P.k3_smem, st);
         fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
-        fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, S.plan.p, (const fb200_subframe_info *)S.psubs.p,
-                     (const uint32_t *)S.poffs.p, (const unsigned long long *)S.offsets.p, d_out, out_cap,
-                     (const uint32_t *)ctx->ktab.p, P.KPL, st);
+        const bool pairs = P.kp_pairs && d_pcm && ((uintptr_t)d_pcm & 15u) == 0;
+        fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, pairs ? d_pcm : nullptr, S.plan.p,
+                     (const fb200_subframe_info *)S.psubs.p, (const uint32_t *)S.poffs.p,
+                     (const unsigned long long *)S.offsets.p, d_out, out_cap, (const uint32_t *)ctx->ktab.p,
+                     pairs ? P.KPLp : P.KPL, st);
         fb_k4_gather_list<<<148, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
                                                (const unsigned long long *)S.offsets.p, d_out, out_cap,
                                                (const uint32_t *)S.fb_list.p, d_fb_count);

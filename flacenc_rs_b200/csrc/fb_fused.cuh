@@ -117,6 +117,7 @@ FB_HD int fb_xidx(int t) { return t + ((t >> 6) << 2); }
 // fb_xidx is then a halfword index (8 pad bytes per 64 samples keep the 8-byte loads conflict-free).  The flag
 // travels in bit 2 of the variant mode `vm`.
 #define FB_VM_X16 4
+#define FB_VM_PAIRS 8 // one plane of 16-bit stereo pairs (left in the low half); bits 0-1: 0 left, 1 right, 2 mid, 3 side
 
 // ---- CRC-16 tables (poly 0x8005, init 0, MSB first; src/component/bitrepr.rs:40,270-271) ------------
 // Built on the host once per context and read by the kernel:
@@ -252,8 +253,14 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
 
 // Shared memory of the pack kernel KP: planes (int16 when the stream has at most 16 bits per sample), the frame's
 // plan, the chosen subframe records, the unit offsets and the frame's word buffer.  Returned in the same struct.
-FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, int tail_n) {
-    FbKfLayout L = fb_kf_layout(channels, nvar, bps, block_size, tail_n, true);
+// pairs: 16-bit stereo whose packed PCM is at hand (2-byte container, 16-byte aligned): the frame's PCM itself is
+// staged as one plane of (left, right) pairs (x16 = 2) -- plain 16-byte asynchronous copies, no conversion.
+FB_HD bool fb_kp_pairs_format(int channels, int bps, int container_bytes) {
+    return channels == 2 && bps == 16 && container_bytes == 2;
+}
+FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, int tail_n, bool pairs = false) {
+    FbKfLayout L = fb_kf_layout(channels, nvar, bps, block_size, tail_n, !pairs);
+    if (pairs) L.x16 = 2;
     // everything but the planes, then as many planes as fit next to it (channels other than a stereo pair are
     // independent, so they can be staged and packed group by group)
     const uint32_t fixed = fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u) +
@@ -265,7 +272,7 @@ FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, i
     if (channels == 2) gc = 2; // M and S need both planes
     L.group_ch = gc;
     uint32_t o = 0;
-    L.off_x = o;        o += fb_align16(gc * L.x_stride * 4u);
+    L.off_x = o;        o += fb_align16((pairs ? 1u : gc) * L.x_stride * 4u);
     L.off_keep = o;     o += fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u);   // unit offsets
     L.off_choice = o;   o += fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info));
     L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
@@ -405,10 +412,33 @@ FB_DEV void fb_vm_mix(int vm, int32_t *m, int32_t *sh) {
 }
 
 // four samples at plane offset o = fb_xidx(t) (t a multiple of 4, inside the plane incl. its slack)
+// pairs: sample = (ml * left + mr * right) >> sh
+FB_DEV void fb_vm_mix_pairs(int vm, int32_t *ml, int32_t *mr, int32_t *sh) {
+    const int k = vm & 3;
+    *ml = k == 1 ? 0 : 1;
+    *mr = k == 0 ? 0 : (k == 3 ? -1 : 1);
+    *sh = k == 2 ? 1 : 0;
+}
+FB_DEV int32_t fb_mix_pair(int32_t w, int32_t ml, int32_t mr, int32_t sh) {
+    const int32_t l = (int32_t)(int16_t)(uint32_t)w, r = w >> 16;
+    return (int32_t)((uint32_t)ml * (uint32_t)l + (uint32_t)mr * (uint32_t)r) >> sh;
+}
+
+// VMS: the plane formats a caller can meet (the plan kernel only ever sees 32-bit planes: VMS = 0 drops the rest)
+#define FB_VMS_ALL (FB_VM_X16 | FB_VM_PAIRS)
+template <int VMS = FB_VMS_ALL>
 FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, int o, int32_t *dst) {
     int32_t m, sh;
     fb_vm_mix(vm, &m, &sh);
-    if (vm & FB_VM_X16) {
+    if ((VMS & FB_VM_PAIRS) && (vm & FB_VM_PAIRS)) {
+        int32_t ml, mr;
+        fb_vm_mix_pairs(vm, &ml, &mr, &sh);
+        const int4 w = *reinterpret_cast<const int4 *>(xa + o);
+        dst[0] = fb_mix_pair(w.x, ml, mr, sh);
+        dst[1] = fb_mix_pair(w.y, ml, mr, sh);
+        dst[2] = fb_mix_pair(w.z, ml, mr, sh);
+        dst[3] = fb_mix_pair(w.w, ml, mr, sh);
+    } else if ((VMS & FB_VM_X16) && (vm & FB_VM_X16)) {
         const int2 wa = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xa) + o);
         const int2 wb = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xb) + o);
         dst[0] = fb_mix((int32_t)(int16_t)(uint32_t)wa.x, (int32_t)(int16_t)(uint32_t)wb.x, m, sh);
@@ -425,41 +455,47 @@ FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, int o, 
     }
 }
 
+template <int VMS = FB_VMS_ALL>
 FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
-    fb_kf_load4_at(xa, xb, vm, fb_xidx(t), dst);
+    fb_kf_load4_at<VMS>(xa, xb, vm, fb_xidx(t), dst);
 }
 
 FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
     const int o = fb_xidx(t);
     int32_t m, sh;
     fb_vm_mix(vm, &m, &sh);
+    if (vm & FB_VM_PAIRS) {
+        int32_t ml, mr;
+        fb_vm_mix_pairs(vm, &ml, &mr, &sh);
+        return fb_mix_pair(xa[o], ml, mr, sh);
+    }
     if (vm & FB_VM_X16)
         return fb_mix(reinterpret_cast<const int16_t *>(xa)[o], reinterpret_cast<const int16_t *>(xb)[o], m, sh);
     return fb_mix(xa[o], xb[o], m, sh);
 }
 
 // win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4)
-template <int G>
+template <int G, int VMS = FB_VMS_ALL>
 FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, int32_t *win) {
 #pragma unroll
     for (int i = 0; i < G; i += 4) {
         const int t = ta - G + i;
-        if (t >= 0) fb_kf_load4(xa, xb, vm, t, win + i);
+        if (t >= 0) fb_kf_load4<VMS>(xa, xb, vm, t, win + i);
         else { win[i] = 0; win[i + 1] = 0; win[i + 2] = 0; win[i + 3] = 0; }
     }
 }
 
 // win[G..G+RUN) = x[t0 .. t0+RUN) (t0 a multiple of 4); samples at t >= n are don't-cares (their results are masked)
-template <int G>
+template <int G, int VMS = FB_VMS_ALL>
 FB_DEV void fb_kf_fetch_run(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
     if ((t0 & 15) == 0) {
         // a run that starts on a multiple of 16 lies inside one 64-sample block of the padded plane: one index
         const int o = fb_xidx(t0);
 #pragma unroll
-        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4_at(xa, xb, vm, o + i, win + G + i);
+        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4_at<VMS>(xa, xb, vm, o + i, win + G + i);
     } else {
 #pragma unroll
-        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4(xa, xb, vm, t0 + i, win + G + i);
+        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4<VMS>(xa, xb, vm, t0 + i, win + G + i);
     }
 }
 
@@ -574,10 +610,10 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             const int lo = ta > warm ? ta : warm;
             if (tb > ta) {
                 int32_t win[G + FB_KF_RUN];
-                fb_kf_history<G>(xa, xb, vm, ta, win);
+                fb_kf_history<G, 0>(xa, xb, vm, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
-                    fb_kf_fetch_run<G>(xa, xb, vm, t0, win);
+                    fb_kf_fetch_run<G, 0>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
                     fb_kf_csa_run(cw, uu);
                     fb_kf_slide<G>(win);
@@ -769,8 +805,8 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     const int n = g.n;
     const int bps_v = fb_variant_bps(J, v);
     const unsigned long long verbatim_bits = 8ull + (unsigned long long)n * (unsigned long long)bps_v;
-    // sample planes of this variant
-    int vm = L.x16 ? FB_VM_X16 : 0;
+    // sample planes of this variant (the plan kernel always stages 32-bit planes)
+    int vm = 0;
     const int32_t *xa = xs + (size_t)v * L.x_stride, *xb = xa;
     if (J.channels == 2 && v >= 2) { vm |= v; xa = xs; xb = xs + L.x_stride; }
 
@@ -1133,10 +1169,33 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     FB_WARPS_END
 }
 
-// ---- KP: pack a planned frame and store it at out + offsets[f]
+// stages frame f's packed 16-bit stereo PCM as one plane of (left, right) pairs
+FB_DEV void fb_kp_stage_pairs(const FbJob &J, const uint8_t *pcm, uint32_t f, int n, int32_t *xs, int tid, int T) {
+    const int32_t *src = reinterpret_cast<const int32_t *>(pcm + (size_t)f * (size_t)J.block_size * 4u);
+    const int nq = n >> 2;
+    for (int i = tid; i < nq; i += T) fb_copy16_async(xs + fb_xidx(4 * i), src + 4 * i);
+    if (tid < 4 && (n & 3)) { // partial last quad: the samples that exist, zeros behind them (like xt)
+        const int t = 4 * nq + tid;
+        if (t < n) fb_copy4_async(xs + fb_xidx(t), src + t);
+        else xs[fb_xidx(t)] = 0;
+    }
+}
+
+// planes and variant mode of a subframe's variant in the pack kernel
+FB_DEV int fb_kp_planes(const FbJob &J, const FbKfLayout &L, const int32_t *xs, int variant, int c0, const int32_t **xa,
+                        const int32_t **xb) {
+    if (L.x16 == 2) { *xa = *xb = xs; return FB_VM_PAIRS | variant; }
+    int vm = L.x16 ? FB_VM_X16 : 0;
+    *xa = *xb = xs + (size_t)(variant - c0) * L.x_stride;
+    if (J.channels == 2 && variant >= 2) { vm |= variant; *xa = xs; *xb = xs + L.x_stride; }
+    return vm;
+}
+
+// ---- KP: pack a planned frame and store it at out + offsets[f].  pcm: the batch's packed PCM (only read when the
+// layout says pairs)
 template <int G>
-FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, const fb200_subframe_info *psubs,
-                       const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out, unsigned long long out_cap,
+FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, const FbKfPlan *plan,
+                       const fb200_subframe_info *psubs, const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out, unsigned long long out_cap,
                        const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
     const int NW = J.nvar;
     const int T = 32 * NW;
@@ -1171,7 +1230,8 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) fb_copy4_async(poff + i, src + i);
         }
         for (int i = tid; i < 256; i += T) fb_copy16_async((int32_t *)crc_tab + 4 * i, (const int32_t *)ktab + 4 * i);
-        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, GC < J.channels ? GC : J.channels);
+        if (L.x16 == 2) fb_kp_stage_pairs(J, pcm, f, n, xs, tid, T);
+        else fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, GC < J.channels ? GC : J.channels);
         for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
         if (tid == 0) { S->crc_acc = 0; S->crc_last = 0; } // (beyond the part of S that the plan copy fills)
         fb_copy_async_wait();
@@ -1202,9 +1262,8 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
         if (tid < c1 - c0) {
             const FbKfSub &D = S->sub[c0 + tid];
             const fb200_subframe_info &V = psub[c0 + tid];
-            int vm = L.x16 ? FB_VM_X16 : 0;
-            const int32_t *xa = xs + (size_t)(D.variant - c0) * L.x_stride, *xb = xa;
-            if (J.channels == 2 && D.variant >= 2) { vm |= D.variant; xa = xs; xb = xs + L.x_stride; }
+            const int32_t *xa, *xb;
+            const int vm = fb_kp_planes(J, L, xs, D.variant, c0, &xa, &xb);
             FbBitRun r;
             fb_run_init(r, words, D.start_bit, D.start_bit + 1);
             r.w_last = 0xFFFFFFFFu;
@@ -1238,9 +1297,8 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const FbKfPlan *plan, 
             if (D.type == FB200_SF_CONSTANT) continue;
             int ta, tb;
             fb_kf_unit_range(g, unit, &ta, &tb);
-            int vm = L.x16 ? FB_VM_X16 : 0;
-            const int32_t *xa = xs + (size_t)(D.variant - c0) * L.x_stride, *xb = xa;
-            if (J.channels == 2 && D.variant >= 2) { vm |= D.variant; xa = xs; xb = xs + L.x_stride; }
+            const int32_t *xa, *xb;
+            const int vm = fb_kp_planes(J, L, xs, D.variant, c0, &xa, &xb);
             if (D.type == FB200_SF_VERBATIM) {
                 // Verbatim::write (src/component/bitrepr.rs:463-470): bps bits per sample at fixed positions
                 if (tb <= ta) continue;

@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int3
     fb_ka_body<FB_INST_G>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
 }
 
-__global__ void __launch_bounds__(256) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const FbKfPlan *plan,
+__global__ void __launch_bounds__(256) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
                                                              const fb200_subframe_info *psubs, const uint32_t *poffs,
                                                              const unsigned long long *offsets, uint8_t *out,
                                                              unsigned long long out_cap, const uint32_t *ktab, FbKfLayout L) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_kp_body<FB_INST_G>(J, xt, plan, psubs, poffs, offsets, out, out_cap, ktab, blockIdx.x, fb_smem, L);
+    fb_kp_body<FB_INST_G>(J, xt, pcm, plan, psubs, poffs, offsets, out, out_cap, ktab, blockIdx.x, fb_smem, L);
 }
 
 void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
@@ -99,10 +99,10 @@ void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const FbAnalysis
                                                                      infos, fb_list, fb_count, ktab, L);
 }
 
-void FB_NAME(fb_launch_kp_g)(const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,
+void FB_NAME(fb_launch_kp_g)(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const void *plan, const fb200_subframe_info *psubs,
                              const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,
                              unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-    FB_NAME(fb_kp_pack_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, (const FbKfPlan *)plan, psubs, poffs, offsets, out,
+    FB_NAME(fb_kp_pack_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, pcm, (const FbKfPlan *)plan, psubs, poffs, offsets, out,
                                                                      out_cap, ktab, L);
 }
 

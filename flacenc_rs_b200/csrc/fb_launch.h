@@ -23,7 +23,8 @@ enum { FB_KERNEL_K2 = 2, FB_KERNEL_K3 = 3, FB_KERNEL_KF = 5 };
                            uint32_t *frame_bytes,                                                                   \
                            fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,    \
                            const FbKfLayout &L, cudaStream_t st);                                                   \
-    void fb_launch_kp_g##G(const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,    \
+    void fb_launch_kp_g##G(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const void *plan,                  \
+                           const fb200_subframe_info *psubs,                                                        \
                            const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,                  \
                            unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st); \
     cudaError_t fb_set_smem_g##G(int kernel, int bytes);
@@ -75,10 +76,11 @@ static inline void fb_launch_ka(int ring, const FbJob &J, const int32_t *xt, con
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }
-static inline void fb_launch_kp(int ring, const FbJob &J, const int32_t *xt, const void *plan, const fb200_subframe_info *psubs,
+static inline void fb_launch_kp(int ring, const FbJob &J, const int32_t *xt, const uint8_t *pcm, const void *plan,
+                                const fb200_subframe_info *psubs,
                                 const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,
                                 unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-#define FB_CALL(G) fb_launch_kp_g##G(J, xt, plan, psubs, poffs, offsets, out, out_cap, ktab, L, st)
+#define FB_CALL(G) fb_launch_kp_g##G(J, xt, pcm, plan, psubs, poffs, offsets, out, out_cap, ktab, L, st)
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }

@@ -86,6 +86,11 @@ def set_force_generic(flag: bool) -> None:
     lib().fbemu_set_force_generic(1 if flag else 0)
 
 
+def set_kp_pairs(flag: bool) -> None:
+    """False: the pack kernel always stages planes from the planar store (default True: PCM pairs when the format allows)."""
+    lib().fbemu_set_kp_pairs(1 if flag else 0)
+
+
 def fused_counts(reset: bool = True):
     """(frames encoded by the fused kernel, frames it handed to the generic kernels)"""
     out = (C.c_ulonglong * 2)()

@@ -21,8 +21,11 @@ void fbemu_mode_counts(unsigned long long *out4, int reset) {
 
 // 0 = fused kernel when eligible (like the library), 1 = generic K2/K3 kernels only
 static int fb_emu_force_generic = 0;
+// 1 = the pack kernel stages 16-bit stereo PCM as (left, right) pairs when the format allows (like the library)
+static int fb_emu_kp_pairs = 1;
 static unsigned long long fb_emu_fused_frames = 0, fb_emu_fallback_frames = 0;
 void fbemu_set_force_generic(int v) { fb_emu_force_generic = v; }
+void fbemu_set_kp_pairs(int v) { fb_emu_kp_pairs = v; }
 void fbemu_fused_counts(unsigned long long *out2, int reset) {
     out2[0] = fb_emu_fused_frames; out2[1] = fb_emu_fallback_frames;
     if (reset) fb_emu_fused_frames = fb_emu_fallback_frames = 0;
@@ -178,13 +181,15 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     const unsigned long long total = B.offsets[J.n_frames];
     B.stream.assign((size_t)total + 16, 0x77);
     if (fused) {
-        const FbKfLayout KPL = fb_kp_layout(J.channels, J.nvar, J.bps, J.block_size, J.tail_n);
+        const bool pairs = !planar && fb_emu_kp_pairs && fb_kp_pairs_format(J.channels, J.bps, container_bytes) &&
+                           ((uintptr_t)pcm & 15u) == 0;
+        const FbKfLayout KPL = fb_kp_layout(J.channels, J.nvar, J.bps, J.block_size, J.tail_n, pairs);
         std::vector<uint8_t> smem(KPL.total + 64);
         std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
         fb_kf_build_ktab(KL.crc_chunk, ktab.data());
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KP(GG) fb_kp_body<GG>(J, B.xv.data(), plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL)
+#define EMU_KP(GG) fb_kp_body<GG>(J, B.xv.data(), pairs ? (const uint8_t *)pcm : nullptr, plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KP(4); break;
             case 8: EMU_KP(8); break;

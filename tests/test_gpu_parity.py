@@ -60,8 +60,12 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
     container = container or (bps + 7) // 8
     ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
     # both device paths: the fused per-frame kernel (default, when the batch is eligible) and the generic kernels
-    for force_generic in ("0", "1"):
+    modes = [("0", "1"), ("1", "1")]
+    if channels == 2 and bps == 16 and container == 2:
+        modes.insert(1, ("0", "0"))  # 16-bit stereo: also with the pack kernel staging planes instead of PCM pairs
+    for force_generic, kp_pairs in modes:
         os.environ["FB200_FORCE_GENERIC"] = force_generic
+        os.environ["FB200_KP_PAIRS"] = kp_pairs
         try:
             with Context(vcfg, channels, bps, rate, block_size) as ctx:
                 got, sizes, infos = ctx.encode_interleaved(pack_pcm(signal, container), container, n, first_frame,
@@ -73,6 +77,7 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
                     assert t.fused_frames == 0 and t.fallback_frames == 0
         finally:
             os.environ.pop("FB200_FORCE_GENERIC", None)
+            os.environ.pop("FB200_KP_PAIRS", None)
         assert list(sizes) == list(ref_sizes), f"force_generic={force_generic}"
         if got != ref:
             off = 0

@@ -20,14 +20,20 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
     n = len(signal)
     container = container or (bps + 7) // 8
     ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
-    # both device paths: the fused per-frame kernel (when the batch is eligible) and the generic K2/K3 kernels
-    for force_generic in (False, True):
+    # the device paths: the fused per-frame kernels (when the batch is eligible; 16-bit stereo in a 2-byte container
+    # also with the pack kernel staging planes instead of the PCM pairs) and the generic K2/K3 kernels
+    modes = [(False, True), (True, True)]
+    if channels == 2 and bps == 16 and container == 2:
+        modes.insert(1, (False, False))
+    for force_generic, kp_pairs in modes:
         E.set_force_generic(force_generic)
+        E.set_kp_pairs(kp_pairs)
         try:
             rc, got, sizes, _ = E.encode_interleaved(ecfg, pack_pcm(signal, container), container, n, channels, bps,
                                                      rate, block_size, first_frame)
         finally:
             E.set_force_generic(False)
+            E.set_kp_pairs(True)
         assert rc == 0
         assert list(sizes) == list(ref_sizes), f"force_generic={force_generic}"
         if got != ref:
@@ -183,9 +189,9 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     E.fused_counts()
     x = sigen.noisy_sine_pcm(4096 * 3 + 2728, 2, 16, 44100)
     _compare(x, 2, 16, 44100, 4096)
-    assert E.fused_counts() == [3, 1]
+    assert E.fused_counts() == [6, 2]  # (16-bit stereo runs the fused path twice: PCM pairs and planes in the packer)
     _compare(x[: 4096 * 3 + 2048], 2, 16, 44100, 4096)
-    assert E.fused_counts() == [4, 0]
+    assert E.fused_counts() == [8, 0]
     E.mode_counts()
     _compare(crafted_huge_residual_stereo(), 2, 24, 96000, 4096, lpc_order=24)
     assert E.fused_counts() == [0, 1]
