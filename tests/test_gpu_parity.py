@@ -152,6 +152,16 @@ def test_channels_and_sample_formats(channels, bps, container):
     _compare(np.stack(chans, axis=1), channels, bps, 48000, 1024, container=container)
 
 
+@pytest.mark.parametrize("channels", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_many_short_frames_every_channel_count(channels):
+    """70 frames + a short tail of 128-sample blocks: the analysis kernel's warps (32 channel variants each) span many
+    frames, frames straddle warps for 3, 5, 6 and 7 channels (more than 32 staged rows), and the last warp mixes frame
+    lengths."""
+    n = 128 * 70 + 37
+    chans = [sigen.Sine(23 + 5 * c, 0.6).noise(0.02, seed=40 + c).to_vec_quantized(16, n) for c in range(channels)]
+    _compare(np.stack(chans, axis=1), channels, 16, 44100, 128)
+
+
 def test_special_signals():
     _compare(np.zeros((3000, 2), np.int32), 2, 16, 44100, 1024)
     c = np.full((3000, 2), -1234, np.int32)
@@ -396,6 +406,24 @@ def test_device_resident_api_matches_host_api():
         d_out = torch.empty(38 * ctx.max_frame_bytes(), dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
         olen, sizes = ctx.encode_device(d_in.data_ptr(), 2, len(x), d_out.data_ptr(), d_out.numel())
+        assert olen == len(host_bytes) and list(sizes) == list(host_sizes)
+        assert d_out[:olen].cpu().numpy().tobytes() == host_bytes
+
+
+def test_device_resident_api_unaligned_pcm():
+    """a device PCM pointer that is only 4-byte aligned: the ingest kernel's generic loads and the pack kernel's plane
+    staging (the PCM-pair staging needs 16-byte alignment) give the same bytes"""
+    import torch
+    x = sigen.noisy_sine_pcm(4096 * 5 + 999, 2, 16, 44100, config_id=4)
+    pcm = pack_pcm(x, 2)
+    with Context(Encoder().into_verified(), 2, 16, 44100, 4096) as ctx:
+        host_bytes, host_sizes, _ = ctx.encode_interleaved(pcm, 2, len(x))
+        host_bytes = host_bytes.tobytes()
+        d_buf = torch.zeros(len(pcm) + 64, dtype=torch.uint8, device="cuda")
+        d_buf[4:4 + len(pcm)] = torch.from_numpy(pcm.copy()).cuda()
+        d_out = torch.empty(6 * ctx.max_frame_bytes(), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        olen, sizes = ctx.encode_device(d_buf.data_ptr() + 4, 2, len(x), d_out.data_ptr(), d_out.numel())
         assert olen == len(host_bytes) and list(sizes) == list(host_sizes)
         assert d_out[:olen].cpu().numpy().tobytes() == host_bytes
 
