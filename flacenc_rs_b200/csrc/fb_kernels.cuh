@@ -532,10 +532,10 @@ FB_DEV void fb_k1_finish_ent(const FbJob &J, const FbK1Var &V, const FbK1Ent &S,
     }
     out->fixed_order = -1;
     for (int k = 0; k < 5; k++) out->fixed_est[k] = 0;
-    if (taps) {
-        memset(taps, 0, sizeof(*taps));
+    if (taps) { // (the autocorrelation / LPC fields belong to fb_k1_finish_lpc, which may run in another thread)
         taps->is_constant = allsame ? 1 : 0;
         taps->fixed_order = -1;
+        for (int k = 0; k < 5; k++) taps->fixed_est_bits[k] = 0;
     }
     if (V.do_ent) {
         // estimate_entropy per order + bits_per_sample * order; first minimum wins; accepted only
@@ -564,6 +564,13 @@ template <int R>
 FB_DEV void fb_k1_finish_lpc(const FbJob &J, const FbK1Var &V, const FbK1Acc<R> &A, FbAnalysis *out, fb200_variant_taps *taps) {
     out->qlp_order = 0;
     out->qlp_shift = 0;
+    if (taps) {
+        for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) taps->autocorr[i] = 0.0;
+        for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) taps->lpc[i] = 0.0;
+        for (int i = 0; i < 32; i++) taps->qlp[i] = 0;
+        taps->qlp_order = 0;
+        taps->qlp_shift = 0;
+    }
     if (!V.do_lpc) {
         for (int i = 0; i < 32; i++) out->qlp[i] = 0;
         return;
@@ -801,8 +808,14 @@ FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &
 template <int R>
 FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail, FbAnalysis *ana,
                        fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
+    // The grid holds every block of 128 variants twice: the first half runs pass A (the longer one, so it is scheduled
+    // first), the second half pass E.  Half-length CTAs pack the SMs' slots better at the end of a launch, and small
+    // batches (latency-bound: one thread walks a whole frame) finish in roughly half the time.
+    const uint32_t nblk = gridDim.x >> 1;
+    const bool role_a = blockIdx.x < nblk;
+    const uint32_t blk = role_a ? blockIdx.x : blockIdx.x - nblk;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t gv = blockIdx.x * (uint32_t)FB_K1_THREADS + threadIdx.x;
+    const uint32_t gv = blk * (uint32_t)FB_K1_THREADS + threadIdx.x;
     const uint32_t gv0 = gv - lane;
     if (gv0 >= n_variants) return; // the whole warp has nothing to do
     const bool valid = gv < n_variants;
@@ -854,7 +867,7 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full,
     }
 
     // ---- pass E
-    {
+    if (!role_a) {
         FbK1Ent S;
         fb_k1_ent_init(S, V.n, V.psize, 0);
         S.xmin = 2147483647;
@@ -872,6 +885,7 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full,
                 else fb_k1_ent_group<true, false>(S, xs, g * 8);
             });
         if (valid) fb_k1_finish_ent(J, V, S, out, taps);
+        return;
     }
 
     // ---- pass A
