@@ -73,6 +73,73 @@ def bind_to_gpu_numa_node(local_rank: int):
         return orig, f"unchanged ({type(e).__name__})"
 
 
+class NvmlClockSampler:
+    """The same readings through NVML calls in this process (a light thread, 20 ms period)."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.sm, self.smax, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+
+    def _run(self, handle):
+        import pynvml
+        bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                self.smax.append(float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+
+    def start(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = getattr(torch.cuda.get_device_properties(self.device), "uuid", None)
+            handle = None
+            if uuid is not None:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.thread = threading.Thread(target=self._run, args=(handle,), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+
+    def stop(self) -> dict:
+        if not self.thread:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.smax) if self.smax else None, "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "source": "nvml"}
+
+
+class OffSampler:
+    def __init__(self, device: int):
+        pass
+
+    def start(self):
+        pass
+
+    def stop(self) -> dict:
+        return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["sampling off"]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -194,6 +261,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=int, default=SECONDS, help="audio seconds per rank (default: the 1 h workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-sampler", default="auto", choices=["auto", "smi", "nvml", "off"],
+                    help="how SM clocks / throttle reasons are sampled during the timed regions")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,7 +327,14 @@ def main() -> None:
 
     # ---- timed: device-resident (value).  Inputs (635 MB) and the planar working set (2.5 GB) are far larger
     # than the 126 MB L2, so every step streams from HBM.
-    sampler = ClockSampler(local_rank)
+    kind = args.clock_sampler
+    if kind == "auto":  # NVML in-process gives a sample every 20 ms; the nvidia-smi loop (100 ms) is the fallback
+        try:
+            import pynvml  # noqa: F401
+            kind = "nvml"
+        except Exception:
+            kind = "smi"
+    sampler = {"smi": ClockSampler, "nvml": NvmlClockSampler, "off": OffSampler}[kind](local_rank)
     barrier()
     sampler.start()
     # "plan" = KA (Rice search, decisions, frame plan), "pack" = KP (bit packing + CRC + store at the final offset),
@@ -285,10 +361,12 @@ def main() -> None:
     barrier()
     e2e_ms = 0.0
     h2d_ms = d2h_ms = 0.0
+    e2e_steps = []
     w1 = time.perf_counter()
     for _ in range(args.steps):
         out_len_h, t = step_host()
         e2e_ms += t.total_ms
+        e2e_steps.append(round(t.total_ms, 3))
         h2d_ms += t.h2d_ms
         d2h_ms += t.d2h_ms
     barrier()
@@ -334,7 +412,7 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(in_bytes),
                     "d2h_bytes_per_step": int(out_len + 4 * n_frames + 16),
                     "h2d_ms_per_step": h2d_ms / args.steps, "d2h_ms_per_step": d2h_ms / args.steps,
-                    "ms_per_step": e2e_ms_max / args.steps,
+                    "ms_per_step": e2e_ms_max / args.steps, "ms_steps_rank0": e2e_steps,
                     "api": "fb200_encode_interleaved, pinned host buffers; chunks pipelined over H2D / compute / D2H "
                            "streams (h2d_ms / d2h_ms are summed copy times and overlap the kernels)"},
             "gpu_launches": int(launches),
