@@ -98,7 +98,7 @@ struct ChunkSet {
     bool d2h_pending = false;  // ev[8] has been recorded for a chunk whose D2H time is not accounted yet
 };
 
-#define FB_NSETS 3
+#define FB_NSETS_MAX 6
 
 struct fb200_ctx {
     fb200_config cfg;
@@ -107,7 +107,8 @@ struct fb200_ctx {
     cudaStream_t s_k1 = nullptr;     // compute stream 1 (pipelined path: chunks alternate)
     cudaStream_t s_in = nullptr, s_out = nullptr; // H2D / D2H streams of the pipelined path
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    ChunkSet sets[FB_NSETS];
+    ChunkSet sets[FB_NSETS_MAX];
+    int nsets = 3; // buffer sets the pipelined host path rotates (FB200_NSETS, 2..6)
     DevBuf win_full, win_tail, ktab;
     int win_tail_n = -1;
     fb200_timing timing;
@@ -207,6 +208,8 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
         ctx->no_pairs = kp && kp[0] == '0';
         const char *cf = getenv("FB200_CHUNK_FRAMES");
         if (cf) ctx->pipe_chunk_frames = strtoull(cf, nullptr, 10);
+        const char *ns = getenv("FB200_NSETS");
+        if (ns) ctx->nsets = std::max(2, std::min(FB_NSETS_MAX, atoi(ns)));
     }
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -214,7 +217,7 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
               cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
-    for (int k = 0; ok && k < FB_NSETS; k++) {
+    for (int k = 0; ok && k < FB_NSETS_MAX; k++) {
         ChunkSet &S = ctx->sets[k];
         for (int i = 0; ok && i < 11; i++) {
             ok = cudaEventCreate(&S.ev[i]) == cudaSuccess;
@@ -613,9 +616,10 @@ int fb_encode_serial(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P) {
 // ---- pipelined path: host PCM in, host frame bytes out.  The batch is cut into chunks; chunk c's H2D copy
 // (stream s_in), kernels (compute streams, alternating so the latency-bound analysis kernel of one chunk overlaps
 // the fused kernel of the previous one) and D2H copy (stream s_out) overlap with those of its neighbours.
-// FB_NSETS buffer sets rotate; a set is reused once its D2H copy has been enqueued and is waited for by event.
+// ctx->nsets buffer sets rotate; a set is reused once its D2H copy has been enqueued and is waited for by event.
 int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint64_t chunk_frames) {
     int rc;
+    const uint64_t FB_NSETS = (uint64_t)ctx->nsets;
     // chunk schedule: the H2D stream is the bottleneck, so what matters at the end is how much work is left once the
     // last copy has landed.  One short final chunk (a quarter of the nominal size) keeps that tail small; more than
     // one does not pay, because every chunk costs about a millisecond of kernel latency.  The frames before it are
@@ -756,7 +760,7 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_k1));
-    for (int k = 0; k < FB_NSETS; k++) {
+    for (int k = 0; k < (int)FB_NSETS; k++) {
         ChunkSet &S = ctx->sets[k];
         if (S.d2h_pending) {
             float t;
@@ -813,7 +817,7 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     // host batches of more than one chunk are pipelined; the chunk is sized so that the per-variant analysis
     // kernel still has a few thousand threads and the copies of neighbouring chunks overlap the kernels
     if (A.pcm_host && !A.analyze_only) {
-        uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 4864;
+        uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 2432;
         const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + 2 * P.slot_bytes + 4096u;
         chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(64, (1024ull << 20) / per_frame));
         if (total_frames > chunk + chunk / 2) return fb_encode_pipelined(ctx, A, P, chunk);
