@@ -722,7 +722,24 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
         }
     }
 
-    // ---- pass 4a: totals per level (lane partials -> exchange -> one lane per level)
+    // ---- pass 4a: totals per level.  GPU: two warp-wide integer reductions per level (low / high 16 bits of the lane
+    // partials, each < 2^30); the emulation exchanges the partials through shared memory instead.
+#if FB_GPU
+    for (int lvl = 0; lvl <= g.o0; lvl++) {
+        const int nodes = 1 << lvl;
+        const int lane = (int)(threadIdx.x & 31u);
+        uint32_t part = 0; // <= 8 nodes per lane, each < 2^27
+        for (int node = lane; node < nodes; node += 32) {
+            const uint32_t v = best_val[nodes - 1 + node];
+            if (v >= FB_RICE_SAT) M->fail = 1;
+            part += v;
+        }
+        const uint32_t lo = __reduce_add_sync(0xFFFFFFFFu, part & 0xFFFFu);
+        const uint32_t hi = __reduce_add_sync(0xFFFFFFFFu, part >> 16);
+        if (lane == 0) lvl_bits[lvl] = ((unsigned long long)hi << 16) + (unsigned long long)lo;
+    }
+    __syncwarp();
+#else
     uint32_t *lx = tbl_a; // (o0 + 1) x 32 exchange words
     FB_WPHASE(lane)
         for (int lvl = 0; lvl <= g.o0; lvl++) {
@@ -743,6 +760,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             lvl_bits[lane] = s;
         }
     FB_WPHASE_END
+#endif
     if (M->fail) return;
     // ---- pass 4b: partition order: strictly smaller total wins while going coarser (src/rice.rs:276-291)
     FB_WPHASE(lane)

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int3
     fb_ka_body<FB_INST_G>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
 }
 
-__global__ void __launch_bounds__(256) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
+__global__ void __maxnreg__(96) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
                                                              const fb200_subframe_info *psubs, const uint32_t *poffs,
                                                              const unsigned long long *offsets, uint8_t *out,
                                                              unsigned long long out_cap, const uint32_t *ktab, FbKfLayout L) {
