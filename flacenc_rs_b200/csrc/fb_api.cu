@@ -54,12 +54,10 @@ __global__ void __launch_bounds__(256) fb_k0b_expand(FbJob J, const int32_t *xc,
 __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *frame_bytes, unsigned long long *offsets,
                                                            uint32_t n_frames, unsigned long long *total) {
     __shared__ unsigned long long partials[FB_K4_THREADS];
-    fb_k4_scan_body(frame_bytes, offsets, n_frames, partials);
     const unsigned long long base = *total;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= n_frames; i += FB_K4_THREADS) offsets[i] += base;
-    __syncthreads();
-    if (threadIdx.x == 0) *total = offsets[n_frames];
+    __syncthreads(); // everybody has read the running total before the last thread replaces it
+    fb_k4_scan_body(frame_bytes, offsets, n_frames, partials, base);
+    if (threadIdx.x == FB_K4_THREADS - 1) *total = offsets[n_frames];
 }
 
 // gather of the frames on the fused path's fallback list only (everything else is stored in place by KP)

@@ -1837,7 +1837,7 @@ FB_DEV void fb_k3_body(const FbJob &J, const int32_t *xv, const fb200_subframe_i
 #define FB_K4_THREADS 1024
 
 FB_DEV void fb_k4_scan_body(const uint32_t *frame_bytes, unsigned long long *offsets, uint32_t n_frames,
-                            unsigned long long *partials /* smem, T entries */) {
+                            unsigned long long *partials /* smem, T entries */, unsigned long long base = 0) {
     const int T = FB_K4_THREADS;
     const uint32_t per = (n_frames + (uint32_t)T - 1u) / (uint32_t)T;
     FB_PHASE(tid, T)
@@ -1845,14 +1845,44 @@ FB_DEV void fb_k4_scan_body(const uint32_t *frame_bytes, unsigned long long *off
         for (uint32_t i = (uint32_t)tid * per; i < ((uint32_t)tid + 1u) * per && i < n_frames; i++) s += frame_bytes[i];
         partials[tid] = s;
     FB_PHASE_END
+#if FB_GPU
+    {
+        // exclusive scan of the T partials: shuffles inside each warp, then over the 32 warp totals
+        const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        __shared__ unsigned long long warp_tot[FB_K4_THREADS / 32];
+        const unsigned long long v = partials[tid];
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = warp_tot[lane];
+            unsigned long long winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+                if (lane >= d) winc += o;
+            }
+            warp_tot[lane] = winc - w; // exclusive
+        }
+        __syncthreads();
+        partials[tid] = warp_tot[warp] + inc - v;
+        __syncthreads();
+    }
+#else
     FB_PHASE(tid, T)
         if (tid == 0) {
             unsigned long long s = 0;
             for (int i = 0; i < T; i++) { unsigned long long v = partials[i]; partials[i] = s; s += v; }
         }
     FB_PHASE_END
+#endif
     FB_PHASE(tid, T)
-        unsigned long long s = partials[tid];
+        unsigned long long s = base + partials[tid];
         for (uint32_t i = (uint32_t)tid * per; i < ((uint32_t)tid + 1u) * per && i < n_frames; i++) {
             offsets[i] = s;
             s += frame_bytes[i];
