@@ -99,6 +99,14 @@ FB_HD FbKfGeom fb_kf_geom(int n) {
     return g;
 }
 
+// which frames of a job need the ODD kernel instances (units that do not start on multiples of 4 samples):
+// 0 = none, 1 = only the last (shorter) frame, 2 = all
+FB_HD int fb_kf_odd_mode(const FbJob &J) {
+    if (fb_kf_geom(J.block_size).leaf_len & 3) return 2;
+    if (J.n_frames > 0 && J.tail_n != J.block_size && (fb_kf_geom(J.tail_n).leaf_len & 3)) return J.n_frames > 1 ? 1 : 2;
+    return 0;
+}
+
 // sample range [t0, t1) of unit u
 FB_HD void fb_kf_unit_range(const FbKfGeom &g, int u, int *t0, int *t1) {
     const int leaf = u >> g.lgm, k = u & (g.m - 1);
@@ -460,23 +468,39 @@ FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int
     fb_kf_load4_at<VMS>(xa, xb, vm, fb_xidx(t), dst);
 }
 
+template <int VMS = FB_VMS_ALL>
 FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
     const int o = fb_xidx(t);
     int32_t m, sh;
     fb_vm_mix(vm, &m, &sh);
-    if (vm & FB_VM_PAIRS) {
+    if ((VMS & FB_VM_PAIRS) && (vm & FB_VM_PAIRS)) {
         int32_t ml, mr;
         fb_vm_mix_pairs(vm, &ml, &mr, &sh);
         return fb_mix_pair(xa[o], ml, mr, sh);
     }
-    if (vm & FB_VM_X16)
+    if ((VMS & FB_VM_X16) && (vm & FB_VM_X16))
         return fb_mix(reinterpret_cast<const int16_t *>(xa)[o], reinterpret_cast<const int16_t *>(xb)[o], m, sh);
     return fb_mix(xa[o], xb[o], m, sh);
 }
 
-// win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4)
-template <int G, int VMS = FB_VMS_ALL>
+// win[idx] = v for a run-time idx: a chain of predicated moves, so the window stays in registers
+template <int G>
+FB_DEV void fb_kf_win_set(int32_t *win, int idx, int32_t v) {
+#pragma unroll
+    for (int j = 0; j < G + FB_KF_RUN; j++) win[j] = (j == idx) ? v : win[j];
+}
+
+// ODD instantiations serve frames whose units do not start on multiples of 4 samples (finest partitions of odd
+// tail frames): the same arithmetic with sample-by-sample window loads.  They are separate template instances, so
+// the hot loops of the regular frames carry none of that code.
+// win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4 unless ODD)
+template <int G, int VMS = FB_VMS_ALL, bool ODD = false>
 FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, int32_t *win) {
+    if (ODD) {
+#pragma unroll 1
+        for (int i = 0; i < G; i++) fb_kf_win_set<G>(win, i, ta - G + i >= 0 ? fb_kf_load1<VMS>(xa, xb, vm, ta - G + i) : 0);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < G; i += 4) {
         const int t = ta - G + i;
@@ -485,9 +509,14 @@ FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, 
     }
 }
 
-// win[G..G+RUN) = x[t0 .. t0+RUN) (t0 a multiple of 4); samples at t >= n are don't-cares (their results are masked)
-template <int G, int VMS = FB_VMS_ALL>
+// win[G..G+RUN) = x[t0 .. t0+RUN) (t0 a multiple of 4 unless ODD); samples at t >= n are don't-cares (masked)
+template <int G, int VMS = FB_VMS_ALL, bool ODD = false>
 FB_DEV void fb_kf_fetch_run(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
+    if (ODD) {
+#pragma unroll 1
+        for (int i = 0; i < FB_KF_RUN; i++) fb_kf_win_set<G>(win, G + i, fb_kf_load1<VMS>(xa, xb, vm, t0 + i));
+        return;
+    }
     if ((t0 & 15) == 0) {
         // a run that starts on a multiple of 16 lies inside one 64-sample block of the padded plane: one index
         const int o = fb_xidx(t0);
@@ -577,7 +606,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
 // unit_bits[0..U) (bits of every unit without the parameter fields).
 // Sets M->fail when the frame must be redone by the literal path.
 // =====================================================================================================
-template <int G>
+template <int G, bool ODD>
 FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, const int32_t *xb, int vm,
                          const FbKfCand &cd, uint8_t *scratch, const FbKfLayout &L, uint32_t *unit_bits, FbKfRes *res) {
     uint32_t *words = (uint32_t *)(scratch + L.s_words);
@@ -610,10 +639,10 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             const int lo = ta > warm ? ta : warm;
             if (tb > ta) {
                 int32_t win[G + FB_KF_RUN];
-                fb_kf_history<G, 0>(xa, xb, vm, ta, win);
+                fb_kf_history<G, 0, ODD>(xa, xb, vm, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
-                    fb_kf_fetch_run<G, 0>(xa, xb, vm, t0, win);
+                    fb_kf_fetch_run<G, 0, ODD>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
                     fb_kf_csa_run(cw, uu);
                     fb_kf_slide<G>(win);
@@ -811,7 +840,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 // One variant (one warp): fixed_lpc / estimated_qlpc / encode_subframe (src/coding.rs:298-418) on top
 // of K1's analysis.  Writes the decision record `out` (shared memory) and S->cand[v].
 // =====================================================================================================
-template <int G>
+template <int G, bool ODD>
 FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, const FbAnalysis &A, int v,
                           uint8_t *smem, const FbKfLayout &L, fb200_subframe_info *out) {
     FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
@@ -875,7 +904,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             for (int j = 0; j < A.qlp_order; j++) sumabs += (unsigned long long)(A.qlp[j] < 0 ? -A.qlp[j] : A.qlp[j]);
             cd.narrow = (unsigned long long)A.max_abs * sumabs < 0x7FFFFFFFull;
         }
-        fb_kf_search<G>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), res[c]);
+        fb_kf_search<G, ODD>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), res[c]);
         if (M->fail) return;
         cbits[c] = c == 0 ? 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0]->res_bits
                           : 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
@@ -1031,7 +1060,7 @@ FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *p
 }
 
 // ---- KA: analysis and plan.  psubs: [frame][channels] chosen subframe records; poffs: [frame][channels][U_max+1]
-template <int G>
+template <int G, bool ODD = false>
 FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *vsubs,
                        fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                        uint32_t *fb_count, const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
@@ -1047,7 +1076,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
 
     // units must start on multiples of 4 samples (16-byte window loads): frames whose finest partitions are not a
     // multiple of 4 long (odd tail frames, odd block sizes) are left to the generic kernels
-    if ((g.leaf_len & 3) != 0) {
+    if (!ODD && (g.leaf_len & 3) != 0) {
         FB_PHASE(tid, T)
             if (tid == 0) fb_kf_to_fallback(fb_list, fb_count, plan, f);
         FB_PHASE_END
@@ -1063,7 +1092,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
 
     // ---- analysis: one warp per variant
     FB_WARPS_BEGIN(w, NW)
-        fb_kf_variant<G>(J, g, xs, ana[(size_t)f * (size_t)J.nvar + (size_t)w], w, smem, L, &choice[w]);
+        fb_kf_variant<G, ODD>(J, g, xs, ana[(size_t)f * (size_t)J.nvar + (size_t)w], w, smem, L, &choice[w]);
         const FbKfMisc *M = (const FbKfMisc *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_misc);
         FB_WPHASE(lane)
             if (lane == 0 && M->fail) S->frame_fail = 1; // benign race between warps
@@ -1211,7 +1240,7 @@ FB_DEV int fb_kp_planes(const FbJob &J, const FbKfLayout &L, const int32_t *xs, 
 
 // ---- KP: pack a planned frame and store it at out + offsets[f].  pcm: the batch's packed PCM (only read when the
 // layout says pairs)
-template <int G>
+template <int G, bool ODD = false>
 FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, const FbKfPlan *plan,
                        const fb200_subframe_info *psubs, const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out, unsigned long long out_cap,
                        const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
@@ -1362,10 +1391,10 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             const uint32_t rmask = (1u << rp) - 1u, rone = 1u << rp;
             if (tb > lo) {
                 int32_t win[G + FB_KF_RUN];
-                fb_kf_history<G>(xa, xb, vm, ta, win);
+                fb_kf_history<G, FB_VMS_ALL, ODD>(xa, xb, vm, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
-                    fb_kf_fetch_run<G>(xa, xb, vm, t0, win);
+                    fb_kf_fetch_run<G, FB_VMS_ALL, ODD>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
 #pragma unroll
                     for (int i = 0; i < FB_KF_RUN; i++) {

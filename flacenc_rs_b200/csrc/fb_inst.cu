@@ -57,17 +57,30 @@ __global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int3
                                                              fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,
                                                              uint32_t *frame_bytes, fb200_frame_info *infos,
                                                              uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,
-                                                             FbKfLayout L) {
+                                                             FbKfLayout L, int odd_mode) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_ka_body<FB_INST_G>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, blockIdx.x, fb_smem, L);
+    // odd_mode (fb_kf_odd_mode): 0 = every frame has 4-sample aligned units; 1 = all but the last frame (its CTA comes
+    // first: it is the slow one); 2 = none.  The ODD instance loads its windows sample by sample.
+    const bool odd = odd_mode == 2 || (odd_mode == 1 && blockIdx.x == 0);
+    const uint32_t f = odd_mode == 1 ? (blockIdx.x == 0 ? J.n_frames - 1u : blockIdx.x - 1u) : blockIdx.x;
+    if (odd)
+        fb_ka_body<FB_INST_G, true>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, f, fb_smem, L);
+    else
+        fb_ka_body<FB_INST_G, false>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, f, fb_smem, L);
 }
 
 __global__ void __maxnreg__(96) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
                                                              const fb200_subframe_info *psubs, const uint32_t *poffs,
                                                              const unsigned long long *offsets, uint8_t *out,
-                                                             unsigned long long out_cap, const uint32_t *ktab, FbKfLayout L) {
+                                                             unsigned long long out_cap, const uint32_t *ktab, FbKfLayout L,
+                                                             int odd_mode) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_kp_body<FB_INST_G>(J, xt, pcm, plan, psubs, poffs, offsets, out, out_cap, ktab, blockIdx.x, fb_smem, L);
+    const bool odd = odd_mode == 2 || (odd_mode == 1 && blockIdx.x == 0);
+    const uint32_t f = odd_mode == 1 ? (blockIdx.x == 0 ? J.n_frames - 1u : blockIdx.x - 1u) : blockIdx.x;
+    if (odd)
+        fb_kp_body<FB_INST_G, true>(J, xt, pcm, plan, psubs, poffs, offsets, out, out_cap, ktab, f, fb_smem, L);
+    else
+        fb_kp_body<FB_INST_G, false>(J, xt, pcm, plan, psubs, poffs, offsets, out, out_cap, ktab, f, fb_smem, L);
 }
 
 void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
@@ -96,14 +109,14 @@ void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const FbAnalysis
                              uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                              uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
     FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, ana, (FbKfPlan *)plan, vsubs, psubs, poffs, frame_bytes,
-                                                                     infos, fb_list, fb_count, ktab, L);
+                                                                     infos, fb_list, fb_count, ktab, L, fb_kf_odd_mode(J));
 }
 
 void FB_NAME(fb_launch_kp_g)(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const void *plan, const fb200_subframe_info *psubs,
                              const uint32_t *poffs, const unsigned long long *offsets, uint8_t *out,
                              unsigned long long out_cap, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
     FB_NAME(fb_kp_pack_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, pcm, (const FbKfPlan *)plan, psubs, poffs, offsets, out,
-                                                                     out_cap, ktab, L);
+                                                                     out_cap, ktab, L, fb_kf_odd_mode(J));
 }
 
 cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {

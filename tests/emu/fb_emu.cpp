@@ -113,7 +113,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         poffs.assign((size_t)J.n_frames * J.channels * (KL.U_max + 1), 0xDDDDDDDDu);
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KA(GG) fb_ka_body<GG>(J, B.xv.data(), B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL)
+#define EMU_KA(GG) if (fb_kf_geom(fb_frame_len(J, f)).leaf_len & 3) fb_ka_body<GG, true>(J, B.xv.data(), B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL); else fb_ka_body<GG, false>(J, B.xv.data(), B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KA(4); break;
             case 8: EMU_KA(8); break;
@@ -189,7 +189,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         fb_kf_build_ktab(KL.crc_chunk, ktab.data());
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KP(GG) fb_kp_body<GG>(J, B.xv.data(), pairs ? (const uint8_t *)pcm : nullptr, plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL)
+#define EMU_KP(GG) if (fb_kf_geom(fb_frame_len(J, f)).leaf_len & 3) fb_kp_body<GG, true>(J, B.xv.data(), pairs ? (const uint8_t *)pcm : nullptr, plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL); else fb_kp_body<GG, false>(J, B.xv.data(), pairs ? (const uint8_t *)pcm : nullptr, plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KP(4); break;
             case 8: EMU_KP(8); break;

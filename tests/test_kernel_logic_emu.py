@@ -182,14 +182,14 @@ def test_pathological_lpc_gain_chunked_saturation_path():
 
 
 def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
-    """Default config: every full frame goes through the fused kernel.  Frames whose finest Rice partitions are not
-    a multiple of 4 samples (the 2728-sample tail: 8 x 341), residuals >= 2^27 (the reference's chunked saturating
+    """Default config: every frame goes through the fused kernel, also tails whose finest Rice partitions are not
+    a multiple of 4 samples (the 2728-sample tail: 8 x 341; the kernels' ODD instances).  Residuals >= 2^27 (the reference's chunked saturating
     sums become order dependent) and saturated table minima are handed to the generic kernels; BitCount order
     selection and frames that do not fit shared memory never enter the fused kernel."""
     E.fused_counts()
     x = sigen.noisy_sine_pcm(4096 * 3 + 2728, 2, 16, 44100)
     _compare(x, 2, 16, 44100, 4096)
-    assert E.fused_counts() == [6, 2]  # (16-bit stereo runs the fused path twice: PCM pairs and planes in the packer)
+    assert E.fused_counts() == [8, 0]  # (16-bit stereo runs the fused path twice: PCM pairs and planes in the packer)
     _compare(x[: 4096 * 3 + 2048], 2, 16, 44100, 4096)
     assert E.fused_counts() == [8, 0]
     E.mode_counts()
