@@ -263,6 +263,17 @@ def test_pipelined_chunk_schedule(monkeypatch):
     assert list(sizes) == list(ref_sizes) and got.tobytes() == ref
 
 
+def test_odd_block_size_every_frame_on_the_odd_instances():
+    """block 1000 = 8 partitions of 125 samples: no unit of any frame starts on a multiple of 4 samples"""
+    n = 1000 * 7 + 333
+    x = sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=9)
+    _compare(x, 2, 16, 44100, 1000)
+    with Context(make_config(block_size=1000).into_verified(), 2, 16, 44100, 1000) as ctx:
+        ctx.encode_interleaved(pack_pcm(x, 2), 2, n)
+        t = ctx.timing()
+        assert (t.fused_frames, t.fallback_frames) == (8, 0)
+
+
 def test_fused_geometry_odd_block_sizes():
     rng = np.random.default_rng(11)
     for n in (64, 66, 127, 128, 341 * 8, 3136, 98 * 32, 5000, 4100, 8192, 9216, 12345, 16383):

@@ -208,6 +208,13 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     assert E.fused_counts() == [0, 0]
 
 
+def test_odd_block_size_every_frame_on_the_odd_instances():
+    E.fused_counts()
+    x = sigen.noisy_sine_pcm(1000 * 7 + 333, 2, 16, 44100, config_id=9)
+    _compare(x, 2, 16, 44100, 1000)
+    assert E.fused_counts() == [16, 0]
+
+
 def test_fused_geometry_covers_every_block_size():
     """units tile every leaf exactly, are <= 112 samples and there are >= 32 of them (host-side geometry check
     through the encode of odd sizes, incl. leaves that are not a multiple of 4 samples)"""
