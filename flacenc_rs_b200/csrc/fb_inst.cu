@@ -85,7 +85,7 @@ __global__ void __maxnreg__(96) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt
 
 void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
                              FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
-    const unsigned grid = 2u * ((nvars + FB_K1_THREADS - 1) / FB_K1_THREADS); // pass A blocks, then pass E blocks
+    const unsigned grid = 2u * ((fb_k1_slots(J, nvars) + FB_K1_THREADS - 1) / FB_K1_THREADS); // pass A blocks, then pass E blocks
     const uint32_t smem = fb_k1_smem_bytes(J.channels, J.nvar);
     if (smem > 48u * 1024u)
         cudaFuncSetAttribute(FB_NAME(fb_k1_analyze_g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

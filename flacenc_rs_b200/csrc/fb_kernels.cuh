@@ -675,6 +675,14 @@ FB_HD int fb_k1_pitch_rows(int channels, int nvar) {
 }
 #define FB_K1_THREADS 128
 #define FB_K1_NQ 32 // quads of every staged row in a warp's ring (128 samples)
+// lane slots of a launch: the variants in order; a shorter last frame is moved to the next warp boundary
+FB_HD uint32_t fb_k1_full_variants(const FbJob &J, uint32_t n_variants) {
+    return (J.n_frames > 1 && J.tail_n != J.block_size) ? n_variants - (uint32_t)J.nvar : n_variants;
+}
+FB_HD uint32_t fb_k1_slots(const FbJob &J, uint32_t n_variants) {
+    const uint32_t n_full = fb_k1_full_variants(J, n_variants);
+    return n_full < n_variants ? ((n_full + 31u) & ~31u) + (n_variants - n_full) : n_variants;
+}
 FB_HD uint32_t fb_k1_smem_bytes(int channels, int nvar) {
     return (uint32_t)(FB_K1_THREADS / 32) * FB_K1_NQ * (uint32_t)fb_k1_pitch_rows(channels, nvar) * 16u;
 }
@@ -815,15 +823,22 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full,
     const bool role_a = blockIdx.x < nblk;
     const uint32_t blk = role_a ? blockIdx.x : blockIdx.x - nblk;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t gv = blk * (uint32_t)FB_K1_THREADS + threadIdx.x;
-    const uint32_t gv0 = gv - lane;
-    if (gv0 >= n_variants) return; // the whole warp has nothing to do
-    const bool valid = gv < n_variants;
-    const uint32_t gve = valid ? gv : n_variants - 1u; // surplus lanes shadow the last variant (they still copy)
     const uint32_t nvar = (uint32_t)J.nvar, ch = (uint32_t)J.channels;
+    // Variants to lanes: in order, 32 per warp -- except that the variants of a shorter last frame start a warp of
+    // their own (fb_k1_slots), so that every warp walks frames of one length and can use the unguarded groups.
+    const uint32_t slot = blk * (uint32_t)FB_K1_THREADS + threadIdx.x, slot0 = slot - lane;
+    const uint32_t n_full = fb_k1_full_variants(J, n_variants); // variants before the isolated last frame
+    const uint32_t tail_slot = (n_full + 31u) & ~31u;
+    const bool tail_warp = n_full < n_variants && slot0 >= tail_slot;
+    const uint32_t gv0 = tail_warp ? n_full + (slot0 - tail_slot) : slot0;
+    const uint32_t lim = tail_warp ? n_variants : n_full;        // end of the variants this warp may take
+    if (gv0 >= lim) return; // the whole warp has nothing to do
+    const uint32_t gv = gv0 + lane;
+    const bool valid = gv < lim;
+    const uint32_t gve = valid ? gv : lim - 1u; // surplus lanes shadow the last variant (they still copy)
     const uint32_t f = gve / nvar;
     const int v = (int)(gve - f * nvar);
-    const uint32_t gvl = gv0 + 31u < n_variants ? gv0 + 31u : n_variants - 1u;
+    const uint32_t gvl = gv0 + 31u < lim ? gv0 + 31u : lim - 1u;
     const uint32_t f_lo = gv0 / nvar, f_hi = gvl / nvar;
     const uint32_t rlo = f_lo * ch;
     const uint32_t NR = (f_hi - f_lo + 1u) * ch;
