@@ -209,8 +209,8 @@ def cpu_port_throughput(pcm: np.ndarray, threads: int, target_seconds: float):
 
 
 MODEL_OPS_PER_SAMPLE = 250.0  # minimal integer/FP lane-ops per inter-channel sample (stereo, default config)
-NCU_KF = {  # dominant kernel (fb_ka_plan: Rice search + frame plan), `ncu --set full` (profiles/r1h_ncu_summary.md)
-    "dram_bytes_per_frame": 36299.0, "issue_active_pct": 58.7, "warp_inst_per_frame": 42031.0}
+NCU_KF = {  # dominant kernel (fb_ka_plan: Rice search + frame plan), `ncu --set full` (profiles/r1i_ncu_summary.md)
+    "dram_bytes_per_frame": 36185.0, "issue_active_pct": 59.6, "warp_inst_per_frame": 41510.0}
 
 
 def issue_roofline(value: float, clocks: dict) -> dict:
