@@ -52,6 +52,13 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
     }
 }
 
+// the pack kernel fits 96 registers (5 CTAs of 128 threads per SM) for tap windows up to 16; the wide windows would spill
+#if FB_INST_G <= 16
+#define FB_KP_BOUNDS __maxnreg__(96)
+#else
+#define FB_KP_BOUNDS __launch_bounds__(256)
+#endif
+
 // fused path (fb_fused.cuh), one CTA of 32 * nvar threads per frame: KA = analysis + plan, KP = pack + store
 __global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int32_t *xt, const FbAnalysis *ana, FbKfPlan *plan,
                                                              fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int3
         fb_ka_body<FB_INST_G, false>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, f, fb_smem, L);
 }
 
-__global__ void __maxnreg__(96) FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
+__global__ void FB_KP_BOUNDS FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
                                                              const fb200_subframe_info *psubs, const uint32_t *poffs,
                                                              const unsigned long long *offsets, uint8_t *out,
                                                              unsigned long long out_cap, const uint32_t *ktab, FbKfLayout L,
