@@ -59,8 +59,15 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
 #define FB_KP_BOUNDS __launch_bounds__(256)
 #endif
 
+// the plan kernel of the wide windows: 168 registers = 3 CTAs of 128 threads per SM (what its shared memory allows)
+#if FB_INST_G >= 20
+#define FB_KA_BOUNDS __maxnreg__(168)
+#else
+#define FB_KA_BOUNDS __launch_bounds__(256)
+#endif
+
 // fused path (fb_fused.cuh), one CTA of 32 * nvar threads per frame: KA = analysis + plan, KP = pack + store
-__global__ void __launch_bounds__(256) FB_NAME(fb_ka_plan_g)(FbJob J, const int32_t *xt, const FbAnalysis *ana, FbKfPlan *plan,
+__global__ void FB_KA_BOUNDS FB_NAME(fb_ka_plan_g)(FbJob J, const int32_t *xt, const FbAnalysis *ana, FbKfPlan *plan,
                                                              fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,
                                                              uint32_t *frame_bytes, fb200_frame_info *infos,
                                                              uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,
