@@ -9,8 +9,13 @@
 #define FB_CAT(a, b) FB_CAT2(a, b)
 #define FB_NAME(base) FB_CAT(base, FB_INST_G)
 
+#if FB_INST_G >= 20
+#define FB_K1_BOUNDS __maxnreg__(168)
+#else
+#define FB_K1_BOUNDS __launch_bounds__(FB_K1_THREADS)
+#endif
 // analysis: one thread per channel variant, rows staged per warp (fb_kernels.cuh)
-__global__ void __launch_bounds__(FB_K1_THREADS) FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt, const float *win_full,
+__global__ void FB_K1_BOUNDS FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt, const float *win_full,
                                                                           const float *win_tail, FbAnalysis *ana,
                                                                           fb200_variant_taps *taps, uint32_t n_variants) {
     extern __shared__ __align__(16) uint8_t fb_smem[];

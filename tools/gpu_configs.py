@@ -38,8 +38,12 @@ def make_cfg(kw):
     return e.into_verified()
 
 
+ONLY = os.environ.get("FB_CFG_ONLY", "")        # run only the cases whose name starts with this
+SCALE = int(os.environ.get("FB_CFG_SCALE", "1"))  # multiply the audio length
 for name, ch, bps, rate, block, secs, kw in CASES:
-    n = secs * rate
+    if not name.startswith(ONLY):
+        continue
+    n = secs * rate * SCALE
     x = sigen.noisy_sine_pcm(n, ch, bps, rate, config_id=3)
     cb = (bps + 7) // 8
     packed = pack_samples(x, cb)
