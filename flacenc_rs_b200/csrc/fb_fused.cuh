@@ -18,18 +18,21 @@
 //             in registers right after the unit's last run when a unit is a whole partition)
 //     pass 3  bottom-up partition tree (src/rice.rs:246-298) over the parameter window
 //             [min leaf minimiser, max leaf minimiser] -- the minimiser of every merged node lies in it
-//             (sum of convex functions) -- in passes of 8 parameters
+//             (sum of convex functions) -- in passes of FB_KF_COLS parameters
 //     pass 4  partition order, parameters, exact Residual::count_bits (src/component/bitrepr.rs:532-544)
 //             and the bit length of every unit (again from the counters)
 //   subframe decision (src/coding.rs:384-418); then per frame: stereo decision (src/coding.rs:454-527),
 //   header + CRC-8, bit offsets of all units by a warp scan; the plan and the frame size go to global memory.
-// KP (after the scan of the frame sizes): stages the channels again, every thread packs one unit (residuals
-//   recomputed, every code OR-ed on its own into the zeroed word buffer), CRC-16, store at out + offsets[f].
+// KP (after the scan of the frame sizes): stages the channels again (16-bit stereo: the packed PCM itself, as
+//   (left, right) pairs), every thread packs one unit (residuals recomputed, every code OR-ed on its own into the
+//   zeroed word buffer), CRC-16, store at out + offsets[f].
 //
+// Frames whose units do not start on multiples of 4 samples (finest partitions of odd tail frames) run through a
+// second template instance of both bodies (ODD: sample-by-sample window loads) inside the same launches.
 // Whatever KA cannot reproduce exactly -- a residual >= 2^26 (the reference's 16-sample chunked saturating
-// accumulation matters, src/rice.rs:75-98), a saturated table minimum, finest partitions that are not a multiple
-// of 4 samples -- is not guessed: the frame is appended to a fallback list and redone by the generic K2/K3
-// kernels (fb_kernels.cuh), which replay the reference literally.  Results are byte-identical either way.
+// accumulation matters, src/rice.rs:75-98) or a saturated table minimum -- is not guessed: the frame is appended to
+// a fallback list and redone by the generic K2/K3 kernels (fb_kernels.cuh), which replay the reference literally.
+// Results are byte-identical either way.
 #pragma once
 
 #include "fb_kernels.cuh"

@@ -221,8 +221,8 @@ FB_HD int32_t fb_mix(int32_t a, int32_t b, int32_t m, int32_t sh) {
     return (int32_t)((uint32_t)a + (uint32_t)m * (uint32_t)b) >> sh;
 }
 
-// software prefetch of the quad at t into L1 (no registers are tied up; the later load hits the cache).
-// Below ~20 K variants per launch the analysis kernel has too few warps per SM to hide DRAM latency otherwise.
+// software prefetch of the quad at t into L1 (kept for experiments; the analysis kernel stages its rows in shared
+// memory instead)
 FB_DEV void fb_rows_prefetch4(const FbVarRows &r, int t) {
 #if FB_GPU
     const size_t o = fb_xt_quad(t);
@@ -259,7 +259,7 @@ FB_DEV void fb_k0b_expand4(const FbJob &J, const int32_t *xt, int32_t *xv4, uint
 }
 
 // =================================================================================================
-// K1: analyze one channel variant with a single sequential pass (thread per variant).
+// K1: analyze one channel variant (thread per variant and pass).
 //
 // Everything whose result depends on floating-point evaluation order is done here in exactly the
 // reference's (stable build) order, so the floats are bit-identical to the scalar CPU code:
@@ -269,8 +269,8 @@ FB_DEV void fb_k0b_expand4(const FbJob &J, const int32_t *xt, int32_t *xv4, uint
 //     FMAs starting at t = lpc_order for every lag (src/lpc.rs:533-548)
 //   * symmetric_levinson_recursion::<f64> (src/lpc.rs:633-705), quantize_parameters (:234-302)
 // R = ring size = lpc_order rounded up to a multiple of 4; lags 0..R are accumulated, lags above
-// lpc_order are ignored.  Independent variants give the parallelism (32 per warp, and a warp's 16-byte
-// loads of "the next four samples of my row" fall in one 512-byte block of the row-interleaved store),
+// lpc_order are ignored.  Independent variants give the parallelism (32 per warp; the rows a warp walks are
+// adjacent 16-byte pieces of the row-interleaved store and are staged together in a shared-memory ring),
 // the R+1 independent FMA chains per thread give the ILP.
 // =================================================================================================
 
