@@ -213,14 +213,21 @@ NCU_KF = {  # dominant kernel (fb_ka_plan: Rice search + frame plan), `ncu --set
     "dram_bytes_per_frame": 36185.0, "issue_active_pct": 59.6, "warp_inst_per_frame": 41510.0}
 
 
+# executed warp instructions per 4096-sample stereo frame of the three heavy kernels (profiles/r1i_ncu_summary.md)
+NCU_WARP_INST_PER_FRAME = {"analyze": 23432.0, "plan": 41510.0, "pack": 24057.0}
+
+
 def issue_roofline(value: float, clocks: dict) -> dict:
     sm_mhz = float(clocks.get("sm_mhz") or 1965.0)
     peak = 148 * 4 * 32 * sm_mhz * 1e6  # SMs x schedulers x lanes x clock: lane-ops/s of one issue slot per scheduler
+    executed = sum(NCU_WARP_INST_PER_FRAME.values()) * 32.0 / BLOCK  # lane-ops per inter-channel sample actually issued
     return {"bound": "issue", "model_ops_per_sample": MODEL_OPS_PER_SAMPLE, "peak_lane_ops_per_s": peak,
             "peak_samples_per_s": peak / MODEL_OPS_PER_SAMPLE, "frac": value * MODEL_OPS_PER_SAMPLE / peak,
+            "executed_ops_per_sample": executed, "executed_frac": value * executed / peak,
             "ncu_dominant_kernel": NCU_KF,
-            "note": "frac = value x 250 ops / (148 SM x 4 x 32 lanes x SM clock), per GPU at N=1; ncu numbers are from the "
-                    "committed capture, not this run"}
+            "note": "frac = value x 250 ops / (148 SM x 4 x 32 lanes x SM clock), per GPU at N=1; executed_frac uses the "
+                    "instructions the kernels really issue (whole step, incl. the HBM-bound ingest); ncu numbers are from "
+                    "the committed capture, not this run"}
 
 
 def run_reference(args, rank: int, world: int) -> None:
