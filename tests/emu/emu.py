@@ -86,6 +86,16 @@ def set_force_generic(flag: bool) -> None:
     lib().fbemu_set_force_generic(1 if flag else 0)
 
 
+def launch_geometry(channels: int, bps: int, rate: int, block_size: int, n_samples: int):
+    """(frames, lane slots of the analysis launch, variants before an isolated last frame, odd mode, staged rows)"""
+    out = (C.c_uint32 * 4)()
+    L = lib()
+    L.fbemu_launch_geometry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint32)]
+    L.fbemu_launch_geometry.restype = C.c_int
+    frames = L.fbemu_launch_geometry(channels, bps, rate, block_size, n_samples, out)
+    return frames, out[0], out[1], out[2], out[3]
+
+
 def set_kp_pairs(flag: bool) -> None:
     """False: the pack kernel always stages planes from the planar store (default True: PCM pairs when the format allows)."""
     lib().fbemu_set_kp_pairs(1 if flag else 0)

@@ -34,6 +34,21 @@ void fbemu_fused_counts(unsigned long long *out2, int reset) {
 void fbemu_config_default(fb200_config *c) { fbh_config_default(c); }
 int fbemu_config_verify(const fb200_config *c) { return fbh_config_verify(c); }
 
+// launch geometry helpers shared by the host launchers and the kernels:
+// out4 = {lane slots of the analysis launch, variants before an isolated last frame, odd mode of the fused kernels,
+//         rows staged per quad by an analysis warp}
+int fbemu_launch_geometry(int channels, int bps, int rate, int block_size, uint64_t n_samples, uint32_t *out4) {
+    fb200_config cfg;
+    fbh_config_default(&cfg);
+    const FbJob J = fbh_make_job(cfg, channels, bps, rate, block_size, 4, n_samples, 0);
+    const uint32_t nvars = J.n_frames * (uint32_t)J.nvar;
+    out4[0] = fb_k1_slots(J, nvars);
+    out4[1] = fb_k1_full_variants(J, nvars);
+    out4[2] = (uint32_t)fb_kf_odd_mode(J);
+    out4[3] = (uint32_t)fb_k1_pitch_rows(J.channels, J.nvar);
+    return (int)J.n_frames;
+}
+
 int fbemu_frame_header(int n, int ch_tag, int bps, int rate, uint32_t number, uint8_t *out) {
     return fb_frame_header(n, ch_tag, bps, rate, number, out);
 }

@@ -208,6 +208,26 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     assert E.fused_counts() == [0, 0]
 
 
+def test_launch_geometry_helpers():
+    """host/device shared launch geometry: a shorter last frame starts a warp of its own in the analysis launch, the
+    fused kernels' ODD instances are chosen from the frame geometry, the staged rows cover what a warp can span"""
+    # (channels, block, samples) -> expectations
+    frames, slots, full, odd, rows = E.launch_geometry(2, 16, 44100, 4096, 4096 * 107 + 2728)
+    assert (frames, full, slots, odd, rows) == (108, 107 * 4, ((107 * 4 + 31) // 32) * 32 + 4, 1, 16)  # 2728 = 8 x 341
+    frames, slots, full, odd, rows = E.launch_geometry(2, 16, 44100, 4096, 4096 * 108)
+    assert (frames, full, slots, odd, rows) == (108, 432, 432, 0, 16)
+    frames, slots, full, odd, rows = E.launch_geometry(2, 16, 44100, 4096, 4096 * 9 + 3136)
+    assert (frames, full, odd) == (10, 36, 1) and slots == 64 + 4                                  # 3136 = 32 x 98
+    frames, slots, full, odd, rows = E.launch_geometry(2, 16, 44100, 1000, 7333)
+    assert (frames, odd) == (8, 2)                                                                   # 1000 = 8 x 125
+    frames, slots, full, odd, rows = E.launch_geometry(2, 16, 44100, 4096, 3136)
+    assert (frames, slots, full, odd) == (1, 4, 4, 2)                                                # a single odd frame
+    frames, slots, full, odd, rows = E.launch_geometry(1, 16, 44100, 4096, 4096 * 40 + 2048)
+    assert (frames, full, slots, odd, rows) == (41, 40, 64 + 1, 0, 32)
+    for ch, want in ((3, 48), (4, 32), (5, 48), (6, 48), (7, 48), (8, 32)):
+        assert E.launch_geometry(ch, 16, 44100, 4096, 4096 * 3)[4] == want
+
+
 def test_odd_block_size_every_frame_on_the_odd_instances():
     E.fused_counts()
     x = sigen.noisy_sine_pcm(1000 * 7 + 333, 2, 16, 44100, config_id=9)
