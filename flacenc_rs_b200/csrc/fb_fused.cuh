@@ -1309,37 +1309,47 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             fb_run_flush(r);
         }
 #define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, (t)))
-        if (tid < c1 - c0) {
-            const FbKfSub &D = S->sub[c0 + tid];
-            const fb200_subframe_info &V = psub[c0 + tid];
+        // subframe heads (src/component/bitrepr.rs:443-528): every field has a known bit position, so the lanes of
+        // warp w write the fields of subframe c0 + w side by side -- type byte, warm-up samples, precision / shift,
+        // coefficients, residual method and partition order
+        if ((tid >> 5) < c1 - c0) {
+            const int sc = c0 + (tid >> 5), lane = tid & 31;
+            const FbKfSub &D = S->sub[sc];
+            const fb200_subframe_info &V = psub[sc];
             const int32_t *xa, *xb;
             const int vm = fb_kp_planes(J, L, xs, D.variant, c0, &xa, &xb);
-            FbBitRun r;
-            fb_run_init(r, words, D.start_bit, D.start_bit + 1);
-            r.w_last = 0xFFFFFFFFu;
             const uint32_t mask = D.bps >= 32 ? 0xFFFFFFFFu : ((1u << D.bps) - 1u);
-#define FB_PUT_ATOMIC(val, nb) do { r.w_first = r.cur_w; fb_run_put(r, (uint32_t)(val), (uint32_t)(nb)); } while (0)
-            if (D.type == FB200_SF_CONSTANT) {
-                FB_PUT_ATOMIC(0x00, 8);
-                FB_PUT_ATOMIC(FB_KF_X(0) & mask, D.bps);
-            } else if (D.type == FB200_SF_VERBATIM) {
-                FB_PUT_ATOMIC(0x02, 8);
-            } else if (D.type == FB200_SF_FIXED) {
-                FB_PUT_ATOMIC(0x10 | (D.order << 1), 8);
-                for (int t = 0; t < D.order; t++) FB_PUT_ATOMIC(FB_KF_X(t) & mask, D.bps);
-                FB_PUT_ATOMIC(((D.rice2 ? 1 : 0) << 4) | D.part_order, 6);
-            } else {
-                FB_PUT_ATOMIC(0x40 | ((D.order - 1) << 1), 8);
-                for (int t = 0; t < D.order; t++) FB_PUT_ATOMIC(FB_KF_X(t) & mask, D.bps);
-                FB_PUT_ATOMIC(D.precision - 1, 4);
-                FB_PUT_ATOMIC((uint32_t)D.shift & 31u, 5);
-                const uint32_t pmask = (1u << D.precision) - 1u;
-                for (int j = 0; j < D.order; j++) FB_PUT_ATOMIC((uint32_t)(int32_t)V.qlp[j] & pmask, D.precision);
-                FB_PUT_ATOMIC(((D.rice2 ? 1 : 0) << 4) | D.part_order, 6);
+            const uint32_t base = D.start_bit;
+            const bool lpc = D.type == FB200_SF_LPC, fixed = D.type == FB200_SF_FIXED;
+            const int warm = (lpc || fixed) ? D.order : (D.type == FB200_SF_CONSTANT ? 1 : 0);
+            const int ncoef = lpc ? D.order : 0;
+            const int nitems = 1 + warm + (lpc ? 1 : 0) + ncoef + ((lpc || fixed) ? 1 : 0);
+            for (int item = lane; item < nitems; item += 32) {
+                if (item == 0) {
+                    const uint32_t tb = D.type == FB200_SF_CONSTANT ? 0x00u
+                                       : D.type == FB200_SF_VERBATIM ? 0x02u
+                                       : fixed ? (0x10u | ((uint32_t)D.order << 1)) : (0x40u | ((uint32_t)(D.order - 1) << 1));
+                    fb_or_bits(words, base, tb, 8u);
+                } else if (item <= warm) {
+                    const int t = item - 1;
+                    fb_or_bits(words, base + 8u + (uint32_t)t * (uint32_t)D.bps, FB_KF_X(t) & mask, (uint32_t)D.bps);
+                } else {
+                    const uint32_t after_warm = base + 8u + (uint32_t)warm * (uint32_t)D.bps;
+                    int k = item - 1 - warm;
+                    if (lpc && k == 0) {
+                        fb_or_bits(words, after_warm, ((uint32_t)(D.precision - 1) << 5) | ((uint32_t)D.shift & 31u), 9u);
+                    } else {
+                        if (lpc) k--;
+                        if (k < ncoef) {
+                            const uint32_t pmask = (1u << D.precision) - 1u;
+                            fb_or_bits(words, after_warm + 9u + (uint32_t)k * (uint32_t)D.precision,
+                                       (uint32_t)(int32_t)V.qlp[k] & pmask, (uint32_t)D.precision);
+                        } else {
+                            fb_or_bits(words, D.res_bit, ((D.rice2 ? 1u : 0u) << 4) | (uint32_t)D.part_order, 6u);
+                        }
+                    }
+                }
             }
-#undef FB_PUT_ATOMIC
-            r.w_first = r.cur_w;
-            fb_run_flush(r);
         }
         for (int item = tid; item < (c1 - c0) * g.U; item += T) {
             const int c = c0 + (item >> g.lgU), unit = item & (g.U - 1);
