@@ -1297,17 +1297,9 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
         FB_PHASE_END
     }
     FB_PHASE(tid, T)
-        if (tid == 0 && c0 == 0) {
-            FbBitRun r;
-            fb_run_init(r, words, 0, 1);
-            r.w_last = 0xFFFFFFFFu;
-            for (int i = 0; i < S->header_len; i++) {
-                r.w_first = r.cur_w; // every flush through the atomic path
-                fb_run_put(r, S->header[i], 8);
-            }
-            r.w_first = r.cur_w;
-            fb_run_flush(r);
-        }
+        // frame header bytes: one lane each, in the last warp (the first warps write the subframe heads)
+        if (c0 == 0 && (tid >> 5) == NW - 1 && (tid & 31) < S->header_len)
+            fb_or_bits(words, 8u * (uint32_t)(tid & 31), S->header[tid & 31], 8u);
 #define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, (t)))
         // subframe heads (src/component/bitrepr.rs:443-528): every field has a known bit position, so the lanes of
         // warp w write the fields of subframe c0 + w side by side -- type byte, warm-up samples, precision / shift,
