@@ -204,6 +204,11 @@ struct FbKfSub {
     uint32_t start_bit, res_bit, code_bit;
 };
 
+struct FbKfVHead { // what the frame-level decisions need of a variant's record (the full record is in global memory)
+    unsigned long long bits;
+    int32_t type, order, bps, precision, shift, part_order, rice2, pad;
+};
+
 struct FbKfFrame {
     FbKfSub sub[FB200_MAX_CHANNELS];
     uint8_t header[16];
@@ -212,6 +217,7 @@ struct FbKfFrame {
     uint32_t frame_fail;
     int32_t  cand[FB200_MAX_CHANNELS]; // per variant: result set of the chosen coding (0 fixed, 1 lpc)
     uint32_t crc_acc, crc_last;
+    FbKfVHead vh[FB200_MAX_CHANNELS]; // plan kernel only
 };
 
 FB_HD uint32_t fb_align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -872,6 +878,9 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             out->rice2 = 0;
             out->reserved = n;
             out->bits = verbatim_bits;
+            FbKfVHead &H = S->vh[v];
+            H.bits = verbatim_bits; H.type = FB200_SF_VERBATIM; H.order = 0; H.bps = bps_v; H.precision = 0; H.shift = 0;
+            H.part_order = 0; H.rice2 = 0; H.pad = 0;
             S->cand[v] = 0;
         }
         out->qlp[lane] = 0;
@@ -879,7 +888,10 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
 
     if (J.cfg.use_constant && A.is_constant) {
         FB_WPHASE(lane)
-            if (lane == 0) { out->type = FB200_SF_CONSTANT; out->bits = 8ull + (unsigned long long)bps_v; }
+            if (lane == 0) {
+                out->type = FB200_SF_CONSTANT; out->bits = 8ull + (unsigned long long)bps_v;
+                S->vh[v].type = FB200_SF_CONSTANT; S->vh[v].bits = 8ull + (unsigned long long)bps_v;
+            }
         FB_WPHASE_END
         return;
     }
@@ -936,6 +948,10 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             out->partition_order = R->part_order;
             out->rice2 = R->rice2;
             out->bits = pick == 1 ? lpc_bits : fixed_bits;
+            FbKfVHead &H = S->vh[v];
+            H.type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED; H.order = pick == 1 ? A.qlp_order : kf; H.precision = pick == 1 ? J.cfg.quant_precision : 0;
+            H.shift = pick == 1 ? A.qlp_shift : 0; H.part_order = R->part_order; H.rice2 = R->rice2;
+            H.bits = pick == 1 ? lpc_bits : fixed_bits;
             S->cand[v] = pick;
         }
         if (pick == 1) out->qlp[lane] = A.qlp[lane];
@@ -1119,7 +1135,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             for (int c = 0; c < J.channels; c++) sel[c] = c;
             if (J.channels == 2) {
                 // try_stereo_coding (src/coding.rs:469-527): strict <, order I, L/S, R/S, M/S
-                const unsigned long long bl = choice[0].bits, br = choice[1].bits, bm = choice[2].bits, bs = choice[3].bits;
+                const unsigned long long bl = S->vh[0].bits, br = S->vh[1].bits, bm = S->vh[2].bits, bs = S->vh[3].bits;
                 unsigned long long min_bits = bl + br;
                 if (J.cfg.use_leftside && bl + bs < min_bits) { min_bits = bl + bs; ch_tag = 8; }
                 if (J.cfg.use_rightside && br + bs < min_bits) { min_bits = br + bs; ch_tag = 9; }
@@ -1133,17 +1149,17 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                                             ktab + FB_KTAB_C8);
             uint32_t bit = (uint32_t)S->header_len * 8u;
             for (int c = 0; c < J.channels; c++) {
-                const fb200_subframe_info &V = choice[sel[c]];
+                const FbKfVHead &V = S->vh[sel[c]];
                 FbKfSub &D = S->sub[c];
                 D.variant = sel[c];
                 D.cand = S->cand[sel[c]];
-                D.type = V.type; D.order = V.order; D.bps = V.bits_per_sample;
-                D.precision = V.precision; D.shift = V.shift; D.part_order = V.partition_order; D.rice2 = V.rice2;
+                D.type = V.type; D.order = V.order; D.bps = V.bps;
+                D.precision = V.precision; D.shift = V.shift; D.part_order = V.part_order; D.rice2 = V.rice2;
                 D.start_bit = bit;
                 uint32_t hb = 8;
-                if (V.type == FB200_SF_FIXED) hb += (uint32_t)(V.order * V.bits_per_sample);
+                if (V.type == FB200_SF_FIXED) hb += (uint32_t)(V.order * V.bps);
                 if (V.type == FB200_SF_LPC)
-                    hb += (uint32_t)(V.order * V.bits_per_sample) + 4u + 5u + (uint32_t)(V.precision * V.order);
+                    hb += (uint32_t)(V.order * V.bps) + 4u + 5u + (uint32_t)(V.precision * V.order);
                 D.res_bit = bit + hb;
                 D.code_bit = D.res_bit + 6u;
                 bit += (uint32_t)V.bits;
