@@ -175,6 +175,7 @@ struct FbKfLayout {
     uint32_t k_unit_bits, k_res, res_stride;
     uint32_t off_choice; // pack kernel: channels x fb200_subframe_info
     uint32_t off_frame;  // FbKfFrame
+    uint32_t off_ana;    // plan kernel: the frame's FbAnalysis records (K1's results)
     uint32_t off_scratch; // per warp scratch, aliased by the frame words during packing
     uint32_t scratch_bytes;
     uint32_t s_words, s_tbl_a, s_tbl_b, s_best_val, s_best_p, s_lvl_bits, s_misc;
@@ -206,7 +207,7 @@ struct FbKfSub {
 
 struct FbKfVHead { // what the frame-level decisions need of a variant's record (the full record is in global memory)
     unsigned long long bits;
-    int32_t type, order, bps, precision, shift, part_order, rice2, pad;
+    int16_t type, order, bps, precision, shift, part_order, rice2, pad;
 };
 
 struct FbKfFrame {
@@ -246,6 +247,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.off_keep = o;     o += (uint32_t)nvar * k;
     L.off_choice = 0;   // (the plan kernel keeps the variants' records in global memory)
     L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
+    L.off_ana = o;      o += fb_align16((uint32_t)nvar * (uint32_t)sizeof(FbAnalysis));
     // scratch per warp
     uint32_t s = 0;
     L.s_words = s;      s += fb_align16(FB_KF_NWORDS * U * 4u);
@@ -879,7 +881,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             out->reserved = n;
             out->bits = verbatim_bits;
             FbKfVHead &H = S->vh[v];
-            H.bits = verbatim_bits; H.type = FB200_SF_VERBATIM; H.order = 0; H.bps = bps_v; H.precision = 0; H.shift = 0;
+            H.bits = verbatim_bits; H.type = FB200_SF_VERBATIM; H.order = 0; H.bps = (int16_t)bps_v; H.precision = 0; H.shift = 0;
             H.part_order = 0; H.rice2 = 0; H.pad = 0;
             S->cand[v] = 0;
         }
@@ -949,8 +951,9 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             out->rice2 = R->rice2;
             out->bits = pick == 1 ? lpc_bits : fixed_bits;
             FbKfVHead &H = S->vh[v];
-            H.type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED; H.order = pick == 1 ? A.qlp_order : kf; H.precision = pick == 1 ? J.cfg.quant_precision : 0;
-            H.shift = pick == 1 ? A.qlp_shift : 0; H.part_order = R->part_order; H.rice2 = R->rice2;
+            H.type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED; H.order = (int16_t)(pick == 1 ? A.qlp_order : kf);
+            H.precision = (int16_t)(pick == 1 ? J.cfg.quant_precision : 0);
+            H.shift = (int16_t)(pick == 1 ? A.qlp_shift : 0); H.part_order = (int16_t)R->part_order; H.rice2 = (int16_t)R->rice2;
             H.bits = pick == 1 ? lpc_bits : fixed_bits;
             S->cand[v] = pick;
         }
@@ -1105,17 +1108,24 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     // ---- stage the independent channels from the row-interleaved store xt (16-byte asynchronous copies)
     FB_PHASE(tid, T)
         fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, J.channels);
+        {
+            // K1's results for the frame's variants: read often and early, so they come along into shared memory
+            static_assert(sizeof(FbAnalysis) % 8 == 0, "async copy granularity");
+            const uint64_t *src = (const uint64_t *)(ana + (size_t)f * (size_t)J.nvar);
+            uint64_t *dst = (uint64_t *)(smem + L.off_ana);
+            for (int i = tid; i < J.nvar * (int)(sizeof(FbAnalysis) / 8); i += T) fb_copy8_async(dst + i, src + i);
+        }
         if (tid == 0) S->frame_fail = 0;
         fb_copy_async_wait();
     FB_PHASE_END
 
     // ---- analysis: one warp per variant
     FB_WARPS_BEGIN(w, NW)
-        fb_kf_variant<G, ODD>(J, g, xs, ana[(size_t)f * (size_t)J.nvar + (size_t)w], w, smem, L, &choice[w]);
+        fb_kf_variant<G, ODD>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w]);
         const FbKfMisc *M = (const FbKfMisc *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_misc);
         FB_WPHASE(lane)
             if (lane == 0 && M->fail) S->frame_fail = 1; // benign race between warps
-            if (lane == 0) choice[w].reserved = (int32_t)ana[(size_t)f * (size_t)J.nvar + (size_t)w].max_abs;
+            if (lane == 0) choice[w].reserved = (int32_t)((const FbAnalysis *)(smem + L.off_ana))[w].max_abs;
         FB_WPHASE_END
     FB_WARPS_END
 
