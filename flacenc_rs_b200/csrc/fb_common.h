@@ -269,13 +269,16 @@ FB_HD int fb_sample_rate_tag(uint32_t f, int *extra_bits, uint32_t *extra) {
     return 0;
 }
 
-// CRC-8/SMBUS: poly 0x07, init 0 (src/component/bitrepr.rs:39,356-357)
+// CRC-8/SMBUS: poly 0x07, init 0 (src/component/bitrepr.rs:39,356-357).  One byte step v -> v * x^8 mod P in closed
+// form: the low six bits multiply by x^2 + x + 1 without overflowing, bits 6 and 7 contribute 0xC7 and 0x89
+// (tests/test_kernel_logic_emu.py checks it against the bit-serial definition).
+FB_HD uint32_t fb_crc8_step(uint32_t v) {
+    const uint32_t l = v & 63u;
+    return ((l ^ (l << 1) ^ (l << 2)) ^ ((v & 64u) ? 0xC7u : 0u) ^ ((v & 128u) ? 0x89u : 0u)) & 0xFFu;
+}
 FB_HD uint8_t fb_crc8(const uint8_t *d, int len) {
     uint32_t crc = 0;
-    for (int i = 0; i < len; i++) {
-        crc ^= d[i];
-        for (int b = 0; b < 8; b++) crc = (crc & 0x80) ? (((crc << 1) ^ 0x07) & 0xFF) : ((crc << 1) & 0xFF);
-    }
+    for (int i = 0; i < len; i++) crc = fb_crc8_step(crc ^ d[i]);
     return (uint8_t)crc;
 }
 

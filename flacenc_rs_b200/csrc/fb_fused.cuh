@@ -1155,8 +1155,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
                 else if (ch_tag == 10) { sel[0] = 2; sel[1] = 3; }
             }
             S->ch_tag = ch_tag;
-            S->header_len = fb_frame_header(n, ch_tag, J.bps, J.sample_rate, J.first_frame_number + f, S->header,
-                                            ktab + FB_KTAB_C8);
+            S->header_len = fb_frame_header(n, ch_tag, J.bps, J.sample_rate, J.first_frame_number + f, S->header);
             uint32_t bit = (uint32_t)S->header_len * 8u;
             for (int c = 0; c < J.channels; c++) {
                 const FbKfVHead &V = S->vh[sel[c]];

@@ -49,6 +49,8 @@ int fbemu_launch_geometry(int channels, int bps, int rate, int block_size, uint6
     return (int)J.n_frames;
 }
 
+int fbemu_crc8(const uint8_t *d, int len) { return fb_crc8(d, len); }
+
 int fbemu_frame_header(int n, int ch_tag, int bps, int rate, uint32_t number, uint8_t *out) {
     return fb_frame_header(n, ch_tag, bps, rate, number, out);
 }

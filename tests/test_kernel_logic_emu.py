@@ -208,6 +208,31 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     assert E.fused_counts() == [0, 0]
 
 
+def test_crc8_closed_form_matches_bit_serial_definition():
+    """CRC-8/SMBUS (poly 0x07, init 0): the kernels' closed-form byte step against the bit-serial definition, for every
+    byte value and for random strings"""
+    import ctypes as C
+
+    def ref(data):
+        c = 0
+        for b in data:
+            c ^= b
+            for _ in range(8):
+                c = ((c << 1) ^ 0x07) & 0xFF if c & 0x80 else (c << 1) & 0xFF
+        return c
+    L = E.lib()
+    L.fbemu_crc8.argtypes = [C.c_char_p, C.c_int]
+    L.fbemu_crc8.restype = C.c_int
+    for v in range(256):
+        assert L.fbemu_crc8(bytes([v]), 1) == ref([v])
+    rng = np.random.default_rng(5)
+    for n in (2, 5, 8, 16):
+        for _ in range(50):
+            d = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+            assert L.fbemu_crc8(d, n) == ref(d)
+    assert L.fbemu_crc8(bytes([0xFF, 0xF9, 0x10, 0x10, 0x00]), 5) == 0b01101001  # src/component/bitrepr.rs:645-666
+
+
 def test_launch_geometry_helpers():
     """host/device shared launch geometry: a shorter last frame starts a warp of its own in the analysis launch, the
     fused kernels' ODD instances are chosen from the frame geometry, the staged rows cover what a warp can span"""
