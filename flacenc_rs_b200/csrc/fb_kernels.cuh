@@ -221,18 +221,6 @@ FB_HD int32_t fb_mix(int32_t a, int32_t b, int32_t m, int32_t sh) {
     return (int32_t)((uint32_t)a + (uint32_t)m * (uint32_t)b) >> sh;
 }
 
-// software prefetch of the quad at t into L1 (kept for experiments; the analysis kernel stages its rows in shared
-// memory instead)
-FB_DEV void fb_rows_prefetch4(const FbVarRows &r, int t) {
-#if FB_GPU
-    const size_t o = fb_xt_quad(t);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(r.pa + o));
-    if (r.pb != r.pa) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.pb + o));
-#else
-    (void)r; (void)t;
-#endif
-}
-
 // four samples t..t+3 of a variant (t a multiple of 4)
 FB_DEV void fb_rows_load4(const FbVarRows &r, int t, int32_t *dst) {
     const size_t o = fb_xt_quad(t);
