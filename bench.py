@@ -38,7 +38,7 @@ WORKLOAD = "C2: 1 h 44.1 kHz 16-bit stereo, default config::Encoder, block 4096 
 
 
 def make_pcm(rank: int, n: int) -> np.ndarray:
-    """Synthetic noisy sine; generated in chunks of 10 s and tiled with per-minute seeds to keep start-up short."""
+    """Synthetic noisy sine, a different seed per rank; the whole signal is generated, nothing is tiled."""
     from flacenc_rs_b200 import sigen
     return sigen.noisy_sine_pcm(n, CHANNELS, BPS, RATE, config_id=2 + 16 * rank)
 
@@ -194,18 +194,40 @@ def cpu_port_throughput(pcm: np.ndarray, threads: int, target_seconds: float):
     as many whole passes over `pcm` as fit in about `target_seconds` (at least one)."""
     from oracle import oracle as O
     cfg = O.default_config()
-    frames = len(pcm) // BLOCK
-    sample = pcm[: frames * BLOCK]
+    frames = (len(pcm) + BLOCK - 1) // BLOCK  # incl. a shorter last frame
+    sample = pcm
     probe = sample[: max(threads * 8, 64) * BLOCK]
     O.encode_frames(cfg, probe, CHANNELS, BPS, RATE, BLOCK, nthreads=threads)  # warm the thread pool / page in
-    passes, total_s, nbytes = 0, 0.0, 0
+    passes, total_s = 0, 0.0
+    data, sizes = b"", []
     while passes == 0 or (total_s < target_seconds and passes < 64):
         t0 = time.perf_counter()
         data, sizes = O.encode_frames(cfg, sample, CHANNELS, BPS, RATE, BLOCK, nthreads=threads)
         total_s += time.perf_counter() - t0
         passes += 1
-        nbytes = len(data)
-    return passes * len(sample) / total_s, frames, total_s, nbytes, passes
+    return passes * len(sample) / total_s, frames, total_s, (data, sizes), passes
+
+
+def compare_with_oracle(gpu_bytes: np.ndarray, gpu_sizes: np.ndarray, ref_bytes: bytes, ref_sizes: np.ndarray) -> dict:
+    """Byte-compares the frames the timed GPU step produced with the oracle's frames of the same input (the second
+    half of BASELINE.json's metric: stream size ratio GPU / reference, 1.0 when every decision matches)."""
+    ref = np.frombuffer(ref_bytes, np.uint8)
+    nf = min(len(gpu_sizes), len(ref_sizes))
+    differing = abs(len(gpu_sizes) - len(ref_sizes))
+    if len(gpu_bytes) == len(ref) and np.array_equal(gpu_sizes[:nf], ref_sizes[:nf]):
+        if not np.array_equal(gpu_bytes, ref):
+            neq = (gpu_bytes != ref).astype(np.uint8)
+            starts = np.concatenate([[0], np.cumsum(ref_sizes[:nf], dtype=np.int64)[:-1]])
+            differing += int(np.count_nonzero(np.add.reduceat(neq, starts)))
+    else:
+        go = np.concatenate([[0], np.cumsum(gpu_sizes, dtype=np.int64)])
+        ro = np.concatenate([[0], np.cumsum(ref_sizes, dtype=np.int64)])
+        for i in range(nf):
+            if gpu_sizes[i] != ref_sizes[i] or not np.array_equal(gpu_bytes[go[i]:go[i + 1]], ref[ro[i]:ro[i + 1]]):
+                differing += 1
+    return {"frames_compared": int(max(len(gpu_sizes), len(ref_sizes))), "frames_differing": int(differing),
+            "gpu_bytes": int(len(gpu_bytes)), "oracle_bytes": int(len(ref)),
+            "stream_size_ratio_vs_oracle": len(gpu_bytes) / max(len(ref), 1)}
 
 
 MODEL_OPS_PER_SAMPLE = 250.0  # SURVEY.md 8(d): minimal integer/FP lane-ops per inter-channel sample (stereo, default config)
@@ -234,8 +256,9 @@ def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # bounded sample: the first 20 minutes of the workload per step (about 0.5-1 s of CPU wall on a 16-core host)
-    n = min(args.seconds * RATE, 1200 * RATE)
+    # every step is one pass over the whole workload of the GPU arm (the full hour: 2-3 s of CPU wall on a 16-core
+    # host), minus the short tail frame the frame-worker pool of the oracle binding does not take
+    n = args.seconds * RATE
     pcm = make_pcm(0, n)
     vals = []
     frames = secs = 0
@@ -244,13 +267,14 @@ def run_reference(args, rank: int, world: int) -> None:
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
-    sample = f"{frames} frames ({frames * BLOCK / RATE:.1f} s of audio) of the C2 signal per step, {secs:.2f} s CPU wall"
+    sample = f"all {frames} frames ({n / RATE:.1f} s of audio) of the workload per step, {secs:.2f} s CPU wall per pass"
     line = {
         "impl": "reference", "metric": "PCM inter-channel samples/sec encoded", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * frames * BLOCK / value, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1000.0 * n / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample,
+        "config": {"workload": WORKLOAD if args.seconds == SECONDS else f"{args.seconds} s slice of " + WORKLOAD,
+                   "frames_per_step": frames, "sample": sample,
                    "note": "CPU port (C oracle) of the reference's scalar path with par.rs-style frame workers; "
                            "the Rust reference cannot be built in this image"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
@@ -322,8 +346,11 @@ def main() -> None:
         olen, _ = ctx.encode_device(d_in.data_ptr(), 2, n, d_out.data_ptr(), cap, 0, sizes)
         return olen, ctx.timing()
 
+    host_sizes = [None]
+
     def step_host():
-        got, _, _ = ctx.encode_interleaved(h_in, 2, n, 0, out=h_out)
+        got, hs, _ = ctx.encode_interleaved(h_in, 2, n, 0, out=h_out)
+        host_sizes[0] = hs
         return len(got), ctx.timing()
 
     # ---- warm-up of the device-resident path (the host path is warmed right before its own timed region)
@@ -412,7 +439,8 @@ def main() -> None:
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.seconds == SECONDS else f"{args.seconds} s slice of " + WORKLOAD,
                        "pcm_samples_per_s": value * CHANNELS, "frames_per_step": n_frames,
-                       "stream_size_ratio": out_len / in_bytes,
+                       "compression_ratio": out_len / in_bytes,
+                       "stream_size_ratio_vs_oracle": None, "frames_differing": None, "frames_compared": 0,
                        "fused_frames": int(fused_frames), "fallback_frames": int(fallback_frames),
                        "l2": "inputs (635 MB/step) and working set exceed the 126 MB L2; no flush needed",
                        "cpu_affinity": affinity_note,
@@ -457,10 +485,19 @@ def main() -> None:
                                           "Python, MD5 and STREAMINFO; MD5-bound (one host core)"}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, frames, secs, _, passes = cpu_port_throughput(pcm_i32[: min(n, 1200 * RATE)], threads, target_seconds=12.0)
+            v, frames, secs, (ref_bytes, ref_sizes), passes = cpu_port_throughput(pcm_i32, threads, target_seconds=12.0)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                                    "sample": f"{passes} passes over {frames} frames ({frames * BLOCK / RATE:.1f} s of audio) "
-                                              f"of the same signal, {secs:.2f} s wall, C oracle with {threads} frame workers"}
+                                    "sample": f"{passes} passes over the same {frames} frames ({n / RATE:.1f} s of audio) "
+                                              f"the GPU step encodes, {secs:.2f} s wall, C oracle with {threads} frame workers"}
+            # parity on the measured workload: the bytes the last timed e2e step left in the pinned host buffer (and
+            # the device-resident step's bytes) against the oracle's frames of the same PCM
+            cmp_host = compare_with_oracle(h_out[:out_len_h], host_sizes[0], ref_bytes, ref_sizes)
+            cmp_dev = compare_with_oracle(d_out[:out_len].cpu().numpy(), sizes, ref_bytes, ref_sizes)
+            line["config"].update({"stream_size_ratio_vs_oracle": cmp_host["stream_size_ratio_vs_oracle"],
+                                   "frames_differing": cmp_host["frames_differing"] + cmp_dev["frames_differing"],
+                                   "frames_compared": cmp_host["frames_compared"],
+                                   "parity": {"e2e_step": cmp_host, "device_step": cmp_dev,
+                                              "note": "every frame of the timed workload byte-compared with the C oracle"}})
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

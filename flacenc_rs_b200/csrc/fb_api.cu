@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <array>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -73,6 +74,16 @@ __global__ void __launch_bounds__(256) fb_k4_gather(const uint8_t *slots, uint32
                                                     const unsigned long long *offsets, uint8_t *out,
                                                     unsigned long long out_cap) {
     fb_k4_gather_thread(slots, slot_bytes, frame_bytes, offsets, out, out_cap, blockIdx.x, (int)threadIdx.x, 256);
+}
+
+// parity pins: device builds of fb_log2f / fb_find_shift on caller-provided inputs (fb200_debug_*)
+__global__ void __launch_bounds__(256) fb_dbg_log2f(uint32_t first_bits, uint64_t count, uint32_t *out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x; i < count; i += (uint64_t)gridDim.x * 256u)
+        out[i] = fb_f2u(fb_log2f(fb_u2f(first_bits + (uint32_t)i)));
+}
+__global__ void __launch_bounds__(256) fb_dbg_find_shift(const double *values, uint64_t count, int precision, int32_t *out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x; i < count; i += (uint64_t)gridDim.x * 256u)
+        out[i] = fb_find_shift(values + i, 1, precision);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,6 +186,38 @@ const char *fb200_strerror(int code) {
     case FB200_ERR_CAPACITY: return "output buffer too small";
     default: return "unknown";
     }
+}
+
+static int fb_dbg_run(int device, const void *in, size_t in_bytes, void *out, size_t out_bytes,
+                      const std::function<void(const void *, void *)> &launch) {
+    if (device < 0 || device >= fb200_device_count()) return FB200_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FB200_ERR_CUDA;
+    void *d_in = nullptr, *d_out = nullptr;
+    int rc = FB200_OK;
+    if ((in_bytes && cudaMalloc(&d_in, in_bytes) != cudaSuccess) || cudaMalloc(&d_out, out_bytes) != cudaSuccess) rc = FB200_ERR_CUDA;
+    if (!rc && in_bytes && cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = FB200_ERR_CUDA;
+    if (!rc) {
+        launch(d_in, d_out);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = FB200_ERR_CUDA;
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int fb200_debug_log2f(int device, uint32_t first_bits, uint64_t count, uint32_t *out_bits) {
+    if (!out_bits || count == 0 || count > (1ull << 28)) return FB200_ERR_SOURCE;
+    return fb_dbg_run(device, nullptr, 0, out_bits, (size_t)count * 4u, [&](const void *, void *d_out) {
+        fb_dbg_log2f<<<1184, 256>>>(first_bits, count, (uint32_t *)d_out);
+    });
+}
+
+int fb200_debug_find_shift(int device, const double *values, uint64_t count, int precision, int32_t *out_shift) {
+    if (!values || !out_shift || count == 0 || count > (1ull << 26) || precision < 1 || precision > 15) return FB200_ERR_SOURCE;
+    return fb_dbg_run(device, values, (size_t)count * 8u, out_shift, (size_t)count * 4u, [&](const void *d_in, void *d_out) {
+        fb_dbg_find_shift<<<296, 256>>>((const double *)d_in, count, precision, (int32_t *)d_out);
+    });
 }
 
 const char *fb200_version(void) { return "flacenc_b200 0.2.0 (sm_100a)"; }
@@ -464,7 +507,8 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
                      d_fb, d_infos, (const uint32_t *)S.fb_list.p, d_fb_count, 148, P.k3_smem, st);
         fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
-        const bool pairs = P.kp_pairs && d_pcm && ((uintptr_t)d_pcm & 15u) == 0;
+        // (16-byte copies: frame f starts at f * block_size * 4 bytes, so the block size must be a multiple of 4 too)
+        const bool pairs = P.kp_pairs && d_pcm && ((uintptr_t)d_pcm & 15u) == 0 && (ctx->block_size & 3) == 0;
         fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, pairs ? d_pcm : nullptr, S.plan.p,
                      (const fb200_subframe_info *)S.psubs.p, (const uint32_t *)S.poffs.p,
                      (const unsigned long long *)S.offsets.p, d_out, out_cap, (const uint32_t *)ctx->ktab.p,
@@ -640,7 +684,8 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
     const uint64_t nchunks = chunks.size();
     const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
     const uint64_t in_chunk = std::min(chunk_frames * P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb, in_bytes_total);
-    for (ChunkSet &S : ctx->sets) {
+    for (uint64_t k = 0; k < FB_NSETS; k++) { // only the sets that rotate
+        ChunkSet &S = ctx->sets[k];
         if ((rc = fb_reserve_set(ctx, P, A, S, chunk_frames, in_chunk, chunk_frames, chunk_frames * (uint64_t)P.mb + 16)))
             return rc;
         if ((rc = fb_reserve_pinned(ctx, S, 64 + chunk_frames * 4u))) return rc;

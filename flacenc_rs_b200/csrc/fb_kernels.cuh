@@ -109,8 +109,8 @@ FB_DEV void fb_k0_quad(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t
 }
 
 // K0 fast path for packed 24-bit samples (container 3): the 12 * CH bytes of a quad are read as 3 * CH aligned words
-// and the samples cut out with compile-time shifts.  Requires a 4-byte aligned PCM base and a whole quad inside the
-// frame; everything else takes fb_k0_quad.
+// and the samples cut out with compile-time shifts.  Requires the quad's first byte 4-byte aligned and a whole quad
+// inside the frame (fb_k0_p24_ok); everything else takes fb_k0_quad.
 template <int CH>
 FB_DEV void fb_k0_quad_p24(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t *err_flag, uint32_t f, int t4) {
     const int t = 4 * t4;
@@ -141,7 +141,11 @@ FB_DEV void fb_k0_quad_p24(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint
 }
 
 FB_DEV bool fb_k0_p24_ok(const FbJob &J, const uint8_t *pcm, uint32_t f, int t4) {
-    return J.container_bytes == 3 && 4 * t4 + 4 <= fb_frame_len(J, f) && (((uintptr_t)pcm) & 3u) == 0;
+    if (J.container_bytes != 3 || 4 * t4 + 4 > fb_frame_len(J, f)) return false;
+    // the quad's first byte must be 4-byte aligned: a frame starts at f * block_size * 3 * channels bytes, which is
+    // not a multiple of 4 for odd frames of e.g. mono block 1001 (a quad itself is 12 * channels bytes long)
+    const uint64_t s = (uint64_t)f * (uint64_t)J.block_size + (uint64_t)(4 * t4);
+    return (((uintptr_t)pcm + s * (uint64_t)(3 * J.channels)) & 3u) == 0;
 }
 
 FB_DEV void fb_k0_quad_any(const FbJob &J, const uint8_t *pcm, int32_t *xt, uint32_t *err_flag, uint32_t f, int t4) {
@@ -287,21 +291,36 @@ FB_DEV void fb_levinson(const double *coefs, const double *ys, int order, double
     }
 }
 
-// src/lpc.rs:234-255 find_shift.  ceil(log2(max|a|)) is taken from the binary exponent (exact);
-// libm's log2 agrees except when max|a| >= 16 sits one ulp above a power of two.
+// src/lpc.rs:234-255 find_shift: shift = clamp((precision - 1) - ceil(log2(max|a|)), 0, 15).
+// ceil(log2(x)) is read off the binary representation x = 2^k * (1 + m * 2^-52) and reproduces what the reference's
+// libm call returns, including its one inexact case: log2 is a rounded double, so for m != 0 the true value
+// k + log2(1 + m * 2^-52) can round back to k itself when |k| >= 4 and m is tiny (log2(16 * (1 + 2^-52)) == 4.0 in
+// double arithmetic), and the ceiling is then k, not k + 1.  glibc evaluates k + m * 2^-52 / ln 2 to far more than
+// double precision before its final rounding, so "does k + t round to k" decides it (t never comes near a rounding
+// boundary: the nearest case is 0.25 % of half an ulp away).  tests/test_kernel_logic_emu.py and the GPU test
+// sweep k and m around every power of two against the host libm.
+FB_DEV int fb_ceil_log2(double x) { // x >= 0, not NaN
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    const int e = (int)((bits >> 52) & 0x7FF);
+    const uint64_t mant = bits & 0xFFFFFFFFFFFFFull;
+    if (e == 0x7FF) return 32767;      // +inf: the `as i16` cast saturates
+    if (e == 0) return -32752;         // zero (log2 = -inf -> i16::MIN + 16) or subnormal (<= -1022): shift saturates at 15
+    const int k = e - 1023;
+    if (mant == 0) return k;           // an exact power of two
+    const double t = FB_DMUL((double)(int64_t)mant, 0x1.71547652b82fep-52); // m * 2^-52 / ln 2
+    const double kd = (double)k;
+    return FB_DADD(kd, t) == kd ? k : k + 1;
+}
+
 FB_DEV int fb_find_shift(const double *coefs, int n, int precision) {
     double max_abs = 0.0;
-    for (int i = 0; i < n; i++) {
+    bool any = false;
+    for (int i = 0; i < n; i++) { // f64::max ignores NaN operands (reduce(T::max))
         double a = coefs[i] < 0 ? -coefs[i] : coefs[i];
-        if (a > max_abs) max_abs = a;
+        if (a == a && (!any || a > max_abs)) { max_abs = a; any = true; }
     }
-    uint64_t bits;
-    memcpy(&bits, &max_abs, 8);
-    int e = (int)((bits >> 52) & 0x7FF);
-    uint64_t mant = bits & 0xFFFFFFFFFFFFFull;
-    int abs_log2;
-    if (e == 0) abs_log2 = -32752;                 // zero / subnormal: shift saturates at 15
-    else abs_log2 = (e - 1023) + (mant != 0 ? 1 : 0); // 2^k exactly -> k, otherwise k+1
+    const int abs_log2 = any ? fb_ceil_log2(max_abs) : -32752; // all NaN: Float::max(NaN, lo) = lo
     int shift = (precision - 1) - abs_log2;
     if (shift < 0) shift = 0;
     if (shift > 15) shift = 15;

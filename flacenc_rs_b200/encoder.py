@@ -8,6 +8,8 @@ Every call goes through ``_ffi.lib()`` (ctypes -> extern "C" -> CUDA kernels).  
 from __future__ import annotations
 
 import ctypes as C
+import threading
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -215,7 +217,14 @@ def encode_with_fixed_block_size(config: Verified, src: MemSource, block_size: i
     ch, bps, rate = src.channels(), src.bits_per_sample(), src.sample_rate()
     n = len(src)
     cb = (bps + 7) // 8
-    pcm = pack_samples(src.as_interleaved(), cb)
+    samples = np.ascontiguousarray(src.as_interleaved(), np.int32)
+    # FrameBuf::verify_samples (src/source.rs:262-275): packing below truncates to the container, so values outside
+    # the range of bits_per_sample must be rejected here -- the device's range check only sees what survives packing
+    if samples.size:
+        lo, hi = -(1 << (bps - 1)), (1 << (bps - 1)) - 1
+        if int(samples.min()) < lo or int(samples.max()) > hi:
+            raise VerifyError("input.framebuf", f"input sample must be in the range of bits={bps}")
+    pcm = pack_samples(samples, cb)
     n_frames = (n + block_size - 1) // block_size
     cap = 64 + n_frames * (32 + ch * ((block_size * (bps + 1) + 7) // 8 + 2))
     out = np.empty(cap, np.uint8)
@@ -229,6 +238,28 @@ def encode_with_fixed_block_size(config: Verified, src: MemSource, block_size: i
     return Stream(out[: olen.value].tobytes())
 
 
+# The reference calls encode_fixed_size_frame in its inner loop (src/par.rs:384-389) and keeps all scratch in
+# thread-local `reusable!` storage (src/lib.rs:92-116).  The mirror keeps one device context per thread and
+# (config, format, block size, device): device buffers, window and CRC tables are built once, not per frame.
+_CTX_CACHE = threading.local()
+_CTX_CACHE_MAX = 8
+
+
+def _cached_context(config: Verified, channels: int, bps: int, rate: int, block_size: int, device: int) -> Context:
+    cache = getattr(_CTX_CACHE, "ctxs", None)
+    if cache is None:
+        cache = _CTX_CACHE.ctxs = OrderedDict()
+    key = (bytes(config.pod), channels, bps, rate, block_size, device)
+    ctx = cache.get(key)
+    if ctx is None:
+        ctx = cache[key] = Context(config, channels, bps, rate, block_size, device)
+        while len(cache) > _CTX_CACHE_MAX:
+            cache.popitem(last=False)[1].close()
+    else:
+        cache.move_to_end(key)
+    return ctx
+
+
 def encode_fixed_size_frame(config: Verified, framebuf: FrameBuf, frame_number: int, stream_info: StreamInfo,
                             device: int = 0) -> Frame:
     """``flacenc::encode_fixed_size_frame`` (src/coding.rs:581-606): FrameBuf -> Frame."""
@@ -236,9 +267,9 @@ def encode_fixed_size_frame(config: Verified, framebuf: FrameBuf, frame_number: 
         raise TypeError("config must be Verified (use Encoder().into_verified())")
     if not 0 <= frame_number < (1 << 31):
         raise VerifyError("encode_fixed_size_frame (frame_number)", "must be < 2^31")
-    with Context(config, stream_info.channels, stream_info.bits_per_sample, stream_info.sample_rate,
-                 framebuf.size(), device) as ctx:
-        planar = framebuf.samples.reshape(framebuf.channels(), framebuf.size())
-        data, info = ctx.encode_planar_frame(planar, framebuf.filled_size(), frame_number)
+    ctx = _cached_context(config, stream_info.channels, stream_info.bits_per_sample, stream_info.sample_rate,
+                          framebuf.size(), device)
+    planar = framebuf.samples.reshape(framebuf.channels(), framebuf.size())
+    data, info = ctx.encode_planar_frame(planar, framebuf.filled_size(), frame_number)
     subs = [SubFrame.from_info(info.sub[c]) for c in range(stream_info.channels)]
     return Frame(info.channel_assignment, info.block_size, info.frame_number, subs, data)

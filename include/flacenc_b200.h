@@ -175,6 +175,14 @@ int fb200_encode_stream(const fb200_config *cfg, const void *pcm, int container_
                         int block_size, const int *devices, int n_devices,
                         uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* ---- parity pins (diagnostics) ----
+ * Device builds of the two scalar float helpers whose last bit decides encoder choices, evaluated on
+ * caller-provided inputs so tests can compare them with the host libm the reference uses:
+ *   log2f of estimate_entropy (src/coding.rs:200-227): out_bits[i] = bits of log2f(float with bits first_bits + i)
+ *   find_shift (src/lpc.rs:234-255) of the one-coefficient set {values[i]}: out_shift[i] */
+int fb200_debug_log2f(int device, uint32_t first_bits, uint64_t count, uint32_t *out_bits);
+int fb200_debug_find_shift(int device, const double *values, uint64_t count, int precision, int32_t *out_shift);
+
 /* ---- diagnostics ---- */
 int  fb200_last_timing(const fb200_ctx *ctx, fb200_timing *t);
 const char *fb200_strerror(int code);

@@ -166,6 +166,37 @@ int fo_find_shift(const double *coefs, int n, int precision) {
     return shift;
 }
 
+void fo_find_shift_each(const double *values, uint64_t count, int precision, int32_t *shifts) {
+    for (uint64_t i = 0; i < count; i++) shifts[i] = fo_find_shift(values + i, 1, precision);
+}
+
+struct fo_log2f_job { uint32_t first; uint64_t a, b; uint32_t *out; };
+static void *fo_log2f_worker(void *arg) {
+    struct fo_log2f_job *j = (struct fo_log2f_job *)arg;
+    for (uint64_t i = j->a; i < j->b; i++) {
+        uint32_t u = j->first + (uint32_t)i;
+        float x, y;
+        memcpy(&x, &u, 4);
+        y = log2f(x); /* the libm call behind Rust's f32::log2 on linux-gnu (src/coding.rs:219-221) */
+        memcpy(&j->out[i], &y, 4);
+    }
+    return NULL;
+}
+void fo_log2f_bits(uint32_t first, uint64_t count, int threads, uint32_t *out) {
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    pthread_t th[64];
+    struct fo_log2f_job jobs[64];
+    for (int w = 0; w < threads; w++) {
+        jobs[w].first = first;
+        jobs[w].a = count * (uint64_t)w / (uint64_t)threads;
+        jobs[w].b = count * (uint64_t)(w + 1) / (uint64_t)threads;
+        jobs[w].out = out;
+        pthread_create(&th[w], NULL, fo_log2f_worker, &jobs[w]);
+    }
+    for (int w = 0; w < threads; w++) pthread_join(th[w], NULL);
+}
+
 /* src/lpc.rs:258-271  quantize_parameter */
 static int16_t fo_quantize_parameter(double p, int shift) {
     double scalefac = ldexp(1.0, shift); /* powi(2, shift) */

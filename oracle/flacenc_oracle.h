@@ -106,6 +106,10 @@ void   fo_auto_correlation_f32(int order, const float *signal, int n, float *des
 void   fo_levinson_f64(const double *coefs, const double *ys, int order, double *dest);
 void   fo_levinson_f32(const float *coefs, const float *ys, int order, float *dest);
 int    fo_find_shift(const double *coefs, int n, int precision);
+/* host libm tables for the parity pins of the device helpers: out[i] = bits of log2f(float with bits first + i)
+ * (the f32::log2 of estimate_entropy), on `threads` host threads; shifts[i] = fo_find_shift of {values[i]} */
+void   fo_log2f_bits(uint32_t first, uint64_t count, int threads, uint32_t *out);
+void   fo_find_shift_each(const double *values, uint64_t count, int precision, int32_t *shifts);
 /* returns the truncated order; q_out has FO_MAX_LPC_ORDER entries */
 int    fo_quantize_parameters(const double *coefs, int n, int precision, int16_t *q_out, int *shift_out);
 void   fo_compute_error(const int16_t *q, int order, int shift, const int32_t *signal, int n, int32_t *errors);

@@ -129,6 +129,8 @@ def lib() -> C.CDLL:
             "fo_levinson_f64": (None, [f64p, f64p, C.c_int, f64p]),
             "fo_levinson_f32": (None, [f32p, f32p, C.c_int, f32p]),
             "fo_find_shift": (C.c_int, [f64p, C.c_int, C.c_int]),
+            "fo_log2f_bits": (None, [C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),
+            "fo_find_shift_each": (None, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
             "fo_quantize_parameters": (C.c_int, [f64p, C.c_int, C.c_int, i16p, C.POINTER(C.c_int)]),
             "fo_compute_error": (None, [i16p, C.c_int, C.c_int, i32p, C.c_int, i32p]),
             "fo_lpc_from_autocorr": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, f64p, f64p]),
@@ -208,6 +210,20 @@ def levinson(coefs, ys, dtype=np.float64) -> np.ndarray:
         lib().fo_levinson_f64(_p(c, C.c_double), _p(y, C.c_double), len(y), _p(out, C.c_double))
     else:
         lib().fo_levinson_f32(_p(c, C.c_float), _p(y, C.c_float), len(y), _p(out, C.c_float))
+    return out
+
+
+def log2f_bits(first: int, count: int, threads: int = 8) -> np.ndarray:
+    """bits of the host libm's log2f over the float bit patterns [first, first + count)"""
+    out = np.empty(count, np.uint32)
+    lib().fo_log2f_bits(first, count, threads, out.ctypes.data)
+    return out
+
+
+def find_shift_each(values, precision: int) -> np.ndarray:
+    v = np.ascontiguousarray(values, np.float64)
+    out = np.empty(len(v), np.int32)
+    lib().fo_find_shift_each(v.ctypes.data, len(v), precision, out.ctypes.data)
     return out
 
 

@@ -56,6 +56,21 @@ def crafted_huge_residual_stereo(order: int = 24) -> np.ndarray:
     return np.stack([s, -s], axis=1)
 
 
+def shift_cases():
+    """max|coef| values around every power of two 2^k: mantissa offsets m = 0..300 ulps above it, the ulps just below
+    the next one, and random mantissas -- where ceil(log2(x)) read off the exponent and libm's rounded log2 can part
+    ways (/root/reference/src/lpc.rs:234-255)."""
+    rng = np.random.default_rng(7)
+    vals = [0.0, 5e-324, 2.2250738585072014e-308, 1e-300, 1e300, float("inf")]
+    for k in list(range(-40, 41)) + [-1000, -500, 500, 1000]:
+        base = np.float64(2.0) ** k
+        b0 = int(np.array([base], np.float64).view(np.uint64)[0])
+        ms = list(range(0, 301)) + [(1 << 52) - d for d in range(1, 40)] + [int(v) for v in rng.integers(1, 1 << 52, 40)]
+        ms += [1 << j for j in range(9, 52)]
+        vals.extend(np.array([b0 + m for m in ms], np.uint64).view(np.float64).tolist())
+    return vals
+
+
 def random_case(rng):
     """One seeded fuzz case: (signal, channels, bps, rate, block size, first frame number, oracle-style config kwargs)."""
     channels = int(rng.choice([1, 2, 2, 2, 3, 4, 6, 8]))

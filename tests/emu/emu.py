@@ -24,6 +24,10 @@ def lib():
         L = C.CDLL(_LIB)
         L.fbemu_log2f.restype = C.c_float
         L.fbemu_log2f.argtypes = [C.c_float]
+        L.fbemu_log2f_sweep.restype = C.c_ulonglong
+        L.fbemu_log2f_sweep.argtypes = [C.c_uint32, C.c_ulonglong, C.c_int, C.POINTER(C.c_uint32)]
+        L.fbemu_find_shift.restype = C.c_int
+        L.fbemu_find_shift.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
         L.fbemu_config_default.argtypes = [C.POINTER(F.Config)]
         L.fbemu_config_verify.argtypes = [C.POINTER(F.Config)]
         L.fbemu_frame_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_uint8)]

@@ -10,9 +10,41 @@
 #include <stdlib.h>
 #include <vector>
 
+#include <thread>
+#include <vector>
+
 extern "C" {
 
 float fbemu_log2f(float x) { return fb_log2f(x); }
+
+// fb_log2f (the device code) against the host libm's log2f for the bit patterns [first, first + count), on
+// `threads` host threads; returns the number of mismatches (NaN == NaN) and the first mismatching pattern
+unsigned long long fbemu_log2f_sweep(uint32_t first, unsigned long long count, int threads, uint32_t *first_bad) {
+    if (threads < 1) threads = 1;
+    std::vector<unsigned long long> bad((size_t)threads, 0);
+    std::vector<uint32_t> fb((size_t)threads, 0xFFFFFFFFu);
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; w++)
+        pool.emplace_back([&, w] {
+            const unsigned long long a = count * (unsigned long long)w / (unsigned long long)threads;
+            const unsigned long long b = count * (unsigned long long)(w + 1) / (unsigned long long)threads;
+            for (unsigned long long i = a; i < b; i++) {
+                const uint32_t u = first + (uint32_t)i;
+                const float x = fb_u2f(u), y = fb_log2f(x), z = log2f(x);
+                if (fb_f2u(y) != fb_f2u(z) && !(y != y && z != z)) {
+                    if (bad[(size_t)w]++ == 0) fb[(size_t)w] = u;
+                }
+            }
+        });
+    for (auto &t : pool) t.join();
+    unsigned long long total = 0;
+    uint32_t f = 0xFFFFFFFFu;
+    for (int w = 0; w < threads; w++) { total += bad[(size_t)w]; if (fb[(size_t)w] < f) f = fb[(size_t)w]; }
+    if (first_bad) *first_bad = f;
+    return total;
+}
+
+int fbemu_find_shift(const double *coefs, int n, int precision) { return fb_find_shift(coefs, n, precision); }
 
 // Rice-search statistics: [0] narrow-window runs, [1] full-range reruns, [2] chunk-exact runs, [3] sum of widths
 void fbemu_mode_counts(unsigned long long *out4, int reset) {

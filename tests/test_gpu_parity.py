@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case
+from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case, shift_cases
 from flacenc_rs_b200 import _ffi, sigen
 from flacenc_rs_b200.config import Encoder, Fixed, OrderSel, Qlpc, StereoCoding, SubFrameCoding, Window, Prc
 from flacenc_rs_b200.encoder import (Context, StreamInfo, encode_fixed_size_frame, encode_with_fixed_block_size)
@@ -51,14 +51,16 @@ def make_config(**kw) -> Encoder:
     return e
 
 
-def _compare(signal, channels, bps, rate, block_size, container=None, first_frame=0, check_infos=False, **cfgkw):
+def _compare(signal, channels, bps, rate, block_size, container=None, first_frame=0, check_infos=False,
+             oracle_threads=1, **cfgkw):
     ocfg = O.default_config(**cfgkw)
     vcfg = make_config(**cfgkw).into_verified()
     assert bytes(vcfg.pod) == bytes(ocfg)  # the POD the C ABI receives equals the oracle's config
     signal = np.ascontiguousarray(signal, np.int32).reshape(-1, channels)
     n = len(signal)
     container = container or (bps + 7) // 8
-    ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame)
+    ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame,
+                                     nthreads=oracle_threads)
     # both device paths: the fused per-frame kernel (default, when the batch is eligible) and the generic kernels
     modes = [("0", "1"), ("1", "1")]
     if channels == 2 and bps == 16 and container == 2:
@@ -112,6 +114,38 @@ def test_96k_24bit_order24_block4608_c3():
 def test_8ch_24bit_c5_slice():
     x = sigen.noisy_sine_pcm(4096 * 6 + 1000, 8, 24, 48000, config_id=5)
     _compare(x, 8, 24, 48000, 4096)
+
+
+def test_c3_1000_frames_byte_exact():
+    """BASELINE config 3 at scale: 1 000 frames + a tail of 96 kHz / 24-bit stereo, block 4608, lpc_order 24 -- every
+    frame byte-compared with the oracle, on all device paths"""
+    x = sigen.noisy_sine_pcm(4608 * 1000 + 1234, 2, 24, 96000, config_id=3)
+    _compare(x, 2, 24, 96000, 4608, oracle_threads=os.cpu_count() or 1, lpc_order=24, quant_precision=15)
+
+
+def test_c5_1000_frames_byte_exact():
+    """BASELINE config 5 at scale: 1 000 frames + a tail of 48 kHz / 24-bit 8-channel audio (8 000 subframes)"""
+    x = sigen.noisy_sine_pcm(4096 * 1000 + 777, 8, 24, 48000, config_id=5)
+    _compare(x, 8, 24, 48000, 4096, oracle_threads=os.cpu_count() or 1)
+
+
+@pytest.mark.parametrize("block_size", [1001, 4097, 4098, 1002])
+def test_stereo_16bit_odd_block_sizes_frame_starts_unaligned(block_size):
+    """16-bit stereo in a 2-byte container with block sizes that are not multiples of 4: every other frame starts at an
+    address that is not 16-byte aligned, so neither the ingest kernel's 16-byte loads nor the pack kernel's staging of
+    the packed PCM pairs may assume alignment (5 frames + tail)"""
+    n = block_size * 5 + 333
+    x = sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=11)
+    _compare(x, 2, 16, 44100, block_size)
+
+
+@pytest.mark.parametrize("channels,block_size", [(1, 1001), (1, 4097), (1, 4098), (3, 4098), (3, 1001), (5, 999), (2, 1001), (7, 4097)])
+def test_packed_24bit_odd_block_sizes_frame_starts_unaligned(channels, block_size):
+    """packed 24-bit samples (3-byte container): frames whose first byte is not 4-byte aligned must not take the
+    ingest kernel's aligned-word fast path"""
+    n = block_size * 4 + 100
+    x = sigen.noisy_sine_pcm(n, channels, 24, 48000, config_id=12)
+    _compare(x, channels, 24, 48000, block_size, container=3)
 
 
 def test_rectangle_window_c4_shape():
@@ -456,3 +490,35 @@ def test_large_batch_properties_c2_slice():
         blk = x[f * 4096:(f + 1) * 4096]
         ref, _ = O.encode_frames(O.default_config(), blk, 2, 16, 44100, 4096, first_frame_number=f)
         assert got[offs[f]:offs[f + 1]].tobytes() == ref, f
+
+
+def test_device_log2f_matches_libm_exhaustive():
+    """The device build of fb_log2f (estimate_entropy's log2, /root/reference/src/coding.rs:200-227) against the host
+    glibc log2f for every non-negative float bit pattern + a slice of the negative ones: bit-equal or both NaN."""
+    lib = _ffi.lib()
+    threads = min(32, os.cpu_count() or 1)
+    step = 1 << 26
+    ranges = [(f, min(step, 0x7F800000 + 4096 - f)) for f in range(0, 0x7F800000 + 4096, step)] + [(0x80000000, 1 << 22)]
+    out = np.empty(step, np.uint32)
+    for first, cnt in ranges:
+        assert lib.fb200_debug_log2f(0, first, cnt, out.ctypes.data) == 0
+        ref = O.log2f_bits(first, cnt, threads)
+        got = out[:cnt]
+        neq = got != ref
+        if neq.any():
+            both_nan = np.isnan(got.view(np.float32)) & np.isnan(ref.view(np.float32))
+            bad = np.flatnonzero(neq & ~both_nan)
+            assert len(bad) == 0, f"{len(bad)} mismatches, first at bits {first + int(bad[0]):#010x}"
+
+
+def test_device_find_shift_matches_libm_around_powers_of_two():
+    """fb_find_shift on the device == ceil(log2()) through the host libm (the oracle), incl. the inexact cases
+    (/root/reference/src/lpc.rs:234-255)"""
+    lib = _ffi.lib()
+    vals = np.array(shift_cases(), np.float64)
+    vals = np.concatenate([vals, -vals])
+    for prec in (1, 4, 8, 15):
+        got = np.empty(len(vals), np.int32)
+        assert lib.fb200_debug_find_shift(0, vals.ctypes.data, len(vals), prec, got.ctypes.data) == 0
+        want = O.find_shift_each(vals, prec)
+        assert np.array_equal(got, want), np.flatnonzero(got != want)[:5]

@@ -1,10 +1,12 @@
 """Checks the CUDA kernel bodies' logic against the oracle on the CPU, by running
 flacenc_rs_b200/csrc/fb_kernels.cuh under the phase-by-phase CTA emulation in tests/emu.
 The same comparisons run against the real kernels in tests/test_gpu_parity.py (-m gpu)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case
+from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case, shift_cases
 from flacenc_rs_b200 import sigen
 from oracle import oracle as O
 from emu import emu as E
@@ -48,20 +50,42 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
     assert np.array_equal(out, signal)
 
 
-def test_log2f_matches_libm_sampled():
-    """fb_log2f (device code) vs glibc log2f; the exhaustive run is tests/test_log2f_compat.py (slow)"""
+def test_log2f_matches_libm_exhaustive():
+    """fb_log2f -- the device code of estimate_entropy's log2 (/root/reference/src/coding.rs:200-227), compiled for
+    the CPU -- against the host glibc log2f for EVERY non-negative float bit pattern (zero, subnormals, normals,
+    +inf, and the first NaNs), plus a slice of the negative ones.  Bit-equal or both NaN.  (The -m gpu suite runs
+    the same sweep on the device build of the function.)"""
     import ctypes as C
-    libm = C.CDLL("libm.so.6")
-    libm.log2f.restype = C.c_float
-    libm.log2f.argtypes = [C.c_float]
-    rng = np.random.default_rng(1)
-    bits = np.concatenate([rng.integers(1, 0x7F800000, 200000, dtype=np.uint32),
-                           np.array([1, 0x00800000, 0x3F800000, 0x3F7FFFFF, 0x3F800001, 0x7F7FFFFF, 0], np.uint32)])
-    xs = bits.view(np.float32)
     L = E.lib()
-    for x in xs[:20000].tolist() + xs[-7:].tolist():
-        a, b = L.fbemu_log2f(x), libm.log2f(x)
-        assert a == b or (a != a and b != b), x
+    first_bad = C.c_uint32(0)
+    threads = min(16, os.cpu_count() or 1)
+    bad = L.fbemu_log2f_sweep(0, 0x7F800000 + 4096, threads, C.byref(first_bad))
+    assert bad == 0, f"{bad} mismatches, first at bits {first_bad.value:#010x}"
+    bad = L.fbemu_log2f_sweep(0x80000000, 1 << 22, threads, C.byref(first_bad))   # -0, negative: NaN / -inf
+    assert bad == 0, f"{bad} mismatches, first at bits {first_bad.value:#010x}"
+
+
+def test_find_shift_matches_libm_around_powers_of_two():
+    """fb_find_shift (device code) == the oracle's ceil(log2()) through the host libm, on crafted coefficients"""
+    import ctypes as C
+    L = E.lib()
+    vals = shift_cases()
+    n_inexact = 0
+    for i, v in enumerate(vals):
+        # every value at the default precision; every 40th also negated and at the other precisions
+        for prec in ((1, 4, 8, 15) if i % 40 == 0 else (15,)):
+            for sign in ((1.0, -1.0) if i % 40 == 0 else (1.0,)):
+                c = (C.c_double * 3)(sign * v, 0.0, v * 0.5)
+                got, want = L.fbemu_find_shift(c, 3, prec), O.find_shift([sign * v, 0.0, v * 0.5], prec)
+                assert got == want, (v.hex() if isinstance(v, float) else v, prec, got, want)
+    # the sweep really contains values whose rounded log2 falls back onto the integer (the inexact case)
+    import math
+    for v in vals:
+        if 0 < v < float("inf"):
+            m, e = math.frexp(v)
+            if m != 0.5 and math.log2(v) == float(e - 1):
+                n_inexact += 1
+    assert n_inexact > 50
 
 
 def test_default_config_matches_oracle():
