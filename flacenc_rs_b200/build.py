@@ -59,6 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(unit):
         src, obj, extra = unit
+        extra = extra + os.environ.get("FB200_NVCC_EXTRA", "").split()  # experiments: e.g. -DFB_KAP_MAXNREG=96
         cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         return subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
 

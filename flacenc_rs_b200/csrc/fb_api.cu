@@ -51,6 +51,25 @@ __global__ void __launch_bounds__(256) fb_k0b_expand(FbJob J, const int32_t *xc,
     }
 }
 
+// the same from packed 16-bit stereo PCM (pairs mode: there is no planar store), for the frames of the fallback list
+__global__ void __launch_bounds__(256) fb_k0b_expand_pairs(FbJob J, const uint8_t *pcm, int32_t *xv4, const uint32_t *list,
+                                                           const uint32_t *count) {
+    const uint32_t total = *count;
+    for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
+        const uint32_t f = list[i];
+        const int n = fb_frame_len(J, f);
+        const int32_t *src = reinterpret_cast<const int32_t *>(pcm) + (size_t)f * (size_t)J.block_size;
+        for (int t = (int)threadIdx.x; t < J.stride; t += 256) {
+            const int32_t w = t < n ? src[t] : 0;
+            for (int v = 0; v < 4; v++) {
+                int32_t mb, sh;
+                fb_pair_mix(v, &mb, &sh);
+                xv4[((size_t)f * 4u + (size_t)v) * (size_t)J.stride + (size_t)t] = fb_dp2a_lo(w, mb, 0) >> sh;
+            }
+        }
+    }
+}
+
 // offsets[i] = *total + exclusive prefix; *total advances by the chunk's bytes (single CTA)
 __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *frame_bytes, unsigned long long *offsets,
                                                            uint32_t n_frames, unsigned long long *total) {
@@ -343,8 +362,9 @@ struct Plan {
     uint32_t mb = 0;
     const float *d_win_tail = nullptr;
     FbK2Layout L;
-    FbKfLayout KL, KPL, KPLp; // shared-memory layouts of the plan kernel and of the pack kernel (planes / PCM pairs)
+    FbKfLayout KL, KLp, KPL, KPLp; // shared-memory layouts of the plan kernel and of the pack kernel (planes / PCM pairs)
     bool kp_pairs = false;    // 16-bit stereo in a 2-byte container: the pack kernel may stage the PCM itself
+    bool pairs = false;       // ... and so may the analysis and plan kernels: no ingest kernel, no planar store
     size_t k2_smem = 0, k3_smem = 0;
     bool fused = false;
 };
@@ -401,6 +421,9 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
     P.KPL = fb_kp_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n);
     P.kp_pairs = !ctx->no_pairs && fb_kp_pairs_format(ctx->channels, ctx->bps, P.cb) && A.planar_host == nullptr;
     P.KPLp = fb_kp_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n, P.kp_pairs);
+    P.pairs = !ctx->no_pairs && fb_pairs_format(ctx->channels, ctx->bps, P.cb, ctx->block_size) && A.planar_host == nullptr &&
+              (P.fused || A.analyze_only);
+    P.KLp = fb_kf_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n, false, P.pairs);
     if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
         std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk));
         fb_kf_build_ktab(P.KL.crc_chunk, kt.data());
@@ -409,7 +432,7 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
         ctx->ktab_chunk = P.KL.crc_chunk;
     }
-    const int kf_smem = (int)std::max(P.KL.total, std::max(P.KPL.total, P.KPLp.total)); // plan kernel and pack kernel
+    const int kf_smem = (int)std::max(std::max(P.KL.total, P.KLp.total), std::max(P.KPL.total, P.KPLp.total)); // plan and pack kernels
     if (P.fused && kf_smem > ctx->kf_smem_set) {
         FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, kf_smem));
         ctx->kf_smem_set = kf_smem;
@@ -467,8 +490,13 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     uint32_t *d_err = (uint32_t *)S.scalars.p;
     unsigned long long *d_total = d_total_shared ? d_total_shared : (unsigned long long *)((uint8_t *)S.scalars.p + 8);
     uint32_t *d_fb_count = (uint32_t *)((uint8_t *)S.scalars.p + 16);
+    // pairs mode: 16-bit stereo PCM (16-byte aligned) is read as (left, right) pairs by every kernel: no ingest, no xt
+    // (a 16-bit sample in a 2-byte container cannot be out of range, so the range check of the ingest kernel is moot)
+    const bool pairs = P.pairs && d_pcm && ((uintptr_t)d_pcm & 15u) == 0;
+    const uint8_t *pcm_pairs = pairs ? d_pcm : nullptr;
     FB_CUDA(ctx, cudaEventRecord(S.ev[1], st));
-    if (A.planar_host) {
+    if (pairs) {
+    } else if (A.planar_host) {
         fb_k0_ingest_planar<<<(unsigned)((J.stride / 4 + 255) / 256), 256, 0, st>>>(J, (const int32_t *)S.pcm.p,
                                                                                    A.planar_stride, (int32_t *)S.xv.p, d_err);
     } else {
@@ -477,10 +505,10 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         fb_k0_ingest<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv.p, d_err, n_items);
     }
     FB_CUDA(ctx, cudaEventRecord(S.ev[2], st));
-    fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
-                 A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
+    fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail,
+                 (FbAnalysis *)S.ana.p, A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
     FB_CUDA(ctx, cudaEventRecord(S.ev[3], st));
-    acc.launches += 2;
+    acc.launches += pairs ? 1 : 2;
     if (A.analyze_only) return FB200_OK;
     if (st_back && st_back != st) {
         FB_CUDA(ctx, cudaStreamWaitEvent(st_back, S.ev[3], 0));
@@ -495,12 +523,15 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         // their slots by the generic kernels.  Then the scan of all frame sizes, KP packs every planned frame
         // straight to its final offset, and the listed frames are gathered from their slots.
         FB_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, 4, st));
-        fb_launch_ka(P.ring, J, (const int32_t *)S.xv.p, (const FbAnalysis *)S.ana.p, S.plan.p,
+        fb_launch_ka(P.ring, J, (const int32_t *)S.xv.p, pcm_pairs, (const FbAnalysis *)S.ana.p, S.plan.p,
                      (fb200_subframe_info *)S.choice.p, (fb200_subframe_info *)S.psubs.p, (uint32_t *)S.poffs.p, d_fb, d_infos, (uint32_t *)S.fb_list.p,
-                     d_fb_count, (const uint32_t *)ctx->ktab.p, P.KL, st);
+                     d_fb_count, (const uint32_t *)ctx->ktab.p, pairs ? P.KLp : P.KL, st);
         FB_CUDA(ctx, cudaEventRecord(S.ev[4], st));
-        fb_k0b_expand<<<148, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, (const uint32_t *)S.fb_list.p,
-                                           d_fb_count);
+        if (pairs)
+            fb_k0b_expand_pairs<<<148, 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv4.p, (const uint32_t *)S.fb_list.p, d_fb_count);
+        else
+            fb_k0b_expand<<<148, 256, 0, st>>>(J, (const int32_t *)S.xv.p, (int32_t *)S.xv4.p, (const uint32_t *)S.fb_list.p,
+                                               d_fb_count);
         fb_launch_k2(P.ring, J, xg, (const FbAnalysis *)S.ana.p, (fb200_subframe_info *)S.choice.p,
                      P.L, (const uint32_t *)S.fb_list.p, d_fb_count, 296, P.k2_smem, st);
         fb_launch_k3(P.ring, J, xg, (const fb200_subframe_info *)S.choice.p, (uint8_t *)S.slots.p,
@@ -508,11 +539,11 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         fb_k4_scan<<<1, FB_K4_THREADS, 0, st>>>(d_fb, (unsigned long long *)S.offsets.p, J.n_frames, d_total);
         FB_CUDA(ctx, cudaEventRecord(S.ev[5], st));
         // (16-byte copies: frame f starts at f * block_size * 4 bytes, so the block size must be a multiple of 4 too)
-        const bool pairs = P.kp_pairs && d_pcm && ((uintptr_t)d_pcm & 15u) == 0 && (ctx->block_size & 3) == 0;
-        fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, pairs ? d_pcm : nullptr, S.plan.p,
+        const bool kp_pairs = pairs || (P.kp_pairs && d_pcm && ((uintptr_t)d_pcm & 15u) == 0 && (ctx->block_size & 3) == 0);
+        fb_launch_kp(P.ring, J, (const int32_t *)S.xv.p, kp_pairs ? d_pcm : nullptr, S.plan.p,
                      (const fb200_subframe_info *)S.psubs.p, (const uint32_t *)S.poffs.p,
                      (const unsigned long long *)S.offsets.p, d_out, out_cap, (const uint32_t *)ctx->ktab.p,
-                     pairs ? P.KPLp : P.KPL, st);
+                     kp_pairs ? P.KPLp : P.KPL, st);
         fb_k4_gather_list<<<148, 256, 0, st>>>((const uint8_t *)S.slots.p, J.slot_bytes, d_fb,
                                                (const unsigned long long *)S.offsets.p, d_out, out_cap,
                                                (const uint32_t *)S.fb_list.p, d_fb_count);

@@ -128,6 +128,26 @@ FB_DEV int64_t fb_mad_wide(int32_t a, int32_t b, int64_t c) {
 #endif
 }
 
+// c + lo16(a) * byte0(b) + hi16(a) * byte1(b), all signed: one IDP.2A on the GPU.  With a = a packed 16-bit stereo
+// sample pair (left in the low half) and b = FB_PAIR_L / _R / _M / _S it yields L, R, L + R or L - R.
+#define FB_PAIR_L 0x0001
+#define FB_PAIR_R 0x0100
+#define FB_PAIR_M 0x0101
+#define FB_PAIR_S 0xFF01
+FB_DEV int32_t fb_dp2a_lo(int32_t a, int32_t b, int32_t c) {
+#if FB_GPU
+    return __dp2a_lo(a, b, c);
+#else
+    return c + (int32_t)(int16_t)((uint32_t)a & 0xFFFFu) * (int32_t)(int8_t)((uint32_t)b & 0xFFu) +
+           (int32_t)(int16_t)((uint32_t)a >> 16) * (int32_t)(int8_t)(((uint32_t)b >> 8) & 0xFFu);
+#endif
+}
+// multiplier bytes and shift of a stereo variant (0 L, 1 R, 2 M, 3 S) formed from a packed pair
+FB_HD void fb_pair_mix(int v, int32_t *mb, int32_t *sh) {
+    *mb = v == 0 ? FB_PAIR_L : (v == 1 ? FB_PAIR_R : (v == 2 ? FB_PAIR_M : FB_PAIR_S));
+    *sh = v == 2 ? 1 : 0;
+}
+
 // M = (L + R) >> 1 (arithmetic), S = L - R (src/coding.rs:476-484); unsigned adds so that stale padding
 // words (whose results are masked) cannot overflow a signed int
 FB_HD int32_t fb_mid(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b) >> 1; }

@@ -223,7 +223,7 @@ struct FbKfFrame {
 
 FB_HD uint32_t fb_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
-FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, int tail_n, bool x16 = false) {
+FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, int tail_n, bool x16 = false, bool pairs = false) {
     FbKfLayout L;
     const FbKfGeom ga = fb_kf_geom(block_size), gb = fb_kf_geom(tail_n);
     const uint32_t U = (uint32_t)(ga.U > gb.U ? ga.U : gb.U);
@@ -236,8 +236,9 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
     L.x16 = (x16 && bps <= 16) ? 1u : 0u;
     L.x_stride = (uint32_t)((fb_xidx(block_size + 32) + 8 + 3) & ~3);
     if (L.x16) L.x_stride = ((L.x_stride + 1u) / 2u + 3u) & ~3u;
+    if (pairs) L.x16 = 2; // one plane of (left, right) pairs: the frame's packed PCM itself
     uint32_t o = 0;
-    L.off_x = o;        o += fb_align16((uint32_t)channels * L.x_stride * 4u);
+    L.off_x = o;        o += fb_align16((pairs ? 1u : (uint32_t)channels) * L.x_stride * 4u);
     // kept per warp
     uint32_t k = 0;
     L.k_unit_bits = k;  k += fb_align16(2u * (U + 1u) * 4u);
@@ -431,17 +432,7 @@ FB_DEV void fb_vm_mix(int vm, int32_t *m, int32_t *sh) {
 }
 
 // four samples at plane offset o = fb_xidx(t) (t a multiple of 4, inside the plane incl. its slack)
-// pairs: sample = (ml * left + mr * right) >> sh
-FB_DEV void fb_vm_mix_pairs(int vm, int32_t *ml, int32_t *mr, int32_t *sh) {
-    const int k = vm & 3;
-    *ml = k == 1 ? 0 : 1;
-    *mr = k == 0 ? 0 : (k == 3 ? -1 : 1);
-    *sh = k == 2 ? 1 : 0;
-}
-FB_DEV int32_t fb_mix_pair(int32_t w, int32_t ml, int32_t mr, int32_t sh) {
-    const int32_t l = (int32_t)(int16_t)(uint32_t)w, r = w >> 16;
-    return (int32_t)((uint32_t)ml * (uint32_t)l + (uint32_t)mr * (uint32_t)r) >> sh;
-}
+// pairs: sample = dp2a(pair, mb) >> sh = (ml * left + mr * right) >> sh (fb_pair_mix)
 
 // VMS: the plane formats a caller can meet (the plan kernel only ever sees 32-bit planes: VMS = 0 drops the rest)
 #define FB_VMS_ALL (FB_VM_X16 | FB_VM_PAIRS)
@@ -449,14 +440,14 @@ template <int VMS = FB_VMS_ALL>
 FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, int o, int32_t *dst) {
     int32_t m, sh;
     fb_vm_mix(vm, &m, &sh);
-    if ((VMS & FB_VM_PAIRS) && (vm & FB_VM_PAIRS)) {
-        int32_t ml, mr;
-        fb_vm_mix_pairs(vm, &ml, &mr, &sh);
+    if ((VMS & FB_VM_PAIRS) && (VMS == FB_VM_PAIRS || (vm & FB_VM_PAIRS))) {
+        int32_t mb;
+        fb_pair_mix(vm & 3, &mb, &sh);
         const int4 w = *reinterpret_cast<const int4 *>(xa + o);
-        dst[0] = fb_mix_pair(w.x, ml, mr, sh);
-        dst[1] = fb_mix_pair(w.y, ml, mr, sh);
-        dst[2] = fb_mix_pair(w.z, ml, mr, sh);
-        dst[3] = fb_mix_pair(w.w, ml, mr, sh);
+        dst[0] = fb_dp2a_lo(w.x, mb, 0) >> sh;
+        dst[1] = fb_dp2a_lo(w.y, mb, 0) >> sh;
+        dst[2] = fb_dp2a_lo(w.z, mb, 0) >> sh;
+        dst[3] = fb_dp2a_lo(w.w, mb, 0) >> sh;
     } else if ((VMS & FB_VM_X16) && (vm & FB_VM_X16)) {
         const int2 wa = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xa) + o);
         const int2 wb = *reinterpret_cast<const int2 *>(reinterpret_cast<const int16_t *>(xb) + o);
@@ -484,10 +475,10 @@ FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) 
     const int o = fb_xidx(t);
     int32_t m, sh;
     fb_vm_mix(vm, &m, &sh);
-    if ((VMS & FB_VM_PAIRS) && (vm & FB_VM_PAIRS)) {
-        int32_t ml, mr;
-        fb_vm_mix_pairs(vm, &ml, &mr, &sh);
-        return fb_mix_pair(xa[o], ml, mr, sh);
+    if ((VMS & FB_VM_PAIRS) && (VMS == FB_VM_PAIRS || (vm & FB_VM_PAIRS))) {
+        int32_t mb;
+        fb_pair_mix(vm & 3, &mb, &sh);
+        return fb_dp2a_lo(xa[o], mb, 0) >> sh;
     }
     if ((VMS & FB_VM_X16) && (vm & FB_VM_X16))
         return fb_mix(reinterpret_cast<const int16_t *>(xa)[o], reinterpret_cast<const int16_t *>(xb)[o], m, sh);
@@ -617,7 +608,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
 // unit_bits[0..U) (bits of every unit without the parameter fields).
 // Sets M->fail when the frame must be redone by the literal path.
 // =====================================================================================================
-template <int G, bool ODD>
+template <int G, bool ODD, int VMS>
 FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, const int32_t *xb, int vm,
                          const FbKfCand &cd, uint8_t *scratch, const FbKfLayout &L, uint32_t *unit_bits, FbKfRes *res) {
     uint32_t *words = (uint32_t *)(scratch + L.s_words);
@@ -650,10 +641,10 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             const int lo = ta > warm ? ta : warm;
             if (tb > ta) {
                 int32_t win[G + FB_KF_RUN];
-                fb_kf_history<G, 0, ODD>(xa, xb, vm, ta, win);
+                fb_kf_history<G, VMS, ODD>(xa, xb, vm, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
-                    fb_kf_fetch_run<G, 0, ODD>(xa, xb, vm, t0, win);
+                    fb_kf_fetch_run<G, VMS, ODD>(xa, xb, vm, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
                     fb_kf_csa_run(cw, uu);
                     fb_kf_slide<G>(win);
@@ -851,7 +842,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 // One variant (one warp): fixed_lpc / estimated_qlpc / encode_subframe (src/coding.rs:298-418) on top
 // of K1's analysis.  Writes the decision record `out` (shared memory) and S->cand[v].
 // =====================================================================================================
-template <int G, bool ODD>
+template <int G, bool ODD, int VMS>
 FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, const FbAnalysis &A, int v,
                           uint8_t *smem, const FbKfLayout &L, fb200_subframe_info *out) {
     FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
@@ -863,10 +854,11 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     const int n = g.n;
     const int bps_v = fb_variant_bps(J, v);
     const unsigned long long verbatim_bits = 8ull + (unsigned long long)n * (unsigned long long)bps_v;
-    // sample planes of this variant (the plan kernel always stages 32-bit planes)
+    // sample planes of this variant: 32-bit planes, or (VMS = FB_VM_PAIRS) the one plane of 16-bit stereo pairs
     int vm = 0;
     const int32_t *xa = xs + (size_t)v * L.x_stride, *xb = xa;
-    if (J.channels == 2 && v >= 2) { vm |= v; xa = xs; xb = xs + L.x_stride; }
+    if (VMS == FB_VM_PAIRS) { vm = FB_VM_PAIRS | v; xa = xb = xs; }
+    else if (J.channels == 2 && v >= 2) { vm |= v; xa = xs; xb = xs + L.x_stride; }
 
     FB_WPHASE(lane)
         if (lane == 0) {
@@ -921,7 +913,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             for (int j = 0; j < A.qlp_order; j++) sumabs += (unsigned long long)(A.qlp[j] < 0 ? -A.qlp[j] : A.qlp[j]);
             cd.narrow = (unsigned long long)A.max_abs * sumabs < 0x7FFFFFFFull;
         }
-        fb_kf_search<G, ODD>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), res[c]);
+        fb_kf_search<G, ODD, VMS>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)c * (L.U_max + 1), res[c]);
         if (M->fail) return;
         cbits[c] = c == 0 ? 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0]->res_bits
                           : 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
@@ -1071,6 +1063,18 @@ FB_DEV void fb_kf_stage(const FbJob &J, const int32_t *xv, uint32_t f, int n, in
     }
 }
 
+// stages frame f's packed 16-bit stereo PCM as one plane of (left, right) pairs
+FB_DEV void fb_kp_stage_pairs(const FbJob &J, const uint8_t *pcm, uint32_t f, int n, int32_t *xs, int tid, int T) {
+    const int32_t *src = reinterpret_cast<const int32_t *>(pcm + (size_t)f * (size_t)J.block_size * 4u);
+    const int nq = n >> 2;
+    for (int i = tid; i < nq; i += T) fb_copy16_async(xs + fb_xidx(4 * i), src + 4 * i);
+    if (tid < 4 && (n & 3)) { // partial last quad: the samples that exist, zeros behind them (like xt)
+        const int t = 4 * nq + tid;
+        if (t < n) fb_copy4_async(xs + fb_xidx(t), src + t);
+        else xs[fb_xidx(t)] = 0;
+    }
+}
+
 FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *plan, uint32_t f) {
 #if FB_GPU
     const uint32_t slot_i = atomicAdd(fb_count, 1u);
@@ -1082,8 +1086,10 @@ FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *p
 }
 
 // ---- KA: analysis and plan.  psubs: [frame][channels] chosen subframe records; poffs: [frame][channels][U_max+1]
-template <int G, bool ODD = false>
-FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *vsubs,
+// VMS = 0: 32-bit planes staged from the planar store xv; VMS = FB_VM_PAIRS: the frame's packed 16-bit stereo PCM
+// (pcm) staged as one plane of pairs, xv is not read
+template <int G, bool ODD = false, int VMS = 0>
+FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *vsubs,
                        fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                        uint32_t *fb_count, const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
     const int NW = J.nvar;
@@ -1107,7 +1113,8 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
 
     // ---- stage the independent channels from the row-interleaved store xt (16-byte asynchronous copies)
     FB_PHASE(tid, T)
-        fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, J.channels);
+        if (VMS == FB_VM_PAIRS) fb_kp_stage_pairs(J, pcm, f, n, xs, tid, T);
+        else fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, J.channels);
         {
             // K1's results for the frame's variants: read often and early, so they come along into shared memory
             static_assert(sizeof(FbAnalysis) % 8 == 0, "async copy granularity");
@@ -1121,7 +1128,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
 
     // ---- analysis: one warp per variant
     FB_WARPS_BEGIN(w, NW)
-        fb_kf_variant<G, ODD>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w]);
+        fb_kf_variant<G, ODD, VMS>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w]);
         const FbKfMisc *M = (const FbKfMisc *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_misc);
         FB_WPHASE(lane)
             if (lane == 0 && M->fail) S->frame_fail = 1; // benign race between warps
@@ -1242,18 +1249,6 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
             }
         FB_WPHASE_END
     FB_WARPS_END
-}
-
-// stages frame f's packed 16-bit stereo PCM as one plane of (left, right) pairs
-FB_DEV void fb_kp_stage_pairs(const FbJob &J, const uint8_t *pcm, uint32_t f, int n, int32_t *xs, int tid, int T) {
-    const int32_t *src = reinterpret_cast<const int32_t *>(pcm + (size_t)f * (size_t)J.block_size * 4u);
-    const int nq = n >> 2;
-    for (int i = tid; i < nq; i += T) fb_copy16_async(xs + fb_xidx(4 * i), src + 4 * i);
-    if (tid < 4 && (n & 3)) { // partial last quad: the samples that exist, zeros behind them (like xt)
-        const int t = 4 * nq + tid;
-        if (t < n) fb_copy4_async(xs + fb_xidx(t), src + t);
-        else xs[fb_xidx(t)] = 0;
-    }
 }
 
 // planes and variant mode of a subframe's variant in the pack kernel

@@ -15,11 +15,11 @@
 #define FB_K1_BOUNDS __launch_bounds__(FB_K1_THREADS)
 #endif
 // analysis: one thread per channel variant, rows staged per warp (fb_kernels.cuh)
-__global__ void FB_K1_BOUNDS FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt, const float *win_full,
+__global__ void FB_K1_BOUNDS FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const float *win_full,
                                                                           const float *win_tail, FbAnalysis *ana,
                                                                           fb200_variant_taps *taps, uint32_t n_variants) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_k1_warp<FB_INST_G>(J, xt, win_full, win_tail, ana, taps, n_variants, fb_smem);
+    fb_k1_warp<FB_INST_G>(J, xt, pcm, win_full, win_tail, ana, taps, n_variants, fb_smem);
 }
 
 // generic Rice search: one CTA per channel variant.  list == nullptr: variant blockIdx.x; else the variants of the
@@ -67,26 +67,36 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
 // the plan kernel of the wide windows: 168 registers = 3 CTAs of 128 threads per SM (what its shared memory allows)
 #if FB_INST_G >= 20
 #define FB_KA_BOUNDS __maxnreg__(168)
+#define FB_KAP_BOUNDS __maxnreg__(168)
 #else
 #define FB_KA_BOUNDS __launch_bounds__(256)
+#ifndef FB_KAP_MAXNREG
+#define FB_KAP_MAXNREG 96
+#endif
+#define FB_KAP_BOUNDS __maxnreg__(FB_KAP_MAXNREG)
 #endif
 
 // fused path (fb_fused.cuh), one CTA of 32 * nvar threads per frame: KA = analysis + plan, KP = pack + store
-__global__ void FB_KA_BOUNDS FB_NAME(fb_ka_plan_g)(FbJob J, const int32_t *xt, const FbAnalysis *ana, FbKfPlan *plan,
-                                                             fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,
-                                                             uint32_t *frame_bytes, fb200_frame_info *infos,
-                                                             uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,
-                                                             FbKfLayout L, int odd_mode) {
-    extern __shared__ __align__(16) uint8_t fb_smem[];
-    // odd_mode (fb_kf_odd_mode): 0 = every frame has 4-sample aligned units; 1 = all but the last frame (its CTA comes
-    // first: it is the slow one); 2 = none.  The ODD instance loads its windows sample by sample.
-    const bool odd = odd_mode == 2 || (odd_mode == 1 && blockIdx.x == 0);
-    const uint32_t f = odd_mode == 1 ? (blockIdx.x == 0 ? J.n_frames - 1u : blockIdx.x - 1u) : blockIdx.x;
-    if (odd)
-        fb_ka_body<FB_INST_G, true>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, f, fb_smem, L);
-    else
-        fb_ka_body<FB_INST_G, false>(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, f, fb_smem, L);
-}
+// odd_mode (fb_kf_odd_mode): 0 = every frame has 4-sample aligned units; 1 = all but the last frame (its CTA comes
+// first: it is the slow one); 2 = none.  The ODD instance loads its windows sample by sample.
+#define FB_KA_KERNEL(NAME, BOUNDS, VMS)                                                                                          \
+    __global__ void BOUNDS NAME(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbAnalysis *ana, FbKfPlan *plan,           \
+                                fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes,  \
+                                fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,            \
+                                FbKfLayout L, int odd_mode) {                                                                    \
+        extern __shared__ __align__(16) uint8_t fb_smem[];                                                                       \
+        const bool odd = odd_mode == 2 || (odd_mode == 1 && blockIdx.x == 0);                                                    \
+        const uint32_t f = odd_mode == 1 ? (blockIdx.x == 0 ? J.n_frames - 1u : blockIdx.x - 1u) : blockIdx.x;                   \
+        if (odd)                                                                                                                 \
+            fb_ka_body<FB_INST_G, true, VMS>(J, xt, pcm, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count,  \
+                                             ktab, f, fb_smem, L);                                                               \
+        else                                                                                                                     \
+            fb_ka_body<FB_INST_G, false, VMS>(J, xt, pcm, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, \
+                                              ktab, f, fb_smem, L);                                                              \
+    }
+FB_KA_KERNEL(FB_NAME(fb_ka_plan_g), FB_KA_BOUNDS, 0)
+// 16-bit stereo straight from the packed PCM: one plane of (left, right) pairs
+FB_KA_KERNEL(FB_NAME(fb_ka_planp_g), FB_KAP_BOUNDS, FB_VM_PAIRS)
 
 __global__ void FB_KP_BOUNDS FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
                                                              const fb200_subframe_info *psubs, const uint32_t *poffs,
@@ -102,13 +112,14 @@ __global__ void FB_KP_BOUNDS FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, c
         fb_kp_body<FB_INST_G, false>(J, xt, pcm, plan, psubs, poffs, offsets, out, out_cap, ktab, f, fb_smem, L);
 }
 
-void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
-                             FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
+// pcm_pairs != nullptr: the rows come straight from the packed 16-bit stereo PCM (fb_pairs_format), xv is not read
+void FB_NAME(fb_launch_k1_g)(const FbJob &J, const int32_t *xv, const uint8_t *pcm_pairs, const float *win_full,
+                             const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
     const unsigned grid = 2u * ((fb_k1_slots(J, nvars) + FB_K1_THREADS - 1) / FB_K1_THREADS); // pass A blocks, then pass E blocks
-    const uint32_t smem = fb_k1_smem_bytes(J.channels, J.nvar);
+    const uint32_t smem = fb_k1_smem_bytes(J.channels, J.nvar, pcm_pairs != nullptr);
     if (smem > 48u * 1024u)
         cudaFuncSetAttribute(FB_NAME(fb_k1_analyze_g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    FB_NAME(fb_k1_analyze_g)<<<grid, FB_K1_THREADS, smem, st>>>(J, xv, win_full, win_tail, ana, taps, nvars);
+    FB_NAME(fb_k1_analyze_g)<<<grid, FB_K1_THREADS, smem, st>>>(J, xv, pcm_pairs, win_full, win_tail, ana, taps, nvars);
 }
 
 void FB_NAME(fb_launch_k2_g)(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, fb200_subframe_info *choice,
@@ -123,12 +134,17 @@ void FB_NAME(fb_launch_k3_g)(const FbJob &J, const int32_t *xv, const fb200_subf
     FB_NAME(fb_k3_pack_g)<<<grid, FB_K3_THREADS, smem, st>>>(J, xv, choice, slots, frame_bytes, infos, list, count);
 }
 
-void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan, fb200_subframe_info *vsubs,
-                             fb200_subframe_info *psubs,
+// pcm_pairs != nullptr: L is the pairs layout and the frames are staged from the packed PCM, xt is not read
+void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const uint8_t *pcm_pairs, const FbAnalysis *ana, void *plan,
+                             fb200_subframe_info *vsubs, fb200_subframe_info *psubs,
                              uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                              uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-    FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, ana, (FbKfPlan *)plan, vsubs, psubs, poffs, frame_bytes,
-                                                                     infos, fb_list, fb_count, ktab, L, fb_kf_odd_mode(J));
+    if (pcm_pairs)
+        FB_NAME(fb_ka_planp_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, pcm_pairs, ana, (FbKfPlan *)plan, vsubs, psubs, poffs,
+                                                                          frame_bytes, infos, fb_list, fb_count, ktab, L, fb_kf_odd_mode(J));
+    else
+        FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, nullptr, ana, (FbKfPlan *)plan, vsubs, psubs, poffs,
+                                                                         frame_bytes, infos, fb_list, fb_count, ktab, L, fb_kf_odd_mode(J));
 }
 
 void FB_NAME(fb_launch_kp_g)(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const void *plan, const fb200_subframe_info *psubs,
@@ -146,6 +162,8 @@ cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {
         return cudaFuncSetAttribute(FB_NAME(fb_k3_pack_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     case FB_KERNEL_KF: {
         cudaError_t e = cudaFuncSetAttribute(FB_NAME(fb_ka_plan_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(FB_NAME(fb_ka_planp_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(FB_NAME(fb_kp_pack_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     }

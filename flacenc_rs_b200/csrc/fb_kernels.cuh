@@ -363,7 +363,15 @@ FB_DEV int fb_quantize(const double *coefs, int n, int precision, int16_t *q, in
 
 // ---- pass E state: registers of one thread
 struct FbK1Ent {
-    float s0, s1, s2, s3, s4;       // running f32 sums of |e_k| of the current estimate partition
+    // Sums of |e_k| of the current estimate partition.  The reference adds them one by one in f32; as long as a sum
+    // stays below 2^24 every such addition is exact, so the sum is kept as an INTEGER (i0..i4: one |a - b| + c
+    // instruction per sample and order instead of a conversion and an addition) and converted once when the partition
+    // ends.  A group of 8 samples is added speculatively; when some lane of the warp would reach 2^24 in some order, the
+    // whole warp replays that group -- and the rest of the partition -- with the sequential f32 additions (s0..s4,
+    // `fmode`), which are valid in either case.
+    uint32_t i0, i1, i2, i3, i4;
+    bool fmode;
+    float s0, s1, s2, s3, s4;       // running f32 sums of |e_k| of the current estimate partition (float mode)
     int32_t pe0, pe1, pe2, pe3;     // previous e_0..e_3 (zero history)
     int32_t xmin, xmax;
     int pstart, pend, psize, n;
@@ -372,6 +380,8 @@ struct FbK1Ent {
 
 FB_DEV void fb_k1_ent_init(FbK1Ent &S, int n, int psize, int32_t first) {
     S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = 0.f;
+    S.i0 = S.i1 = S.i2 = S.i3 = S.i4 = 0u;
+    S.fmode = false;
     S.pe0 = S.pe1 = S.pe2 = S.pe3 = 0;
     S.pstart = 0;
     S.psize = psize;
@@ -390,8 +400,19 @@ FB_DEV unsigned long long fb_k1_part_bits(float sum, int k, int end, int len) {
 }
 
 // a partition ends: its five estimates are independent chains (evaluated side by side), then the sums restart
+// integer sums -> the f32 sums they stand for (exact: all below 2^24); from here on the partition is in float mode
+FB_DEV void fb_k1_ent_to_float(FbK1Ent &S) {
+    if (!S.fmode) {
+        S.s0 = (float)S.i0; S.s1 = (float)S.i1; S.s2 = (float)S.i2; S.s3 = (float)S.i3; S.s4 = (float)S.i4;
+        S.fmode = true;
+    }
+}
+
 FB_DEV void fb_k1_ent_close(FbK1Ent &S) {
     const int end = S.pend, len = end - S.pstart;
+    fb_k1_ent_to_float(S);
+    S.i0 = S.i1 = S.i2 = S.i3 = S.i4 = 0u;
+    S.fmode = false;
     if (len > 0) {
         S.b0 += fb_k1_part_bits(S.s0, 0, end, len);
         S.b1 += fb_k1_part_bits(S.s1, 1, end, len);
@@ -420,8 +441,9 @@ FbK1Bits5 fb_k1_part_bits5(float s0, float s1, float s2, float s3, float s4, int
     r.b[4] = fb_k1_part_bits(s4, 4, end, len);
     return r;
 }
-FB_DEV void fb_k1_ent_close_tail(FbK1Ent &S) {
+FB_DEV void fb_k1_ent_close_tail(FbK1Ent &S) { // (guarded groups: always in float mode, and they stay in it)
     const int end = S.pend, len = end - S.pstart;
+    S.i0 = S.i1 = S.i2 = S.i3 = S.i4 = 0u;
     if (len > 0) {
         const FbK1Bits5 r = fb_k1_part_bits5(S.s0, S.s1, S.s2, S.s3, S.s4, end, len);
         S.b0 += r.b[0]; S.b1 += r.b[1]; S.b2 += r.b[2]; S.b3 += r.b[3]; S.b4 += r.b[4];
@@ -431,11 +453,61 @@ FB_DEV void fb_k1_ent_close_tail(FbK1Ent &S) {
     S.pend = (end + S.psize < S.n) ? end + S.psize : S.n;
 }
 
+// |a| + c on unsigned accumulators (one VABSDIFF-class instruction on the GPU)
+FB_DEV uint32_t fb_abs_acc(int32_t a, uint32_t c) {
+#if FB_GPU
+    return __sad(a, 0, c);
+#else
+    return c + (a < 0 ? 0u - (uint32_t)a : (uint32_t)a);
+#endif
+}
+// true when `ok` holds in every lane of the warp (the emulation runs one thread at a time: either answer is valid,
+// both paths of the caller give the same sums)
+FB_DEV bool fb_warp_all(bool ok) {
+#if FB_GPU
+    return __all_sync(0xFFFFFFFFu, ok);
+#else
+    return ok;
+#endif
+}
+
 // 8 samples starting at t0.  GUARDED: samples may lie beyond n and a partition may end at any sample; otherwise all
 // 8 are valid and a partition can only end with the group.  zero-history differences, wrapping i32
-// (src/coding.rs:188-195); |e| is taken on the float (the conversion is symmetric; |e| < 2^31 always).
+// (src/coding.rs:188-195); in float mode |e| is taken on the float (the conversion is symmetric; |e| < 2^31 always).
 template <bool GUARDED, bool DO_ENT>
 FB_DEV void fb_k1_ent_group(FbK1Ent &S, const int32_t *xs, int t0) {
+    if (DO_ENT && !GUARDED && !S.fmode) {
+        // speculative integer group (see FbK1Ent): inputs are at most 25 bits wide, so |e_4| <= 2^28 and eight of them
+        // plus a sum below 2^24 cannot wrap
+        uint32_t j0 = S.i0, j1 = S.i1, j2 = S.i2, j3 = S.i3, j4 = S.i4;
+        int32_t p0 = S.pe0, p1 = S.pe1, p2 = S.pe2, p3 = S.pe3;
+        int32_t mn = S.xmin, mx = S.xmax;
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            const int32_t e0 = xs[s];
+            mn = e0 < mn ? e0 : mn;
+            mx = e0 > mx ? e0 : mx;
+            const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)p0);
+            const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)p1);
+            const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)p2);
+            const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)p3);
+            p0 = e0; p1 = e1; p2 = e2; p3 = e3;
+            j0 = fb_abs_acc(e0, j0);
+            j1 = fb_abs_acc(e1, j1);
+            j2 = fb_abs_acc(e2, j2);
+            j3 = fb_abs_acc(e3, j3);
+            j4 = fb_abs_acc(e4, j4);
+        }
+        if (fb_warp_all((j0 | j1 | j2 | j3 | j4) < (1u << 24))) {
+            S.i0 = j0; S.i1 = j1; S.i2 = j2; S.i3 = j3; S.i4 = j4;
+            S.pe0 = p0; S.pe1 = p1; S.pe2 = p2; S.pe3 = p3;
+            S.xmin = mn; S.xmax = mx;
+            if (t0 + 8 == S.pend) fb_k1_ent_close(S);
+            return;
+        }
+        fb_k1_ent_to_float(S); // the sums before this group, then the group again in f32
+    }
+    if (DO_ENT && GUARDED) fb_k1_ent_to_float(S);
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         const int t = t0 + s;
@@ -690,8 +762,14 @@ FB_HD uint32_t fb_k1_slots(const FbJob &J, uint32_t n_variants) {
     const uint32_t n_full = fb_k1_full_variants(J, n_variants);
     return n_full < n_variants ? ((n_full + 31u) & ~31u) + (n_variants - n_full) : n_variants;
 }
-FB_HD uint32_t fb_k1_smem_bytes(int channels, int nvar) {
-    return (uint32_t)(FB_K1_THREADS / 32) * FB_K1_NQ * (uint32_t)fb_k1_pitch_rows(channels, nvar) * 16u;
+FB_HD uint32_t fb_k1_smem_bytes(int channels, int nvar, bool pairs = false) {
+    const uint32_t rows = pairs ? 8u : (uint32_t)fb_k1_pitch_rows(channels, nvar); // pairs: a warp's 32 variants are 8 frames
+    return (uint32_t)(FB_K1_THREADS / 32) * FB_K1_NQ * rows * 16u;
+}
+// 16-bit stereo in a 2-byte container with a block size that is a multiple of 4 and 16-byte aligned PCM: the analysis,
+// plan and pack kernels read the packed PCM itself (as (left, right) pairs) and the planar store is never built
+FB_HD bool fb_pairs_format(int channels, int bps, int container_bytes, int block_size) {
+    return channels == 2 && bps == 16 && container_bytes == 2 && (block_size & 3) == 0;
 }
 
 #if FB_GPU
@@ -712,6 +790,13 @@ struct FbK1Stage {
     // read role
     uint32_t ra, rb;        // byte offsets of this lane's a / b row inside a staged quad
     int32_t m, sh;          // sample = (a + m * b) >> sh
+    // pairs mode (16-bit stereo straight from the packed PCM, no planar store): a staged "row" is a frame, a quad holds
+    // four (left, right) pairs, the lane copies quads qsub, qsub + 4, ... of frame lane & 7 and forms its variant's
+    // samples as dp2a(pair, mb) >> sh.  The last quad of a frame whose length is not a multiple of 4 is copied with
+    // `last_bytes` source bytes and zero fill (nothing is read beyond the PCM buffer).
+    bool pairs;
+    int32_t mb;
+    uint32_t last_bytes;
 };
 
 template <int N>
@@ -753,9 +838,43 @@ FB_DEV void fb_k1_stage_issue(const FbK1Stage &T, uint32_t slot_addr, int q0) {
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// pairs mode: the lane copies quads qsub, qsub + 4, ... of the chunk (four lanes cover 64 contiguous bytes of a frame)
+template <int QC>
+FB_DEV void fb_k1_stage_issue_pairs(const FbK1Stage &T, uint32_t slot_addr, int q0) {
+#pragma unroll
+    for (int k = 0; 4 * k < QC; k++) {
+        const int qi = T.qsub + 4 * k, q = q0 + qi;
+        if (qi < QC && q < T.cp_quads) {
+            const uint32_t bytes = (q + 1 == T.cp_quads) ? T.last_bytes : 16u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_addr + T.d0 + (uint32_t)(4 * k) * T.pitch),
+                         "l"(T.g0 + (size_t)(q0 + 4 * k) * 4u), "r"(bytes) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int QC>
+FB_DEV void fb_k1_stage_issue_any(const FbK1Stage &T, uint32_t slot_addr, int q0) {
+    if (T.pairs) fb_k1_stage_issue_pairs<QC>(T, slot_addr, q0);
+    else fb_k1_stage_issue<QC>(T, slot_addr, q0);
+}
+
 // the lane's 4 * QG samples of the group slot at shared address `slot_addr`
 template <int QG>
 FB_DEV void fb_k1_stage_read(const FbK1Stage &T, uint32_t slot_addr, int32_t *xs) {
+    if (T.pairs) {
+#pragma unroll
+        for (int i = 0; i < QG; i++) {
+            int4 a;
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                         : "r"(slot_addr + (uint32_t)i * T.pitch + T.ra));
+            xs[4 * i + 0] = fb_dp2a_lo(a.x, T.mb, 0) >> T.sh;
+            xs[4 * i + 1] = fb_dp2a_lo(a.y, T.mb, 0) >> T.sh;
+            xs[4 * i + 2] = fb_dp2a_lo(a.z, T.mb, 0) >> T.sh;
+            xs[4 * i + 3] = fb_dp2a_lo(a.w, T.mb, 0) >> T.sh;
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < QG; i++) {
         const uint32_t base = slot_addr + (uint32_t)i * T.pitch;
@@ -780,14 +899,14 @@ FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
     const uint32_t group_bytes = (uint32_t)QG * T.pitch, slot_bytes = (uint32_t)GC * group_bytes;
     const uint32_t ring_end = T.ring + (uint32_t)NC * slot_bytes;
 #pragma unroll 1
-    for (int c = 0; c < D; c++) fb_k1_stage_issue<QC>(T, T.ring + (uint32_t)c * slot_bytes, c * QC);
+    for (int c = 0; c < D; c++) fb_k1_stage_issue_any<QC>(T, T.ring + (uint32_t)c * slot_bytes, c * QC);
     uint32_t slot_r = T.ring, slot_w = T.ring + (uint32_t)D * slot_bytes;
     int q_w = D * QC;
 #pragma unroll 1
     for (int g0 = 0; g0 < groups; g0 += GC) {
         fb_k1_cp_wait<D - 1>(); // this chunk has landed (this lane's copies) ...
         __syncwarp();           // ... and everybody's; all lanes are also done reading the previous chunk
-        fb_k1_stage_issue<QC>(T, slot_w, q_w);
+        fb_k1_stage_issue_any<QC>(T, slot_w, q_w);
         q_w += QC;
         slot_w += slot_bytes;
         slot_w = slot_w == ring_end ? T.ring : slot_w;
@@ -820,9 +939,10 @@ FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &
     });
 }
 
+// pcm != nullptr: pairs mode (fb_pairs_format), xt is not read
 template <int R>
-FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full, const float *win_tail, FbAnalysis *ana,
-                       fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
+FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
+                       FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
     // The grid holds every block of 128 variants twice: the first half runs pass A (the longer one, so it is scheduled
     // first), the second half pass E.  Half-length CTAs pack the SMs' slots better at the end of a launch, and small
     // batches (latency-bound: one thread walks a whole frame) finish in roughly half the time.
@@ -856,7 +976,27 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const float *win_full,
     fb200_variant_taps *taps = taps_all ? taps_all + gve : nullptr;
 
     FbK1Stage T;
-    {
+    T.pairs = pcm != nullptr;
+    T.mb = 0;
+    T.last_bytes = 16u;
+    if (T.pairs) {
+        // rows = the warp's (up to 8) frames; lane & 7 = frame to copy, lane >> 3 = first quad of every four
+        T.pitch = 8u * 16u;
+        T.ring = (uint32_t)__cvta_generic_to_shared(smem) + warp * (uint32_t)FB_K1_NQ * T.pitch;
+        fb_pair_mix(v, &T.mb, &T.sh);
+        T.m = 0;
+        T.ra = T.rb = (f - f_lo) * 16u;
+        const uint32_t fi = lane & 7u;
+        T.qsub = (int)(lane >> 3);
+        T.qstep = 4;
+        const uint32_t fc = f_lo + fi <= f_hi ? f_lo + fi : f_lo;
+        const int n_c = fb_frame_len(J, fc);
+        T.g0 = reinterpret_cast<const int32_t *>(pcm) + (size_t)fc * (size_t)J.block_size + (size_t)T.qsub * 4u;
+        T.d0 = fi * 16u + (uint32_t)T.qsub * T.pitch;
+        T.cp_quads = f_lo + fi <= f_hi ? (n_c + 3) >> 2 : 0;
+        T.last_bytes = (n_c & 3) ? (uint32_t)(n_c & 3) * 4u : 16u;
+        T.g1_off = 0;
+    } else {
         const uint32_t prow = (uint32_t)fb_k1_pitch_rows(J.channels, J.nvar);
         T.pitch = prow * 16u;
         T.ring = (uint32_t)__cvta_generic_to_shared(smem) + warp * (uint32_t)FB_K1_NQ * T.pitch;

@@ -10,15 +10,16 @@
 enum { FB_KERNEL_K2 = 2, FB_KERNEL_K3 = 3, FB_KERNEL_KF = 5 };
 
 #define FB_DECLARE_LAUNCHERS(G)                                                                                       \
-    void fb_launch_k1_g##G(const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,          \
-                           FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st);              \
+    void fb_launch_k1_g##G(const FbJob &J, const int32_t *xv, const uint8_t *pcm_pairs, const float *win_full,       \
+                           const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars,         \
+                           cudaStream_t st);                                                                         \
     void fb_launch_k2_g##G(const FbJob &J, const int32_t *xv, const FbAnalysis *ana, fb200_subframe_info *choice,     \
                            const FbK2Layout &L, const uint32_t *list, const uint32_t *count, uint32_t grid,          \
                            size_t smem, cudaStream_t st);                                                            \
     void fb_launch_k3_g##G(const FbJob &J, const int32_t *xv, const fb200_subframe_info *choice, uint8_t *slots,      \
                            uint32_t *frame_bytes, fb200_frame_info *infos, const uint32_t *list,                     \
                            const uint32_t *count, uint32_t grid, size_t smem, cudaStream_t st);                      \
-    void fb_launch_ka_g##G(const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan,                     \
+    void fb_launch_ka_g##G(const FbJob &J, const int32_t *xt, const uint8_t *pcm_pairs, const FbAnalysis *ana, void *plan, \
                            fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs,                 \
                            uint32_t *frame_bytes,                                                                   \
                            fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,    \
@@ -47,9 +48,10 @@ FB_DECLARE_LAUNCHERS(24)
     }
 
 #ifndef FB_INST_G // dispatchers, used by fb_api.cu only
-static inline void fb_launch_k1(int ring, const FbJob &J, const int32_t *xv, const float *win_full, const float *win_tail,
-                                FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars, cudaStream_t st) {
-#define FB_CALL(G) fb_launch_k1_g##G(J, xv, win_full, win_tail, ana, taps, nvars, st)
+static inline void fb_launch_k1(int ring, const FbJob &J, const int32_t *xv, const uint8_t *pcm_pairs, const float *win_full,
+                                const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps, uint32_t nvars,
+                                cudaStream_t st) {
+#define FB_CALL(G) fb_launch_k1_g##G(J, xv, pcm_pairs, win_full, win_tail, ana, taps, nvars, st)
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }
@@ -68,11 +70,11 @@ static inline void fb_launch_k3(int ring, const FbJob &J, const int32_t *xv, con
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }
-static inline void fb_launch_ka(int ring, const FbJob &J, const int32_t *xt, const FbAnalysis *ana, void *plan,
+static inline void fb_launch_ka(int ring, const FbJob &J, const int32_t *xt, const uint8_t *pcm_pairs, const FbAnalysis *ana, void *plan,
                                 fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos,
                                 uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L,
                                 cudaStream_t st) {
-#define FB_CALL(G) fb_launch_ka_g##G(J, xt, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, L, st)
+#define FB_CALL(G) fb_launch_ka_g##G(J, xt, pcm_pairs, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, ktab, L, st)
     FB_FOR_G(ring, FB_CALL)
 #undef FB_CALL
 }

@@ -147,6 +147,11 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     std::vector<uint32_t> todo;
     FbKfLayout KL;
     const bool fused = !fb_emu_force_generic && fbh_fused_ok(J, J.tail_n, &KL);
+    // pairs mode like the library: 16-bit stereo PCM is staged as (left, right) pairs by the plan and pack kernels
+    const bool ka_pairs = fused && !planar && fb_emu_kp_pairs && fb_pairs_format(J.channels, J.bps, container_bytes, J.block_size) &&
+                          ((uintptr_t)pcm & 15u) == 0;
+    if (ka_pairs) KL = fb_kf_layout(J.channels, J.nvar, J.bps, J.block_size, J.tail_n, false, true);
+    const uint8_t *pcm8 = (const uint8_t *)pcm;
     std::vector<FbKfPlan> plan;
     std::vector<fb200_subframe_info> psubs;
     std::vector<uint32_t> poffs;
@@ -162,7 +167,10 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         poffs.assign((size_t)J.n_frames * J.channels * (KL.U_max + 1), 0xDDDDDDDDu);
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
-#define EMU_KA(GG) if (fb_kf_geom(fb_frame_len(J, f)).leaf_len & 3) fb_ka_body<GG, true>(J, B.xv.data(), B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL); else fb_ka_body<GG, false>(J, B.xv.data(), B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL)
+#define EMU_KA_ARGS B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL
+#define EMU_KA(GG) do { const bool odd__ = fb_kf_geom(fb_frame_len(J, f)).leaf_len & 3; \
+            if (ka_pairs) { if (odd__) fb_ka_body<GG, true, FB_VM_PAIRS>(J, nullptr, pcm8, EMU_KA_ARGS); else fb_ka_body<GG, false, FB_VM_PAIRS>(J, nullptr, pcm8, EMU_KA_ARGS); } \
+            else { if (odd__) fb_ka_body<GG, true, 0>(J, B.xv.data(), nullptr, EMU_KA_ARGS); else fb_ka_body<GG, false, 0>(J, B.xv.data(), nullptr, EMU_KA_ARGS); } } while (0)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KA(4); break;
             case 8: EMU_KA(8); break;
@@ -231,7 +239,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     B.stream.assign((size_t)total + 16, 0x77);
     if (fused) {
         const bool pairs = !planar && fb_emu_kp_pairs && fb_kp_pairs_format(J.channels, J.bps, container_bytes) &&
-                           ((uintptr_t)pcm & 15u) == 0;
+                           ((uintptr_t)pcm & 15u) == 0 && (J.block_size & 3) == 0;
         const FbKfLayout KPL = fb_kp_layout(J.channels, J.nvar, J.bps, J.block_size, J.tail_n, pairs);
         std::vector<uint8_t> smem(KPL.total + 64);
         std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
