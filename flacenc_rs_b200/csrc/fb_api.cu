@@ -425,8 +425,8 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
               (P.fused || A.analyze_only);
     P.KLp = fb_kf_layout(ctx->channels, J0.nvar, ctx->bps, ctx->block_size, P.tail_n, false, P.pairs);
     if (P.fused && ctx->ktab_chunk != P.KL.crc_chunk) {
-        std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk));
-        fb_kf_build_ktab(P.KL.crc_chunk, kt.data());
+        std::vector<uint32_t> kt(fb_kf_ktab_words(P.KL.crc_chunk, 32u * (uint32_t)J0.nvar));
+        fb_kf_build_ktab(P.KL.crc_chunk, 32u * (uint32_t)J0.nvar, kt.data());
         if ((rc = fb_reserve(ctx, ctx->ktab, kt.size() * 4u))) return rc;
         FB_CUDA(ctx, cudaMemcpyAsync(ctx->ktab.p, kt.data(), kt.size() * 4u, cudaMemcpyHostToDevice, ctx->stream));
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end

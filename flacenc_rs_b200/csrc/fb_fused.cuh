@@ -133,18 +133,20 @@ FB_HD int fb_xidx(int t) { return t + ((t >> 6) << 2); }
 // ---- CRC-16 tables (poly 0x8005, init 0, MSB first; src/component/bitrepr.rs:40,270-271) ------------
 // Built on the host once per context and read by the kernel:
 //   [0, 1024)            slicing-by-4 tables: T[k][b] = CRC of byte b followed by k zero bytes
-//   [1024, 1280)         xp[j] = x^(8 * Lc * j) mod P, j < 256   (Lc = bytes per CRC chunk, see fb_kf_crc_chunk)
 //   [1280, 1536)         CRC-8 (poly 0x07, init 0) byte table for the frame header
-//   [1536, 1536 + Lc+4)  xb[i] = x^(8 * i) mod P, i <= Lc
-#define FB_KTAB_XP 1024
+//   [1536, 1536 + Lm+4)  xb[i] = x^(8 * i) mod P, i <= Lm   (Lm = largest CRC chunk in bytes, see fb_kf_crc_chunk)
+//   [XP, XP + Lm/4 * T)  xp[m - 1][j] = x^(8 * 4m * j) mod P, j < T: the shifts for chunks of 4m bytes.  A frame of B
+//                        bytes is cut into chunks of Lc = 4 * ceil(B / 4T) bytes, so that (nearly) all T threads of
+//                        the CTA get one, however short the frame is
 #define FB_KTAB_C8 1280
 #define FB_KTAB_XB 1536
 FB_HD uint32_t fb_kf_crc_chunk(int channels, int bps, int block_size, int threads) {
     const uint32_t mb = fb_max_frame_bytes(channels, bps, block_size);
     return ((mb + (uint32_t)threads - 1u) / (uint32_t)threads + 3u) & ~3u;
 }
-FB_HD uint32_t fb_kf_ktab_words(uint32_t Lc) { return FB_KTAB_XB + Lc + 4u; }
-inline void fb_kf_build_ktab(uint32_t Lc, uint32_t *t) {
+FB_HD uint32_t fb_kf_ktab_xp(uint32_t Lm) { return FB_KTAB_XB + Lm + 4u; }
+FB_HD uint32_t fb_kf_ktab_words(uint32_t Lm, uint32_t T) { return fb_kf_ktab_xp(Lm) + (Lm / 4u) * T; }
+inline void fb_kf_build_ktab(uint32_t Lc, uint32_t T, uint32_t *t) {
     for (uint32_t b = 0; b < 256; b++) {
         uint32_t c = fb_crc16_table_entry(b);
         t[b] = c;
@@ -160,9 +162,12 @@ inline void fb_kf_build_ktab(uint32_t Lc, uint32_t *t) {
     // x^(8*i): start from 1 and multiply by x^8 (= 0x100 reduced: as a 16-bit polynomial x^8 is 0x0100)
     uint32_t v = 1;
     for (uint32_t i = 0; i <= Lc + 3; i++) { t[FB_KTAB_XB + i] = v; v = fb_crc16_mulmod(v, 0x0100u); }
-    const uint32_t step = t[FB_KTAB_XB + Lc];
-    v = 1;
-    for (uint32_t j = 0; j < 256; j++) { t[FB_KTAB_XP + j] = v; v = fb_crc16_mulmod(v, step); }
+    for (uint32_t m = 1; m <= Lc / 4u; m++) {
+        const uint32_t step = t[FB_KTAB_XB + 4u * m];
+        uint32_t *row = t + fb_kf_ktab_xp(Lc) + (m - 1u) * T;
+        v = 1;
+        for (uint32_t j = 0; j < T; j++) { row[j] = v; v = fb_crc16_mulmod(v, step); }
+    }
 }
 
 // ---- shared-memory layout (bytes), identical on host and device ---------------------------------
@@ -555,7 +560,14 @@ FB_DEV void fb_kf_fixed_coefs(int order, int32_t *fc) {
 }
 
 // zigzag residuals of the run t0..t0+15 from its window; samples outside [lo, hi) give 0.
-template <int G>
+// ROT: the zigzag value rotated right by one bit instead, v ^ ((v >> 31) & 0x7FFFFFFF) = sign in bit 31 above |v| or
+// |v| - 1 -- two instructions instead of three.  The plan kernel only counts bit planes, so it rotates the counter words
+// of a unit back (bit plane b of the rotated values is plane b + 1 of the zigzag values) instead of every sample.
+template <bool ROT>
+FB_DEV uint32_t fb_kf_zz(int32_t v) {
+    return ROT ? ((uint32_t)v ^ ((uint32_t)(v >> 31) & 0x7FFFFFFFu)) : fb_zigzag(v);
+}
+template <int G, bool ROT = false>
 FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCand &cd, const int32_t *qq, uint32_t *u) {
     // bit i of vmask: sample t0 + i lies in [lo, hi)
     const int a = lo - t0, b = hi - t0;
@@ -569,7 +581,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
             const uint32_t e = (uint32_t)win[G + i] + (uint32_t)cd.fc[0] * (uint32_t)win[G + i - 1] +
                                (uint32_t)cd.fc[1] * (uint32_t)win[G + i - 2] + (uint32_t)cd.fc[2] * (uint32_t)win[G + i - 3] +
                                (uint32_t)cd.fc[3] * (uint32_t)win[G + i - 4];
-            u[i] = fb_zigzag((int32_t)e);
+            u[i] = fb_kf_zz<ROT>((int32_t)e);
         }
     } else if (cd.narrow && G >= 8 && cd.order <= G - 2) {
         // the common orders (e.g. 10 with G = 12) leave the last two taps zero: skip them
@@ -578,7 +590,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
             uint32_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G - 2; j++) acc += (uint32_t)qq[j] * (uint32_t)win[G + i - 1 - j];
-            u[i] = fb_zigzag((int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> cd.shift)));
+            u[i] = fb_kf_zz<ROT>((int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> cd.shift)));
         }
     } else if (cd.narrow) {
 #pragma unroll
@@ -586,7 +598,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
             uint32_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) acc += (uint32_t)qq[j] * (uint32_t)win[G + i - 1 - j];
-            u[i] = fb_zigzag((int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> cd.shift)));
+            u[i] = fb_kf_zz<ROT>((int32_t)((uint32_t)win[G + i] - (uint32_t)((int32_t)acc >> cd.shift)));
         }
     } else {
 #pragma unroll
@@ -594,7 +606,7 @@ FB_DEV void fb_kf_run_u(const int32_t *win, int t0, int lo, int hi, const FbKfCa
             int64_t acc = 0;
 #pragma unroll
             for (int j = 0; j < G; j++) acc = fb_mad_wide(qq[j], win[G + i - 1 - j], acc);
-            u[i] = fb_zigzag((int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> cd.shift)));
+            u[i] = fb_kf_zz<ROT>((int32_t)(uint32_t)((uint64_t)(int64_t)win[G + i] - (uint64_t)(acc >> cd.shift)));
         }
     }
     if (vmask != full) {
@@ -645,10 +657,12 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
                     fb_kf_fetch_run<G, VMS, ODD>(xa, xb, vm, t0, win);
-                    fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
+                    fb_kf_run_u<G, true>(win, t0, lo, tb, cd, qq, uu);
                     fb_kf_csa_run(cw, uu);
                     fb_kf_slide<G>(win);
                 }
+#pragma unroll
+                for (int j = 0; j < FB_KF_NWORDS; j++) cw[j] = (cw[j] << 1) | (cw[j] >> 31); // back to zigzag bit planes
             }
             uint32_t orm_u = 0;
 #pragma unroll
@@ -1443,7 +1457,8 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
     // to the end of the data with x^(8*Lc*k) (table xp) and one final x^(8*len(last chunk)) (table xb):
     //   crc = (xor_{i<K-1} crc_i * xp[K-2-i]) * xb[len_last]  xor  crc_{K-1}
     const uint32_t B = S->data_bytes;
-    const uint32_t Lc = L.crc_chunk;
+    uint32_t Lc = 4u * ((B + 4u * (uint32_t)T - 1u) / (4u * (uint32_t)T)); // <= L.crc_chunk: B <= fb_max_frame_bytes
+    Lc = Lc ? Lc : 4u;
     const uint32_t K = (B + Lc - 1u) / Lc; // >= 1 chunks, K <= T by the choice of Lc
     FB_PHASE(tid, T)
         if ((uint32_t)tid < K) {
@@ -1463,7 +1478,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             if ((uint32_t)tid + 1u == K) {
                 S->crc_last = crc;
             } else {
-                const uint32_t sh = fb_crc16_mulmod(crc, ktab[FB_KTAB_XP + (K - 2u - (uint32_t)tid)]);
+                const uint32_t sh = fb_crc16_mulmod(crc, ktab[fb_kf_ktab_xp(L.crc_chunk) + (Lc / 4u - 1u) * (uint32_t)T + (K - 2u - (uint32_t)tid)]);
 #if FB_GPU
                 if (sh) atomicXor(&S->crc_acc, sh);
 #else

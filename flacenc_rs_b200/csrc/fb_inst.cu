@@ -19,7 +19,8 @@ __global__ void FB_K1_BOUNDS FB_NAME(fb_k1_analyze_g)(FbJob J, const int32_t *xt
                                                                           const float *win_tail, FbAnalysis *ana,
                                                                           fb200_variant_taps *taps, uint32_t n_variants) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
-    fb_k1_warp<FB_INST_G>(J, xt, pcm, win_full, win_tail, ana, taps, n_variants, fb_smem);
+    if (pcm) fb_k1_warp<FB_INST_G, true>(J, xt, pcm, win_full, win_tail, ana, taps, n_variants, fb_smem);
+    else fb_k1_warp<FB_INST_G, false>(J, xt, pcm, win_full, win_tail, ana, taps, n_variants, fb_smem);
 }
 
 // generic Rice search: one CTA per channel variant.  list == nullptr: variant blockIdx.x; else the variants of the

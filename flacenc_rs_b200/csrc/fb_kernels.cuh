@@ -853,16 +853,16 @@ FB_DEV void fb_k1_stage_issue_pairs(const FbK1Stage &T, uint32_t slot_addr, int 
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int QC>
+template <int QC, bool PAIRS>
 FB_DEV void fb_k1_stage_issue_any(const FbK1Stage &T, uint32_t slot_addr, int q0) {
-    if (T.pairs) fb_k1_stage_issue_pairs<QC>(T, slot_addr, q0);
+    if (PAIRS) fb_k1_stage_issue_pairs<QC>(T, slot_addr, q0);
     else fb_k1_stage_issue<QC>(T, slot_addr, q0);
 }
 
 // the lane's 4 * QG samples of the group slot at shared address `slot_addr`
-template <int QG>
+template <int QG, bool PAIRS>
 FB_DEV void fb_k1_stage_read(const FbK1Stage &T, uint32_t slot_addr, int32_t *xs) {
-    if (T.pairs) {
+    if (PAIRS) {
 #pragma unroll
         for (int i = 0; i < QG; i++) {
             int4 a;
@@ -890,7 +890,7 @@ FB_DEV void fb_k1_stage_read(const FbK1Stage &T, uint32_t slot_addr, int32_t *xs
 
 // One pass of the warp over its rows in groups of 4 * QG samples, staged in chunks of GC groups.  body(g, xs) gets
 // group g's samples of this lane.  NC chunk slots: NC - 1 copies in flight while one chunk is read.
-template <int QG, int GC, typename Body>
+template <int QG, int GC, bool PAIRS, typename Body>
 FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
     constexpr int QC = QG * GC;
     constexpr int NC = FB_K1_NQ / QC;
@@ -899,14 +899,14 @@ FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
     const uint32_t group_bytes = (uint32_t)QG * T.pitch, slot_bytes = (uint32_t)GC * group_bytes;
     const uint32_t ring_end = T.ring + (uint32_t)NC * slot_bytes;
 #pragma unroll 1
-    for (int c = 0; c < D; c++) fb_k1_stage_issue_any<QC>(T, T.ring + (uint32_t)c * slot_bytes, c * QC);
+    for (int c = 0; c < D; c++) fb_k1_stage_issue_any<QC, PAIRS>(T, T.ring + (uint32_t)c * slot_bytes, c * QC);
     uint32_t slot_r = T.ring, slot_w = T.ring + (uint32_t)D * slot_bytes;
     int q_w = D * QC;
 #pragma unroll 1
     for (int g0 = 0; g0 < groups; g0 += GC) {
         fb_k1_cp_wait<D - 1>(); // this chunk has landed (this lane's copies) ...
         __syncwarp();           // ... and everybody's; all lanes are also done reading the previous chunk
-        fb_k1_stage_issue_any<QC>(T, slot_w, q_w);
+        fb_k1_stage_issue_any<QC, PAIRS>(T, slot_w, q_w);
         q_w += QC;
         slot_w += slot_bytes;
         slot_w = slot_w == ring_end ? T.ring : slot_w;
@@ -914,7 +914,7 @@ FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
         for (int gi = 0; gi < GC; gi++) {
             if (g0 + gi >= groups) break;
             int32_t xs[4 * QG];
-            fb_k1_stage_read<QG>(T, slot_r + (uint32_t)gi * group_bytes, xs);
+            fb_k1_stage_read<QG, PAIRS>(T, slot_r + (uint32_t)gi * group_bytes, xs);
             body(g0 + gi, xs);
         }
         slot_r += slot_bytes;
@@ -924,9 +924,9 @@ FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
     __syncwarp(); // the ring may be refilled by the next pass
 }
 
-template <int R, int SKIP>
+template <int R, int SKIP, bool PAIRS>
 FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &V, int n_w, bool uniform) {
-    fb_k1_stream<R / 4, (R <= 8 ? 4 : (R <= 16 ? 2 : 1))>(T, (n_w + R - 1) / R, [&](int g, const int32_t *xs) {
+    fb_k1_stream<R / 4, (R <= 8 ? 4 : (R <= 16 ? 2 : 1)), PAIRS>(T, (n_w + R - 1) / R, [&](int g, const int32_t *xs) {
         const int t0 = g * R;
         float ws[R];
         if (uniform && g > 0 && t0 + R <= n_w) {
@@ -939,8 +939,8 @@ FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &
     });
 }
 
-// pcm != nullptr: pairs mode (fb_pairs_format), xt is not read
-template <int R>
+// PAIRS: pairs mode (fb_pairs_format): the rows come from pcm, xt is not read
+template <int R, bool PAIRS>
 FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
                        FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
     // The grid holds every block of 128 variants twice: the first half runs pass A (the longer one, so it is scheduled
@@ -976,10 +976,10 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
     fb200_variant_taps *taps = taps_all ? taps_all + gve : nullptr;
 
     FbK1Stage T;
-    T.pairs = pcm != nullptr;
+    T.pairs = PAIRS;
     T.mb = 0;
     T.last_bytes = 16u;
-    if (T.pairs) {
+    if (PAIRS) {
         // rows = the warp's (up to 8) frames; lane & 7 = frame to copy, lane >> 3 = first quad of every four
         T.pitch = 8u * 16u;
         T.ring = (uint32_t)__cvta_generic_to_shared(smem) + warp * (uint32_t)FB_K1_NQ * T.pitch;
@@ -1036,13 +1036,17 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
         S.xmax = -2147483647 - 1;
         const bool ent_w = J.cfg.use_fixed && J.cfg.fixed_order_sel == 1 && n_w >= FB_MIN_PRED_BLOCK;
         const bool whole = uniform && (!ent_w || (V.psize & 7) == 0);
+#ifdef FB_K1_E_NOARITH // (timing experiments only: results are wrong)
+        if (false)
+#else
         if (ent_w)
-            fb_k1_stream<2, 4>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
+#endif
+            fb_k1_stream<2, 4, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
                 if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, true>(S, xs, g * 8);
                 else fb_k1_ent_group<true, true>(S, xs, g * 8);
             });
         else
-            fb_k1_stream<2, 4>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
+            fb_k1_stream<2, 4, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
                 if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, false>(S, xs, g * 8);
                 else fb_k1_ent_group<true, false>(S, xs, g * 8);
             });
@@ -1056,12 +1060,16 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
     for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < R; i++) A.ring[i] = 0.0;
+#ifdef FB_K1_SKIP_A // (timing experiments only: results are wrong)
+    if (false) {
+#else
     if (J.cfg.use_lpc && n_w >= FB_MIN_PRED_BLOCK) {
+#endif
         switch (R - V.P) {
-        case 0: fb_k1_warp_pass_a<R, 0>(T, A, V, n_w, uniform); break;
-        case 1: fb_k1_warp_pass_a<R, 1>(T, A, V, n_w, uniform); break;
-        case 2: fb_k1_warp_pass_a<R, 2>(T, A, V, n_w, uniform); break;
-        default: fb_k1_warp_pass_a<R, 3>(T, A, V, n_w, uniform); break;
+        case 0: fb_k1_warp_pass_a<R, 0, PAIRS>(T, A, V, n_w, uniform); break;
+        case 1: fb_k1_warp_pass_a<R, 1, PAIRS>(T, A, V, n_w, uniform); break;
+        case 2: fb_k1_warp_pass_a<R, 2, PAIRS>(T, A, V, n_w, uniform); break;
+        default: fb_k1_warp_pass_a<R, 3, PAIRS>(T, A, V, n_w, uniform); break;
         }
     }
     if (valid) fb_k1_finish_lpc<R>(J, V, A, out, taps);

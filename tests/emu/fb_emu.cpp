@@ -159,8 +159,8 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
         std::vector<uint32_t> list(J.n_frames + 1, 0);
         uint32_t count = 0;
         std::vector<uint8_t> smem(KL.total + 64);
-        std::vector<uint32_t> ktab_a(fb_kf_ktab_words(KL.crc_chunk));
-        fb_kf_build_ktab(KL.crc_chunk, ktab_a.data());
+        std::vector<uint32_t> ktab_a(fb_kf_ktab_words(KL.crc_chunk, 32u * (uint32_t)J.nvar));
+        fb_kf_build_ktab(KL.crc_chunk, 32u * (uint32_t)J.nvar, ktab_a.data());
         plan.resize(J.n_frames);
         memset(plan.data(), 0xEE, plan.size() * sizeof(FbKfPlan));
         psubs.resize((size_t)J.n_frames * J.channels);
@@ -242,8 +242,8 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
                            ((uintptr_t)pcm & 15u) == 0 && (J.block_size & 3) == 0;
         const FbKfLayout KPL = fb_kp_layout(J.channels, J.nvar, J.bps, J.block_size, J.tail_n, pairs);
         std::vector<uint8_t> smem(KPL.total + 64);
-        std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk));
-        fb_kf_build_ktab(KL.crc_chunk, ktab.data());
+        std::vector<uint32_t> ktab(fb_kf_ktab_words(KL.crc_chunk, 32u * (uint32_t)J.nvar));
+        fb_kf_build_ktab(KL.crc_chunk, 32u * (uint32_t)J.nvar, ktab.data());
         for (uint32_t f = 0; f < J.n_frames; f++) {
             memset(smem.data(), 0xAB, smem.size());
 #define EMU_KP(GG) if (fb_kf_geom(fb_frame_len(J, f)).leaf_len & 3) fb_kp_body<GG, true>(J, B.xv.data(), pairs ? (const uint8_t *)pcm : nullptr, plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL); else fb_kp_body<GG, false>(J, B.xv.data(), pairs ? (const uint8_t *)pcm : nullptr, plan.data(), psubs.data(), poffs.data(), B.offsets.data(), B.stream.data(), total, ktab.data(), f, smem.data(), KPL)
