@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -141,7 +142,6 @@ struct fb200_ctx {
     int win_tail_n = -1;
     fb200_timing timing;
     std::string last_error;
-    int k2_smem_set = 0, k3_smem_set = 0, kf_smem_set = 0;
     uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
     bool no_pairs = false;      // FB200_KP_PAIRS=0: the pack kernel always stages planes (tests exercise both)
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
@@ -241,7 +241,9 @@ int fb200_debug_find_shift(int device, const double *values, uint64_t count, int
 
 const char *fb200_version(void) { return "flacenc_b200 0.2.0 (sm_100a)"; }
 
-const char *fb200_last_error(const fb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+// ctx == NULL: detail text of the last failed stream-level call (fb200_encode_stream / _streams) on this thread
+static thread_local std::string g_stream_error;
+const char *fb200_last_error(const fb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_stream_error.c_str(); }
 
 fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_sample, int sample_rate, int block_size,
                         int device, int *err) {
@@ -432,18 +434,22 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `kt` dies at scope end
         ctx->ktab_chunk = P.KL.crc_chunk;
     }
-    const int kf_smem = (int)std::max(std::max(P.KL.total, P.KLp.total), std::max(P.KPL.total, P.KPLp.total)); // plan and pack kernels
-    if (P.fused && kf_smem > ctx->kf_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, kf_smem));
-        ctx->kf_smem_set = kf_smem;
-    }
-    if ((int)P.k2_smem > ctx->k2_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K2, (int)P.k2_smem));
-        ctx->k2_smem_set = (int)P.k2_smem;
-    }
-    if ((int)P.k3_smem > ctx->k3_smem_set) {
-        FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K3, (int)P.k3_smem));
-        ctx->k3_smem_set = (int)P.k3_smem;
+    // Dynamic shared memory opt-in of the kernels of this tap-window size: a per-function, per-device attribute that is
+    // shared by every context of the process, so it is raised to the device maximum once and never lowered (a context
+    // that set it to its own smaller need would break the launches of another one).
+    {
+        static std::mutex smem_mu;
+        static bool smem_done[64][32];
+        std::lock_guard<std::mutex> lock(smem_mu);
+        const int di = ctx->device & 63, ri = (P.ring / 4) & 31;
+        if (!smem_done[di][ri]) {
+            int optin = 0;
+            FB_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+            FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_KF, optin));
+            FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K2, optin));
+            FB_CUDA(ctx, fb_set_smem(P.ring, FB_KERNEL_K3, optin));
+            smem_done[di][ri] = true;
+        }
     }
     return FB200_OK;
 }
@@ -690,8 +696,17 @@ int fb_encode_serial(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P) {
 // (stream s_in), kernels (compute streams, alternating so the latency-bound analysis kernel of one chunk overlaps
 // the fused kernel of the previous one) and D2H copy (stream s_out) overlap with those of its neighbours.
 // ctx->nsets buffer sets rotate; a set is reused once its D2H copy has been enqueued and is waited for by event.
-int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint64_t chunk_frames) {
+//
+// Several contexts (one per device, same configuration and format) share the work by frame range: chunk c is encoded
+// on device c mod N with that device's own streams and buffer sets (what src/par.rs:355-449 does with worker threads).
+// Frames are independent, so there is no exchange between the devices; the only ordered state is the byte offset of a
+// chunk in the output, which the host learns from the chunk before it (each chunk's bytes are copied straight to
+// their final place in the caller's buffer: no per-device staging, no gather pass).
+int fb_encode_pipelined(const std::vector<fb200_ctx *> &cs, const EncodeArgs &A, const std::vector<Plan> &Ps, uint64_t chunk_frames) {
     int rc;
+    fb200_ctx *ctx = cs[0];              // carries the error text and the timing record of the call
+    const Plan &P = Ps[0];
+    const uint64_t N = cs.size();
     const uint64_t FB_NSETS = (uint64_t)ctx->nsets;
     // chunk schedule: the H2D stream is the bottleneck, so what matters at the end is how much work is left once the
     // last copy has landed.  One short final chunk (a quarter of the nominal size) keeps that tail small; more than
@@ -715,26 +730,38 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
     const uint64_t nchunks = chunks.size();
     const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
     const uint64_t in_chunk = std::min(chunk_frames * P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb, in_bytes_total);
-    for (uint64_t k = 0; k < FB_NSETS; k++) { // only the sets that rotate
-        ChunkSet &S = ctx->sets[k];
-        if ((rc = fb_reserve_set(ctx, P, A, S, chunk_frames, in_chunk, chunk_frames, chunk_frames * (uint64_t)P.mb + 16)))
-            return rc;
-        if ((rc = fb_reserve_pinned(ctx, S, 64 + chunk_frames * 4u))) return rc;
-        S.d2h_pending = false;
+    const uint64_t n_used = std::min<uint64_t>(N, nchunks); // devices that get at least one chunk
+    for (uint64_t d = 0; d < n_used; d++) {
+        fb200_ctx *C = cs[d];
+        FB_CUDA(ctx, cudaSetDevice(C->device));
+        for (uint64_t k = 0; k < FB_NSETS; k++) { // only the sets that rotate
+            ChunkSet &S = C->sets[k];
+            if ((rc = fb_reserve_set(C, Ps[d], A, S, chunk_frames, in_chunk, chunk_frames, chunk_frames * (uint64_t)P.mb + 16))) {
+                ctx->last_error = C->last_error;
+                return rc;
+            }
+            if ((rc = fb_reserve_pinned(C, S, 64 + chunk_frames * 4u))) { ctx->last_error = C->last_error; return rc; }
+            S.d2h_pending = false;
+        }
     }
-    Accum acc;
+    std::vector<Accum> accs(N);
     unsigned long long host_off = 0;
     int result = FB200_OK;
-    // FB200_TRACE=1: device timeline per chunk (ms since the start of the call) on stderr
+    // FB200_TRACE=1: device timeline per chunk (ms since the start of the call on that chunk's device) on stderr
     const bool trace = getenv("FB200_TRACE") != nullptr;
     std::vector<std::array<float, 6>> tr(trace ? nchunks : 0);
-    std::vector<uint64_t> set_chunk(FB_NSETS, 0); // chunk whose D2H events a set currently holds
-    auto trace_d2h = [&](ChunkSet &S, uint64_t c) {
+    std::vector<uint64_t> set_chunk(N * FB_NSETS, 0); // chunk whose D2H events a set currently holds
+    auto dev_of = [&](uint64_t c) { return c % N; };
+    auto set_of = [&](uint64_t c) { return (c / N) % FB_NSETS; };
+    auto trace_d2h = [&](fb200_ctx *C, ChunkSet &S, uint64_t c) {
         if (!trace) return;
-        cudaEventElapsedTime(&tr[c][4], ctx->ev_begin, S.ev[7]);
-        cudaEventElapsedTime(&tr[c][5], ctx->ev_begin, S.ev[8]);
+        cudaEventElapsedTime(&tr[c][4], C->ev_begin, S.ev[7]);
+        cudaEventElapsedTime(&tr[c][5], C->ev_begin, S.ev[8]);
     };
-    FB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->s_in));
+    for (uint64_t d = 0; d < n_used; d++) {
+        FB_CUDA(ctx, cudaSetDevice(cs[d]->device));
+        FB_CUDA(ctx, cudaEventRecord(cs[d]->ev_begin, cs[d]->s_in));
+    }
 
     auto chunk_range = [&](uint64_t c, uint64_t &f0, uint64_t &nf, uint64_t &s0, uint64_t &ns) {
         f0 = chunks[c].first;
@@ -743,39 +770,47 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
         ns = std::min(A.n_samples - s0, nf * P.bs);
     };
     auto enqueue = [&](uint64_t c) -> int {
-        ChunkSet &S = ctx->sets[c % FB_NSETS];
+        fb200_ctx *C = cs[dev_of(c)];
+        ChunkSet &S = C->sets[set_of(c)];
+        Accum &acc = accs[dev_of(c)];
         uint64_t f0, nf, s0, ns;
         chunk_range(c, f0, nf, s0, ns);
+        FB_CUDA(ctx, cudaSetDevice(C->device));
         if (S.d2h_pending) {
             // the set's previous chunk: its D2H must have drained before the buffers are overwritten
             FB_CUDA(ctx, cudaEventSynchronize(S.ev[8]));
             float t;
             FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
             acc.ms_d2h += t;
-            trace_d2h(S, set_chunk[c % FB_NSETS]);
+            trace_d2h(C, S, set_chunk[dev_of(c) * FB_NSETS + set_of(c)]);
             S.d2h_pending = false;
         }
         const uint64_t off = s0 * (uint64_t)ctx->channels * (uint64_t)P.cb;
         const uint64_t len = ns * (uint64_t)ctx->channels * (uint64_t)P.cb;
-        FB_CUDA(ctx, cudaEventRecord(S.ev[0], ctx->s_in));
-        FB_CUDA(ctx, cudaMemcpyAsync(S.pcm.p, (const uint8_t *)A.pcm_host + off, len, cudaMemcpyHostToDevice, ctx->s_in));
-        cudaStream_t sk = (c & 1) ? ctx->s_k1 : ctx->stream;
-        FB_CUDA(ctx, cudaEventRecord(S.ev[9], ctx->s_in));
+        FB_CUDA(ctx, cudaEventRecord(S.ev[0], C->s_in));
+        FB_CUDA(ctx, cudaMemcpyAsync(S.pcm.p, (const uint8_t *)A.pcm_host + off, len, cudaMemcpyHostToDevice, C->s_in));
+        cudaStream_t sk = ((c / N) & 1) ? C->s_k1 : C->stream;
+        FB_CUDA(ctx, cudaEventRecord(S.ev[9], C->s_in));
         FB_CUDA(ctx, cudaStreamWaitEvent(sk, S.ev[9], 0));
         FB_CUDA(ctx, cudaMemsetAsync(S.scalars.p, 0, 64, sk));
-        return fb_enqueue_kernels(ctx, P, A, S, f0, ns, (const uint8_t *)S.pcm.p, (uint32_t *)S.frame_bytes.p,
-                                  (uint8_t *)S.out.p, (unsigned long long)S.out.cap, sk, acc);
+        const int rc2 = fb_enqueue_kernels(C, Ps[dev_of(c)], A, S, f0, ns, (const uint8_t *)S.pcm.p, (uint32_t *)S.frame_bytes.p,
+                                           (uint8_t *)S.out.p, (unsigned long long)S.out.cap, sk, acc);
+        if (rc2 && C != ctx) ctx->last_error = C->last_error;
+        return rc2;
     };
     auto finish = [&](uint64_t c) -> int {
-        ChunkSet &S = ctx->sets[c % FB_NSETS];
+        fb200_ctx *C = cs[dev_of(c)];
+        ChunkSet &S = C->sets[set_of(c)];
+        Accum &acc = accs[dev_of(c)];
         uint64_t f0, nf, s0, ns;
         chunk_range(c, f0, nf, s0, ns);
+        FB_CUDA(ctx, cudaSetDevice(C->device));
         FB_CUDA(ctx, cudaEventSynchronize(S.ev[6]));
         float t;
         FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[0], S.ev[9]));
         acc.ms_h2d += t;
         int rc2;
-        if ((rc2 = fb_harvest_kernel_times(ctx, S, false, acc))) return rc2;
+        if ((rc2 = fb_harvest_kernel_times(C, S, false, acc))) { ctx->last_error = C->last_error; return rc2; }
         const uint32_t err_flag = *(const uint32_t *)S.pinned;
         const unsigned long long total = *(const unsigned long long *)(S.pinned + 8);
         acc.fallback += *(const uint32_t *)(S.pinned + 16);
@@ -787,26 +822,24 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
             ctx->last_error = "output capacity too small";
             result = FB200_ERR_CAPACITY;
         }
-        cudaStream_t sk = (c & 1) ? ctx->s_k1 : ctx->stream;
-        (void)sk;
-        FB_CUDA(ctx, cudaEventRecord(S.ev[7], ctx->s_out));
+        FB_CUDA(ctx, cudaEventRecord(S.ev[7], C->s_out));
         if (result == FB200_OK) {
             if (A.out_host && total)
-                FB_CUDA(ctx, cudaMemcpyAsync(A.out_host + host_off, S.out.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->s_out));
+                FB_CUDA(ctx, cudaMemcpyAsync(A.out_host + host_off, S.out.p, (size_t)total, cudaMemcpyDeviceToHost, C->s_out));
             if (A.frame_sizes) {
                 // via pinned staging so the copy stays asynchronous; handed over after the final synchronize
-                FB_CUDA(ctx, cudaMemcpyAsync(S.pinned + 64, S.frame_bytes.p, (size_t)nf * 4u, cudaMemcpyDeviceToHost, ctx->s_out));
+                FB_CUDA(ctx, cudaMemcpyAsync(S.pinned + 64, S.frame_bytes.p, (size_t)nf * 4u, cudaMemcpyDeviceToHost, C->s_out));
             }
             if (A.infos)
                 FB_CUDA(ctx, cudaMemcpyAsync(A.infos + f0, S.infos.p, (size_t)nf * sizeof(fb200_frame_info),
-                                             cudaMemcpyDeviceToHost, ctx->s_out));
+                                             cudaMemcpyDeviceToHost, C->s_out));
         }
-        FB_CUDA(ctx, cudaEventRecord(S.ev[8], ctx->s_out));
+        FB_CUDA(ctx, cudaEventRecord(S.ev[8], C->s_out));
         S.d2h_pending = true;
-        set_chunk[c % FB_NSETS] = c;
+        set_chunk[dev_of(c) * FB_NSETS + set_of(c)] = c;
         if (trace) {
             const int idx[4] = {0, 9, 1, 6};
-            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&tr[c][i], ctx->ev_begin, S.ev[idx[i]]);
+            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&tr[c][i], C->ev_begin, S.ev[idx[i]]);
         }
         host_off += total;
         return FB200_OK;
@@ -814,54 +847,73 @@ int fb_encode_pipelined(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P, uint
     // frame sizes staged in a set's pinned area must be copied out before the set is reused
     auto collect_sizes = [&](uint64_t c) -> int {
         if (!A.frame_sizes || result != FB200_OK) return FB200_OK;
-        ChunkSet &S = ctx->sets[c % FB_NSETS];
+        fb200_ctx *C = cs[dev_of(c)];
+        ChunkSet &S = C->sets[set_of(c)];
         uint64_t f0, nf, s0, ns;
         chunk_range(c, f0, nf, s0, ns);
+        FB_CUDA(ctx, cudaSetDevice(C->device));
         FB_CUDA(ctx, cudaEventSynchronize(S.ev[8]));
         memcpy(A.frame_sizes + f0, S.pinned + 64, (size_t)nf * 4u);
         return FB200_OK;
     };
 
-    const uint64_t ahead = FB_NSETS - 1;
+    const uint64_t in_flight = N * FB_NSETS;       // chunks that own a buffer set at any time
+    const uint64_t ahead = N * (FB_NSETS - 1);
     for (uint64_t c = 0; c < nchunks + ahead; c++) {
-        if (c >= FB_NSETS && (rc = collect_sizes(c - FB_NSETS))) return rc; // before chunk c reuses that set
+        if (c >= in_flight && (rc = collect_sizes(c - in_flight))) return rc; // before chunk c reuses that set
         if (c < nchunks && (rc = enqueue(c))) return rc;
         if (c >= ahead && (rc = finish(c - ahead))) return rc;
     }
-    for (uint64_t c = nchunks > FB_NSETS ? nchunks - FB_NSETS : 0; c < nchunks; c++)
+    for (uint64_t c = nchunks > in_flight ? nchunks - in_flight : 0; c < nchunks; c++)
         if ((rc = collect_sizes(c))) return rc;
-    FB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->s_out));
-    FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
-    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    FB_CUDA(ctx, cudaStreamSynchronize(ctx->s_k1));
-    for (int k = 0; k < (int)FB_NSETS; k++) {
-        ChunkSet &S = ctx->sets[k];
-        if (S.d2h_pending) {
-            float t;
-            FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
-            acc.ms_d2h += t;
-            trace_d2h(S, set_chunk[(size_t)k]);
-            S.d2h_pending = false;
+    float t_total = 0;
+    Accum acc;
+    for (uint64_t d = 0; d < n_used; d++) {
+        fb200_ctx *C = cs[d];
+        FB_CUDA(ctx, cudaSetDevice(C->device));
+        FB_CUDA(ctx, cudaEventRecord(C->ev_end, C->s_out));
+        FB_CUDA(ctx, cudaStreamSynchronize(C->s_out));
+        FB_CUDA(ctx, cudaStreamSynchronize(C->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(C->s_k1));
+        for (int k = 0; k < (int)FB_NSETS; k++) {
+            ChunkSet &S = C->sets[k];
+            if (S.d2h_pending) {
+                float t;
+                FB_CUDA(ctx, cudaEventElapsedTime(&t, S.ev[7], S.ev[8]));
+                accs[d].ms_d2h += t;
+                trace_d2h(C, S, set_chunk[d * FB_NSETS + (uint64_t)k]);
+                S.d2h_pending = false;
+            }
         }
+        // the call's device time: the longest span (first copy in .. last copy out) over the devices
+        float t_dev = 0;
+        FB_CUDA(ctx, cudaEventElapsedTime(&t_dev, C->ev_begin, C->ev_end));
+        t_total = std::max(t_total, t_dev);
+        const Accum &a = accs[d];
+        acc.fused |= a.fused;
+        acc.ms_h2d += a.ms_h2d;
+        acc.ms_d2h += a.ms_d2h;
+        for (int k = 0; k < 5; k++) acc.ms_k[k] += a.ms_k[k];
+        acc.launches += a.launches;
+        acc.fused_frames += a.fused_frames;
+        acc.fallback += a.fallback;
     }
+    FB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (A.out_len) *A.out_len = (size_t)host_off;
     if (result != FB200_OK) return result;
     if (trace) {
         for (uint64_t c = 0; c < nchunks; c++)
-            fprintf(stderr, "fb200 trace: chunk %llu frames %llu  h2d %.3f-%.3f  kernels %.3f-%.3f  d2h %.3f-%.3f\n",
-                    (unsigned long long)c, (unsigned long long)chunks[c].second, tr[c][0], tr[c][1], tr[c][2], tr[c][3],
-                    tr[c][4], tr[c][5]);
+            fprintf(stderr, "fb200 trace: chunk %llu dev %d frames %llu  h2d %.3f-%.3f  kernels %.3f-%.3f  d2h %.3f-%.3f\n",
+                    (unsigned long long)c, cs[dev_of(c)]->device, (unsigned long long)chunks[c].second, tr[c][0], tr[c][1], tr[c][2],
+                    tr[c][3], tr[c][4], tr[c][5]);
     }
-    float t_total = 0;
-    FB_CUDA(ctx, cudaEventElapsedTime(&t_total, ctx->ev_begin, ctx->ev_end));
     fb_store_timing(ctx, acc, t_total, in_bytes_total, host_off);
     return FB200_OK;
 }
 
-int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
-    std::lock_guard<std::mutex> lock(ctx->mu);
+// checks of an encode call that do not depend on the device; fills the frame / variant counts
+int fb_encode_prologue(fb200_ctx *ctx, const EncodeArgs &A, uint64_t *total_frames_out) {
     ctx->last_error.clear();
-    FB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int cb = A.container_bytes;
     if (!A.planar_host && (cb < 1 || cb > 4)) {
         ctx->last_error = "container_bytes must be 1, 2, 3 or 4";
@@ -878,6 +930,7 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
     const int nvar = ctx->channels == 2 ? 4 : ctx->channels;
     if (A.n_variants) *A.n_variants = (size_t)(total_frames * (uint64_t)nvar);
     memset(&ctx->timing, 0, sizeof(ctx->timing));
+    *total_frames_out = total_frames;
     if (total_frames == 0) return FB200_OK;
     // frame_number < 2^31 (src/coding.rs:587-591)
     if (A.first_frame + total_frames > (1ull << 31)) {
@@ -885,18 +938,64 @@ int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
         return FB200_ERR_CONFIG;
     }
     if (A.analyze_only && (uint64_t)A.taps_cap < total_frames * (uint64_t)nvar) return FB200_ERR_CAPACITY;
+    return FB200_OK;
+}
+
+// frames per chunk of the pipelined host path: sized so that the per-variant analysis kernel still has a few thousand
+// threads and the copies of neighbouring chunks overlap the kernels; with several devices every device should get
+// about six chunks
+uint64_t fb_pipe_chunk_frames(const fb200_ctx *ctx, const Plan &P, uint64_t total_frames, uint64_t n_devices) {
+    uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 2432;
+    if (!ctx->pipe_chunk_frames && n_devices > 1)
+        chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(304, total_frames / (n_devices * 6)));
+    const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + 2 * P.slot_bytes + 4096u;
+    return std::min<uint64_t>(chunk, std::max<uint64_t>(64, (1024ull << 20) / per_frame));
+}
+
+int fb_encode(fb200_ctx *ctx, const EncodeArgs &A) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    FB_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t total_frames = 0;
+    int rc = fb_encode_prologue(ctx, A, &total_frames);
+    if (rc || total_frames == 0) return rc;
     Plan P;
-    int rc = fb_make_plan(ctx, A, P);
+    rc = fb_make_plan(ctx, A, P);
     if (rc) return rc;
-    // host batches of more than one chunk are pipelined; the chunk is sized so that the per-variant analysis
-    // kernel still has a few thousand threads and the copies of neighbouring chunks overlap the kernels
+    // host batches of more than one chunk are pipelined
     if (A.pcm_host && !A.analyze_only) {
-        uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 2432;
-        const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + 2 * P.slot_bytes + 4096u;
-        chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(64, (1024ull << 20) / per_frame));
-        if (total_frames > chunk + chunk / 2) return fb_encode_pipelined(ctx, A, P, chunk);
+        const uint64_t chunk = fb_pipe_chunk_frames(ctx, P, total_frames, 1);
+        if (total_frames > chunk + chunk / 2) return fb_encode_pipelined({ctx}, A, {P}, chunk);
     }
     return fb_encode_serial(ctx, A, P);
+}
+
+// one batch over several contexts (one per device, same configuration and format): frame ranges, chunk by chunk
+int fb_encode_multi(const std::vector<fb200_ctx *> &cs, const EncodeArgs &A) {
+    fb200_ctx *ctx = cs[0];
+    if (cs.size() == 1) return fb_encode(ctx, A);
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (fb200_ctx *C : cs) locks.emplace_back(C->mu);
+    for (fb200_ctx *C : cs) {
+        if (memcmp(&C->cfg, &ctx->cfg, sizeof(fb200_config)) != 0 || C->channels != ctx->channels || C->bps != ctx->bps ||
+            C->sample_rate != ctx->sample_rate || C->block_size != ctx->block_size) {
+            ctx->last_error = "contexts of one sharded call must share configuration and stream format";
+            return FB200_ERR_SOURCE;
+        }
+    }
+    uint64_t total_frames = 0;
+    int rc = fb_encode_prologue(ctx, A, &total_frames);
+    if (rc || total_frames == 0) return rc;
+    std::vector<Plan> Ps(cs.size());
+    for (size_t d = 0; d < cs.size(); d++) {
+        FB_CUDA(ctx, cudaSetDevice(cs[d]->device));
+        if ((rc = fb_make_plan(cs[d], A, Ps[d]))) { ctx->last_error = cs[d]->last_error; return rc; }
+    }
+    const uint64_t chunk = fb_pipe_chunk_frames(ctx, Ps[0], total_frames, cs.size());
+    if (total_frames <= chunk + chunk / 2) { // too small to share
+        FB_CUDA(ctx, cudaSetDevice(ctx->device));
+        return fb_encode_serial(ctx, A, Ps[0]);
+    }
+    return fb_encode_pipelined(cs, A, Ps, chunk);
 }
 
 } // namespace
@@ -972,9 +1071,178 @@ int fb200_analyze(fb200_ctx *ctx, const void *pcm, int container_bytes, uint64_t
     return fb_encode(ctx, A);
 }
 
-// encode_with_fixed_block_size (src/coding.rs:645-695) with par.rs-style sharding: contiguous frame
-// ranges over the devices (one host thread + context per device), MD5 on its own host thread
-// (src/par.rs:196-277), STREAMINFO finalised on the calling thread.
+// Same hot path over several devices: ctxs[0..n_ctx) are contexts of one configuration and stream format on different
+// devices; the frames are shared by frame range (chunk c on device c mod n_ctx, what src/par.rs:355-449 does with
+// worker threads) and every chunk's bytes land at their final offset in out_bytes.  No collective is involved.
+int fb200_encode_interleaved_sharded(fb200_ctx *const *ctxs, int n_ctx, const void *pcm, int container_bytes,
+                                     uint64_t n_samples_per_ch, uint64_t first_frame_number, uint8_t *out_bytes,
+                                     size_t out_cap, uint32_t *frame_sizes, size_t *n_frames, size_t *out_len) {
+    if (!ctxs || n_ctx < 1 || n_ctx > 64 || (!pcm && n_samples_per_ch) || (!out_bytes && out_cap)) return FB200_ERR_SOURCE;
+    std::vector<fb200_ctx *> cs;
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i]) return FB200_ERR_SOURCE;
+        for (fb200_ctx *c : cs)
+            if (c == ctxs[i]) return FB200_ERR_SOURCE; // a context can take part once
+        cs.push_back(ctxs[i]);
+    }
+    EncodeArgs A;
+    A.pcm_host = pcm;
+    A.container_bytes = container_bytes;
+    A.n_samples = n_samples_per_ch;
+    A.first_frame = first_frame_number;
+    A.out_host = out_bytes;
+    A.out_cap = out_cap;
+    A.frame_sizes = frame_sizes;
+    A.n_frames = n_frames;
+    A.out_len = out_len;
+    return fb_encode_multi(cs, A);
+}
+
+} // extern "C"
+
+namespace {
+
+// ---- contexts kept between stream-level calls (the reference keeps its scratch in thread-local `reusable!` storage,
+// src/lib.rs:92-116): device buffers, window and CRC tables are built once per (config, format, device)
+struct PoolEntry {
+    fb200_config cfg;
+    int channels, bps, rate, block, device;
+    fb200_ctx *ctx;
+};
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool; // idle contexts
+const size_t FB_POOL_MAX = 16;
+
+fb200_ctx *fb_pool_acquire(const fb200_config *cfg, int channels, int bps, int rate, int block, int device, int *err) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            PoolEntry &e = g_pool[i];
+            if (memcmp(&e.cfg, cfg, sizeof(*cfg)) == 0 && e.channels == channels && e.bps == bps && e.rate == rate &&
+                e.block == block && e.device == device) {
+                fb200_ctx *c = e.ctx;
+                g_pool.erase(g_pool.begin() + (long)i);
+                *err = FB200_OK;
+                return c;
+            }
+        }
+    }
+    return fb200_create(cfg, channels, bps, rate, block, device, err);
+}
+
+void fb_pool_release(fb200_ctx *ctx) {
+    if (!ctx) return;
+    fb200_ctx *victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        g_pool.push_back({ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, ctx->device, ctx});
+        if (g_pool.size() > FB_POOL_MAX) {
+            victim = g_pool.front().ctx;
+            g_pool.erase(g_pool.begin());
+        }
+    }
+    if (victim) fb200_destroy(victim);
+}
+
+// MD5 over the packed little-endian samples of ceil(bps/8) bytes (src/source.rs:406-429)
+void fb_md5_of_pcm(const void *pcm, int container_bytes, int bits_per_sample, uint64_t count, uint8_t md5[16]) {
+    FbMd5 h;
+    const int bytes_per_sample = (bits_per_sample + 7) / 8;
+    if (bytes_per_sample == container_bytes) {
+        h.update((const uint8_t *)pcm, (size_t)(count * (uint64_t)container_bytes));
+    } else if (container_bytes == 4 && bytes_per_sample == 2) {
+        // int32 samples (Fill::fill_interleaved): packed to 16 bits in cache-sized pieces right before they are hashed
+        uint16_t tmp[4096];
+        const int32_t *p = (const int32_t *)pcm;
+        for (uint64_t i = 0; i < count; i += 4096) {
+            const size_t m = (size_t)std::min<uint64_t>(4096, count - i);
+            for (size_t k = 0; k < m; k++) tmp[k] = (uint16_t)p[i + k];
+            h.update((const uint8_t *)tmp, 2 * m);
+        }
+    } else {
+        uint8_t tmp[3 * 4096];
+        size_t k = 0;
+        const uint8_t *p = (const uint8_t *)pcm;
+        for (uint64_t i = 0; i < count; i++) {
+            for (int b = 0; b < bytes_per_sample; b++) tmp[k++] = p[i * (uint64_t)container_bytes + (uint64_t)b];
+            if (k + 4 > sizeof(tmp)) { h.update(tmp, k); k = 0; }
+        }
+        if (k) h.update(tmp, k);
+    }
+    h.finish(md5);
+}
+
+// "fLaC" + STREAMINFO in front of frames that already sit at out + 42
+// (src/component/datatype.rs:514-523, src/coding.rs:676-693, src/component/bitrepr.rs:240-267)
+void fb_write_stream_header(uint8_t *p, const uint32_t *sizes, uint64_t n_frames, uint64_t n_samples, int channels,
+                            int bits_per_sample, int sample_rate, int block_size, const uint8_t md5[16]) {
+    const uint64_t bs = (uint64_t)block_size;
+    uint32_t min_block = 0xFFFF, max_block = 0, min_frame = 0xFFFFFFFFu, max_frame = 0;
+    for (uint64_t fi = 0; fi < n_frames; fi++) {
+        const uint32_t b = (uint32_t)std::min<uint64_t>(bs, n_samples - fi * bs);
+        min_block = std::min(min_block, b);
+        max_block = std::max(max_block, b);
+        min_frame = std::min(min_frame, sizes[fi]);
+        max_frame = std::max(max_frame, sizes[fi]);
+    }
+    if (n_frames > 0) min_block = max_block;
+    memcpy(p, "fLaC", 4);
+    p[4] = 0x80; p[5] = 0; p[6] = 0; p[7] = 34;
+    p[8] = (uint8_t)(min_block >> 8); p[9] = (uint8_t)min_block;
+    p[10] = (uint8_t)(max_block >> 8); p[11] = (uint8_t)max_block;
+    p[12] = (uint8_t)(min_frame >> 16); p[13] = (uint8_t)(min_frame >> 8); p[14] = (uint8_t)min_frame;
+    p[15] = (uint8_t)(max_frame >> 16); p[16] = (uint8_t)(max_frame >> 8); p[17] = (uint8_t)max_frame;
+    // 20 bits rate | 3 bits channels-1 | 5 bits bps-1 | 36 bits total samples
+    const uint64_t v = ((uint64_t)(uint32_t)sample_rate << 44) | ((uint64_t)(channels - 1) << 41) |
+                       ((uint64_t)(bits_per_sample - 1) << 36) | (n_samples & 0xFFFFFFFFFull);
+    for (int i = 0; i < 8; i++) p[18 + i] = (uint8_t)(v >> (56 - 8 * i));
+    memcpy(p + 26, md5, 16);
+}
+
+// the frames of one stream into out + 42 over the given devices (pooled contexts); *frames_len = their bytes
+int fb_stream_frames(const fb200_config *cfg, const void *pcm, int container_bytes, uint64_t n_samples, int channels,
+                     int bits_per_sample, int sample_rate, int block_size, const int *devices, int nd, uint8_t *out,
+                     size_t out_cap, std::vector<uint32_t> &sizes, size_t *frames_len) {
+    *frames_len = 0;
+    if (n_samples == 0) return FB200_OK;
+    std::vector<fb200_ctx *> cs;
+    int rc = FB200_OK;
+    for (int d = 0; d < nd && rc == FB200_OK; d++) {
+        bool dup = false;
+        for (int k = 0; k < d; k++) dup |= devices[k] == devices[d];
+        if (dup) continue; // a device listed twice works once
+        int err = 0;
+        fb200_ctx *c = fb_pool_acquire(cfg, channels, bits_per_sample, sample_rate, block_size, devices[d], &err);
+        if (!c) rc = err ? err : FB200_ERR_CUDA;
+        else cs.push_back(c);
+    }
+    if (rc == FB200_OK) {
+        EncodeArgs A;
+        A.pcm_host = pcm;
+        A.container_bytes = container_bytes;
+        A.n_samples = n_samples;
+        A.out_host = out + 42;
+        A.out_cap = out_cap - 42;
+        A.frame_sizes = sizes.data();
+        size_t nf = 0;
+        A.n_frames = &nf;
+        A.out_len = frames_len;
+        rc = fb_encode_multi(cs, A);
+        if (rc) g_stream_error = cs[0]->last_error;
+    } else {
+        g_stream_error = "could not create a context on one of the devices";
+    }
+    for (fb200_ctx *c : cs) fb_pool_release(c);
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+// encode_with_fixed_block_size (src/coding.rs:645-695) with par.rs-style sharding: frame ranges over the devices,
+// MD5 on its own host thread (src/par.rs:196-277) next to the device work, STREAMINFO finalised on the calling thread.
+// The frames are encoded straight into `out` behind the 42 header bytes; contexts are kept between calls.
 int fb200_encode_stream(const fb200_config *cfg, const void *pcm, int container_bytes, uint64_t n_samples,
                         int channels, int bits_per_sample, int sample_rate, int block_size, const int *devices,
                         int n_devices, uint8_t *out, size_t out_cap, size_t *out_len) {
@@ -989,101 +1257,91 @@ int fb200_encode_stream(const fb200_config *cfg, const void *pcm, int container_
     const uint64_t bs = (uint64_t)block_size;
     const uint64_t n_frames = (n_samples + bs - 1) / bs;
     if (n_frames > (1ull << 31)) return FB200_ERR_CONFIG;
-    const int nd = (int)std::min<uint64_t>((uint64_t)n_devices, std::max<uint64_t>(n_frames, 1));
 
-    // MD5 over the packed little-endian samples of ceil(bps/8) bytes (src/source.rs:406-429)
     uint8_t md5[16];
-    std::thread md5_thread([&] {
-        FbMd5 h;
-        const int bytes_per_sample = (bits_per_sample + 7) / 8;
-        const uint64_t count = n_samples * (uint64_t)channels;
-        if (bytes_per_sample == container_bytes) {
-            h.update((const uint8_t *)pcm, (size_t)(count * (uint64_t)container_bytes));
-        } else {
-            uint8_t tmp[3 * 4096];
-            size_t k = 0;
-            const uint8_t *p = (const uint8_t *)pcm;
-            for (uint64_t i = 0; i < count; i++) {
-                for (int b = 0; b < bytes_per_sample; b++) tmp[k++] = p[i * (uint64_t)container_bytes + (uint64_t)b];
-                if (k + 4 > sizeof(tmp)) { h.update(tmp, k); k = 0; }
-            }
-            if (k) h.update(tmp, k);
-        }
-        h.finish(md5);
-    });
-
-    struct Shard {
-        uint64_t f0 = 0, nf = 0;
-        std::vector<uint8_t> bytes;
-        std::vector<uint32_t> sizes;
-        size_t len = 0;
-        int rc = FB200_OK;
-    };
-    std::vector<Shard> shards((size_t)nd);
-    std::vector<std::thread> workers;
-    const size_t max_frame_bytes = fb_max_frame_bytes(channels, bits_per_sample, block_size);
-    for (int d = 0; d < nd; d++) {
-        Shard &S = shards[(size_t)d];
-        S.f0 = (n_frames * (uint64_t)d + (uint64_t)nd - 1) / (uint64_t)nd; // ceil(F*g/G), SURVEY.md 8(e)
-        uint64_t f1 = (n_frames * (uint64_t)(d + 1) + (uint64_t)nd - 1) / (uint64_t)nd;
-        S.nf = f1 - S.f0;
-        if (S.nf == 0) continue;
-        workers.emplace_back([&, d] {
-            Shard &S2 = shards[(size_t)d];
-            int err = 0;
-            fb200_ctx *ctx = fb200_create(cfg, channels, bits_per_sample, sample_rate, block_size, devices[d], &err);
-            if (!ctx) { S2.rc = err; return; }
-            const uint64_t s0 = S2.f0 * bs;
-            const uint64_t ns = std::min(n_samples - s0, S2.nf * bs);
-            S2.bytes.resize((size_t)(S2.nf * max_frame_bytes));
-            S2.sizes.resize((size_t)S2.nf);
-            size_t nf_out = 0;
-            S2.rc = fb200_encode_interleaved(
-                ctx, (const uint8_t *)pcm + s0 * (uint64_t)channels * (uint64_t)container_bytes, container_bytes, ns,
-                S2.f0, S2.bytes.data(), S2.bytes.size(), S2.sizes.data(), nullptr, &nf_out, &S2.len);
-            fb200_destroy(ctx);
-        });
-    }
-    for (auto &w : workers) w.join();
+    std::thread md5_thread([&] { fb_md5_of_pcm(pcm, container_bytes, bits_per_sample, n_samples * (uint64_t)channels, md5); });
+    std::vector<uint32_t> sizes((size_t)std::max<uint64_t>(n_frames, 1));
+    size_t frames_len = 0;
+    rc = fb_stream_frames(cfg, pcm, container_bytes, n_samples, channels, bits_per_sample, sample_rate, block_size, devices,
+                          n_devices, out, out_cap, sizes, &frames_len);
     md5_thread.join();
-    for (auto &S : shards)
-        if (S.rc) return S.rc;
-
-    // STREAMINFO (src/component/datatype.rs:514-523, src/coding.rs:676-693, src/component/bitrepr.rs:240-267)
-    uint32_t min_block = 0xFFFF, max_block = 0, min_frame = 0xFFFFFFFFu, max_frame = 0;
-    size_t total = 42;
-    for (auto &S : shards) {
-        for (uint64_t i = 0; i < S.nf; i++) {
-            uint64_t fi = S.f0 + i;
-            uint32_t b = (uint32_t)std::min<uint64_t>(bs, n_samples - fi * bs);
-            min_block = std::min(min_block, b);
-            max_block = std::max(max_block, b);
-            min_frame = std::min(min_frame, S.sizes[(size_t)i]);
-            max_frame = std::max(max_frame, S.sizes[(size_t)i]);
-        }
-        total += S.len;
-    }
-    if (n_frames > 0) min_block = max_block;
-    if (out_len) *out_len = total;
-    if (total > out_cap) return FB200_ERR_CAPACITY;
-    uint8_t *p = out;
-    memcpy(p, "fLaC", 4);
-    p[4] = 0x80; p[5] = 0; p[6] = 0; p[7] = 34;
-    p[8] = (uint8_t)(min_block >> 8); p[9] = (uint8_t)min_block;
-    p[10] = (uint8_t)(max_block >> 8); p[11] = (uint8_t)max_block;
-    p[12] = (uint8_t)(min_frame >> 16); p[13] = (uint8_t)(min_frame >> 8); p[14] = (uint8_t)min_frame;
-    p[15] = (uint8_t)(max_frame >> 16); p[16] = (uint8_t)(max_frame >> 8); p[17] = (uint8_t)max_frame;
-    // 20 bits rate | 3 bits channels-1 | 5 bits bps-1 | 36 bits total samples
-    uint64_t v = ((uint64_t)(uint32_t)sample_rate << 44) | ((uint64_t)(channels - 1) << 41) |
-                 ((uint64_t)(bits_per_sample - 1) << 36) | (n_samples & 0xFFFFFFFFFull);
-    for (int i = 0; i < 8; i++) p[18 + i] = (uint8_t)(v >> (56 - 8 * i));
-    memcpy(p + 26, md5, 16);
-    size_t o = 42;
-    for (auto &S : shards) {
-        if (S.len) memcpy(out + o, S.bytes.data(), S.len);
-        o += S.len;
-    }
+    if (out_len) *out_len = 42 + frames_len;
+    if (rc) return rc;
+    fb_write_stream_header(out, sizes.data(), n_frames, n_samples, channels, bits_per_sample, sample_rate, block_size, md5);
     return FB200_OK;
+}
+
+// A batch of streams of one format (the 10 h / 8-channel batch of BASELINE config 5 is many files): one MD5 thread per
+// stream, all started up front and bounded by the host's cores, while the calling thread feeds the devices stream by
+// stream.  rcs[i] (nullable) receives every stream's result; the call returns the first failure.
+int fb200_encode_streams(const fb200_config *cfg, int n_streams, const void *const *pcm, const uint64_t *n_samples,
+                         int container_bytes, int channels, int bits_per_sample, int sample_rate, int block_size,
+                         const int *devices, int n_devices, uint8_t *const *out, const size_t *out_cap, size_t *out_len,
+                         int *rcs) {
+    if (!cfg || n_streams < 0 || (n_streams && (!pcm || !n_samples || !out || !out_cap))) return FB200_ERR_SOURCE;
+    int rc = fbh_config_verify(cfg);
+    if (rc) return rc;
+    if ((rc = fbh_format_verify(channels, bits_per_sample, sample_rate, block_size))) return rc;
+    if (container_bytes < 1 || container_bytes > 4 || container_bytes * 8 < bits_per_sample) return FB200_ERR_SOURCE;
+    int dev0 = 0;
+    if (!devices || n_devices <= 0) { devices = &dev0; n_devices = 1; }
+    std::vector<std::array<uint8_t, 16>> md5((size_t)n_streams);
+    // MD5 workers: streams are claimed in order by min(streams, cores) threads
+    std::atomic<int> next(0);
+    const int nthreads = std::max(1, std::min<int>(n_streams, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; w++)
+        pool.emplace_back([&] {
+            for (int i = next.fetch_add(1); i < n_streams; i = next.fetch_add(1))
+                if (pcm[i] || n_samples[i] == 0)
+                    fb_md5_of_pcm(pcm[i], container_bytes, bits_per_sample, n_samples[i] * (uint64_t)channels, md5[(size_t)i].data());
+        });
+    int first_rc = FB200_OK;
+    std::vector<std::vector<uint32_t>> sizes((size_t)n_streams);
+    std::vector<size_t> flen((size_t)n_streams, 0);
+    std::vector<int> src((size_t)n_streams, FB200_OK);
+    for (int i = 0; i < n_streams; i++) {
+        int r = FB200_OK;
+        const uint64_t nf = (n_samples[i] + (uint64_t)block_size - 1) / (uint64_t)block_size;
+        if ((!pcm[i] && n_samples[i]) || !out[i]) r = FB200_ERR_SOURCE;
+        else if (out_cap[i] < 42) r = FB200_ERR_CAPACITY;
+        else if (nf > (1ull << 31)) r = FB200_ERR_CONFIG;
+        else {
+            sizes[(size_t)i].resize((size_t)std::max<uint64_t>(nf, 1));
+            r = fb_stream_frames(cfg, pcm[i], container_bytes, n_samples[i], channels, bits_per_sample, sample_rate, block_size,
+                                 devices, n_devices, out[i], out_cap[i], sizes[(size_t)i], &flen[(size_t)i]);
+        }
+        src[(size_t)i] = r;
+        if (r && first_rc == FB200_OK) first_rc = r;
+    }
+    for (auto &t : pool) t.join();
+    for (int i = 0; i < n_streams; i++) {
+        if (out_len) out_len[i] = src[(size_t)i] == FB200_OK || src[(size_t)i] == FB200_ERR_CAPACITY ? 42 + flen[(size_t)i] : 0;
+        if (rcs) rcs[i] = src[(size_t)i];
+        if (src[(size_t)i] == FB200_OK) {
+            const uint64_t nf = (n_samples[i] + (uint64_t)block_size - 1) / (uint64_t)block_size;
+            fb_write_stream_header(out[i], sizes[(size_t)i].data(), nf, n_samples[i], channels, bits_per_sample, sample_rate,
+                                   block_size, md5[(size_t)i].data());
+        }
+    }
+    return first_rc;
+}
+
+// MD5 of a byte range with the library's own implementation (the floor of every stream-level call: sequential host work)
+void fb200_md5(const void *data, size_t len, uint8_t digest[16]) {
+    FbMd5 h;
+    h.update((const uint8_t *)data, len);
+    h.finish(digest);
+}
+
+// destroys the contexts kept by the stream-level calls
+void fb200_pool_clear(void) {
+    std::vector<PoolEntry> victims;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        victims.swap(g_pool);
+    }
+    for (PoolEntry &e : victims) fb200_destroy(e.ctx);
 }
 
 } // extern "C"

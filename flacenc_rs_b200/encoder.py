@@ -82,11 +82,17 @@ class Stream:
     """component::Stream: STREAMINFO + frames; ``write()`` yields the .flac bytes
     (src/component/bitrepr.rs:172-197)."""
 
-    def __init__(self, data: bytes):
-        self._data = data
+    def __init__(self, data):
+        self._data = data  # bytes, or the uint8 array the library filled (no copy until write() is asked for bytes)
 
     def write(self) -> bytes:
+        if not isinstance(self._data, bytes):
+            self._data = self._data.tobytes()
         return self._data
+
+    def as_array(self) -> np.ndarray:
+        """the stream bytes as a uint8 array, without a copy when the library's output buffer is still held"""
+        return np.frombuffer(self._data, np.uint8) if isinstance(self._data, bytes) else self._data
 
     def count_bits(self) -> int:
         return len(self._data) * 8
@@ -216,15 +222,13 @@ def encode_with_fixed_block_size(config: Verified, src: MemSource, block_size: i
     lib = _ffi.lib()
     ch, bps, rate = src.channels(), src.bits_per_sample(), src.sample_rate()
     n = len(src)
-    cb = (bps + 7) // 8
+    # the int32 samples go to the library as they are (container 4 = Fill::fill_interleaved); its MD5 thread packs them
+    # to ceil(bps / 8) bytes piece by piece (src/source.rs:406-418), so no packed copy of the stream is ever made here
+    cb = 4
+    # (nothing is truncated on the way: FrameBuf::verify_samples, src/source.rs:262-275, is the ingest kernel's range
+    # check on the true int32 values -> VerifyError)
     samples = np.ascontiguousarray(src.as_interleaved(), np.int32)
-    # FrameBuf::verify_samples (src/source.rs:262-275): packing below truncates to the container, so values outside
-    # the range of bits_per_sample must be rejected here -- the device's range check only sees what survives packing
-    if samples.size:
-        lo, hi = -(1 << (bps - 1)), (1 << (bps - 1)) - 1
-        if int(samples.min()) < lo or int(samples.max()) > hi:
-            raise VerifyError("input.framebuf", f"input sample must be in the range of bits={bps}")
-    pcm = pack_samples(samples, cb)
+    pcm = samples.reshape(-1)
     n_frames = (n + block_size - 1) // block_size
     cap = 64 + n_frames * (32 + ch * ((block_size * (bps + 1) + 7) // 8 + 2))
     out = np.empty(cap, np.uint8)
@@ -234,8 +238,65 @@ def encode_with_fixed_block_size(config: Verified, src: MemSource, block_size: i
     pod = config.pod
     rc = lib.fb200_encode_stream(C.byref(pod), pcm.ctypes.data, cb, n, ch, bps, rate, block_size, dev_arr, len(devs),
                                  out.ctypes.data, cap, C.byref(olen))
-    raise_for_code(rc, "fb200_encode_stream")
-    return Stream(out[: olen.value].tobytes())
+    raise_for_code(rc, "fb200_encode_stream: " + (lib.fb200_last_error(None) or b"").decode())
+    return Stream(out[: olen.value])
+
+
+def encode_streams_with_fixed_block_size(config: Verified, sources: Sequence[MemSource], block_size: int,
+                                         devices: Optional[Sequence[int]] = None) -> List[Stream]:
+    """A batch of sources of ONE format (fb200_encode_streams): what calling ``encode_with_fixed_block_size`` per file
+    does, with the MD5 of every stream on its own host thread (src/par.rs:196-277) while the devices are fed stream by
+    stream."""
+    if not isinstance(config, Verified):
+        raise TypeError("config must be Verified (use Encoder().into_verified())")
+    if not sources:
+        return []
+    lib = _ffi.lib()
+    ch, bps, rate = sources[0].channels(), sources[0].bits_per_sample(), sources[0].sample_rate()
+    pcms, outs, ns = [], [], []
+    for src in sources:
+        if (src.channels(), src.bits_per_sample(), src.sample_rate()) != (ch, bps, rate):
+            raise ValueError("all sources of a batch must share channels, bits_per_sample and sample_rate")
+        x = np.ascontiguousarray(src.as_interleaved(), np.int32).reshape(-1)  # range-checked on the device
+        n = len(src)
+        n_frames = (n + block_size - 1) // block_size
+        pcms.append(x)
+        ns.append(n)
+        outs.append(np.empty(64 + n_frames * (32 + ch * ((block_size * (bps + 1) + 7) // 8 + 2)), np.uint8))
+    k = len(sources)
+    pcm_arr = (C.c_void_p * k)(*[x.ctypes.data for x in pcms])
+    out_arr = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+    n_arr = (C.c_uint64 * k)(*ns)
+    cap_arr = (C.c_size_t * k)(*[len(o) for o in outs])
+    len_arr = (C.c_size_t * k)()
+    rc_arr = (C.c_int * k)()
+    devs = list(devices) if devices else [0]
+    dev_arr = (C.c_int * len(devs))(*devs)
+    pod = config.pod
+    rc = lib.fb200_encode_streams(C.byref(pod), k, pcm_arr, n_arr, 4, ch, bps, rate, block_size, dev_arr, len(devs), out_arr,
+                                  cap_arr, len_arr, rc_arr)
+    raise_for_code(rc, "fb200_encode_streams: " + (lib.fb200_last_error(None) or b"").decode())
+    return [Stream(outs[i][: len_arr[i]]) for i in range(k)]
+
+
+def encode_interleaved_sharded(contexts: Sequence[Context], pcm, container_bytes: int, n_samples: int,
+                               first_frame_number: int = 0, out: Optional[np.ndarray] = None):
+    """fb200_encode_interleaved_sharded: one batch over the devices of ``contexts`` by frame range (src/par.rs:355-449);
+    returns (frame bytes view, frame sizes).  ``contexts[0].timing()`` describes the call."""
+    c0 = contexts[0]
+    buf = np.ascontiguousarray(pcm).view(np.uint8).reshape(-1)
+    n_frames = (n_samples + c0.block_size - 1) // c0.block_size
+    cap = max(16, n_frames * c0.max_frame_bytes())
+    if out is None or len(out) < cap:
+        out = np.empty(cap, np.uint8)
+    sizes = np.zeros(max(n_frames, 1), np.uint32)
+    handles = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    nf, olen = C.c_size_t(0), C.c_size_t(0)
+    rc = c0._lib.fb200_encode_interleaved_sharded(handles, len(contexts), buf.ctypes.data, container_bytes, n_samples,
+                                                  first_frame_number, out.ctypes.data, len(out), sizes.ctypes.data,
+                                                  C.byref(nf), C.byref(olen))
+    raise_for_code(rc, c0._err())
+    return out[: olen.value], sizes[: nf.value]
 
 
 # The reference calls encode_fixed_size_frame in its inner loop (src/par.rs:384-389) and keeps all scratch in

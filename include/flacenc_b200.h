@@ -164,6 +164,15 @@ int fb200_encode_planar_frame(fb200_ctx *ctx, const int32_t *planar, int stride,
 int fb200_analyze(fb200_ctx *ctx, const void *pcm, int container_bytes, uint64_t n_samples_per_ch,
                   fb200_variant_taps *taps, size_t taps_cap, size_t *n_variants);
 
+/* The same over several devices of one box: ctxs[0..n_ctx) are contexts of ONE configuration and stream format on
+ * different devices.  Frames are independent, so they are shared by frame range -- chunk c of the batch goes to
+ * device c mod n_ctx, each device with its own copy / compute streams, what src/par.rs:355-449 does with worker
+ * threads -- and every chunk's bytes are copied straight to their final offset in out_bytes.  No collective.
+ * fb200_last_timing(ctxs[0]) reports the call: total_ms = the longest per-device span, kernel times summed. */
+int fb200_encode_interleaved_sharded(fb200_ctx *const *ctxs, int n_ctx, const void *pcm, int container_bytes,
+                                     uint64_t n_samples_per_ch, uint64_t first_frame_number, uint8_t *out_bytes,
+                                     size_t out_cap, uint32_t *frame_sizes, size_t *n_frames, size_t *out_len);
+
 /* ---- stream level: host assembly around the hot path ---- */
 /* Replaces encode_with_fixed_block_size end to end (src/coding.rs:645-695): "fLaC" + STREAMINFO
  * (min/max block and frame size, total samples, MD5 of the packed LE samples, src/source.rs:406-429)
@@ -174,6 +183,21 @@ int fb200_encode_stream(const fb200_config *cfg, const void *pcm, int container_
                         uint64_t n_samples_per_ch, int channels, int bits_per_sample, int sample_rate,
                         int block_size, const int *devices, int n_devices,
                         uint8_t *out, size_t out_cap, size_t *out_len);
+
+/* A batch of streams of one format (src/par.rs:196-277 runs one MD5 thread per stream; a batch of files gives as many
+ * independent MD5 chains as there are files): the MD5 of every stream runs on its own host thread, bounded by the
+ * host's cores, while the calling thread feeds the devices stream by stream.  pcm[i] / n_samples[i] / out[i] /
+ * out_cap[i] describe stream i; out_len[i] and rcs[i] (nullable) receive its length and result.  Returns the first
+ * failure (FB200_OK if none). */
+int fb200_encode_streams(const fb200_config *cfg, int n_streams, const void *const *pcm, const uint64_t *n_samples,
+                         int container_bytes, int channels, int bits_per_sample, int sample_rate, int block_size,
+                         const int *devices, int n_devices, uint8_t *const *out, const size_t *out_cap, size_t *out_len,
+                         int *rcs);
+/* MD5 (RFC 1321) of a byte range with the library's implementation: the sequential floor of the stream-level calls. */
+void fb200_md5(const void *data, size_t len, uint8_t digest[16]);
+/* The stream-level calls keep their device contexts between calls (like the reference's thread-local scratch,
+ * src/lib.rs:92-116); this destroys them. */
+void fb200_pool_clear(void);
 
 /* ---- parity pins (diagnostics) ----
  * Device builds of the two scalar float helpers whose last bit decides encoder choices, evaluated on
@@ -186,7 +210,8 @@ int fb200_debug_find_shift(int device, const double *values, uint64_t count, int
 /* ---- diagnostics ---- */
 int  fb200_last_timing(const fb200_ctx *ctx, fb200_timing *t);
 const char *fb200_strerror(int code);
-const char *fb200_last_error(const fb200_ctx *ctx); /* detail text of the last failure on ctx */
+const char *fb200_last_error(const fb200_ctx *ctx); /* detail text of the last failure on ctx; ctx == NULL: of the last
+                                                       failed stream-level call on the calling thread */
 const char *fb200_version(void);
 
 #ifdef __cplusplus

@@ -425,9 +425,8 @@ def test_encode_with_fixed_block_size_stream():
 
 
 def test_stream_sharded_over_devices():
-    """fb200_encode_stream with a device list: contiguous frame ranges per device (one host thread + context each, no
-    collective), concatenated in order; min/max frame size merged.  With one visible GPU the list repeats device 0,
-    which still exercises the sharding arithmetic (3 shards of a 29-frame stream, short tail)."""
+    """fb200_encode_stream with a device list: frame ranges shared by the devices (chunk c on device c mod N, no
+    collective), bytes placed in order; min/max frame size over all frames.  A device listed twice works once."""
     ndev = _ffi.lib().fb200_device_count()
     devices = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
     n = 1024 * 28 + 300
@@ -438,6 +437,68 @@ def test_stream_sharded_over_devices():
     assert stream.write() == ref
     out, info = O.decode_stream(stream.write())
     assert np.array_equal(out, signal) and info.total_samples == n
+
+
+@pytest.mark.parametrize("n_ctx,chunk", [(2, 7), (3, 5), (5, 64)])
+def test_frame_range_sharding_over_contexts(monkeypatch, n_ctx, chunk):
+    """fb200_encode_interleaved_sharded: chunk c of the batch is encoded by context c mod N with that context's own
+    streams and buffer sets, and its bytes land at their final offset (the offset of a chunk is only known once the
+    chunks before it are done).  Contexts on different devices when the box has them; several contexts on one
+    device exercise exactly the same hand-over logic.  Bytes, sizes and order must equal the oracle's."""
+    from flacenc_rs_b200.encoder import encode_interleaved_sharded
+    monkeypatch.setenv("FB200_CHUNK_FRAMES", str(chunk))
+    ndev = max(1, _ffi.lib().fb200_device_count())
+    vcfg = Encoder().into_verified()
+    n = 1024 * 61 + 333
+    x = sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=31)
+    ref, ref_sizes = O.encode_frames(O.default_config(), x, 2, 16, 44100, 1024, first_frame_number=3)
+    ctxs = [Context(vcfg, 2, 16, 44100, 1024, device=i % ndev) for i in range(n_ctx)]
+    try:
+        for _ in range(2):  # the second call reuses the buffer sets
+            got, sizes = encode_interleaved_sharded(ctxs, pack_pcm(x, 2), 2, n, 3)
+            assert list(sizes) == list(ref_sizes)
+            assert got.tobytes() == ref
+        t = ctxs[0].timing()
+        assert t.fused_frames == 62 and t.total_ms > 0
+        # a late out-of-range sample is still a VerifyError, and the contexts stay usable
+        bad = x.copy()
+        bad[1024 * 50 + 5, 0] = 40000
+        with pytest.raises(VerifyError):
+            encode_interleaved_sharded(ctxs, pack_pcm(bad, 4), 4, n, 3)
+        got, sizes = encode_interleaved_sharded(ctxs, pack_pcm(x, 4), 4, n, 3)
+        assert got.tobytes() == ref
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_stream_api_rejects_samples_outside_bits_per_sample():
+    """FrameBuf::verify_samples (/root/reference/src/source.rs:262-275): a sample that does not fit bits_per_sample is a
+    VerifyError -- also one that packing to ceil(bps / 8) bytes would silently wrap (40000 at 16 bits -> -25536): the
+    stream-level mirror hands the int32 samples to the library unpacked, so the device's range check sees true values."""
+    from flacenc_rs_b200.encoder import encode_streams_with_fixed_block_size
+    for bps, bad in ((16, 40000), (16, -32769), (8, 128), (24, 1 << 23), (12, 2048), (12, -2049)):
+        x = np.zeros((300, 2), np.int32)
+        x[123, 1] = bad
+        with pytest.raises(VerifyError):
+            encode_with_fixed_block_size(Encoder().into_verified(), MemSource.from_samples(x, 2, bps, 44100), 128)
+        with pytest.raises(VerifyError):
+            encode_streams_with_fixed_block_size(Encoder().into_verified(), [MemSource.from_samples(x, 2, bps, 44100)], 128)
+
+
+def test_batch_of_streams():
+    """fb200_encode_streams: every stream of a batch equals the oracle's stream (MD5 threads run next to the device
+    work); lengths differ, one stream is shorter than a block"""
+    from flacenc_rs_b200.encoder import encode_streams_with_fixed_block_size
+    ndev = max(1, _ffi.lib().fb200_device_count())
+    lens = [4096 * 9 + 17, 100, 4096 * 3, 4096 * 20 + 4000, 4096]
+    sigs = [sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=40 + i) for i, n in enumerate(lens)]
+    srcs = [MemSource.from_samples(sg, 2, 16, 44100) for sg in sigs]
+    streams = encode_streams_with_fixed_block_size(Encoder().into_verified(), srcs, 4096, devices=list(range(min(ndev, 2))))
+    assert len(streams) == len(lens)
+    for sg, st in zip(sigs, streams):
+        assert st.write() == O.encode_stream(O.default_config(), sg, 2, 16, 44100, 4096)
+    _ffi.lib().fb200_pool_clear()
 
 
 def test_device_resident_api_matches_host_api():

@@ -67,18 +67,6 @@ def test_no_device_means_error_not_fallback():
     assert not h and err.value == _ffi.ERR_CUDA
 
 
-def test_stream_api_rejects_samples_outside_bits_per_sample():
-    """FrameBuf::verify_samples (/root/reference/src/source.rs:262-275): a sample that does not fit bits_per_sample is a
-    VerifyError -- also when packing to the container would silently wrap it (40000 at 16 bits -> -25536).  The check
-    runs on the host before any device call, so it is testable here."""
-    from flacenc_rs_b200.encoder import encode_with_fixed_block_size
-    for bps, bad in ((16, 40000), (16, -32769), (8, 128), (24, 1 << 23), (12, 2048), (12, -2049)):
-        x = np.zeros((300, 2), np.int32)
-        x[123, 1] = bad
-        with pytest.raises(VerifyError):
-            encode_with_fixed_block_size(Encoder().into_verified(), MemSource.from_samples(x, 2, bps, 44100), 128)
-
-
 def test_config_default_matches_reference_defaults():
     """config::Encoder::default() (src/config.rs:97-107 and children)."""
     cfg = _ffi.Config()

@@ -58,4 +58,36 @@ try:
 except Exception as e:  # noqa: BLE001
     out.append(f"\n(launch list unavailable: {e})\n")
 open(f"profiles/{tag}_ncu_summary.md", "w").write("".join(out))
+
+# machine-readable numbers for bench.py (roofline.traffic, issue_roofline): first launch of each heavy kernel
+import json
+roles = {"fb_k0_ingest": "ingest", "fb_k1_analyze": "analyze", "fb_ka_plan": "plan", "fb_kp_pack": "pack"}
+col = {k: hdr.index(k) for k in ("launch__grid_size", "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                  "gpu__time_duration.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active") if k in hdr}
+
+
+def num(r, k):
+    v = float(r[col[k]].replace(",", ""))
+    u = units[col[k]]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6}.get(u, 1.0)
+    return v * scale
+
+
+frames = None
+for r, name in zip(body, names):
+    if name.startswith("fb_ka_plan") or name.startswith("fb_kp_pack"):
+        frames = int(num(r, "launch__grid_size"))
+        break
+kern = {}
+for r, name in zip(body, names):
+    role = next((v for k, v in roles.items() if name.startswith(k)), None)
+    if role is None or role in kern:
+        continue
+    kern[role] = {"kernel": name, "frames": frames, "warp_inst": num(r, "smsp__inst_executed.sum"),
+                  "dram_bytes": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"),
+                  "time_ms": num(r, "gpu__time_duration.sum"),
+                  "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")}
+json.dump({"tag": tag, "source": f"profiles/{tag}_ncu_summary.md (ncu --set full --clock-control none, first launch of each kernel "
+                                 "of `python bench.py --steps 1 --warmup 1`)", "kernels": kern},
+          open("profiles/ncu_metrics.json", "w"), indent=1)
 print("".join(out))
