@@ -640,8 +640,11 @@ def main() -> None:
             sh_steps.append(round(tm.total_ms, 3))
         wall_sh = time.perf_counter() - ws
         same = len(got2) == out_len_h and np.array_equal(got2, h_out[:out_len_h]) and np.array_equal(sizes2, host_sizes[0])
+        # the copies of ONE stream spread over N devices cannot beat the box's duplex ceiling at this N either
+        sh_floor = max(in_bytes / (world * ceiling["h2d_gbs_per_gpu"] * 1e6), out_len / (world * ceiling["d2h_gbs_per_gpu"] * 1e6))
         sharded = {"value": float(n) * args.steps / (sh_ms / 1e3), "unit": "samples/s", "n_devices": world, "scaling": "strong",
                    "ms_per_step": sh_ms / args.steps, "ms_steps": sh_steps, "wall_ms_per_step": 1e3 * wall_sh / args.steps,
+                   "copy_floor_ms": sh_floor, "frac_of_copy_ceiling": sh_floor / (sh_ms / args.steps),
                    "bytes_equal_to_single_gpu_result": bool(same),
                    "api": "fb200_encode_interleaved_sharded: one process, one context per device, chunk c on device c mod N, "
                           "every chunk copied to its final offset in the caller's pinned buffer; ms_per_step = longest "

@@ -1151,14 +1151,8 @@ void fb_md5_of_pcm(const void *pcm, int container_bytes, int bits_per_sample, ui
     if (bytes_per_sample == container_bytes) {
         h.update((const uint8_t *)pcm, (size_t)(count * (uint64_t)container_bytes));
     } else if (container_bytes == 4 && bytes_per_sample == 2) {
-        // int32 samples (Fill::fill_interleaved): packed to 16 bits in cache-sized pieces right before they are hashed
-        uint16_t tmp[4096];
-        const int32_t *p = (const int32_t *)pcm;
-        for (uint64_t i = 0; i < count; i += 4096) {
-            const size_t m = (size_t)std::min<uint64_t>(4096, count - i);
-            for (size_t k = 0; k < m; k++) tmp[k] = (uint16_t)p[i + k];
-            h.update((const uint8_t *)tmp, 2 * m);
-        }
+        // int32 samples (Fill::fill_interleaved) hashed as 16-bit little-endian values, no packed copy
+        h.update_i32_as_le16((const int32_t *)pcm, (size_t)count);
     } else {
         uint8_t tmp[3 * 4096];
         size_t k = 0;
@@ -1300,20 +1294,41 @@ int fb200_encode_streams(const fb200_config *cfg, int n_streams, const void *con
     std::vector<std::vector<uint32_t>> sizes((size_t)n_streams);
     std::vector<size_t> flen((size_t)n_streams, 0);
     std::vector<int> src((size_t)n_streams, FB200_OK);
-    for (int i = 0; i < n_streams; i++) {
-        int r = FB200_OK;
-        const uint64_t nf = (n_samples[i] + (uint64_t)block_size - 1) / (uint64_t)block_size;
-        if ((!pcm[i] && n_samples[i]) || !out[i]) r = FB200_ERR_SOURCE;
-        else if (out_cap[i] < 42) r = FB200_ERR_CAPACITY;
-        else if (nf > (1ull << 31)) r = FB200_ERR_CONFIG;
-        else {
-            sizes[(size_t)i].resize((size_t)std::max<uint64_t>(nf, 1));
-            r = fb_stream_frames(cfg, pcm[i], container_bytes, n_samples[i], channels, bits_per_sample, sample_rate, block_size,
-                                 devices, n_devices, out[i], out_cap[i], sizes[(size_t)i], &flen[(size_t)i]);
-        }
-        src[(size_t)i] = r;
-        if (r && first_rc == FB200_OK) first_rc = r;
-    }
+    // device feeders: a few host threads per device, each with its own (pooled) context, claim the streams in order --
+    // a stream of a batch is encoded on ONE device, the batch is what spreads over the devices.  Several feeders per
+    // device let the host-side staging of one stream's pageable copies overlap the kernels of another.
+    std::atomic<int> next_enc(0);
+    std::mutex err_mu;
+    std::string batch_err;
+    int per_dev = 4;
+    if (const char *e = getenv("FB200_FEEDERS")) per_dev = std::max(1, std::min(16, atoi(e)));
+    const int nfeed = std::max(1, std::min(n_streams, per_dev * n_devices));
+    std::vector<std::thread> feeders;
+    for (int w = 0; w < nfeed; w++)
+        feeders.emplace_back([&, w] {
+            const int dev = devices[w % n_devices];
+            for (int i = next_enc.fetch_add(1); i < n_streams; i = next_enc.fetch_add(1)) {
+                int r = FB200_OK;
+                const uint64_t nf = (n_samples[i] + (uint64_t)block_size - 1) / (uint64_t)block_size;
+                if ((!pcm[i] && n_samples[i]) || !out[i]) r = FB200_ERR_SOURCE;
+                else if (out_cap[i] < 42) r = FB200_ERR_CAPACITY;
+                else if (nf > (1ull << 31)) r = FB200_ERR_CONFIG;
+                else {
+                    sizes[(size_t)i].resize((size_t)std::max<uint64_t>(nf, 1));
+                    r = fb_stream_frames(cfg, pcm[i], container_bytes, n_samples[i], channels, bits_per_sample, sample_rate,
+                                         block_size, &dev, 1, out[i], out_cap[i], sizes[(size_t)i], &flen[(size_t)i]);
+                }
+                src[(size_t)i] = r;
+                if (r) {
+                    std::lock_guard<std::mutex> lock(err_mu);
+                    if (batch_err.empty()) batch_err = g_stream_error;
+                }
+            }
+        });
+    for (auto &t : feeders) t.join();
+    if (!batch_err.empty()) g_stream_error = batch_err;
+    for (int i = 0; i < n_streams; i++)
+        if (src[(size_t)i] && first_rc == FB200_OK) first_rc = src[(size_t)i];
     for (auto &t : pool) t.join();
     for (int i = 0; i < n_streams; i++) {
         if (out_len) out_len[i] = src[(size_t)i] == FB200_OK || src[(size_t)i] == FB200_ERR_CAPACITY ? 42 + flen[(size_t)i] : 0;

@@ -26,6 +26,29 @@ class FbMd5 {
         if (len) { memcpy(buf_, data, len); fill_ = len; }
     }
 
+    // int32 samples hashed as their packed 16-bit little-endian form (what Context::fill_interleaved feeds the hash for
+    // 16-bit streams, src/source.rs:406-418) without a packed copy: the 16 message words of a block are assembled from 32
+    // samples as they are needed
+    void update_i32_as_le16(const int32_t *x, size_t count) {
+        while (count && fill_) { // finish a partial block byte by byte
+            const uint16_t v = (uint16_t)*x++;
+            const uint8_t b[2] = {(uint8_t)v, (uint8_t)(v >> 8)};
+            update(b, 2);
+            count--;
+        }
+        for (; count >= 32; x += 32, count -= 32) {
+            uint32_t m[16];
+            for (int k = 0; k < 16; k++) m[k] = ((uint32_t)x[2 * k] & 0xFFFFu) | ((uint32_t)x[2 * k + 1] << 16);
+            len_ += 64;
+            block((const uint8_t *)m);
+        }
+        for (; count; count--) {
+            const uint16_t v = (uint16_t)*x++;
+            const uint8_t b[2] = {(uint8_t)v, (uint8_t)(v >> 8)};
+            update(b, 2);
+        }
+    }
+
     void finish(uint8_t digest[16]) {
         const uint64_t bits = len_ * 8;
         uint8_t pad[72] = {0x80};
