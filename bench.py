@@ -340,8 +340,8 @@ CONFIG_CASES = [
     ("C1", "10 s CD stereo, default config (108 frames)", 2, 16, 44100, 4096, 10, {}),
     ("C3", "96 kHz / 24-bit stereo, block 4608, lpc_order 24 (reference maximum), 10 min = 12500 frames", 2, 24, 96000, 4608, 600,
      {"lpc_order": 24}),
-    ("C4-shape", "CD stereo 10 min, Rectangle window + autocorrelation LPC (the direct-MSE estimator of "
-                 "experimental.config.toml is not built)", 2, 16, 44100, 4096, 600, {"window_type": 0}),
+    ("C4", "CD stereo 10 min, report/experimental.config.toml: use_direct_mse (covariance-method LPC) + Rectangle window",
+     2, 16, 44100, 4096, 600, {"window_type": 0, "use_direct_mse": 1}),
     ("C5-slice", "48 kHz / 24-bit 8 channels, 2 min (1407 frames)", 8, 24, 48000, 4096, 120, {}),
 ]
 
@@ -353,6 +353,8 @@ def make_cfg(kw):
         e.subframe_coding.qlpc.lpc_order = kw["lpc_order"]
     if kw.get("window_type") == 0:
         e.subframe_coding.qlpc.window.type = "Rectangle"
+    if kw.get("use_direct_mse"):
+        e.subframe_coding.qlpc.use_direct_mse = True
     return e.into_verified()
 
 

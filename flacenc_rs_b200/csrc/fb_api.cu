@@ -71,6 +71,13 @@ __global__ void __launch_bounds__(256) fb_k0b_expand_pairs(FbJob J, const uint8_
     }
 }
 
+// K1C: direct-MSE LPC estimator, one CTA per channel variant (fb_kernels.cuh)
+__global__ void __launch_bounds__(384) fb_k1c_direct_mse(FbJob J, const int32_t *xt, const uint8_t *pcm, const float *win_full,
+                                                         const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps) {
+    extern __shared__ __align__(16) uint8_t fb_smem_k1c[];
+    fb_k1c_body(J, xt, pcm, win_full, win_tail, ana, taps, blockIdx.x, FB_K1C_TILE, fb_smem_k1c);
+}
+
 // offsets[i] = *total + exclusive prefix; *total advances by the chunk's bytes (single CTA)
 __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *frame_bytes, unsigned long long *offsets,
                                                            uint32_t n_frames, unsigned long long *total) {
@@ -513,6 +520,13 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     FB_CUDA(ctx, cudaEventRecord(S.ev[2], st));
     fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail,
                  (FbAnalysis *)S.ana.p, A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
+    if (ctx->cfg.use_direct_mse && ctx->cfg.use_lpc) {
+        // `experimental` estimator: K1 has skipped its autocorrelation pass; K1C fills the LPC half of the records
+        fb_k1c_direct_mse<<<nvars, fb_k1c_threads(ctx->cfg.lpc_order), fb_k1c_smem_bytes(ctx->cfg.lpc_order, FB_K1C_TILE), st>>>(
+            J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
+            A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr);
+        acc.launches += 1;
+    }
     FB_CUDA(ctx, cudaEventRecord(S.ev[3], st));
     acc.launches += pairs ? 1 : 2;
     if (A.analyze_only) return FB200_OK;

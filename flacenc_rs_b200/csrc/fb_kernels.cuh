@@ -735,7 +735,7 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
     for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < R; i++) A.ring[i] = 0.0;
-    if (V.do_lpc) {
+    if (V.do_lpc && !J.cfg.use_direct_mse) { // (direct MSE: K1C estimates the LPC)
         switch (R - V.P) {
         case 0: fb_k1_pass_a<R, 0>(A, rows, V); break;
         case 1: fb_k1_pass_a<R, 1>(A, rows, V); break;
@@ -1063,7 +1063,7 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
 #ifdef FB_K1_SKIP_A // (timing experiments only: results are wrong)
     if (false) {
 #else
-    if (J.cfg.use_lpc && n_w >= FB_MIN_PRED_BLOCK) {
+    if (J.cfg.use_lpc && !J.cfg.use_direct_mse && n_w >= FB_MIN_PRED_BLOCK) { // (direct MSE: K1C estimates the LPC)
 #endif
         switch (R - V.P) {
         case 0: fb_k1_warp_pass_a<R, 0, PAIRS>(T, A, V, n_w, uniform); break;
@@ -1089,6 +1089,194 @@ inline void fb_k1_dispatch(const FbJob &J, const int32_t *xt, const float *win_f
     }
 }
 #endif
+
+// =================================================================================================
+// K1C: the `experimental` direct-MSE (covariance method) LPC estimator of one channel variant, CTA per variant
+// (src/lpc.rs:852-913 weighted_lpc_with_direct_mse with NoWeight; config key qlpc.use_direct_mse).
+//   y[t] = (f32)x[t] * w[t]                                              (src/lpc.rs:739-756)
+//   r[tau]  += y[t - tau] * y[t],        t = P .. n-1,  tau = 0..P        (src/lpc.rs:533-548, order P + 1)
+//   C[i][j] += y[t - i] * y[t - j],      t = P-1 .. n-2, i <= j < P       (src/lpc.rs:573-600 on y[0..n-1))
+// every sum a sequential f64 FMA chain in t, one chain per thread (P (P + 1) / 2 + P + 1 threads); then one thread
+// solves C a = r[1..P] by Cholesky (nalgebra's operation order, restated in oracle/flacenc_oracle.c fo_solve_sym;
+// parity with the crate is unpinned there), regularising the diagonal by 1, 1, 2, 4 ... while C is not positive definite,
+// and quantises the coefficients (src/lpc.rs:273-302).  K1's pass A is skipped for such configurations; this kernel
+// runs after K1 and fills the LPC half of FbAnalysis.  The frame is walked in tiles of FB_K1C_TILE samples staged as
+// doubles in shared memory (history of P samples carried from tile to tile), so any block size fits.
+// =================================================================================================
+#define FB_K1C_TILE 2048
+FB_HD int fb_k1c_chains(int P) { return P * (P + 1) / 2 + P + 1; }
+FB_HD int fb_k1c_threads(int P) { return (fb_k1c_chains(P) + 31) & ~31; }
+// shared memory: y tile (history + tile) | per-thread accumulators (the emulation keeps them here) | C | r | coefficients
+FB_HD uint32_t fb_k1c_smem_bytes(int P, int tile) {
+    return (uint32_t)((FB200_MAX_LPC_ORDER + tile) * 8 + fb_k1c_threads(P) * 8 + (P * P + 2 * (P + 1)) * 8 + 64);
+}
+
+// sample t of variant v of frame f: from the planar store, or (pcm != nullptr) from packed 16-bit stereo pairs
+FB_DEV int32_t fb_k1c_sample(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const FbVarRows &rows, int32_t mb, int32_t sh,
+                             uint32_t f, int t) {
+    if (pcm) {
+        const int32_t w = reinterpret_cast<const int32_t *>(pcm)[(size_t)f * (size_t)J.block_size + (size_t)t];
+        return fb_dp2a_lo(w, mb, 0) >> sh;
+    }
+    const size_t o = fb_xt_quad(t & ~3) + (size_t)(t & 3);
+    return fb_mix(rows.pa[o], rows.pb[o], rows.m, rows.sh);
+}
+
+// src/lpc.rs:76-87 solve_sym_mut = nalgebra Cholesky::new + solve_mut, in place on the n x n matrix L (row major,
+// lower triangle) and the right-hand side v; false when the matrix is not positive definite
+FB_DEV bool fb_solve_sym(double *L, int n, double *v) {
+    for (int j = 0; j < n; j++) {
+        for (int k = 0; k < j; k++) {
+            const double factor = -L[j * n + k];
+            for (int r = j; r < n; r++) L[r * n + j] = FB_DADD(FB_DMUL(factor, L[r * n + k]), L[r * n + j]);
+        }
+        const double diag = L[j * n + j];
+        if (diag == 0.0 || !(diag >= 0.0)) return false;
+#if FB_GPU
+        const double denom = __dsqrt_rn(diag);
+#else
+        const double denom = sqrt(diag);
+#endif
+        L[j * n + j] = denom;
+        for (int r = j + 1; r < n; r++) L[r * n + j] = FB_DDIV(L[r * n + j], denom);
+    }
+    for (int i = 0; i < n; i++) {
+        const double diag = L[i * n + i];
+        if (diag == 0.0) return false;
+        const double coeff = FB_DDIV(v[i], diag);
+        v[i] = coeff;
+        for (int r = i + 1; r < n; r++) v[r] = FB_DADD(FB_DMUL(-coeff, L[r * n + i]), v[r]);
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        // dot(L[i+1.., i], v[i+1..]) with nalgebra's eight interleaved accumulators
+        const int m = n - 1 - i;
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, res = 0.0;
+        int q = 0;
+        for (; m - q >= 8; q += 8)
+            for (int k = 0; k < 8; k++) acc[k] = FB_DADD(acc[k], FB_DMUL(L[(i + 1 + q + k) * n + i], v[i + 1 + q + k]));
+        res = FB_DADD(res, FB_DADD(acc[0], acc[4]));
+        res = FB_DADD(res, FB_DADD(acc[1], acc[5]));
+        res = FB_DADD(res, FB_DADD(acc[2], acc[6]));
+        res = FB_DADD(res, FB_DADD(acc[3], acc[7]));
+        for (; q < m; q++) res = FB_DADD(res, FB_DMUL(L[(i + 1 + q) * n + i], v[i + 1 + q]));
+        const double diag = L[i * n + i];
+        if (diag == 0.0) return false;
+        v[i] = FB_DDIV(FB_DADD(v[i], -res), diag);
+    }
+    return true;
+}
+
+FB_DEV void fb_k1c_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
+                        FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t gv, int tile, uint8_t *smem) {
+    const int P = J.cfg.lpc_order;
+    const int T = fb_k1c_threads(P);
+    const uint32_t f = gv / (uint32_t)J.nvar;
+    const int v = (int)(gv - f * (uint32_t)J.nvar);
+    const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
+    const int n = V.n;
+    FbAnalysis *out = ana + gv;
+    fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
+    if (!V.do_lpc) return; // K1 has stored the "no LPC" record already
+    const FbVarRows rows = fb_variant_rows(J, xt, f, v);
+    int32_t mb = 0, sh = 0;
+    if (pcm) fb_pair_mix(v, &mb, &sh);
+    double *ys = (double *)smem;                                   // ys[FB200_MAX_LPC_ORDER + (t - tile0)] = y[t]
+    double *accs = ys + FB200_MAX_LPC_ORDER + tile;                // [T]
+    double *Cm = accs + T;                                         // [P * P]
+    double *rv = Cm + P * P;                                       // [P + 1]
+    double *xy = rv + P + 1;                                       // [P + 1]
+    const int ncov = P * (P + 1) / 2;
+#if FB_GPU
+    double acc = 0.0;
+#define FB_K1C_ACC acc
+#else
+#define FB_K1C_ACC accs[tid]
+    FB_PHASE(tid, T)
+        accs[tid] = 0.0;
+    FB_PHASE_END
+#endif
+    for (int tile0 = 0; tile0 < n; tile0 += tile) {
+        const int tile1 = tile0 + tile < n ? tile0 + tile : n;
+        FB_PHASE(tid, T)
+            // history: the last P samples of the previous tile (zeros before the frame: never used, the sums start at P-1)
+            if (tid < FB200_MAX_LPC_ORDER) ys[tid] = tile0 == 0 ? 0.0 : ys[tile + tid];
+        FB_PHASE_END
+        FB_PHASE(tid, T)
+            for (int t = tile0 + tid; t < tile1; t += T) {
+                const int32_t x = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+                ys[FB200_MAX_LPC_ORDER + (t - tile0)] = (double)FB_FMUL((float)x, V.win[t]);
+            }
+        FB_PHASE_END
+        FB_PHASE(tid, T)
+            int a = 0, b = 0, t_lo, t_hi; // the chain adds y[t - a] * y[t - b] for t in [t_lo, t_hi)
+            bool active = true;
+            if (tid < ncov) {
+                // pair (i, j), i <= j, in row-major order of the upper triangle
+                int i = 0, rem = tid;
+                while (rem >= P - i) { rem -= P - i; i++; }
+                a = i; b = i + rem;
+                t_lo = P - 1; t_hi = n - 1;
+            } else if (tid < ncov + P + 1) {
+                a = tid - ncov; b = 0;
+                t_lo = P; t_hi = n;
+            } else {
+                active = false; t_lo = t_hi = 0;
+            }
+            if (active) {
+                const int lo = t_lo > tile0 ? t_lo : tile0, hi = t_hi < tile1 ? t_hi : tile1;
+                const double *pa = ys + FB200_MAX_LPC_ORDER - tile0 - a, *pb = ys + FB200_MAX_LPC_ORDER - tile0 - b;
+                double s = FB_K1C_ACC;
+                for (int t = lo; t < hi; t++) s = FB_FMA(pa[t], pb[t], s);
+                FB_K1C_ACC = s;
+            }
+        FB_PHASE_END
+    }
+    FB_PHASE(tid, T)
+        if (tid < ncov) {
+            int i = 0, rem = tid;
+            while (rem >= P - i) { rem -= P - i; i++; }
+            const int j = i + rem;
+            Cm[i * P + j] = FB_K1C_ACC;
+            Cm[j * P + i] = FB_K1C_ACC;
+        } else if (tid < ncov + P + 1) {
+            rv[tid - ncov] = FB_K1C_ACC;
+        }
+    FB_PHASE_END
+#undef FB_K1C_ACC
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            if (taps) {
+                for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) taps->autocorr[i] = i <= P ? rv[i] : 0.0;
+            }
+            // src/lpc.rs:886-896: solve, regularising the diagonal while the factorisation fails
+            double L[FB200_MAX_LPC_ORDER * FB200_MAX_LPC_ORDER];
+            double lpc[FB200_MAX_LPC_ORDER];
+            double regularizer = 0.0;
+            for (;;) {
+                for (int i = 0; i < P * P; i++) L[i] = Cm[i];
+                for (int i = 0; i < P; i++) xy[i] = rv[1 + i];
+                if (fb_solve_sym(L, P, xy)) break;
+                const double old = regularizer;
+                const double twice = FB_DADD(regularizer, regularizer);
+                regularizer = twice > 1.0 ? twice : 1.0;
+                for (int i = 0; i < P; i++) Cm[i * P + i] = FB_DADD(Cm[i * P + i], FB_DADD(regularizer, -old));
+            }
+            for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) lpc[i] = i < P ? xy[i] : 0.0;
+            int16_t q[32];
+            int shift;
+            const int order = fb_quantize(lpc, P, J.cfg.quant_precision, q, &shift);
+            out->qlp_order = order;
+            out->qlp_shift = shift;
+            for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
+            if (taps) {
+                for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) taps->lpc[i] = lpc[i];
+                for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
+                taps->qlp_order = order;
+                taps->qlp_shift = shift;
+            }
+        }
+    FB_PHASE_END
+}
 
 // =================================================================================================
 // K2: per-variant residual coding search and subframe decision (CTA per variant).

@@ -54,8 +54,9 @@ typedef struct fb200_config {
     int32_t approx_ent_partitions;  /* OrderSel::ApproxEnt.partitions (default 16, 1..=64) */
     int32_t lpc_order;              /* Qlpc.lpc_order (default 10, 1..=24) */
     int32_t quant_precision;        /* Qlpc.quant_precision (default 15, 1..=15) */
-    int32_t use_direct_mse;         /* `experimental` feature only: must be 0 (src/config.rs:305-316) */
-    int32_t mae_optimization_steps; /* `experimental` feature only: must be 0 */
+    int32_t use_direct_mse;         /* Qlpc.use_direct_mse (`experimental` feature, src/config.rs:276-285): covariance-method
+                                       LPC (src/lpc.rs:852-913) instead of autocorrelation + Levinson; 0 (default) or 1 */
+    int32_t mae_optimization_steps; /* `experimental` IRLS refinement (src/lpc.rs:814-850): not built, must be 0 */
     int32_t window_type;            /* Window: 0 = Rectangle, 1 = Tukey (default) */
     float   tukey_alpha;            /* Window::Tukey.alpha (default 0.4, 0..=1) */
     int32_t prc_max_parameter;      /* Prc.max_parameter (default 30, 0..=30) */

@@ -48,7 +48,9 @@ int fo_config_verify(const fo_config *c) {
     if (c->block_size < FO_MIN_BLOCK_SIZE || c->block_size > FO_MAX_BLOCK_SIZE) return 1;
     if (c->lpc_order < 1 || c->lpc_order > FO_MAX_LPC_ORDER) return 1;
     if (c->quant_precision < 1 || c->quant_precision > 15) return 1;
-    if (c->use_direct_mse) return 1;
+    /* use_direct_mse is accepted like a reference built with the `experimental` feature (src/config.rs:305-316);
+     * the IRLS refinement (mae_optimization_steps > 0, src/lpc.rs:814-850) is not restated */
+    if (c->use_direct_mse != 0 && c->use_direct_mse != 1) return 1;
     if (c->mae_optimization_steps != 0) return 1;
     if (c->window_type == 1) {
         if (!(c->tukey_alpha >= 0.0f && c->tukey_alpha <= 1.0f)) return 1;
@@ -281,6 +283,112 @@ void fo_lpc_from_autocorr(const int32_t *signal, int n, int window_type, float a
     fo_levinson_f64(corr, corr + 1, lpc_order, coefs_out);
     for (int i = 0; i < lpc_order; i++) assert(isfinite(coefs_out[i]));
     if (corr_out) memcpy(corr_out, corr, sizeof(double) * (size_t)(lpc_order + 1));
+    free(window);
+    free(windowed);
+}
+
+/* ---- `experimental` feature: direct-MSE (covariance method) LPC estimator -------------------
+ * src/lpc.rs:573-600 weighted_lagged_outer_prod_sum with NoWeight: for t = order-1 .. len-1 of `signal`
+ *   dest[i][j] = fma(signal[t-i], signal[t-j], dest[i][j]), j >= i, sequential in t, then mirrored. */
+void fo_lagged_outer_prod_sum(int order, const float *signal, int len, double *dest /* order x order, row major */) {
+    for (int i = 0; i < order * order; i++) dest[i] = 0.0;
+    for (int t = order - 1; t < len; t++)
+        for (int i = 0; i < order; i++)
+            for (int j = i; j < order; j++)
+                dest[i * order + j] = fma((double)signal[t - i], (double)signal[t - j], dest[i * order + j]);
+    for (int i = 0; i < order; i++)
+        for (int j = i + 1; j < order; j++) dest[j * order + i] = dest[i * order + j];
+}
+
+/* LpcFloat::solve_sym_mut (src/lpc.rs:76-87): `mat.clone().cholesky()` then `solve_mut(v)` of nalgebra 0.32.6
+ * (flacenc-bin/Cargo.lock).  nalgebra is NOT part of /root/reference, so this restates its published algorithm and
+ * PARITY IS UNPINNED for the last bits of this function:
+ *   Cholesky::new      column by column; for k < j: col_j[j..] += (-L[j][k]) * col_k[j..] as separate multiply and add
+ *                      (axpy: y = a*x + 1*y); the diagonal must be non-zero with a real square root, else not SPD;
+ *                      L[j][j] = sqrt(d), col_j[j+1..] /= L[j][j]
+ *   solve_mut          forward substitution, column oriented: b[i] /= L[i][i]; b[i+1..] += (-b[i]) * L[i+1.., i]
+ *                      then back substitution with the transpose: b[i] = (b[i] - dot(L[i+1.., i], b[i+1..])) / L[i][i],
+ *                      the dot product with nalgebra's eight interleaved accumulators (base/blas.rs dotx)
+ * Returns 0 when the matrix is not positive definite. */
+static double fo_na_dot(const double *a, int sa, const double *b, int n) {
+    double res = 0.0, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 0;
+    while (n - i >= 8) {
+        for (int k = 0; k < 8; k++) acc[k] += a[(i + k) * sa] * b[i + k];
+        i += 8;
+    }
+    res += acc[0] + acc[4];
+    res += acc[1] + acc[5];
+    res += acc[2] + acc[6];
+    res += acc[3] + acc[7];
+    for (; i < n; i++) res += a[i * sa] * b[i];
+    return res;
+}
+
+int fo_solve_sym(const double *mat, int n, double *v) {
+    double L[FO_MAX_LPC_ORDER * FO_MAX_LPC_ORDER]; /* row major; only the lower triangle is used */
+    for (int i = 0; i < n * n; i++) L[i] = mat[i];
+    for (int j = 0; j < n; j++) {
+        for (int k = 0; k < j; k++) {
+            const double factor = -L[j * n + k];
+            for (int r = j; r < n; r++) {
+                const double prod = factor * L[r * n + k];
+                L[r * n + j] = prod + L[r * n + j];
+            }
+        }
+        const double diag = L[j * n + j];
+        if (diag == 0.0 || !(diag >= 0.0)) return 0;
+        const double denom = sqrt(diag);
+        L[j * n + j] = denom;
+        for (int r = j + 1; r < n; r++) L[r * n + j] = L[r * n + j] / denom;
+    }
+    for (int i = 0; i < n; i++) {
+        const double diag = L[i * n + i];
+        if (diag == 0.0) return 0;
+        const double coeff = v[i] / diag;
+        v[i] = coeff;
+        for (int r = i + 1; r < n; r++) {
+            const double prod = -coeff * L[r * n + i];
+            v[r] = prod + v[r];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        const double dot = fo_na_dot(&L[(i + 1) * n + i], n, &v[i + 1], n - 1 - i);
+        const double diag = L[i * n + i];
+        if (diag == 0.0) return 0;
+        v[i] = (v[i] - dot) / diag;
+    }
+    return 1;
+}
+
+/* src/lpc.rs:852-903 weighted_lpc_with_direct_mse with NoWeight (lpc_with_direct_mse :905-913) */
+void fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
+                            double *coefs_out, double *corr_out, double *covar_out) {
+    for (int i = 0; i < lpc_order; i++) coefs_out[i] = 0.0;
+    if (lpc_order == 0) return;
+    float *window = (float *)malloc(sizeof(float) * (size_t)n);
+    float *windowed = (float *)malloc(sizeof(float) * (size_t)n);
+    double corr[FO_MAX_LPC_ORDER + 1];
+    double covar[FO_MAX_LPC_ORDER * FO_MAX_LPC_ORDER];
+    fo_window_weights(window_type, alpha, n, window);
+    fo_fill_windowed_signal(signal, window, n, windowed);
+    fo_auto_correlation_f64(lpc_order + 1, windowed, n, corr);
+    /* the statistics of the signal without its last sample, weights shifted by one (NoWeight: no effect) */
+    fo_lagged_outer_prod_sum(lpc_order, windowed, n - 1, covar);
+    if (corr_out) memcpy(corr_out, corr, sizeof(double) * (size_t)(lpc_order + 1));
+    if (covar_out) memcpy(covar_out, covar, sizeof(double) * (size_t)(lpc_order * lpc_order));
+    double xy[FO_MAX_LPC_ORDER];
+    double regularizer = 0.0;
+    for (;;) {
+        for (int i = 0; i < lpc_order; i++) xy[i] = corr[1 + i];
+        if (fo_solve_sym(covar, lpc_order, xy)) break;
+        /* src/lpc.rs:889-896: the diagonal grows by 1, 1, 2, 4, ... until the factorisation succeeds.  (In the
+         * reference a failed attempt leaves `xy` untouched: Cholesky::new fails before solve_mut runs.) */
+        const double old = regularizer;
+        regularizer = fmax(1.0, regularizer + regularizer);
+        for (int i = 0; i < lpc_order; i++) covar[i * lpc_order + i] += regularizer - old;
+    }
+    for (int i = 0; i < lpc_order; i++) coefs_out[i] = xy[i];
     free(window);
     free(windowed);
 }
@@ -561,7 +669,9 @@ static int fo_fixed_lpc(const fo_config *cfg, const int32_t *signal, int n, int 
 static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n, int bps, fo_subframe *out) {
     int lpc_order = cfg->lpc_order;
     double coefs[FO_MAX_LPC_ORDER];
-    fo_lpc_from_autocorr(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL);
+    /* src/coding.rs:333-351 perform_qlpc: the estimator the configuration names */
+    if (cfg->use_direct_mse) fo_lpc_with_direct_mse(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL, NULL);
+    else fo_lpc_from_autocorr(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL);
     fo_subframe_reset(out, FO_SF_LPC, signal, n, bps);
     int16_t q[FO_MAX_LPC_ORDER];
     int shift;

@@ -54,7 +54,7 @@ typedef struct fo_config {
     int32_t approx_ent_partitions; /* OrderSel::ApproxEnt.partitions, default 16 */
     int32_t lpc_order;             /* Qlpc.lpc_order, default 10 */
     int32_t quant_precision;       /* Qlpc.quant_precision, default 15 */
-    int32_t use_direct_mse;        /* experimental only; must be 0 */
+    int32_t use_direct_mse;        /* `experimental` feature: covariance-method LPC (src/lpc.rs:852-903) */
     int32_t mae_optimization_steps;/* experimental only; must be 0 */
     int32_t window_type;           /* 0 = Rectangle, 1 = Tukey */
     float   tukey_alpha;           /* default 0.4 */
@@ -115,6 +115,12 @@ int    fo_quantize_parameters(const double *coefs, int n, int precision, int16_t
 void   fo_compute_error(const int16_t *q, int order, int shift, const int32_t *signal, int n, int32_t *errors);
 void   fo_lpc_from_autocorr(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
                             double *coefs_out, double *corr_out /* nullable, lpc_order+1 */);
+
+/* `experimental` feature (src/lpc.rs:573-600, 76-87, 852-913) */
+void   fo_lagged_outer_prod_sum(int order, const float *signal, int len, double *dest);
+int    fo_solve_sym(const double *mat, int n, double *v);
+void   fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
+                              double *coefs_out, double *corr_out /* nullable */, double *covar_out /* nullable */);
 
 /* ---- rice.rs ---- */
 uint32_t fo_encode_signbit(int32_t v);

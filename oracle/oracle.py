@@ -134,6 +134,9 @@ def lib() -> C.CDLL:
             "fo_quantize_parameters": (C.c_int, [f64p, C.c_int, C.c_int, i16p, C.POINTER(C.c_int)]),
             "fo_compute_error": (None, [i16p, C.c_int, C.c_int, i32p, C.c_int, i32p]),
             "fo_lpc_from_autocorr": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, f64p, f64p]),
+            "fo_lagged_outer_prod_sum": (None, [C.c_int, f32p, C.c_int, f64p]),
+            "fo_solve_sym": (C.c_int, [f64p, C.c_int, f64p]),
+            "fo_lpc_with_direct_mse": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, f64p, f64p, f64p]),
             "fo_encode_signbit": (C.c_uint32, [C.c_int32]),
             "fo_decode_signbit": (C.c_int32, [C.c_uint32]),
             "fo_finest_partition_order": (C.c_int, [C.c_int, C.c_int]),
@@ -255,6 +258,32 @@ def lpc_from_autocorr(signal, window_type: int, alpha: float, lpc_order: int):
     corr = np.zeros(lpc_order + 1, np.float64)
     lib().fo_lpc_from_autocorr(_p(s, C.c_int32), len(s), window_type, alpha, lpc_order, _p(coefs, C.c_double), _p(corr, C.c_double))
     return coefs[:lpc_order].copy(), corr
+
+
+def lagged_outer_prod_sum(order: int, signal) -> np.ndarray:
+    x = np.ascontiguousarray(signal, np.float32)
+    dest = np.zeros((order, order), np.float64)
+    lib().fo_lagged_outer_prod_sum(order, _p(x, C.c_float), len(x), _p(dest, C.c_double))
+    return dest
+
+
+def solve_sym(mat, v):
+    """LpcFloat::solve_sym_mut: (ok, solution)"""
+    m = np.ascontiguousarray(mat, np.float64)
+    x = np.ascontiguousarray(v, np.float64).copy()
+    ok = lib().fo_solve_sym(_p(m, C.c_double), len(x), _p(x, C.c_double))
+    return bool(ok), x
+
+
+def lpc_with_direct_mse(signal, window_type: int, alpha: float, lpc_order: int):
+    """(coefs, autocorrelation lags 0..order, covariance matrix) of the `experimental` covariance-method estimator"""
+    s = np.ascontiguousarray(signal, np.int32)
+    coefs = np.zeros(max(lpc_order, 1), np.float64)
+    corr = np.zeros(lpc_order + 1, np.float64)
+    covar = np.zeros((max(lpc_order, 1), max(lpc_order, 1)), np.float64)
+    lib().fo_lpc_with_direct_mse(_p(s, C.c_int32), len(s), window_type, alpha, lpc_order, _p(coefs, C.c_double),
+                                 _p(corr, C.c_double), _p(covar, C.c_double))
+    return coefs[:lpc_order].copy(), corr, covar[:lpc_order, :lpc_order] if False else covar.reshape(-1)[: lpc_order * lpc_order].reshape(lpc_order, lpc_order)
 
 
 def bit_table_from_errors(errors, offset: int) -> np.ndarray:

@@ -123,6 +123,8 @@ def random_case(rng):
         cfg["fixed_order_sel"] = 0
     rate = int(rng.choice([8000, 22050, 44100, 48000, 96000, 12345]))
     first = int(rng.choice([0, 1, 127, 128, 70000, (1 << 31) - 10]))
+    if rng.random() < 0.2:  # (drawn last, so the cases above are the ones earlier versions of the suite ran)
+        cfg["use_direct_mse"] = 1
     return np.stack(chans, axis=1), channels, bps, rate, block, first, cfg
 
 

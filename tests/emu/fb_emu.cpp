@@ -139,6 +139,16 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     // K1
     for (uint32_t gv = 0; gv < nvars; gv++)
         fb_k1_dispatch(J, B.xv.data(), B.win_full.data(), B.win_tail.data(), B.ana.data(), B.taps.data(), gv);
+    // K1C: direct-MSE estimator (tiles of 256 samples here, so that frames span several tiles)
+    if (cfg->use_direct_mse && cfg->use_lpc) {
+        const int tile = 256;
+        std::vector<uint8_t> smem(fb_k1c_smem_bytes(J.cfg.lpc_order, tile) + 64);
+        for (uint32_t gv = 0; gv < nvars; gv++) {
+            memset(smem.data(), 0xAB, smem.size());
+            fb_k1c_body(J, B.xv.data(), nullptr, B.win_full.data(), B.win_tail.data(), B.ana.data(), B.taps.data(), gv, tile,
+                        smem.data());
+        }
+    }
     if (analyze_only) return FB200_OK;
     B.slots.assign((size_t)J.n_frames * J.slot_bytes, 0xCD);
     B.frame_bytes.assign(J.n_frames, 0);

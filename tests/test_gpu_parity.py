@@ -38,6 +38,8 @@ def make_config(**kw) -> Encoder:
             s.qlpc.lpc_order = v
         elif k == "quant_precision":
             s.qlpc.quant_precision = v
+        elif k == "use_direct_mse":
+            s.qlpc.use_direct_mse = bool(v)
         elif k == "window_type":
             s.qlpc.window.type = "Rectangle" if v == 0 else "Tukey"
         elif k == "tukey_alpha":
@@ -146,6 +148,27 @@ def test_packed_24bit_odd_block_sizes_frame_starts_unaligned(channels, block_siz
     n = block_size * 4 + 100
     x = sigen.noisy_sine_pcm(n, channels, 24, 48000, config_id=12)
     _compare(x, channels, 24, 48000, block_size, container=3)
+
+
+def test_experimental_config_c4_direct_mse():
+    """BASELINE config 4 = report/experimental.config.toml: use_direct_mse + Rectangle window (covariance-method LPC,
+    src/lpc.rs:852-913) on CD stereo; plus Tukey windows, other orders, 24-bit, and degenerate signals whose
+    covariance matrix is not positive definite (regularised diagonal)"""
+    x = sigen.noisy_sine_pcm(4096 * 12 + 1500, 2, 16, 44100, config_id=4)
+    _compare(x, 2, 16, 44100, 4096, use_direct_mse=1, window_type=0)
+    _compare(x[: 4096 * 3], 2, 16, 44100, 4096, use_direct_mse=1)
+    _compare(x[: 1024 * 5 + 77], 2, 16, 44100, 1024, use_direct_mse=1, lpc_order=24, tukey_alpha=0.1)
+    _compare(x[: 1024 * 5, 0], 1, 16, 44100, 1024, use_direct_mse=1, lpc_order=1, quant_precision=5)
+    y = sigen.noisy_sine_pcm(4608 * 3 + 100, 2, 24, 96000, config_id=3)
+    _compare(y, 2, 24, 96000, 4608, use_direct_mse=1, window_type=0, lpc_order=16)
+    _compare(np.zeros((3000, 2), np.int32), 2, 16, 44100, 1024, use_direct_mse=1, window_type=0)
+    c = np.full((3000, 1), 1000, np.int32)
+    c[1500:] = -77
+    _compare(c, 1, 16, 44100, 1024, use_direct_mse=1, window_type=0, use_constant=0)
+    imp = np.zeros((4096, 1), np.int32)
+    imp[1000] = 30000
+    _compare(imp, 1, 16, 44100, 4096, use_direct_mse=1, window_type=0)
+    _compare(sigen.noisy_sine_pcm(20000 * 2 + 5, 2, 16, 44100, config_id=8), 2, 16, 44100, 20000, use_direct_mse=1, window_type=0)
 
 
 def test_rectangle_window_c4_shape():

@@ -85,7 +85,7 @@ def test_config_default_matches_reference_defaults():
     (lambda e: setattr(e.subframe_coding.qlpc, "lpc_order", 25), False),   # src/config.rs:304
     (lambda e: setattr(e.subframe_coding.qlpc, "lpc_order", 0), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "quant_precision", 16), False),
-    (lambda e: setattr(e.subframe_coding.qlpc, "use_direct_mse", True), False),  # experimental only
+    (lambda e: setattr(e.subframe_coding.qlpc, "use_direct_mse", True), True),   # the `experimental` covariance-method estimator is built
     (lambda e: setattr(e.subframe_coding.qlpc, "mae_optimization_steps", 2), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "window", Window.Tukey(1.5)), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "window", Window.Rectangle()), True),

@@ -357,3 +357,26 @@ def test_randomised_formats_signals_and_configs(seed):
     rng = np.random.default_rng(1000 + seed)
     x, channels, bps, rate, block, first, cfg = random_case(rng)
     _compare(x, channels, bps, rate, block, first_frame=first, **cfg)
+
+
+def test_direct_mse_estimator_matches_oracle():
+    """K1C (the `experimental` covariance-method LPC, /root/reference/src/lpc.rs:852-913) under emulation, frames spanning
+    several staging tiles; incl. signals whose covariance matrix is not positive definite"""
+    x = sigen.noisy_sine_pcm(1024 * 3 + 300, 2, 16, 44100, config_id=4)
+    _compare(x, 2, 16, 44100, 1024, use_direct_mse=1, window_type=0)
+    _compare(x[:2048], 2, 16, 44100, 1024, use_direct_mse=1)
+    _compare(x[:1500, 0], 1, 16, 44100, 500, use_direct_mse=1, lpc_order=24, tukey_alpha=0.1)
+    _compare(x[:1100, 1], 1, 16, 44100, 1000, use_direct_mse=1, lpc_order=1, quant_precision=5)
+    _compare(np.zeros((600, 2), np.int32), 2, 16, 44100, 256, use_direct_mse=1, window_type=0)
+    c = np.full((600, 1), 1000, np.int32)
+    c[300:] = -77
+    _compare(c, 1, 16, 44100, 256, use_direct_mse=1, window_type=0, use_constant=0)
+    y = sigen.noisy_sine_pcm(1152 + 100, 2, 24, 96000, config_id=3)
+    _compare(y, 2, 24, 96000, 1152, use_direct_mse=1, window_type=0, lpc_order=16)
+    # float tier: coefficients are bit-identical to the oracle's
+    sig = x[:1024, 0]
+    coefs, corr, _ = O.lpc_with_direct_mse(sig, 0, 0.0, 10)
+    cfg = E.default_config(use_direct_mse=1, window_type=0)
+    rc, taps, nv = E.analyze(cfg, pack_pcm(sig.reshape(-1, 1), 2), 2, 1024, 1, 16, 44100, 1024)
+    assert rc == 0 and nv == 1
+    assert np.array_equal(np.array(taps[0].lpc[:10]), coefs) and np.array_equal(np.array(taps[0].autocorr[:11]), corr)

@@ -552,3 +552,61 @@ def test_fixture_clips_roundtrip_and_compress():
         total_in += signal.size * 2
         total_out += len(data)
     assert total_out < 0.8 * total_in
+
+
+# ---- `experimental` feature: direct-MSE estimator (src/lpc.rs:573-600, 76-87, 852-913) ----------------------------
+def test_lagged_outer_prod_sum_kat():
+    """src/lpc.rs:1341-1361 lagged_outer_prod_sum_computation"""
+    r = O.lagged_outer_prod_sum(2, [4.0, -4.0, 3.0, -3.0, 2.0, -2.0, 1.0, -1.0])
+    assert r[0, 0] == float(-4 * -4 + 3 * 3 + -3 * -3 + 2 * 2 + -2 * -2 + 1 * 1 + -1 * -1)
+    assert r[0, 1] == float(4 * -4 + -4 * 3 + 3 * -3 + -3 * 2 + 2 * -2 + -2 * 1 + 1 * -1)
+    assert r[1, 1] == float(4 * 4 + -4 * -4 + 3 * 3 + -3 * -3 + 2 * 2 + -2 * -2 + 1 * 1)
+    assert r[1, 0] == r[0, 1]
+
+
+def test_lpc_with_known_coefs_dmse_kat():
+    """src/lpc.rs:1194-1212: the direct-MSE estimator recovers the generating filter (1, -1, 0.5) closely"""
+    signal = [0, -512, 0, 512, 256, -256, -256, 128, 256, 0, -192, -64, 128, 96, -64, -96, 16, 80, 16, -56, -32, 32, 36, -12]
+    coefs, _, _ = O.lpc_with_direct_mse(signal, 0, 0.0, 3)
+    assert 0.9 < coefs[0] < 1.1 and -1.1 < coefs[1] < -0.9 and 0.4 < coefs[2] < 0.6
+
+
+def test_solve_sym_kat():
+    """src/lpc.rs:1363-1391 solve_mut_sym: covar * x == autocorr[1..] to the reference's assert_close (1e-5)"""
+    from flacenc_rs_b200 import sigen
+    x = sigen.Sine(32, 0.8).noise(0.01, seed=3).to_vec_quantized(16, 1024).astype(np.float32)
+    order = 12
+    corr = O.auto_correlation(order + 1, x)
+    covar = O.lagged_outer_prod_sum(order, x)
+    ok, sol = O.solve_sym(covar, corr[1:order + 1])
+    assert ok
+    y = covar @ sol
+    assert np.allclose(y, corr[1:order + 1], rtol=1e-5, atol=1e-5)
+    # not positive definite -> false, and the regularised retry of the estimator still terminates
+    ok, _ = O.solve_sym(np.array([[1.0, 2.0], [2.0, 1.0]]), [1.0, 1.0])
+    assert not ok
+    coefs, _, _ = O.lpc_with_direct_mse(np.zeros(64, np.int32), 0, 0.0, 4)
+    assert np.all(np.isfinite(coefs))
+
+
+def test_direct_mse_beats_autocorr_on_a_short_window_kat():
+    """src/lpc.rs:1297-1339 if_direct_mse_is_better_than_autocorr (sus109 clip, 128 samples, order 24)"""
+    sig = load_fixture("sus109", 0)[:128]
+    order = 24
+    ca, _ = O.lpc_from_autocorr(sig, 1, 0.1, order)
+    cd, _, _ = O.lpc_with_direct_mse(sig, 0, 0.0, order)
+
+    def raw_errors(coefs):  # compute_raw_errors, src/lpc.rs:605-618 (f32 fused multiply-adds)
+        e = np.zeros(len(sig), np.float32)
+        for t in range(order, len(sig)):
+            acc = np.float32(-float(sig[t]))
+            for j in range(order):
+                acc = np.float32(np.float64(np.float32(coefs[j])) * np.float64(np.float32(sig[t - 1 - j])) + np.float64(acc))
+            e[t] = acc
+        return e
+
+    energy = lambda v: float(np.sum(np.asarray(v, np.float64) ** 2) / max(len(v), 1))
+    se = energy(sig)
+    snr_a = 10 * np.log10(se / energy(raw_errors(ca)[order:]))
+    snr_d = 10 * np.log10(se / energy(raw_errors(cd)[order:]))
+    assert snr_a < snr_d
