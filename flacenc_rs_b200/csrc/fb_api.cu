@@ -71,6 +71,121 @@ __global__ void __launch_bounds__(256) fb_k0b_expand_pairs(FbJob J, const uint8_
     }
 }
 
+// K1S: the analysis of K1 for SMALL launches, one WARP per channel variant.  K1 gives every variant one thread that walks
+// the whole frame (the floats must be summed in the reference's sequential order), which is the right mapping when
+// there are tens of thousands of variants and a latency floor of two full walks when there are a few hundred (BASELINE
+// config 1: 432 variants).  The sequential chains are independent of one another, so here they are spread over lanes:
+//   * estimate_entropy (src/coding.rs:200-227): lane p sums partition p (its |e_k| in t order, f32) -- 16 chains of
+//     n / 16 samples instead of one of n; the zero-history differences at a partition start are rebuilt from the four
+//     samples before it
+//   * autocorrelation (src/lpc.rs:533-548): lane tau owns lag tau -- one sequential f64 FMA chain each, over tiles of
+//     y = (f32)x * w staged as doubles in shared memory
+// then lane 0 finishes with the same fb_k1_finish_ent / fb_k1_finish_lpc as K1: results are bit-identical.
+#define FB_K1S_TILE 2048
+#define FB_K1S_WARPS 4
+__global__ void __launch_bounds__(32 * FB_K1S_WARPS) fb_k1s_analyze(FbJob J, const int32_t *xt, const uint8_t *pcm,
+                                                                    const float *win_full, const float *win_tail, FbAnalysis *ana,
+                                                                    fb200_variant_taps *taps_all, uint32_t n_variants) {
+    extern __shared__ __align__(16) uint8_t fb_smem_k1s[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t gv = blockIdx.x * FB_K1S_WARPS + warp;
+    if (gv >= n_variants) return;
+    const uint32_t f = gv / (uint32_t)J.nvar;
+    const int v = (int)(gv - f * (uint32_t)J.nvar);
+    const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
+    const int n = V.n, P = V.P;
+    const FbVarRows rows = fb_variant_rows(J, xt, f, v);
+    int32_t mb = 0, sh = 0;
+    if (pcm) fb_pair_mix(v, &mb, &sh);
+    FbAnalysis *out = ana + gv;
+    fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
+    double *ys = (double *)fb_smem_k1s + (size_t)warp * (FB200_MAX_LPC_ORDER + FB_K1S_TILE);
+
+    // ---- pass E: min / max over all samples, entropy estimate partition by partition
+    FbK1Ent S;
+    fb_k1_ent_init(S, n, V.psize, 0);
+    S.xmin = 2147483647;
+    S.xmax = -2147483647 - 1;
+    if (V.do_ent) {
+        const int parts = J.cfg.approx_ent_partitions;
+        for (int p = (int)lane; p < parts; p += 32) {
+            const int t0 = p * V.psize, t1 = t0 + V.psize < n ? t0 + V.psize : n;
+            if (t0 >= t1) continue; // (empty trailing partitions contribute nothing: NaN -> 0, src/coding.rs:219-222)
+            // e_k[t0 - 1] from the four samples before the partition (zeros before the frame)
+            int32_t h[4];
+            for (int i = 0; i < 4; i++) h[i] = t0 - 1 - i >= 0 ? fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t0 - 1 - i) : 0;
+            int32_t pe0 = h[0];
+            int32_t pe1 = (int32_t)((uint32_t)h[0] - (uint32_t)h[1]);
+            int32_t pe2 = (int32_t)((uint32_t)h[0] - 2u * (uint32_t)h[1] + (uint32_t)h[2]);
+            int32_t pe3 = (int32_t)((uint32_t)h[0] - 3u * (uint32_t)h[1] + 3u * (uint32_t)h[2] - (uint32_t)h[3]);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+            for (int t = t0; t < t1; t++) {
+                const int32_t e0 = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+                S.xmin = e0 < S.xmin ? e0 : S.xmin;
+                S.xmax = e0 > S.xmax ? e0 : S.xmax;
+                const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)pe0);
+                const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)pe1);
+                const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)pe2);
+                const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)pe3);
+                pe0 = e0; pe1 = e1; pe2 = e2; pe3 = e3;
+                s0 = FB_FADD(fabsf((float)e0), s0);
+                s1 = FB_FADD(fabsf((float)e1), s1);
+                s2 = FB_FADD(fabsf((float)e2), s2);
+                s3 = FB_FADD(fabsf((float)e3), s3);
+                s4 = FB_FADD(fabsf((float)e4), s4);
+            }
+            S.b0 += fb_k1_part_bits(s0, 0, t1, t1 - t0);
+            S.b1 += fb_k1_part_bits(s1, 1, t1, t1 - t0);
+            S.b2 += fb_k1_part_bits(s2, 2, t1, t1 - t0);
+            S.b3 += fb_k1_part_bits(s3, 3, t1, t1 - t0);
+            S.b4 += fb_k1_part_bits(s4, 4, t1, t1 - t0);
+        }
+    } else {
+        for (int t = (int)lane; t < n; t += 32) {
+            const int32_t e0 = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+            S.xmin = e0 < S.xmin ? e0 : S.xmin;
+            S.xmax = e0 > S.xmax ? e0 : S.xmax;
+        }
+    }
+    // bits are integers: any order of addition gives the reference's per-order totals
+    for (int d = 16; d; d >>= 1) {
+        S.b0 += __shfl_xor_sync(0xFFFFFFFFu, S.b0, d);
+        S.b1 += __shfl_xor_sync(0xFFFFFFFFu, S.b1, d);
+        S.b2 += __shfl_xor_sync(0xFFFFFFFFu, S.b2, d);
+        S.b3 += __shfl_xor_sync(0xFFFFFFFFu, S.b3, d);
+        S.b4 += __shfl_xor_sync(0xFFFFFFFFu, S.b4, d);
+        S.xmin = min(S.xmin, __shfl_xor_sync(0xFFFFFFFFu, S.xmin, d));
+        S.xmax = max(S.xmax, __shfl_xor_sync(0xFFFFFFFFu, S.xmax, d));
+    }
+    if (lane == 0) fb_k1_finish_ent(J, V, S, out, taps);
+
+    // ---- pass A: lane tau accumulates lag tau
+    double acc = 0.0;
+    if (V.do_lpc && !J.cfg.use_direct_mse) {
+        for (int tile0 = 0; tile0 < n; tile0 += FB_K1S_TILE) {
+            const int tile1 = tile0 + FB_K1S_TILE < n ? tile0 + FB_K1S_TILE : n;
+            if (lane < FB200_MAX_LPC_ORDER) ys[lane] = tile0 == 0 ? 0.0 : ys[FB_K1S_TILE + lane];
+            __syncwarp();
+            for (int t = tile0 + (int)lane; t < tile1; t += 32) {
+                const int32_t x = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+                ys[FB200_MAX_LPC_ORDER + (t - tile0)] = (double)FB_FMUL((float)x, V.win[t]);
+            }
+            __syncwarp();
+            if ((int)lane <= P) {
+                const int lo = P > tile0 ? P : tile0;
+                const double *pa = ys + FB200_MAX_LPC_ORDER - tile0 - (int)lane, *pb = ys + FB200_MAX_LPC_ORDER - tile0;
+#pragma unroll 4
+                for (int t = lo; t < tile1; t++) acc = FB_FMA(pa[t], pb[t], acc);
+            }
+            __syncwarp();
+        }
+    }
+    FbK1Acc<FB200_MAX_LPC_ORDER> A;
+#pragma unroll
+    for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) A.acc[i] = __shfl_sync(0xFFFFFFFFu, acc, i);
+    if (lane == 0) fb_k1_finish_lpc<FB200_MAX_LPC_ORDER>(J, V, A, out, taps);
+}
+
 // K1C: direct-MSE LPC estimator, one CTA per channel variant (fb_kernels.cuh)
 __global__ void __launch_bounds__(384) fb_k1c_direct_mse(FbJob J, const int32_t *xt, const uint8_t *pcm, const float *win_full,
                                                          const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps) {
@@ -150,6 +265,8 @@ struct fb200_ctx {
     fb200_timing timing;
     std::string last_error;
     uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
+    int k1_small = -1;          // FB200_K1_SMALL=0/1: never / always analyse with a warp per variant (default: by launch size)
+    bool k1s_smem_set = false;
     bool no_pairs = false;      // FB200_KP_PAIRS=0: the pack kernel always stages planes (tests exercise both)
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
     uint64_t pipe_chunk_frames = 0; // FB200_CHUNK_FRAMES: frames per chunk of the pipelined host path (0 = default)
@@ -275,6 +392,8 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
         ctx->force_generic = fg && fg[0] == '1';
         const char *kp = getenv("FB200_KP_PAIRS");
         ctx->no_pairs = kp && kp[0] == '0';
+        const char *ks = getenv("FB200_K1_SMALL");
+        if (ks) ctx->k1_small = ks[0] == '1' ? 1 : 0;
         const char *cf = getenv("FB200_CHUNK_FRAMES");
         if (cf) ctx->pipe_chunk_frames = strtoull(cf, nullptr, 10);
         const char *ns = getenv("FB200_NSETS");
@@ -518,8 +637,21 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         fb_k0_ingest<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv.p, d_err, n_items);
     }
     FB_CUDA(ctx, cudaEventRecord(S.ev[2], st));
-    fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail,
-                 (FbAnalysis *)S.ana.p, A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
+    // small launches: a warp per variant (K1S) instead of a thread per variant (K1); same results
+    const bool k1_small = ctx->k1_small >= 0 ? ctx->k1_small != 0 : nvars <= 148u * 3u * FB_K1S_WARPS;
+    if (k1_small) {
+        const uint32_t smem = FB_K1S_WARPS * (FB200_MAX_LPC_ORDER + FB_K1S_TILE) * 8u;
+        if (!ctx->k1s_smem_set) {
+            FB_CUDA(ctx, cudaFuncSetAttribute(fb_k1s_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->k1s_smem_set = true;
+        }
+        fb_k1s_analyze<<<(nvars + FB_K1S_WARPS - 1) / FB_K1S_WARPS, 32 * FB_K1S_WARPS, smem, st>>>(
+            J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
+            A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars);
+    } else {
+        fb_launch_k1(P.ring, J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail,
+                     (FbAnalysis *)S.ana.p, A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
+    }
     if (ctx->cfg.use_direct_mse && ctx->cfg.use_lpc) {
         // `experimental` estimator: K1 has skipped its autocorrelation pass; K1C fills the LPC half of the records
         fb_k1c_direct_mse<<<nvars, fb_k1c_threads(ctx->cfg.lpc_order), fb_k1c_smem_bytes(ctx->cfg.lpc_order, FB_K1C_TILE), st>>>(

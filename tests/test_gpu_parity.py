@@ -64,12 +64,16 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
     ref, ref_sizes = O.encode_frames(ocfg, signal, channels, bps, rate, block_size, first_frame_number=first_frame,
                                      nthreads=oracle_threads)
     # both device paths: the fused per-frame kernel (default, when the batch is eligible) and the generic kernels
-    modes = [("0", "1"), ("1", "1")]
+    # (the analysis runs as a warp per variant for small launches -- nearly every case here -- so the classic
+    # thread-per-variant kernel is forced on in the other modes)
+    modes = [("0", "1", None), ("1", "1", "0")]
     if channels == 2 and bps == 16 and container == 2:
-        modes.insert(1, ("0", "0"))  # 16-bit stereo: also with the pack kernel staging planes instead of PCM pairs
-    for force_generic, kp_pairs in modes:
+        modes.insert(1, ("0", "0", "0"))  # 16-bit stereo: also with planes instead of PCM pairs in every kernel
+    for force_generic, kp_pairs, k1_small in modes:
         os.environ["FB200_FORCE_GENERIC"] = force_generic
         os.environ["FB200_KP_PAIRS"] = kp_pairs
+        if k1_small is not None:
+            os.environ["FB200_K1_SMALL"] = k1_small
         try:
             with Context(vcfg, channels, bps, rate, block_size) as ctx:
                 got, sizes, infos = ctx.encode_interleaved(pack_pcm(signal, container), container, n, first_frame,
@@ -82,6 +86,7 @@ def _compare(signal, channels, bps, rate, block_size, container=None, first_fram
         finally:
             os.environ.pop("FB200_FORCE_GENERIC", None)
             os.environ.pop("FB200_KP_PAIRS", None)
+            os.environ.pop("FB200_K1_SMALL", None)
         assert list(sizes) == list(ref_sizes), f"force_generic={force_generic}"
         if got != ref:
             off = 0
