@@ -436,18 +436,26 @@ FB_DEV void fb_vm_mix(int vm, int32_t *m, int32_t *sh) {
     *sh = k == 2 ? 1 : 0;
 }
 
+// The mixing constants of a variant mode, computed once per variant (not per load): planes: sample = (a + m * b) >> sh;
+// pairs: sample = dp2a(pair, multiplier bytes) >> sh (fb_pair_mix)
+struct FbMix { int32_t a, sh; };
+template <int VMS>
+FB_DEV FbMix fb_mix_of(int vm) {
+    FbMix mx;
+    if ((VMS & FB_VM_PAIRS) && (VMS == FB_VM_PAIRS || (vm & FB_VM_PAIRS))) fb_pair_mix(vm & 3, &mx.a, &mx.sh);
+    else fb_vm_mix(vm, &mx.a, &mx.sh);
+    return mx;
+}
+
 // four samples at plane offset o = fb_xidx(t) (t a multiple of 4, inside the plane incl. its slack)
-// pairs: sample = dp2a(pair, mb) >> sh = (ml * left + mr * right) >> sh (fb_pair_mix)
 
 // VMS: the plane formats a caller can meet (the plan kernel only ever sees 32-bit planes: VMS = 0 drops the rest)
 #define FB_VMS_ALL (FB_VM_X16 | FB_VM_PAIRS)
 template <int VMS = FB_VMS_ALL>
-FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, int o, int32_t *dst) {
-    int32_t m, sh;
-    fb_vm_mix(vm, &m, &sh);
+FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, const FbMix &mx, int o, int32_t *dst) {
+    const int32_t m = mx.a, sh = mx.sh;
     if ((VMS & FB_VM_PAIRS) && (VMS == FB_VM_PAIRS || (vm & FB_VM_PAIRS))) {
-        int32_t mb;
-        fb_pair_mix(vm & 3, &mb, &sh);
+        const int32_t mb = mx.a;
         const int4 w = *reinterpret_cast<const int4 *>(xa + o);
         dst[0] = fb_dp2a_lo(w.x, mb, 0) >> sh;
         dst[1] = fb_dp2a_lo(w.y, mb, 0) >> sh;
@@ -471,18 +479,16 @@ FB_DEV void fb_kf_load4_at(const int32_t *xa, const int32_t *xb, int vm, int o, 
 }
 
 template <int VMS = FB_VMS_ALL>
-FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, int t, int32_t *dst) {
-    fb_kf_load4_at<VMS>(xa, xb, vm, fb_xidx(t), dst);
+FB_DEV void fb_kf_load4(const int32_t *xa, const int32_t *xb, int vm, const FbMix &mx, int t, int32_t *dst) {
+    fb_kf_load4_at<VMS>(xa, xb, vm, mx, fb_xidx(t), dst);
 }
 
 template <int VMS = FB_VMS_ALL>
-FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, int t) {
+FB_DEV int32_t fb_kf_load1(const int32_t *xa, const int32_t *xb, int vm, const FbMix &mx, int t) {
     const int o = fb_xidx(t);
-    int32_t m, sh;
-    fb_vm_mix(vm, &m, &sh);
+    const int32_t m = mx.a, sh = mx.sh;
     if ((VMS & FB_VM_PAIRS) && (VMS == FB_VM_PAIRS || (vm & FB_VM_PAIRS))) {
-        int32_t mb;
-        fb_pair_mix(vm & 3, &mb, &sh);
+        const int32_t mb = mx.a;
         return fb_dp2a_lo(xa[o], mb, 0) >> sh;
     }
     if ((VMS & FB_VM_X16) && (vm & FB_VM_X16))
@@ -502,36 +508,36 @@ FB_DEV void fb_kf_win_set(int32_t *win, int idx, int32_t v) {
 // the hot loops of the regular frames carry none of that code.
 // win[0..G) = x[ta - G .. ta), zeros before the start of the frame (ta a multiple of 4 unless ODD)
 template <int G, int VMS = FB_VMS_ALL, bool ODD = false>
-FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, int ta, int32_t *win) {
+FB_DEV void fb_kf_history(const int32_t *xa, const int32_t *xb, int vm, const FbMix &mx, int ta, int32_t *win) {
     if (ODD) {
 #pragma unroll 1
-        for (int i = 0; i < G; i++) fb_kf_win_set<G>(win, i, ta - G + i >= 0 ? fb_kf_load1<VMS>(xa, xb, vm, ta - G + i) : 0);
+        for (int i = 0; i < G; i++) fb_kf_win_set<G>(win, i, ta - G + i >= 0 ? fb_kf_load1<VMS>(xa, xb, vm, mx, ta - G + i) : 0);
         return;
     }
 #pragma unroll
     for (int i = 0; i < G; i += 4) {
         const int t = ta - G + i;
-        if (t >= 0) fb_kf_load4<VMS>(xa, xb, vm, t, win + i);
+        if (t >= 0) fb_kf_load4<VMS>(xa, xb, vm, mx, t, win + i);
         else { win[i] = 0; win[i + 1] = 0; win[i + 2] = 0; win[i + 3] = 0; }
     }
 }
 
 // win[G..G+RUN) = x[t0 .. t0+RUN) (t0 a multiple of 4 unless ODD); samples at t >= n are don't-cares (masked)
 template <int G, int VMS = FB_VMS_ALL, bool ODD = false>
-FB_DEV void fb_kf_fetch_run(const int32_t *xa, const int32_t *xb, int vm, int t0, int32_t *win) {
+FB_DEV void fb_kf_fetch_run(const int32_t *xa, const int32_t *xb, int vm, const FbMix &mx, int t0, int32_t *win) {
     if (ODD) {
 #pragma unroll 1
-        for (int i = 0; i < FB_KF_RUN; i++) fb_kf_win_set<G>(win, G + i, fb_kf_load1<VMS>(xa, xb, vm, t0 + i));
+        for (int i = 0; i < FB_KF_RUN; i++) fb_kf_win_set<G>(win, G + i, fb_kf_load1<VMS>(xa, xb, vm, mx, t0 + i));
         return;
     }
     if ((t0 & 15) == 0) {
         // a run that starts on a multiple of 16 lies inside one 64-sample block of the padded plane: one index
         const int o = fb_xidx(t0);
 #pragma unroll
-        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4_at<VMS>(xa, xb, vm, o + i, win + G + i);
+        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4_at<VMS>(xa, xb, vm, mx, o + i, win + G + i);
     } else {
 #pragma unroll
-        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4<VMS>(xa, xb, vm, t0 + i, win + G + i);
+        for (int i = 0; i < FB_KF_RUN; i += 4) fb_kf_load4<VMS>(xa, xb, vm, mx, t0 + i, win + G + i);
     }
 }
 
@@ -639,6 +645,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 
     // ---- pass 1: residuals -> bit-sliced counters per unit (+ pass 2 in registers when unit == leaf)
     FB_WPHASE(lane)
+        const FbMix mx = fb_mix_of<VMS>(vm);
         int32_t qq[G];
 #pragma unroll
         for (int j = 0; j < G; j++) qq[j] = (cd.kind == 1 && j < cd.order) ? (int32_t)cd.q[j] : 0;
@@ -653,10 +660,10 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
             const int lo = ta > warm ? ta : warm;
             if (tb > ta) {
                 int32_t win[G + FB_KF_RUN];
-                fb_kf_history<G, VMS, ODD>(xa, xb, vm, ta, win);
+                fb_kf_history<G, VMS, ODD>(xa, xb, vm, mx, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
-                    fb_kf_fetch_run<G, VMS, ODD>(xa, xb, vm, t0, win);
+                    fb_kf_fetch_run<G, VMS, ODD>(xa, xb, vm, mx, t0, win);
                     fb_kf_run_u<G, true>(win, t0, lo, tb, cd, qq, uu);
                     fb_kf_csa_run(cw, uu);
                     fb_kf_slide<G>(win);
@@ -1334,7 +1341,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
         // frame header bytes: one lane each, in the last warp (the first warps write the subframe heads)
         if (c0 == 0 && (tid >> 5) == NW - 1 && (tid & 31) < S->header_len)
             fb_or_bits(words, 8u * (uint32_t)(tid & 31), S->header[tid & 31], 8u);
-#define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, (t)))
+#define FB_KF_X(t) ((uint32_t)fb_kf_load1(xa, xb, vm, mx, (t)))
         // subframe heads (src/component/bitrepr.rs:443-528): every field has a known bit position, so the lanes of
         // warp w write the fields of subframe c0 + w side by side -- type byte, warm-up samples, precision / shift,
         // coefficients, residual method and partition order
@@ -1344,6 +1351,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             const fb200_subframe_info &V = psub[sc];
             const int32_t *xa, *xb;
             const int vm = fb_kp_planes(J, L, xs, D.variant, c0, &xa, &xb);
+            const FbMix mx = fb_mix_of<FB_VMS_ALL>(vm);
             const uint32_t mask = D.bps >= 32 ? 0xFFFFFFFFu : ((1u << D.bps) - 1u);
             const uint32_t base = D.start_bit;
             const bool lpc = D.type == FB200_SF_LPC, fixed = D.type == FB200_SF_FIXED;
@@ -1385,6 +1393,7 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             fb_kf_unit_range(g, unit, &ta, &tb);
             const int32_t *xa, *xb;
             const int vm = fb_kp_planes(J, L, xs, D.variant, c0, &xa, &xb);
+            const FbMix mx = fb_mix_of<FB_VMS_ALL>(vm);
             if (D.type == FB200_SF_VERBATIM) {
                 // Verbatim::write (src/component/bitrepr.rs:463-470): bps bits per sample at fixed positions
                 if (tb <= ta) continue;
@@ -1430,10 +1439,10 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             const uint32_t rmask = (1u << rp) - 1u, rone = 1u << rp;
             if (tb > lo) {
                 int32_t win[G + FB_KF_RUN];
-                fb_kf_history<G, FB_VMS_ALL, ODD>(xa, xb, vm, ta, win);
+                fb_kf_history<G, FB_VMS_ALL, ODD>(xa, xb, vm, mx, ta, win);
                 for (int t0 = ta; t0 < tb; t0 += FB_KF_RUN) {
                     uint32_t uu[FB_KF_RUN];
-                    fb_kf_fetch_run<G, FB_VMS_ALL, ODD>(xa, xb, vm, t0, win);
+                    fb_kf_fetch_run<G, FB_VMS_ALL, ODD>(xa, xb, vm, mx, t0, win);
                     fb_kf_run_u<G>(win, t0, lo, tb, cd, qq, uu);
 #pragma unroll
                     for (int i = 0; i < FB_KF_RUN; i++) {
