@@ -160,10 +160,15 @@ FB_HD uint32_t fb_zigzag(int32_t v) { return ((uint32_t)v << 1) ^ (uint32_t)(v >
 FB_HD int fb_finest_partition_order(int n) {
     uint32_t max_splits = (uint32_t)(n / 64);
     if (max_splits == 0) return 0;
+#if defined(__CUDA_ARCH__)
+    const int lg = 31 - __clz((int)max_splits);
+    const int tz = __ffs(n) - 1; // n >= 64 here
+#else
     int lg = 0;
     while ((max_splits >> (lg + 1)) != 0) lg++;
     int tz = 0;
     while (((n >> tz) & 1) == 0 && tz < 31) tz++;
+#endif
     int r = lg < tz ? lg : tz;
     return r < 15 ? r : 15;
 }

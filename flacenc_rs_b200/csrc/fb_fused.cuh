@@ -93,10 +93,10 @@ FB_HD FbKfGeom fb_kf_geom(int n) {
     g.leaf_len = n >> g.o0;
     int m = 1, lgm = 0;
     while (g.leaves * m < 32) { m <<= 1; lgm++; }
-    while (((((g.leaf_len + m - 1) / m) + 3) & ~3) > FB_KF_UNIT_MAX) { m <<= 1; lgm++; }
+    while (((((g.leaf_len + m - 1) >> lgm) + 3) & ~3) > FB_KF_UNIT_MAX) { m <<= 1; lgm++; } // (m = 1 << lgm)
     g.m = m;
     g.lgm = lgm;
-    g.unit_len = (((g.leaf_len + m - 1) / m) + 3) & ~3;
+    g.unit_len = (((g.leaf_len + m - 1) >> lgm) + 3) & ~3;
     g.U = g.leaves * m;
     g.lgU = g.o0 + lgm;
     return g;
