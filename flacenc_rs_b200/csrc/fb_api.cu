@@ -193,6 +193,15 @@ __global__ void __launch_bounds__(384) fb_k1c_direct_mse(FbJob J, const int32_t 
     fb_k1c_body(J, xt, pcm, win_full, win_tail, ana, taps, blockIdx.x, FB_K1C_TILE, fb_smem_k1c);
 }
 
+// K1D: direct-MSE estimator for lpc_order 10 and large launches, thread per channel variant (fb_kernels.cuh)
+__global__ void __maxnreg__(224) fb_k1d_direct_mse10(FbJob J, const int32_t *xt, const uint8_t *pcm, const float *win_full,
+                                                     const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps,
+                                                     uint32_t n_variants) {
+    extern __shared__ __align__(16) uint8_t fb_smem_k1d[];
+    if (pcm) fb_k1d_warp<true>(J, xt, pcm, win_full, win_tail, ana, taps, n_variants, fb_smem_k1d);
+    else fb_k1d_warp<false>(J, xt, pcm, win_full, win_tail, ana, taps, n_variants, fb_smem_k1d);
+}
+
 // offsets[i] = *total + exclusive prefix; *total advances by the chunk's bytes (single CTA)
 __global__ void __launch_bounds__(FB_K4_THREADS) fb_k4_scan(const uint32_t *frame_bytes, unsigned long long *offsets,
                                                            uint32_t n_frames, unsigned long long *total) {
@@ -265,6 +274,7 @@ struct fb200_ctx {
     fb200_timing timing;
     std::string last_error;
     uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
+    bool no_k1d = false;        // FB200_K1D=0: direct MSE always by the CTA-per-variant kernel (tests exercise both)
     int k1_small = -1;          // FB200_K1_SMALL=0/1: never / always analyse with a warp per variant (default: by launch size)
     bool k1s_smem_set = false;
     bool no_pairs = false;      // FB200_KP_PAIRS=0: the pack kernel always stages planes (tests exercise both)
@@ -392,6 +402,8 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
         ctx->force_generic = fg && fg[0] == '1';
         const char *kp = getenv("FB200_KP_PAIRS");
         ctx->no_pairs = kp && kp[0] == '0';
+        const char *kd = getenv("FB200_K1D");
+        ctx->no_k1d = kd && kd[0] == '0';
         const char *ks = getenv("FB200_K1_SMALL");
         if (ks) ctx->k1_small = ks[0] == '1' ? 1 : 0;
         const char *cf = getenv("FB200_CHUNK_FRAMES");
@@ -653,10 +665,20 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
                      (FbAnalysis *)S.ana.p, A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars, st);
     }
     if (ctx->cfg.use_direct_mse && ctx->cfg.use_lpc) {
-        // `experimental` estimator: K1 has skipped its autocorrelation pass; K1C fills the LPC half of the records
-        fb_k1c_direct_mse<<<nvars, fb_k1c_threads(ctx->cfg.lpc_order), fb_k1c_smem_bytes(ctx->cfg.lpc_order, FB_K1C_TILE), st>>>(
-            J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
-            A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr);
+        // `experimental` estimator: K1 has skipped its autocorrelation pass; K1C (CTA per variant) or, for the default
+        // order and launches large enough to fill the GPU with one thread per variant, K1D fills the LPC half of the records
+        fb200_variant_taps *d_taps = A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr;
+        if (ctx->cfg.lpc_order == FB_K1D_P && !k1_small && !ctx->no_k1d) {
+            const uint32_t smem = fb_k1_smem_bytes(J.channels, J.nvar, pairs);
+            if (smem > 48u * 1024u)
+                FB_CUDA(ctx, cudaFuncSetAttribute(fb_k1d_direct_mse10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fb_k1d_direct_mse10<<<(fb_k1_slots(J, nvars) + FB_K1_THREADS - 1) / FB_K1_THREADS, FB_K1_THREADS, smem, st>>>(
+                J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
+                d_taps, nvars);
+        } else {
+            fb_k1c_direct_mse<<<nvars, fb_k1c_threads(ctx->cfg.lpc_order), fb_k1c_smem_bytes(ctx->cfg.lpc_order, FB_K1C_TILE), st>>>(
+                J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p, d_taps);
+        }
         acc.launches += 1;
     }
     FB_CUDA(ctx, cudaEventRecord(S.ev[3], st));

@@ -939,16 +939,21 @@ FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &
     });
 }
 
+// what a lane of the analysis kernels knows about its variant and its share of the warp's staging
+struct FbK1Lane {
+    bool valid;      // the lane has a variant of its own (surplus lanes shadow the last one: they still copy)
+    uint32_t gve;    // index of the variant
+    int n_w;         // frame length of the warp's first frame
+    bool uniform;    // all lanes of the warp walk frames of that length
+    FbK1Var V;
+    FbK1Stage T;
+};
+
+// Variants to lanes for block `blk` of 128 lane slots, and the staging roles.  false: the whole warp has nothing to do.
 // PAIRS: pairs mode (fb_pairs_format): the rows come from pcm, xt is not read
-template <int R, bool PAIRS>
-FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
-                       FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
-    // The grid holds every block of 128 variants twice: the first half runs pass A (the longer one, so it is scheduled
-    // first), the second half pass E.  Half-length CTAs pack the SMs' slots better at the end of a launch, and small
-    // batches (latency-bound: one thread walks a whole frame) finish in roughly half the time.
-    const uint32_t nblk = gridDim.x >> 1;
-    const bool role_a = blockIdx.x < nblk;
-    const uint32_t blk = role_a ? blockIdx.x : blockIdx.x - nblk;
+template <bool PAIRS>
+FB_DEV bool fb_k1_lane_setup(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
+                             uint32_t n_variants, uint32_t blk, uint8_t *smem, FbK1Lane &W) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t nvar = (uint32_t)J.nvar, ch = (uint32_t)J.channels;
     // Variants to lanes: in order, 32 per warp -- except that the variants of a shorter last frame start a warp of
@@ -959,9 +964,10 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
     const bool tail_warp = n_full < n_variants && slot0 >= tail_slot;
     const uint32_t gv0 = tail_warp ? n_full + (slot0 - tail_slot) : slot0;
     const uint32_t lim = tail_warp ? n_variants : n_full;        // end of the variants this warp may take
-    if (gv0 >= lim) return; // the whole warp has nothing to do
+    if (gv0 >= lim) return false; // the whole warp has nothing to do
     const uint32_t gv = gv0 + lane;
-    const bool valid = gv < lim;
+    W.valid = gv < lim;
+    const bool valid = W.valid;
     const uint32_t gve = valid ? gv : lim - 1u; // surplus lanes shadow the last variant (they still copy)
     const uint32_t f = gve / nvar;
     const int v = (int)(gve - f * nvar);
@@ -969,13 +975,11 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
     const uint32_t f_lo = gv0 / nvar, f_hi = gvl / nvar;
     const uint32_t rlo = f_lo * ch;
     const uint32_t NR = (f_hi - f_lo + 1u) * ch;
-    const int n_w = fb_frame_len(J, f_lo);               // frames of a batch only get shorter at its end
-    const bool uniform = fb_frame_len(J, f_hi) == n_w;   // all lanes walk frames of one length
-    const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
-    FbAnalysis *out = ana + gve;
-    fb200_variant_taps *taps = taps_all ? taps_all + gve : nullptr;
-
-    FbK1Stage T;
+    W.n_w = fb_frame_len(J, f_lo);                       // frames of a batch only get shorter at its end
+    W.uniform = fb_frame_len(J, f_hi) == W.n_w;          // all lanes walk frames of one length
+    W.V = fb_k1_var(J, f, v, win_full, win_tail);
+    W.gve = gve;
+    FbK1Stage &T = W.T;
     T.pairs = PAIRS;
     T.mb = 0;
     T.last_bytes = 16u;
@@ -1027,6 +1031,27 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
             T.g1_off = (uint32_t)(fb_xt_off(J.stride, rlo + r2, 0) - fb_xt_off(J.stride, rlo + rc, 0));
         }
     }
+
+    return true;
+}
+
+template <int R, bool PAIRS>
+FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
+                       FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
+    // The grid holds every block of 128 variants twice: the first half runs pass A (the longer one, so it is scheduled
+    // first), the second half pass E.  Half-length CTAs pack the SMs' slots better at the end of a launch, and small
+    // batches (latency-bound: one thread walks a whole frame) finish in roughly half the time.
+    const uint32_t nblk = gridDim.x >> 1;
+    const bool role_a = blockIdx.x < nblk;
+    const uint32_t blk = role_a ? blockIdx.x : blockIdx.x - nblk;
+    FbK1Lane W;
+    if (!fb_k1_lane_setup<PAIRS>(J, xt, pcm, win_full, win_tail, n_variants, blk, smem, W)) return;
+    const FbK1Stage &T = W.T;
+    const FbK1Var &V = W.V;
+    const bool valid = W.valid, uniform = W.uniform;
+    const int n_w = W.n_w;
+    FbAnalysis *out = ana + W.gve;
+    fb200_variant_taps *taps = taps_all ? taps_all + W.gve : nullptr;
 
     // ---- pass E
     if (!role_a) {
@@ -1277,6 +1302,92 @@ FB_DEV void fb_k1c_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, c
         }
     FB_PHASE_END
 }
+
+#if FB_GPU
+// K1D: the same estimator for the default lpc_order (10) and LARGE launches, thread per channel variant like K1: the 55
+// covariance chains and the 11 autocorrelation chains of a variant live in the registers of one thread next to a ring of
+// its last 11 windowed samples, so a sample costs one shared-memory read and 66 DFMAs instead of 66 x (2 reads + 1 DFMA)
+// spread over a CTA (K1C).  Chains are summed in the same order: results are bit-identical to K1C.
+#define FB_K1D_P 10
+template <bool PAIRS>
+FB_DEV void fb_k1d_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
+                        FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t n_variants, uint8_t *smem) {
+    constexpr int P = FB_K1D_P;
+    FbK1Lane W;
+    if (!fb_k1_lane_setup<PAIRS>(J, xt, pcm, win_full, win_tail, n_variants, blockIdx.x, smem, W)) return;
+    const FbK1Var &V = W.V;
+    FbAnalysis *out = ana + W.gve;
+    fb200_variant_taps *taps = taps_all ? taps_all + W.gve : nullptr;
+    double C[P * (P + 1) / 2], Rr[P + 1], ring[P + 1]; // ring[k] = y[t - k]
+#pragma unroll
+    for (int i = 0; i < P * (P + 1) / 2; i++) C[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= P; i++) { Rr[i] = 0.0; ring[i] = 0.0; }
+    if (J.cfg.use_lpc && W.n_w >= FB_MIN_PRED_BLOCK) {
+        const int n = V.n; // (every lane of the warp: fb_k1_slots isolates a shorter last frame in a warp of its own)
+        const float *win = V.win;
+        fb_k1_stream<2, 4, PAIRS>(W.T, (W.n_w + 7) / 8, [&](int g, const int32_t *xs) {
+            const int t0 = g * 8;
+            float ws[8];
+            fb_k1_win_load<8, false>(win, t0, 0, ws); // (the table is zero-padded beyond n)
+            const bool mid = t0 >= P && t0 + 8 <= n - 1; // P <= t <= n - 2 for all eight: every chain takes every sample
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const int t = t0 + s;
+                const double y = (double)FB_FMUL((float)xs[s], ws[s]);
+#pragma unroll
+                for (int k = P; k >= 1; k--) ring[k] = ring[k - 1];
+                ring[0] = y;
+                if (mid || (t >= P && t <= n - 1)) {
+#pragma unroll
+                    for (int tau = 0; tau <= P; tau++) Rr[tau] = FB_FMA(ring[tau], ring[0], Rr[tau]);
+                }
+                if (mid || (t >= P - 1 && t <= n - 2)) {
+                    int c = 0;
+#pragma unroll
+                    for (int i = 0; i < P; i++)
+#pragma unroll
+                        for (int j = i; j < P; j++, c++) C[c] = FB_FMA(ring[i], ring[j], C[c]);
+                }
+            }
+        });
+    }
+    if (!W.valid || !V.do_lpc) return; // (K1 has stored the "no LPC" record already)
+    // solve C a = r[1..P] (src/lpc.rs:886-896) and quantise, like K1C's last phase
+    double Cm[P * P], L[P * P], xy[P], lpc[FB200_MAX_LPC_ORDER];
+    {
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+#pragma unroll
+            for (int j = i; j < P; j++, c++) { Cm[i * P + j] = C[c]; Cm[j * P + i] = C[c]; }
+    }
+    double regularizer = 0.0;
+    for (;;) {
+        for (int i = 0; i < P * P; i++) L[i] = Cm[i];
+        for (int i = 0; i < P; i++) xy[i] = Rr[1 + i];
+        if (fb_solve_sym(L, P, xy)) break;
+        const double old = regularizer;
+        const double twice = FB_DADD(regularizer, regularizer);
+        regularizer = twice > 1.0 ? twice : 1.0;
+        for (int i = 0; i < P; i++) Cm[i * P + i] = FB_DADD(Cm[i * P + i], FB_DADD(regularizer, -old));
+    }
+    for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) lpc[i] = i < P ? xy[i] : 0.0;
+    int16_t q[32];
+    int shift;
+    const int order = fb_quantize(lpc, P, J.cfg.quant_precision, q, &shift);
+    out->qlp_order = order;
+    out->qlp_shift = shift;
+    for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
+    if (taps) {
+        for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) taps->autocorr[i] = i <= P ? Rr[i] : 0.0;
+        for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) taps->lpc[i] = lpc[i];
+        for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
+        taps->qlp_order = order;
+        taps->qlp_shift = shift;
+    }
+}
+#endif
 
 // =================================================================================================
 // K2: per-variant residual coding search and subframe decision (CTA per variant).
