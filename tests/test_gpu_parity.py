@@ -612,3 +612,35 @@ def test_device_find_shift_matches_libm_around_powers_of_two():
         assert lib.fb200_debug_find_shift(0, vals.ctypes.data, len(vals), prec, got.ctypes.data) == 0
         want = O.find_shift_each(vals, prec)
         assert np.array_equal(got, want), np.flatnonzero(got != want)[:5]
+
+
+def test_cli_encodes_wav_files(tmp_path):
+    """the encode command of the reference's binary (flacenc-bin/src/main.rs:204-269) on the library: WAV in (16-bit
+    stereo, 24-bit mono, 8-bit unsigned), FLAC out; the streams equal the oracle's and decode to the WAV's samples"""
+    import wave
+    from flacenc_rs_b200 import cli
+    cases = [(2, 2, 44100, 4096 * 3 + 555), (1, 3, 48000, 5000), (2, 1, 8000, 3000)]
+    paths, sigs = [], []
+    for i, (ch, width, rate, n) in enumerate(cases):
+        bps = width * 8
+        x = sigen.noisy_sine_pcm(n, ch, bps, rate, config_id=50 + i)
+        raw = pack_pcm(x, width)
+        if width == 1:
+            raw = (raw.view(np.int8).astype(np.int32) + 128).astype(np.uint8)  # 8-bit WAV is unsigned
+        path = str(tmp_path / f"in{i}.wav")
+        with wave.open(path, "wb") as w:
+            w.setnchannels(ch); w.setsampwidth(width); w.setframerate(rate)
+            w.writeframes(raw.tobytes())
+        paths.append(path)
+        sigs.append((x, ch, bps, rate))
+    for i, path in enumerate(paths):
+        out = str(tmp_path / f"out{i}.flac")
+        assert cli.main(["encode", "-o", out, path]) == 0
+        x, ch, bps, rate = sigs[i]
+        data = open(out, "rb").read()
+        assert data == O.encode_stream(O.default_config(), x, ch, bps, rate, 4096)
+        dec, info = O.decode_stream(data)
+        assert np.array_equal(dec, x)
+    # two files of one format as a batch
+    assert cli.main(["encode", "-o", str(tmp_path / "b"), paths[0], paths[0]]) == 0
+    assert open(str(tmp_path / "b0.flac"), "rb").read() == open(str(tmp_path / "b1.flac"), "rb").read() == open(str(tmp_path / "out0.flac"), "rb").read()
