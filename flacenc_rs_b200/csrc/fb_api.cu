@@ -860,6 +860,25 @@ int fb_encode_serial(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P) {
     return FB200_OK;
 }
 
+// chunk schedule of the pipelined path (see fb_encode_pipelined): the frames before a short final chunk (a quarter of the
+// nominal size) are spread evenly over chunks of at most the nominal size
+std::vector<std::pair<uint64_t, uint64_t>> fb_chunk_schedule(uint64_t total_frames, uint64_t chunk_frames) {
+    std::vector<std::pair<uint64_t, uint64_t>> chunks; // (first frame, frames)
+    if (total_frames == 0) return chunks;
+    chunk_frames = std::max<uint64_t>(chunk_frames, 1);
+    const uint64_t last = std::max<uint64_t>(1, std::min<uint64_t>(chunk_frames / 4, total_frames / 2));
+    const uint64_t body = total_frames - last;
+    const uint64_t nb = (body + chunk_frames - 1) / chunk_frames;
+    uint64_t f = 0;
+    for (uint64_t i = 0; i < nb; i++) {
+        const uint64_t take = body / nb + (i < body % nb ? 1 : 0);
+        chunks.push_back({f, take});
+        f += take;
+    }
+    chunks.push_back({f, last});
+    return chunks;
+}
+
 // ---- pipelined path: host PCM in, host frame bytes out.  The batch is cut into chunks; chunk c's H2D copy
 // (stream s_in), kernels (compute streams, alternating so the latency-bound analysis kernel of one chunk overlaps
 // the fused kernel of the previous one) and D2H copy (stream s_out) overlap with those of its neighbours.
@@ -880,21 +899,9 @@ int fb_encode_pipelined(const std::vector<fb200_ctx *> &cs, const EncodeArgs &A,
     // last copy has landed.  One short final chunk (a quarter of the nominal size) keeps that tail small; more than
     // one does not pay, because every chunk costs about a millisecond of kernel latency.  The frames before it are
     // spread evenly over chunks of at most the nominal size.
-    std::vector<std::pair<uint64_t, uint64_t>> chunks; // (first frame, frames)
-    {
-        const uint64_t last = std::max<uint64_t>(1, std::min<uint64_t>(chunk_frames / 4, P.total_frames / 2));
-        const uint64_t body = P.total_frames - last;
-        const uint64_t nb = (body + chunk_frames - 1) / chunk_frames;
-        uint64_t f = 0;
-        for (uint64_t i = 0; i < nb; i++) {
-            const uint64_t take = body / nb + (i < body % nb ? 1 : 0);
-            chunks.push_back({f, take});
-            f += take;
-        }
-        chunks.push_back({f, last});
-        chunk_frames = 0;
-        for (auto &c : chunks) chunk_frames = std::max(chunk_frames, c.second);
-    }
+    const std::vector<std::pair<uint64_t, uint64_t>> chunks = fb_chunk_schedule(P.total_frames, chunk_frames); // (first frame, frames)
+    chunk_frames = 0;
+    for (auto &c : chunks) chunk_frames = std::max(chunk_frames, c.second);
     const uint64_t nchunks = chunks.size();
     const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
     const uint64_t in_chunk = std::min(chunk_frames * P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb, in_bytes_total);
@@ -1508,6 +1515,18 @@ int fb200_encode_streams(const fb200_config *cfg, int n_streams, const void *con
         }
     }
     return first_rc;
+}
+
+// The chunk schedule of the (sharded) host path for a batch of total_frames frames and a nominal chunk size: chunk c =
+// frames [first[c], first[c] + count[c]) and is encoded on device c mod n_devices.  Host logic only (no device needed);
+// returns the number of chunks (fills at most `cap` entries).
+size_t fb200_debug_chunk_schedule(uint64_t total_frames, uint64_t chunk_frames, uint64_t *first, uint64_t *count, size_t cap) {
+    const auto chunks = fb_chunk_schedule(total_frames, chunk_frames);
+    for (size_t i = 0; i < chunks.size() && i < cap; i++) {
+        if (first) first[i] = chunks[i].first;
+        if (count) count[i] = chunks[i].second;
+    }
+    return chunks.size();
 }
 
 // MD5 of a byte range with the library's own implementation (the floor of every stream-level call: sequential host work)

@@ -5,6 +5,10 @@ Frames are independent, so GPU ``g`` of ``G`` encodes the contiguous range
 The only per-shard state STREAMINFO needs is min/max frame size, byte and frame counts
 (component::StreamInfo::update_frame_info, src/component/datatype.rs:514-523).  No collective is involved on
 the data path; the same arithmetic is done in C++ by fb200_encode_stream (csrc/fb_api.cu)."""
+# The library's own multi-device call (fb200_encode_interleaved_sharded, csrc/fb_api.cu) shares a batch at CHUNK
+# granularity: the batch is cut by ``chunk_schedule`` and chunk ``c`` is encoded on device ``c mod N`` (frame ranges
+# again, just finer, so that every chunk's bytes can be copied straight to their final offset as soon as the chunk before
+# it is done).  ``chunk_schedule`` / ``device_of_chunk`` mirror that arithmetic; tests compare them with the C++ code.
 from __future__ import annotations
 
 from typing import Dict, Iterable, Tuple
@@ -39,3 +43,25 @@ def merge_shard_stats(stats: Iterable[Dict[str, int]]) -> Dict[str, int]:
         out["bytes"] += s["bytes"]
         out["frames"] += s["frames"]
     return out
+
+
+def chunk_schedule(total_frames: int, chunk_frames: int):
+    """[(first frame, frames)] of the pipelined host path: the frames before a short final chunk (a quarter of the nominal
+    size) spread evenly over chunks of at most the nominal size (fb_chunk_schedule in csrc/fb_api.cu)."""
+    if total_frames == 0:
+        return []
+    chunk_frames = max(chunk_frames, 1)
+    last = max(1, min(chunk_frames // 4, total_frames // 2))
+    body = total_frames - last
+    nb = (body + chunk_frames - 1) // chunk_frames
+    out, f = [], 0
+    for i in range(nb):
+        take = body // nb + (1 if i < body % nb else 0)
+        out.append((f, take))
+        f += take
+    out.append((f, last))
+    return out
+
+
+def device_of_chunk(c: int, n_devices: int) -> int:
+    return c % n_devices

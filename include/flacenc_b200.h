@@ -206,6 +206,10 @@ void fb200_pool_clear(void);
  *   log2f of estimate_entropy (src/coding.rs:200-227): out_bits[i] = bits of log2f(float with bits first_bits + i)
  *   find_shift (src/lpc.rs:234-255) of the one-coefficient set {values[i]}: out_shift[i] */
 int fb200_debug_log2f(int device, uint32_t first_bits, uint64_t count, uint32_t *out_bits);
+/* The chunk schedule of the (sharded) host path: chunk c = frames [first[c], first[c] + count[c]) of a batch of
+ * total_frames frames cut with a nominal chunk size; chunk c is encoded on device c mod n.  Host logic only (no device
+ * needed).  Returns the number of chunks; fills at most cap entries. */
+size_t fb200_debug_chunk_schedule(uint64_t total_frames, uint64_t chunk_frames, uint64_t *first, uint64_t *count, size_t cap);
 int fb200_debug_find_shift(int device, const double *values, uint64_t count, int precision, int32_t *out_shift);
 
 /* ---- diagnostics ---- */

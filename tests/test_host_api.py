@@ -176,6 +176,29 @@ def test_streaminfo_merge_matches_single_shard():
     assert whole == parts == {"min_frame": 14, "max_frame": 4000, "bytes": int(sizes.sum()), "frames": 7}
 
 
+@pytest.mark.parametrize("total,chunk", [(0, 2432), (1, 2432), (2, 1), (108, 2432), (5000, 2432), (38760, 2432), (38760, 807),
+                                         (421875, 304), (62, 5), (7, 64)])
+def test_chunk_schedule_partitions_the_batch_and_matches_the_library(total, chunk):
+    """the chunk schedule of the (sharded) host path: chunks are contiguous, cover the batch, none larger than the nominal
+    size; the Python mirror equals the C++ code (fb200_debug_chunk_schedule: host logic, no GPU needed)"""
+    sched = sharding.chunk_schedule(total, chunk)
+    assert sum(n for _, n in sched) == total
+    f = 0
+    for f0, n in sched:
+        assert f0 == f and n >= 1 and n <= max(chunk, 1)
+        f += n
+    first = np.zeros(max(len(sched), 1) + 4, np.uint64)
+    count = np.zeros(max(len(sched), 1) + 4, np.uint64)
+    k = _ffi.lib().fb200_debug_chunk_schedule(total, chunk, first.ctypes.data, count.ctypes.data, len(first))
+    assert k == len(sched)
+    assert [(int(a), int(b)) for a, b in zip(first[:k], count[:k])] == sched
+    # every device of a sharded call gets a fair share of the chunks
+    for n_dev in (2, 3, 8):
+        owners = [sharding.device_of_chunk(c, n_dev) for c in range(len(sched))]
+        per = [owners.count(d) for d in range(n_dev)]
+        assert max(per) - min(per) <= 1
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, sys.argv[1])
@@ -195,6 +218,22 @@ gathered = [None] * world
 dist.all_gather_object(gathered, (f0, f1, ns, st))
 t = torch.tensor([1.0 + rank], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# the library's own sharded call works at chunk granularity (chunk c on device c mod N): every rank derives the same
+# schedule, the ranks' chunks are disjoint and cover the batch, and the byte offset of a chunk is the sum of the sizes
+# of the chunks before it whichever rank encoded them
+sched = sharding.chunk_schedule(F, 13)
+mine = [(c, f0, nf) for c, (f0, nf) in enumerate(sched) if sharding.device_of_chunk(c, world) == rank]
+mine_bytes = {c: int(sum(100 + (i * 37) % 900 for i in range(f0, f0 + nf))) for c, f0, nf in mine}
+all_bytes = [None] * world
+dist.all_gather_object(all_bytes, mine_bytes)
+if rank == 0:
+    merged_chunks = {}
+    for d in all_bytes:
+        assert not (set(d) & set(merged_chunks))
+        merged_chunks.update(d)
+    assert sorted(merged_chunks) == list(range(len(sched)))
+    offs = np.concatenate([[0], np.cumsum([merged_chunks[c] for c in range(len(sched))])])
+    assert offs[-1] == sum(100 + (i * 37) % 900 for i in range(F))
 if rank == 0:
     gathered.sort()
     assert gathered[0][0] == 0 and gathered[-1][1] == F
