@@ -37,11 +37,13 @@
 
 #include "fb_kernels.cuh"
 
-#define FB_KF_RUN 16       // samples per residual run (register window of G + FB_KF_RUN samples)
+#ifndef FB_KF_RUN
+#define FB_KF_RUN 8        // samples per residual run (register window of G + FB_KF_RUN samples)
+#endif
 #define FB_KF_COLS 4       // Rice parameters evaluated per tree pass
 #define FB_KF_ROW 5        // row stride of the tree tables (one pad word: conflict-free column reads)
 #define FB_KF_NWORDS 7     // bit-sliced counter words per unit (counts <= 127)
-#define FB_KF_UNIT_MAX 112 // samples per unit (7 runs of 16)
+#define FB_KF_UNIT_MAX 112 // samples per unit (14 runs of 8; the counters hold counts <= 127)
 #define FB_KF_SMEM_LIMIT (225u * 1024u) // dynamic shared memory one CTA may ask for (227 KiB on sm_100a, minus slack)
 
 // 16-byte global -> shared copy that does not pass through registers (LDGSTS), so a thread keeps all the copies of

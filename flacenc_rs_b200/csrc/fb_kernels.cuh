@@ -1061,11 +1061,7 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
         S.xmax = -2147483647 - 1;
         const bool ent_w = J.cfg.use_fixed && J.cfg.fixed_order_sel == 1 && n_w >= FB_MIN_PRED_BLOCK;
         const bool whole = uniform && (!ent_w || (V.psize & 7) == 0);
-#ifdef FB_K1_E_NOARITH // (timing experiments only: results are wrong)
-        if (false)
-#else
         if (ent_w)
-#endif
             fb_k1_stream<2, 4, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
                 if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, true>(S, xs, g * 8);
                 else fb_k1_ent_group<true, true>(S, xs, g * 8);
@@ -1085,11 +1081,7 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
     for (int i = 0; i <= R; i++) A.acc[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < R; i++) A.ring[i] = 0.0;
-#ifdef FB_K1_SKIP_A // (timing experiments only: results are wrong)
-    if (false) {
-#else
-    if (J.cfg.use_lpc && !J.cfg.use_direct_mse && n_w >= FB_MIN_PRED_BLOCK) { // (direct MSE: K1C estimates the LPC)
-#endif
+    if (J.cfg.use_lpc && !J.cfg.use_direct_mse && n_w >= FB_MIN_PRED_BLOCK) { // (direct MSE: K1C / K1D estimate the LPC)
         switch (R - V.P) {
         case 0: fb_k1_warp_pass_a<R, 0, PAIRS>(T, A, V, n_w, uniform); break;
         case 1: fb_k1_warp_pass_a<R, 1, PAIRS>(T, A, V, n_w, uniform); break;

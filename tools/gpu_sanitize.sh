@@ -30,8 +30,13 @@ run(2, 16, 2, 1001, sig(2, 16, 1001 * 5 + 333))
 # a frame the fused kernels hand to the generic kernels (residual >= 2^26), between two ordinary frames
 big = crafted_huge_residual_stereo()
 run(2, 24, 3, 4096, np.concatenate([sig(2, 24, 4096), big, sig(2, 24, 4096, 7)]), lpc_order=24)
-# direct-MSE estimator (K1C)
+# direct-MSE estimator: K1C (CTA per variant), then K1D and the thread-per-variant K1 forced on the same small inputs
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
+os.environ["FB200_K1_SMALL"] = "0"
+run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
+run(2, 16, 2, 4096, sig(2, 16, 4096 * 9 + 2728))
+run(8, 24, 3, 1024, sig(8, 24, 1024 * 5 + 37))
+del os.environ["FB200_K1_SMALL"]
 # frame-range sharding over three contexts, chunks of 3 frames
 os.environ["FB200_CHUNK_FRAMES"] = "3"
 x = sig(2, 16, 1024 * 20 + 99)
