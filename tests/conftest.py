@@ -71,6 +71,65 @@ def shift_cases():
     return vals
 
 
+def fuzz_frame_case(rng):
+    """One case in the shape of the reference's fuzz target (/root/reference/fuzz/fuzz_targets/frame_encode.rs:197-212):
+    ONE frame of block size 32..32767, bits per sample 8..24, 1..8 channels, every toggle of the configuration random
+    (orders 1..24, precision 1..15, Tukey alpha or Rectangle, max Rice parameter 0..30, fixed max order 0..4), the signal
+    a random composition of DC, noise, sine, mixes and switches, optionally clipped.  Returns (signal, channels, bps,
+    rate, block size, config kwargs)."""
+    channels = int(rng.integers(1, 9))
+    bps = int(rng.choice([8, 12, 16, 20, 24]))
+    # block sizes: the whole range, with a bias to the extremes and to sizes whose Rice partitions are odd
+    pick = rng.random()
+    if pick < 0.25:
+        block = int(rng.integers(32, 200))
+    elif pick < 0.5:
+        block = int(rng.integers(16000, 32768))
+    elif pick < 0.6:
+        block = int(rng.choice([32767, 32766, 32764, 16384, 8192, 4608, 4096, 1152, 576, 192]))
+    else:
+        block = int(rng.integers(200, 16000))
+    full = float((1 << (bps - 1)) - 1)
+
+    def signal(n, depth=0):
+        kind = int(rng.integers(0, 5 if depth < 3 else 3))
+        t = np.arange(n, dtype=np.float64)
+        if kind == 0:
+            x = np.full(n, rng.random())
+        elif kind == 1:
+            x = rng.random() * rng.uniform(-1, 1, n)
+        elif kind == 2:
+            period = max(1.0, n * rng.random())
+            x = rng.random() * np.sin(2 * np.pi * t / period + 2 * np.pi * rng.random())
+        elif kind == 3:
+            a = rng.random()
+            x = a * signal(n, depth + 1) + (1 - a) * signal(n, depth + 1)
+        else:
+            k = int(n * rng.random())
+            x = np.concatenate([signal(k, depth + 1), signal(n - k, depth + 1)]) if 0 < k < n else signal(n, depth + 1)
+        return x
+
+    chans = []
+    for _ in range(channels):
+        x = signal(block) * (4.0 if rng.random() < 0.3 else 1.0)  # some channels overdrive and clip
+        chans.append(np.clip(np.round(x * full), -full - 1, full).astype(np.int32))
+    cfg = {
+        "use_leftside": int(rng.random() < 0.7), "use_rightside": int(rng.random() < 0.7), "use_midside": int(rng.random() < 0.7),
+        "use_constant": int(rng.random() < 0.8), "use_fixed": int(rng.random() < 0.8), "use_lpc": int(rng.random() < 0.8),
+        "fixed_max_order": int(rng.integers(0, 5)), "prc_max_parameter": int(rng.integers(0, 31)),
+        "lpc_order": int(rng.integers(1, 25)), "quant_precision": int(rng.integers(1, 16)),
+        "fixed_order_sel": int(rng.random() < 0.8),
+    }
+    if rng.random() < 0.3:
+        cfg["window_type"] = 0
+    else:
+        cfg["tukey_alpha"] = float(rng.random())
+    if rng.random() < 0.15:
+        cfg["use_direct_mse"] = 1
+    rate = int(rng.choice([8000, 44100, 48000, 96000, 11025]))
+    return np.stack(chans, axis=1), channels, bps, rate, block, cfg
+
+
 def random_case(rng):
     """One seeded fuzz case: (signal, channels, bps, rate, block size, first frame number, oracle-style config kwargs)."""
     channels = int(rng.choice([1, 2, 2, 2, 3, 4, 6, 8]))

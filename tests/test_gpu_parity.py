@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case, shift_cases
+from conftest import crafted_huge_residual_stereo, fuzz_frame_case, load_fixture, pack_pcm, random_case, shift_cases
 from flacenc_rs_b200 import _ffi, sigen
 from flacenc_rs_b200.config import Encoder, Fixed, OrderSel, Qlpc, StereoCoding, SubFrameCoding, Window, Prc
 from flacenc_rs_b200.encoder import (Context, StreamInfo, encode_fixed_size_frame, encode_with_fixed_block_size)
@@ -350,6 +350,17 @@ def test_randomised_formats_signals_and_configs(seed):
     rng = np.random.default_rng(1000 + seed)
     x, channels, bps, rate, block, first, cfg = random_case(rng)
     _compare(x, channels, bps, rate, block, first_frame=first, **cfg)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_fuzz_frames_at_reference_scale(seed):
+    """the property of the reference's fuzz target (fuzz/fuzz_targets/frame_encode.rs:197-212) at its scale -- one frame of
+    32..32767 samples, 8..24 bits, 1..8 channels, every configuration toggle random -- strengthened from "decodes
+    losslessly" to "bytes equal the oracle's on every device path"; a second frame (shorter) exercises the tail"""
+    rng = np.random.default_rng(9000 + seed)
+    x, channels, bps, rate, block, cfg = fuzz_frame_case(rng)
+    tail = x[: int(rng.integers(1, block + 1))]
+    _compare(np.concatenate([x, tail]), channels, bps, rate, block, **cfg)
 
 
 def test_first_frame_number_and_utf8_lengths():

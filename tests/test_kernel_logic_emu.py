@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import crafted_huge_residual_stereo, load_fixture, pack_pcm, random_case, shift_cases
+from conftest import crafted_huge_residual_stereo, fuzz_frame_case, load_fixture, pack_pcm, random_case, shift_cases
 from flacenc_rs_b200 import sigen
 from oracle import oracle as O
 from emu import emu as E
@@ -380,3 +380,12 @@ def test_direct_mse_estimator_matches_oracle():
     rc, taps, nv = E.analyze(cfg, pack_pcm(sig.reshape(-1, 1), 2), 2, 1024, 1, 16, 44100, 1024)
     assert rc == 0 and nv == 1
     assert np.array_equal(np.array(taps[0].lpc[:10]), coefs) and np.array_equal(np.array(taps[0].autocorr[:11]), corr)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_frames_at_reference_scale_emu(seed):
+    """the reference's fuzz shape (one frame, block up to 32767, 1..8 channels, 8..24 bits, all toggles) under emulation;
+    the -m gpu suite runs 60 seeds of it on the device"""
+    rng = np.random.default_rng(9000 + seed)
+    x, channels, bps, rate, block, cfg = fuzz_frame_case(rng)
+    _compare(x, channels, bps, rate, block, **cfg)
