@@ -266,7 +266,7 @@ FB_HD FbKfLayout fb_kf_layout(int channels, int nvar, int bps, int block_size, i
         if (ta < levels * 32u * 4u) ta = levels * 32u * 4u;
     }
     L.s_tbl_a = s;      s += fb_align16(ta);
-    L.s_tbl_b = s;      s += fb_align16((leaves / 2u + 1u) * FB_KF_ROW * 4u);
+    L.s_tbl_b = s;      // (no second table: the tree levels are merged in place)
     L.s_best_val = s;   s += fb_align16(2u * leaves * 4u);
     L.s_best_p = s;     s += fb_align16(2u * leaves);
     L.s_lvl_bits = s;   s += 16u * 8u;
@@ -292,18 +292,19 @@ FB_HD FbKfLayout fb_kp_layout(int channels, int nvar, int bps, int block_size, i
     // independent, so they can be staged and packed group by group)
     const uint32_t fixed = fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u) +
                            fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info)) +
-                           fb_align16((uint32_t)sizeof(FbKfFrame)) + 4096u + L.words_bytes;
+                           fb_align16((uint32_t)sizeof(FbKfFrame)) + L.words_bytes;
     const uint32_t plane = L.x_stride * 4u;
     uint32_t gc = (uint32_t)channels;
     while (gc > 1u && fixed + fb_align16(gc * plane) > FB_KF_SMEM_LIMIT) gc--;
     if (channels == 2) gc = 2; // M and S need both planes
     L.group_ch = gc;
     uint32_t o = 0;
-    L.off_x = o;        o += fb_align16((pairs ? 1u : gc) * L.x_stride * 4u);
+    // the planes; the four CRC-16 slicing tables (4 KiB) take their place once the frame is packed
+    const uint32_t planes = fb_align16((pairs ? 1u : gc) * L.x_stride * 4u);
+    L.off_x = o;        L.off_crc_tab = o;  o += planes > 4096u ? planes : 4096u;
     L.off_keep = o;     o += fb_align16((uint32_t)channels * (L.U_max + 1u) * 4u);   // unit offsets
     L.off_choice = o;   o += fb_align16((uint32_t)channels * (uint32_t)sizeof(fb200_subframe_info));
     L.off_frame = o;    o += fb_align16((uint32_t)sizeof(FbKfFrame));
-    L.off_crc_tab = o;  o += 4096u;
     L.off_scratch = o;  o += L.words_bytes;                                            // frame words
     L.total = o;
     return L;
@@ -633,7 +634,6 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
                          const FbKfCand &cd, uint8_t *scratch, const FbKfLayout &L, uint32_t *unit_bits, FbKfRes *res) {
     uint32_t *words = (uint32_t *)(scratch + L.s_words);
     uint32_t *tbl_a = (uint32_t *)(scratch + L.s_tbl_a);
-    uint32_t *tbl_b = (uint32_t *)(scratch + L.s_tbl_b);
     uint32_t *best_val = (uint32_t *)(scratch + L.s_best_val);
     uint8_t *best_p = scratch + L.s_best_p;
     unsigned long long *lvl_bits = (unsigned long long *)(scratch + L.s_lvl_bits);
@@ -753,26 +753,39 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
                 if (first || bv < best_val[idx]) { best_val[idx] = bv; best_p[idx] = (uint8_t)bp; }
             }
         FB_WPHASE_END
-        uint32_t *cur = tbl_a, *nxt = tbl_b;
+        // the levels are merged IN PLACE in one table: node i of a level reads rows 2i and 2i + 1 and writes row i.  Nodes
+        // are taken 32 at a time in ascending order, all reads of a batch before its writes: a batch starting at node b
+        // reads rows >= 2b, and everything written so far lies below row b + 32 <= 2b for b >= 32 (for b = 0 the batch's
+        // own reads are done before its writes).
         for (int lvl = g.o0 - 1; lvl >= 0; lvl--) {
             const int nodes = 1 << lvl;
-            FB_WPHASE(lane)
-                for (int node = lane; node < nodes; node += 32) {
-                    const uint32_t *ra = cur + (2 * node) * FB_KF_ROW, *rb = ra + FB_KF_ROW;
-                    uint32_t *ro = nxt + node * FB_KF_ROW;
+            for (int node0 = 0; node0 < nodes; node0 += 32) {
+                FB_WPHASE(lane)
+                    const int node = node0 + lane;
+                    uint32_t v[FB_KF_COLS];
                     uint32_t bv = 0xFFFFFFFFu;
                     int bp = pa;
-                    for (int j = 0; j < Wc; j++) {
-                        uint32_t v = ra[j] + rb[j] - 4u;
-                        v = v < FB_RICE_SAT ? v : FB_RICE_SAT;
-                        ro[j] = v;
-                        if (v < bv) { bv = v; bp = pa + j; }
+                    if (node < nodes) {
+                        const uint32_t *ra = tbl_a + (2 * node) * FB_KF_ROW, *rb = ra + FB_KF_ROW;
+                        for (int j = 0; j < Wc; j++) {
+                            uint32_t x = ra[j] + rb[j] - 4u;
+                            x = x < FB_RICE_SAT ? x : FB_RICE_SAT;
+                            v[j] = x;
+                            if (x < bv) { bv = x; bp = pa + j; }
+                        }
                     }
-                    const int idx = nodes - 1 + node;
-                    if (first || bv < best_val[idx]) { best_val[idx] = bv; best_p[idx] = (uint8_t)bp; }
-                }
-            FB_WPHASE_END
-            uint32_t *tmp = cur; cur = nxt; nxt = tmp;
+#if FB_GPU
+                    __syncwarp(); // (the emulation runs the lanes in ascending order, which is safe as it is: lane k writes
+                                  //  row k after reading rows 2k and 2k + 1, and no lane below k reads row k later)
+#endif
+                    if (node < nodes) {
+                        uint32_t *ro = tbl_a + node * FB_KF_ROW;
+                        for (int j = 0; j < Wc; j++) ro[j] = v[j];
+                        const int idx = nodes - 1 + node;
+                        if (first || bv < best_val[idx]) { best_val[idx] = bv; best_p[idx] = (uint8_t)bp; }
+                    }
+                FB_WPHASE_END
+            }
         }
     }
 
@@ -1322,7 +1335,6 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
             const uint32_t *src = poffs + (size_t)f * (size_t)J.channels * (L.U_max + 1);
             for (int i = tid; i < J.channels * (int)(L.U_max + 1); i += T) fb_copy4_async(poff + i, src + i);
         }
-        for (int i = tid; i < 256; i += T) fb_copy16_async((int32_t *)crc_tab + 4 * i, (const int32_t *)ktab + 4 * i);
         if (L.x16 == 2) fb_kp_stage_pairs(J, pcm, f, n, xs, tid, T);
         else fb_kf_stage<G>(J, xv, f, n, xs, L, tid, T, 0, GC < J.channels ? GC : J.channels);
         for (uint32_t w = (uint32_t)tid; w < max_words; w += (uint32_t)T) words[w] = 0;
@@ -1462,6 +1474,12 @@ FB_DEV void fb_kp_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
 #undef FB_KF_X
     FB_PHASE_END
     } // channel groups
+
+    // ---- the CRC tables replace the planes (every residual is packed: the phase above has ended)
+    FB_PHASE(tid, T)
+        for (int i = tid; i < 256; i += T) fb_copy16_async((int32_t *)crc_tab + 4 * i, (const int32_t *)ktab + 4 * i);
+        fb_copy_async_wait();
+    FB_PHASE_END
 
     // ---- CRC-16 over data_bytes (Frame::write, src/component/bitrepr.rs:289-320).  Chunks of Lc bytes from
     // the start of the frame, one per thread, four bytes per step (slicing tables); the chunk CRCs are shifted

@@ -58,9 +58,13 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
     }
 }
 
-// the pack kernel fits 96 registers (5 CTAs of 128 threads per SM) for tap windows up to 16; the wide windows would spill
+// the pack kernel fits 80 registers for tap windows up to 16 (6 CTAs of 128 threads per SM: its shared memory, 36.9 KB
+// with the CRC tables taking the place of the planes once the frame is packed, allows as many); the wide windows would spill
 #if FB_INST_G <= 16
-#define FB_KP_BOUNDS __maxnreg__(96)
+#ifndef FB_KP_MAXNREG
+#define FB_KP_MAXNREG 80
+#endif
+#define FB_KP_BOUNDS __maxnreg__(FB_KP_MAXNREG)
 #else
 #define FB_KP_BOUNDS __launch_bounds__(256)
 #endif
