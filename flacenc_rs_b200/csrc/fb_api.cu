@@ -1123,6 +1123,10 @@ uint64_t fb_pipe_chunk_frames(const fb200_ctx *ctx, const Plan &P, uint64_t tota
     uint64_t chunk = ctx->pipe_chunk_frames ? ctx->pipe_chunk_frames : 2432;
     if (!ctx->pipe_chunk_frames && n_devices > 1)
         chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(304, total_frames / (n_devices * 6)));
+    // a chunk should not be much more than the 40 MB of input that 2432 CD-stereo frames are (64 MiB at most): wide formats (8 channels of
+    // 24 bits: 98 KB per frame) get proportionally fewer frames per chunk, so that their copies and kernels overlap too
+    const uint64_t in_per_frame = P.bs * (uint64_t)ctx->channels * (uint64_t)P.cb;
+    if (!ctx->pipe_chunk_frames) chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(64, (64ull << 20) / std::max<uint64_t>(in_per_frame, 1)));
     const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + 2 * P.slot_bytes + 4096u;
     return std::min<uint64_t>(chunk, std::max<uint64_t>(64, (1024ull << 20) / per_frame));
 }
