@@ -342,6 +342,8 @@ CONFIG_CASES = [
      {"lpc_order": 24}),
     ("C4", "CD stereo 10 min, report/experimental.config.toml: use_direct_mse (covariance-method LPC) + Rectangle window",
      2, 16, 44100, 4096, 600, {"window_type": 0, "use_direct_mse": 1}),
+    ("C4-irls2", "CD stereo 2 min, C4's config + mae_optimization_steps = 2 (IRLS-MAE refinement, 3 weighted solves per channel variant)",
+     2, 16, 44100, 4096, 120, {"window_type": 0, "use_direct_mse": 1, "mae_optimization_steps": 2}),
     ("C5-slice", "48 kHz / 24-bit 8 channels, 2 min (1407 frames)", 8, 24, 48000, 4096, 120, {}),
 ]
 
@@ -355,6 +357,7 @@ def make_cfg(kw):
         e.subframe_coding.qlpc.window.type = "Rectangle"
     if kw.get("use_direct_mse"):
         e.subframe_coding.qlpc.use_direct_mse = True
+    e.subframe_coding.qlpc.mae_optimization_steps = kw.get("mae_optimization_steps", 0)
     return e.into_verified()
 
 

@@ -122,6 +122,7 @@ SYMBOLS = {
     "fb200_pool_clear": (None, []),
     "fb200_debug_chunk_schedule": (C.c_size_t, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t]),
     "fb200_debug_log2f": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]),
+    "fb200_debug_irls_weight": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_float, C.c_void_p]),
     "fb200_debug_find_shift": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "fb200_last_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "fb200_strerror": (C.c_char_p, [C.c_int]),

@@ -193,6 +193,13 @@ __global__ void __launch_bounds__(384) fb_k1c_direct_mse(FbJob J, const int32_t 
     fb_k1c_body(J, xt, pcm, win_full, win_tail, ana, taps, blockIdx.x, FB_K1C_TILE, fb_smem_k1c);
 }
 
+// K1I: IRLS-MAE refinement of the direct-MSE estimate, one CTA per channel variant (fb_kernels.cuh)
+__global__ void __launch_bounds__(384) fb_k1i_irls_mae(FbJob J, const int32_t *xt, const uint8_t *pcm, const float *win_full,
+                                                       const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps) {
+    extern __shared__ __align__(16) uint8_t fb_smem_k1i[];
+    fb_k1i_body(J, xt, pcm, win_full, win_tail, ana, taps, blockIdx.x, FB_K1I_TILE, fb_smem_k1i);
+}
+
 // K1D: direct-MSE estimator for lpc_order 10 and large launches, thread per channel variant (fb_kernels.cuh)
 __global__ void __maxnreg__(224) fb_k1d_direct_mse10(FbJob J, const int32_t *xt, const uint8_t *pcm, const float *win_full,
                                                      const float *win_tail, FbAnalysis *ana, fb200_variant_taps *taps,
@@ -231,6 +238,10 @@ __global__ void __launch_bounds__(256) fb_k4_gather(const uint8_t *slots, uint32
 __global__ void __launch_bounds__(256) fb_dbg_log2f(uint32_t first_bits, uint64_t count, uint32_t *out) {
     for (uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x; i < count; i += (uint64_t)gridDim.x * 256u)
         out[i] = fb_f2u(fb_log2f(fb_u2f(first_bits + (uint32_t)i)));
+}
+__global__ void __launch_bounds__(256) fb_dbg_irls_weight(uint32_t first_bits, uint64_t count, float normalizer, uint32_t *out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x; i < count; i += (uint64_t)gridDim.x * 256u)
+        out[i] = fb_f2u(fb_irls_weight(fb_u2f(first_bits + (uint32_t)i), normalizer));
 }
 __global__ void __launch_bounds__(256) fb_dbg_find_shift(const double *values, uint64_t count, int precision, int32_t *out) {
     for (uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x; i < count; i += (uint64_t)gridDim.x * 256u)
@@ -363,6 +374,13 @@ int fb200_debug_log2f(int device, uint32_t first_bits, uint64_t count, uint32_t 
     if (!out_bits || count == 0 || count > (1ull << 28)) return FB200_ERR_SOURCE;
     return fb_dbg_run(device, nullptr, 0, out_bits, (size_t)count * 4u, [&](const void *, void *d_out) {
         fb_dbg_log2f<<<1184, 256>>>(first_bits, count, (uint32_t *)d_out);
+    });
+}
+
+int fb200_debug_irls_weight(int device, uint32_t first_bits, uint64_t count, float normalizer, uint32_t *out_bits) {
+    if (!out_bits || count == 0 || count > (1ull << 28)) return FB200_ERR_SOURCE;
+    return fb_dbg_run(device, nullptr, 0, out_bits, (size_t)count * 4u, [&](const void *, void *d_out) {
+        fb_dbg_irls_weight<<<1184, 256>>>(first_bits, count, normalizer, (uint32_t *)d_out);
     });
 }
 
@@ -668,7 +686,11 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         // `experimental` estimator: K1 has skipped its autocorrelation pass; K1C (CTA per variant) or, for the default
         // order and launches large enough to fill the GPU with one thread per variant, K1D fills the LPC half of the records
         fb200_variant_taps *d_taps = A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr;
-        if (ctx->cfg.lpc_order == FB_K1D_P && !k1_small && !ctx->no_k1d) {
+        if (ctx->cfg.mae_optimization_steps > 0) {
+            // IRLS-MAE refinement (src/coding.rs:337-345): K1I re-weights and re-solves mae_optimization_steps times
+            fb_k1i_irls_mae<<<nvars, fb_k1i_threads(ctx->cfg.lpc_order), fb_k1i_smem_bytes(ctx->cfg.lpc_order, FB_K1I_TILE), st>>>(
+                J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p, d_taps);
+        } else if (ctx->cfg.lpc_order == FB_K1D_P && !k1_small && !ctx->no_k1d) {
             const uint32_t smem = fb_k1_smem_bytes(J.channels, J.nvar, pairs);
             if (smem > 48u * 1024u)
                 FB_CUDA(ctx, cudaFuncSetAttribute(fb_k1d_direct_mse10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -243,6 +243,83 @@ FB_DEV float fb_log2f(float x) {
     return (float)y;
 }
 
+// ---- glibc-compatible powf for positive x ----------------------------------------------------------
+// The IRLS refinement of the `experimental` estimator (src/lpc.rs:814-850) weights every sample by
+// (max(|err|, 1) / normalizer).max(0.01).powf(-1.2): f32::powf is the platform libm (glibc: the table-driven algorithm of
+// ARM's optimized routines -- log2 in double from the 16-entry table above with its own degree-5 polynomial, times y,
+// exp2 from a 32-entry table).  Only what that call can meet is implemented: x a positive normal number or +inf, y
+// finite and non-zero.  FB_POWF_FMA selects the expression forms glibc's FMA build contracts (the variant it dispatches
+// to on every x86-64 CPU with FMA); tests/test_kernel_logic_emu.py sweeps every x >= 0.01 for y = -1.2 against the host.
+#if FB_GPU
+__device__ __constant__ unsigned long long FB_EXP2F_TAB[32] = {
+#else
+static const unsigned long long FB_EXP2F_TAB[32] = {
+#endif
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull,
+    0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull,
+    0x3feedea64c123422ull, 0x3feece086061892dull, 0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull,
+    0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull, 0x3feee89f995ad3adull,
+    0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
+    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+
+#ifndef FB_POWF_FMA
+#define FB_POWF_FMA 1
+#endif
+// a * b + c the way the libm build evaluates it
+#if FB_POWF_FMA
+#define FB_PW_MAD(a, b, c) FB_FMA((a), (b), (c))
+#else
+#define FB_PW_MAD(a, b, c) FB_DADD(FB_DMUL((a), (b)), (c))
+#endif
+
+FB_DEV float fb_powf_pos(float x, float y) {
+    uint32_t ix = fb_f2u(x);
+    if (ix == 0x7f800000u) return (fb_f2u(y) & 0x80000000u) ? 0.0f : x; // +inf
+    // log2_inline
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const uint32_t top = tmp & 0xff800000u;
+    const uint32_t iz = ix - top;
+    const int k = (int32_t)top >> 23;
+    const double invc = FB_LOG2F_TAB[2 * i], logc = FB_LOG2F_TAB[2 * i + 1];
+    const double z = (double)fb_u2f(iz);
+    const double r = FB_PW_MAD(z, invc, -1.0);
+    const double y0 = FB_DADD(logc, (double)k);
+    const double r2 = FB_DMUL(r, r);
+    double yy = FB_PW_MAD(0x1.27616c9496e0bp-2, r, -0x1.71969a075c67ap-2);
+    const double p = FB_PW_MAD(0x1.ec70a6ca7baddp-2, r, -0x1.7154748bef6c8p-1);
+    const double r4 = FB_DMUL(r2, r2);
+    double q = FB_PW_MAD(0x1.71547652ab82bp+0, r, y0);
+    q = FB_PW_MAD(p, r2, q);
+    yy = FB_PW_MAD(yy, r4, q);
+    const double ylogx = FB_DMUL((double)y, yy);
+    // |y * log2(x)| >= 126: overflow / underflow thresholds of the float result
+    uint64_t yb;
+    memcpy(&yb, &ylogx, 8);
+    if (((yb >> 47) & 0xffffu) >= (0x405f800000000000ull >> 47)) {
+        if (ylogx > 0x1.fffffffd1d571p+6) return fb_u2f(0x7f800000u);
+        if (ylogx <= -150.0) return 0.0f;
+    }
+    // exp2_inline
+    const double shift = 0x1.8p+47; // 0x1.8p52 / 32
+    double kd = FB_DADD(ylogx, shift);
+    uint64_t ki;
+    memcpy(&ki, &kd, 8);
+    kd = FB_DADD(kd, -shift);
+    const double rr = FB_DADD(ylogx, -kd);
+    uint64_t t = FB_EXP2F_TAB[ki & 31u];
+    t += ki << 47; // (52 - 5)
+    double sc;
+    memcpy(&sc, &t, 8);
+    const double zz = FB_PW_MAD(0x1.c6af84b912394p-5, rr, 0x1.ebfce50fac4f3p-3);
+    const double rr2 = FB_DMUL(rr, rr);
+    double e = FB_PW_MAD(0x1.62e42ff0c52d6p-1, rr, 1.0);
+    e = FB_PW_MAD(zz, rr2, e);
+    e = FB_DMUL(e, sc);
+    return (float)e;
+}
+
 // Rust `f32 as usize`: saturating, NaN -> 0 (src/coding.rs:222)
 FB_HD uint64_t fb_f32_as_u64(float v) {
     if (!(v == v)) return 0;

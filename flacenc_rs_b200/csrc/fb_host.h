@@ -38,10 +38,11 @@ inline int fbh_config_verify(const fb200_config *c) {
     if (c->block_size < 32 || c->block_size > 32767) return FB200_ERR_CONFIG;
     if (c->lpc_order < 1 || c->lpc_order > FB200_MAX_LPC_ORDER) return FB200_ERR_CONFIG;
     if (c->quant_precision < 1 || c->quant_precision > 15) return FB200_ERR_CONFIG;
-    // use_direct_mse is accepted like a reference built with the `experimental` feature (src/config.rs:305-316, the
-    // covariance-method estimator of src/lpc.rs:852-913); its IRLS refinement (mae_optimization_steps) is not built
+    // use_direct_mse and mae_optimization_steps are accepted like a reference built with the `experimental` feature
+    // (src/config.rs:305-321; the covariance-method estimator of src/lpc.rs:852-913 and its IRLS refinement :814-850,
+    // which src/coding.rs:337-345 runs only when use_direct_mse is set)
     if (c->use_direct_mse != 0 && c->use_direct_mse != 1) return FB200_ERR_CONFIG;
-    if (c->mae_optimization_steps != 0) return FB200_ERR_CONFIG;
+    if (c->mae_optimization_steps < 0) return FB200_ERR_CONFIG;
     if (c->window_type == 1) {
         if (!(c->tukey_alpha >= 0.0f && c->tukey_alpha <= 1.0f)) return FB200_ERR_CONFIG;
     } else if (c->window_type != 0) {

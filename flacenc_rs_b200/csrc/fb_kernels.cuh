@@ -1183,6 +1183,21 @@ FB_DEV bool fb_solve_sym(double *L, int n, double *v) {
     return true;
 }
 
+// src/lpc.rs:886-896: solve Cm xy = rv[1..P], regularising the diagonal of Cm while the factorisation fails
+FB_DEV void fb_k1c_solve(double *Cm, const double *rv, int P, double *xy) {
+    double L[FB200_MAX_LPC_ORDER * FB200_MAX_LPC_ORDER];
+    double regularizer = 0.0;
+    for (;;) {
+        for (int i = 0; i < P * P; i++) L[i] = Cm[i];
+        for (int i = 0; i < P; i++) xy[i] = rv[1 + i];
+        if (fb_solve_sym(L, P, xy)) break;
+        const double old = regularizer;
+        const double twice = FB_DADD(regularizer, regularizer);
+        regularizer = twice > 1.0 ? twice : 1.0;
+        for (int i = 0; i < P; i++) Cm[i * P + i] = FB_DADD(Cm[i * P + i], FB_DADD(regularizer, -old));
+    }
+}
+
 FB_DEV void fb_k1c_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
                         FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t gv, int tile, uint8_t *smem) {
     const int P = J.cfg.lpc_order;
@@ -1265,19 +1280,8 @@ FB_DEV void fb_k1c_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, c
             if (taps) {
                 for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) taps->autocorr[i] = i <= P ? rv[i] : 0.0;
             }
-            // src/lpc.rs:886-896: solve, regularising the diagonal while the factorisation fails
-            double L[FB200_MAX_LPC_ORDER * FB200_MAX_LPC_ORDER];
             double lpc[FB200_MAX_LPC_ORDER];
-            double regularizer = 0.0;
-            for (;;) {
-                for (int i = 0; i < P * P; i++) L[i] = Cm[i];
-                for (int i = 0; i < P; i++) xy[i] = rv[1 + i];
-                if (fb_solve_sym(L, P, xy)) break;
-                const double old = regularizer;
-                const double twice = FB_DADD(regularizer, regularizer);
-                regularizer = twice > 1.0 ? twice : 1.0;
-                for (int i = 0; i < P; i++) Cm[i * P + i] = FB_DADD(Cm[i * P + i], FB_DADD(regularizer, -old));
-            }
+            fb_k1c_solve(Cm, rv, P, xy);
             for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) lpc[i] = i < P ? xy[i] : 0.0;
             int16_t q[32];
             int shift;
@@ -1287,6 +1291,222 @@ FB_DEV void fb_k1c_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, c
             for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
             if (taps) {
                 for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) taps->lpc[i] = lpc[i];
+                for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
+                taps->qlp_order = order;
+                taps->qlp_shift = shift;
+            }
+        }
+    FB_PHASE_END
+}
+
+// =================================================================================================
+// K1I: the `experimental` IRLS-MAE refinement of the direct-MSE estimate (src/lpc.rs:814-850 lpc_with_irls_mae; config
+// key qlpc.mae_optimization_steps > 0 with use_direct_mse), CTA per channel variant.  steps + 1 weighted solutions:
+//   solution k:  r[tau]  += y[u - tau] * f32(w_k[u] * y[u]),          u = P .. n-1              (src/lpc.rs:533-548, VecWeight)
+//                C[i][j] += y[u - 1 - i] * f32(w_k[u] * y[u - 1 - j]), u = P .. n-1, i <= j < P   (:573-600, ShiftedWeight<1>)
+//                (u = t + 1 of the reference's loop over the signal without its last sample), chains as in K1C
+//   raw error:   e_k[t] = fma chain in f32 over the taps of -(f32)x[t] + sum_j f32(a_k[j]) * (f32)x[t - 1 - j]   (:606-618)
+//   score:       S_k = sequential f32 sum of |e_k[t]|; the smallest wins, the earliest on ties                   (:839-843)
+//   weights:     w_0 = 1;  w_{k+1}[t] = powf(max(max(|e_k[t]|, 1) / max|x|, 0.01), -1.2) for t >= P               (:827-828, :845-847)
+// Nothing per sample is stored between solutions: pass k over the frame (k = 0 .. steps + 1) recomputes e_{k-1} from the
+// f32 coefficients kept in shared memory, which gives both the weights of solution k and, summed by one otherwise idle
+// thread while the chain threads work, the score of solution k - 1.  Pass steps + 1 only scores.  powf is glibc's
+// (fb_powf_pos, exhaustively equal for this exponent); weights of 1 make pass 0 the plain direct-MSE estimate.
+// =================================================================================================
+#define FB_K1I_TILE 1024
+FB_HD int fb_k1i_threads(int P) { return (fb_k1c_chains(P) + 1 + 31) & ~31; }
+FB_HD uint32_t fb_k1i_smem_bytes(int P, int tile) {
+    const int T = fb_k1i_threads(P);
+    return (uint32_t)((FB200_MAX_LPC_ORDER + tile) * 16 + tile * 8 + T * 8 + (P * P + 2 * (P + 1)) * 8 +
+                      FB200_MAX_LPC_ORDER * 20 + T * 4 + 64);
+}
+
+FB_DEV float fb_irls_weight(float err, float normalizer) {
+    float a = fabsf(err);
+    a = a > 1.0f ? a : 1.0f; // f32::max: a NaN error counts as 1
+    float r = FB_FDIV(a, normalizer);
+    r = r > 0.01f ? r : 0.01f;
+    return fb_powf_pos(r, -1.2f);
+}
+
+FB_DEV void fb_k1i_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const float *win_full, const float *win_tail,
+                        FbAnalysis *ana, fb200_variant_taps *taps_all, uint32_t gv, int tile, uint8_t *smem) {
+    constexpr int H = FB200_MAX_LPC_ORDER;
+    const int P = J.cfg.lpc_order;
+    const int steps = J.cfg.mae_optimization_steps;
+    const int T = fb_k1i_threads(P);
+    const uint32_t f = gv / (uint32_t)J.nvar;
+    const int v = (int)(gv - f * (uint32_t)J.nvar);
+    const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
+    const int n = V.n;
+    FbAnalysis *out = ana + gv;
+    fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
+    if (!V.do_lpc) return; // K1 has stored the "no LPC" record already
+    const FbVarRows rows = fb_variant_rows(J, xt, f, v);
+    int32_t mb = 0, sh = 0;
+    if (pcm) fb_pair_mix(v, &mb, &sh);
+    double *ys = (double *)smem;                    // ys[H + (t - tile0)] = (f64)y[t]
+    double *accs = ys + H + tile;                   // [T]
+    double *Cm = accs + T;                          // [P * P]
+    double *rv = Cm + P * P;                        // [P + 1]
+    double *xy = rv + P + 1;                        // [P + 1]
+    double *lpc_cur = xy + P + 1;                   // [H] solution k
+    double *lpc_best = lpc_cur + H;                 // [H]
+    float *yf = (float *)(lpc_best + H);            // [H + tile] y[t]
+    float *xf = yf + H + tile;                      // [H + tile] (f32)x[t]
+    float *wt = xf + H + tile;                      // [tile] w_k[t]
+    float *ae = wt + tile;                          // [tile] |e_{k-1}[t]|
+    float *cf = ae + tile;                          // [H] f32(a_{k-1}[j])
+    int32_t *red = (int32_t *)(cf + H);             // [T] peak reduction
+    float *sc = (float *)(red + T);                 // [0] running score, [1] best score, [2] normalizer, [3] have_best
+    const int ncov = P * (P + 1) / 2, nch = fb_k1c_chains(P);
+
+    // normalizer = (f32) max |x[t]| (src/lpc.rs:827)
+    FB_PHASE(tid, T)
+        int32_t m = 0;
+        for (int t = tid; t < n; t += T) {
+            const int32_t x = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+            const int32_t a = x < 0 ? -x : x;
+            m = a > m ? a : m;
+        }
+        red[tid] = m;
+    FB_PHASE_END
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            int32_t m = 0;
+            for (int i = 0; i < T; i++) m = red[i] > m ? red[i] : m;
+            sc[0] = 0.0f;
+            sc[1] = 3.402823466e+38f; // f32::MAX
+            sc[2] = (float)m;
+            sc[3] = 0.0f;
+            for (int i = 0; i < H; i++) { lpc_cur[i] = 0.0; lpc_best[i] = 0.0; cf[i] = 0.0f; }
+        }
+    FB_PHASE_END
+
+    for (int k = 0; k <= steps + 1; k++) {
+#if FB_GPU
+        double acc = 0.0;
+#define FB_K1I_ACC acc
+#else
+#define FB_K1I_ACC accs[tid]
+        FB_PHASE(tid, T)
+            accs[tid] = 0.0;
+        FB_PHASE_END
+#endif
+        for (int tile0 = 0; tile0 < n; tile0 += tile) {
+            const int tile1 = tile0 + tile < n ? tile0 + tile : n;
+            FB_PHASE(tid, T)
+                // history: the last H samples of the previous tile (zeros before the frame are never used)
+                if (tid < H) {
+                    ys[tid] = tile0 == 0 ? 0.0 : ys[tile + tid];
+                    yf[tid] = tile0 == 0 ? 0.0f : yf[tile + tid];
+                    xf[tid] = tile0 == 0 ? 0.0f : xf[tile + tid];
+                }
+            FB_PHASE_END
+            FB_PHASE(tid, T)
+                for (int t = tile0 + tid; t < tile1; t += T) {
+                    const float x = (float)fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+                    const float y = FB_FMUL(x, V.win[t]);
+                    xf[H + (t - tile0)] = x;
+                    yf[H + (t - tile0)] = y;
+                    ys[H + (t - tile0)] = (double)y;
+                }
+            FB_PHASE_END
+            if (k > 0) {
+                FB_PHASE(tid, T)
+                    const float normalizer = sc[2];
+                    for (int t = tile0 + tid; t < tile1; t += T) {
+                        float a = 0.0f, w = 1.0f;
+                        if (t >= P) {
+                            const float *xp = xf + H + (t - tile0);
+                            float e = xp[0] == 0.0f ? 0.0f : -xp[0]; // (f32)(-x[t])
+                            for (int j = 0; j < P; j++) e = FB_FMAF(cf[j], xp[-1 - j], e);
+                            a = fabsf(e);
+                            w = fb_irls_weight(e, normalizer);
+                        }
+                        ae[t - tile0] = a;
+                        wt[t - tile0] = w;
+                    }
+                FB_PHASE_END
+            }
+            FB_PHASE(tid, T)
+                if (tid < nch && k <= steps) {
+                    int a, b; // the chain adds y[u - a] * f32(w[u] * y[u - b]) for u in [P, n)
+                    if (tid < ncov) {
+                        // pair (i, j), i <= j, in row-major order of the upper triangle
+                        int i = 0, rem = tid;
+                        while (rem >= P - i) { rem -= P - i; i++; }
+                        a = i + 1; b = i + rem + 1;
+                    } else {
+                        a = tid - ncov; b = 0;
+                    }
+                    const int lo = P > tile0 ? P : tile0, hi = tile1;
+                    const double *pa = ys + H - tile0 - a;
+                    double s = FB_K1I_ACC;
+                    if (k == 0) { // weights of 1: the products are exact
+                        const double *pb = ys + H - tile0 - b;
+                        for (int u = lo; u < hi; u++) s = FB_FMA(pa[u], pb[u], s);
+                    } else {
+                        const float *pb = yf + H - tile0 - b, *pw = wt - tile0;
+                        for (int u = lo; u < hi; u++) s = FB_FMA(pa[u], (double)FB_FMUL(pw[u], pb[u]), s);
+                    }
+                    FB_K1I_ACC = s;
+                } else if (tid == nch && k > 0) {
+                    float s = sc[0];
+                    for (int t = tile0; t < tile1; t++) s = FB_FADD(s, ae[t - tile0]);
+                    sc[0] = s;
+                }
+            FB_PHASE_END
+        }
+        FB_PHASE(tid, T)
+            if (k <= steps) {
+                if (tid < ncov) {
+                    int i = 0, rem = tid;
+                    while (rem >= P - i) { rem -= P - i; i++; }
+                    const int j = i + rem;
+                    Cm[i * P + j] = FB_K1I_ACC;
+                    Cm[j * P + i] = FB_K1I_ACC;
+                } else if (tid < nch) {
+                    rv[tid - ncov] = FB_K1I_ACC;
+                }
+            }
+        FB_PHASE_END
+#undef FB_K1I_ACC
+        FB_PHASE(tid, T)
+            if (tid == 0) {
+                if (k > 0 && sc[0] < sc[1]) { // src/lpc.rs:840-843: solution k - 1 is the best so far
+                    sc[1] = sc[0];
+                    sc[3] = 1.0f;
+                    for (int i = 0; i < H; i++) lpc_best[i] = lpc_cur[i];
+                }
+                sc[0] = 0.0f;
+                if (k <= steps) {
+                    if (k == 0 && taps) {
+                        for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) taps->autocorr[i] = i <= P ? rv[i] : 0.0;
+                    }
+                    fb_k1c_solve(Cm, rv, P, xy);
+                    for (int i = 0; i < H; i++) {
+                        lpc_cur[i] = i < P ? xy[i] : 0.0;
+                        cf[i] = (float)lpc_cur[i];
+                    }
+                }
+            }
+        FB_PHASE_END
+    }
+    FB_PHASE(tid, T)
+        if (tid == 0) {
+            // (the reference unwraps None when no score was below f32::MAX; the last solution stands in here)
+            const double *lpc = sc[3] != 0.0f ? lpc_best : lpc_cur;
+            double lq[FB200_MAX_LPC_ORDER];
+            for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) lq[i] = lpc[i];
+            int16_t q[32];
+            int shift;
+            const int order = fb_quantize(lq, P, J.cfg.quant_precision, q, &shift);
+            out->qlp_order = order;
+            out->qlp_shift = shift;
+            for (int i = 0; i < 32; i++) out->qlp[i] = i < order ? q[i] : (int16_t)0;
+            if (taps) {
+                for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) taps->lpc[i] = lq[i];
                 for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
                 taps->qlp_order = order;
                 taps->qlp_shift = shift;

@@ -56,7 +56,7 @@ typedef struct fb200_config {
     int32_t quant_precision;        /* Qlpc.quant_precision (default 15, 1..=15) */
     int32_t use_direct_mse;         /* Qlpc.use_direct_mse (`experimental` feature, src/config.rs:276-285): covariance-method
                                        LPC (src/lpc.rs:852-913) instead of autocorrelation + Levinson; 0 (default) or 1 */
-    int32_t mae_optimization_steps; /* `experimental` IRLS refinement (src/lpc.rs:814-850): not built, must be 0 */
+    int32_t mae_optimization_steps; /* `experimental` IRLS-MAE refinement steps (src/lpc.rs:814-850); used when use_direct_mse */
     int32_t window_type;            /* Window: 0 = Rectangle, 1 = Tukey (default) */
     float   tukey_alpha;            /* Window::Tukey.alpha (default 0.4, 0..=1) */
     int32_t prc_max_parameter;      /* Prc.max_parameter (default 30, 0..=30) */
@@ -204,8 +204,10 @@ void fb200_pool_clear(void);
  * Device builds of the two scalar float helpers whose last bit decides encoder choices, evaluated on
  * caller-provided inputs so tests can compare them with the host libm the reference uses:
  *   log2f of estimate_entropy (src/coding.rs:200-227): out_bits[i] = bits of log2f(float with bits first_bits + i)
- *   find_shift (src/lpc.rs:234-255) of the one-coefficient set {values[i]}: out_shift[i] */
+ *   find_shift (src/lpc.rs:234-255) of the one-coefficient set {values[i]}: out_shift[i]
+ *   the IRLS weight (src/lpc.rs:828, powf(-1.2) inside) of the raw error with bits first_bits + i: out_bits[i] */
 int fb200_debug_log2f(int device, uint32_t first_bits, uint64_t count, uint32_t *out_bits);
+int fb200_debug_irls_weight(int device, uint32_t first_bits, uint64_t count, float normalizer, uint32_t *out_bits);
 /* The chunk schedule of the (sharded) host path: chunk c = frames [first[c], first[c] + count[c]) of a batch of
  * total_frames frames cut with a nominal chunk size; chunk c is encoded on device c mod n.  Host logic only (no device
  * needed).  Returns the number of chunks; fills at most cap entries. */

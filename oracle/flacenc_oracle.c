@@ -10,6 +10,7 @@
 #include "flacenc_oracle.h"
 
 #include <assert.h>
+#include <float.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -48,10 +49,10 @@ int fo_config_verify(const fo_config *c) {
     if (c->block_size < FO_MIN_BLOCK_SIZE || c->block_size > FO_MAX_BLOCK_SIZE) return 1;
     if (c->lpc_order < 1 || c->lpc_order > FO_MAX_LPC_ORDER) return 1;
     if (c->quant_precision < 1 || c->quant_precision > 15) return 1;
-    /* use_direct_mse is accepted like a reference built with the `experimental` feature (src/config.rs:305-316);
-     * the IRLS refinement (mae_optimization_steps > 0, src/lpc.rs:814-850) is not restated */
+    /* use_direct_mse and mae_optimization_steps are accepted like a reference built with the `experimental`
+     * feature (src/config.rs:305-321 checks them only in a build without it) */
     if (c->use_direct_mse != 0 && c->use_direct_mse != 1) return 1;
-    if (c->mae_optimization_steps != 0) return 1;
+    if (c->mae_optimization_steps < 0) return 1;
     if (c->window_type == 1) {
         if (!(c->tukey_alpha >= 0.0f && c->tukey_alpha <= 1.0f)) return 1;
     } else if (c->window_type != 0) {
@@ -361,20 +362,39 @@ int fo_solve_sym(const double *mat, int n, double *v) {
     return 1;
 }
 
-/* src/lpc.rs:852-903 weighted_lpc_with_direct_mse with NoWeight (lpc_with_direct_mse :905-913) */
-void fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
-                            double *coefs_out, double *corr_out, double *covar_out) {
-    for (int i = 0; i < lpc_order; i++) coefs_out[i] = 0.0;
-    if (lpc_order == 0) return;
-    float *window = (float *)malloc(sizeof(float) * (size_t)n);
-    float *windowed = (float *)malloc(sizeof(float) * (size_t)n);
+/* src/lpc.rs:533-548 weighted_auto_correlation_nosimd with VecWeight (:194-199): the weight multiplies the
+ * newest sample in f32 before the product is widened (`weight == NULL` is NoWeight: the sample itself) */
+static void fo_weighted_auto_correlation(int order, const float *signal, int len, const float *weight, double *dest) {
+    for (int i = 0; i < order; i++) dest[i] = 0.0;
+    for (int t = order - 1; t < len; t++) {
+        const float wyf = weight ? weight[t] * signal[t] : signal[t];
+        const double wy = (double)wyf;
+        for (int tau = 0; tau < order; tau++) dest[tau] = fma((double)signal[t - tau], wy, dest[tau]);
+    }
+}
+
+/* src/lpc.rs:573-600 weighted_lagged_outer_prod_sum under ShiftedWeight<1, VecWeight> (:206-211): the weight of
+ * time t + 1 multiplies signal[t - j] in f32 (`weight == NULL` is NoWeight) */
+static void fo_weighted_lagged_outer_prod_sum(int order, const float *signal, int len, const float *weight, double *dest) {
+    for (int i = 0; i < order * order; i++) dest[i] = 0.0;
+    for (int t = order - 1; t < len; t++)
+        for (int i = 0; i < order; i++)
+            for (int j = i; j < order; j++) {
+                const float wxf = weight ? weight[t + 1] * signal[t - j] : signal[t - j];
+                dest[i * order + j] = fma((double)signal[t - i], (double)wxf, dest[i * order + j]);
+            }
+    for (int i = 0; i < order; i++)
+        for (int j = i + 1; j < order; j++) dest[j * order + i] = dest[i * order + j];
+}
+
+/* src/lpc.rs:852-903 weighted_lpc_with_direct_mse on an already windowed signal */
+static void fo_weighted_direct_mse(const float *windowed, int n, int lpc_order, const float *weight, double *coefs_out,
+                                   double *corr_out, double *covar_out) {
     double corr[FO_MAX_LPC_ORDER + 1];
     double covar[FO_MAX_LPC_ORDER * FO_MAX_LPC_ORDER];
-    fo_window_weights(window_type, alpha, n, window);
-    fo_fill_windowed_signal(signal, window, n, windowed);
-    fo_auto_correlation_f64(lpc_order + 1, windowed, n, corr);
-    /* the statistics of the signal without its last sample, weights shifted by one (NoWeight: no effect) */
-    fo_lagged_outer_prod_sum(lpc_order, windowed, n - 1, covar);
+    fo_weighted_auto_correlation(lpc_order + 1, windowed, n, weight, corr);
+    /* the statistics of the signal without its last sample, weights shifted by one */
+    fo_weighted_lagged_outer_prod_sum(lpc_order, windowed, n - 1, weight, covar);
     if (corr_out) memcpy(corr_out, corr, sizeof(double) * (size_t)(lpc_order + 1));
     if (covar_out) memcpy(covar_out, covar, sizeof(double) * (size_t)(lpc_order * lpc_order));
     double xy[FO_MAX_LPC_ORDER];
@@ -389,8 +409,109 @@ void fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float
         for (int i = 0; i < lpc_order; i++) covar[i * lpc_order + i] += regularizer - old;
     }
     for (int i = 0; i < lpc_order; i++) coefs_out[i] = xy[i];
+}
+
+/* src/lpc.rs:905-913 lpc_with_direct_mse (NoWeight) */
+void fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
+                            double *coefs_out, double *corr_out, double *covar_out) {
+    for (int i = 0; i < lpc_order; i++) coefs_out[i] = 0.0;
+    if (lpc_order == 0) return;
+    float *window = (float *)malloc(sizeof(float) * (size_t)n);
+    float *windowed = (float *)malloc(sizeof(float) * (size_t)n);
+    fo_window_weights(window_type, alpha, n, window);
+    fo_fill_windowed_signal(signal, window, n, windowed);
+    fo_weighted_direct_mse(windowed, n, lpc_order, NULL, coefs_out, corr_out, covar_out);
     free(window);
     free(windowed);
+}
+
+/* src/lpc.rs:606-618 compute_raw_errors: "prediction - signal" in f32 with the coefficients rounded to f32, one fused
+ * multiply-add per tap, taps in ascending order; errors[0..order) are left alone */
+void fo_compute_raw_errors(const int32_t *signal, int n, const double *coefs, int lpc_order, float *errors) {
+    for (int t = lpc_order; t < n; t++) {
+        float e = (float)(-signal[t]);
+        for (int j = 0; j < lpc_order; j++) e = fmaf((float)coefs[j], (float)signal[t - 1 - j], e);
+        errors[t] = e;
+    }
+}
+
+/* the weight of a raw error in src/lpc.rs:828: (|err|.max(1) / normalizer).max(0.01).powf(-1.2), all in f32; powf is
+ * the libm the reference links (glibc here, like log2f in the entropy estimate) */
+float fo_irls_weight(float err, float normalizer) {
+    const float a = fmaxf(fabsf(err), 1.0f);
+    return powf(fmaxf(a / normalizer, 0.01f), -1.2f);
+}
+
+/* bits of fo_irls_weight over the raw errors with float bit patterns [first, first + count), for the sweep tests */
+struct fo_irlsw_job { uint32_t first; uint64_t a, b; float normalizer; uint32_t *out; };
+static void *fo_irlsw_worker(void *arg) {
+    struct fo_irlsw_job *j = (struct fo_irlsw_job *)arg;
+    for (uint64_t i = j->a; i < j->b; i++) {
+        uint32_t u = j->first + (uint32_t)i;
+        float x, y;
+        memcpy(&x, &u, 4);
+        y = fo_irls_weight(x, j->normalizer);
+        memcpy(&j->out[i], &y, 4);
+    }
+    return NULL;
+}
+void fo_irls_weight_bits(uint32_t first, uint64_t count, float normalizer, int threads, uint32_t *out) {
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    pthread_t th[64];
+    struct fo_irlsw_job jobs[64];
+    for (int w = 0; w < threads; w++) {
+        jobs[w].first = first;
+        jobs[w].a = count * (uint64_t)w / (uint64_t)threads;
+        jobs[w].b = count * (uint64_t)(w + 1) / (uint64_t)threads;
+        jobs[w].normalizer = normalizer;
+        jobs[w].out = out;
+        pthread_create(&th[w], NULL, fo_irlsw_worker, &jobs[w]);
+    }
+    for (int w = 0; w < threads; w++) pthread_join(th[w], NULL);
+}
+
+/* src/lpc.rs:814-850 lpc_with_irls_mae: `steps` + 1 weighted direct-MSE solutions, each re-weighted by the raw errors
+ * of the one before; the solution with the smallest sequential f32 sum of |raw error| wins, the earliest on ties.
+ * `sums_out` (may be NULL) receives the steps + 1 sums. */
+void fo_lpc_with_irls_mae(const int32_t *signal, int n, int window_type, float alpha, int lpc_order, int steps,
+                          double *coefs_out, float *sums_out) {
+    for (int i = 0; i < lpc_order; i++) coefs_out[i] = 0.0;
+    float *window = (float *)malloc(sizeof(float) * (size_t)n);
+    float *windowed = (float *)malloc(sizeof(float) * (size_t)n);
+    float *weights = (float *)malloc(sizeof(float) * (size_t)n);
+    float *raw_errors = (float *)calloc((size_t)n, sizeof(float));
+    fo_window_weights(window_type, alpha, n, window);
+    fo_fill_windowed_signal(signal, window, n, windowed);
+    for (int t = 0; t < n; t++) weights[t] = 1.0f;
+    int32_t peak = 0;
+    for (int t = 0; t < n; t++) {
+        const int32_t a = signal[t] < 0 ? -signal[t] : signal[t];
+        if (a > peak) peak = a;
+    }
+    const float normalizer = (float)peak;
+    float best_error = FLT_MAX;
+    int have_best = 0;
+    double coefs[FO_MAX_LPC_ORDER];
+    for (int step = 0; step <= steps; step++) {
+        fo_weighted_direct_mse(windowed, n, lpc_order, weights, coefs, NULL, NULL);
+        fo_compute_raw_errors(signal, n, coefs, lpc_order, raw_errors);
+        float sum_abs_err = 0.0f;
+        for (int t = 0; t < n; t++) sum_abs_err += fabsf(raw_errors[t]);
+        if (sums_out) sums_out[step] = sum_abs_err;
+        if (sum_abs_err < best_error) {
+            best_error = sum_abs_err;
+            have_best = 1;
+            memcpy(coefs_out, coefs, sizeof(double) * (size_t)lpc_order);
+        }
+        for (int t = lpc_order; t < n; t++) weights[t] = fo_irls_weight(raw_errors[t], normalizer);
+    }
+    assert(have_best); /* the reference unwraps an Option here */
+    (void)have_best;
+    free(window);
+    free(windowed);
+    free(weights);
+    free(raw_errors);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -670,7 +791,9 @@ static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n
     int lpc_order = cfg->lpc_order;
     double coefs[FO_MAX_LPC_ORDER];
     /* src/coding.rs:333-351 perform_qlpc: the estimator the configuration names */
-    if (cfg->use_direct_mse) fo_lpc_with_direct_mse(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL, NULL);
+    if (cfg->use_direct_mse && cfg->mae_optimization_steps > 0)
+        fo_lpc_with_irls_mae(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, cfg->mae_optimization_steps, coefs, NULL);
+    else if (cfg->use_direct_mse) fo_lpc_with_direct_mse(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL, NULL);
     else fo_lpc_from_autocorr(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL);
     fo_subframe_reset(out, FO_SF_LPC, signal, n, bps);
     int16_t q[FO_MAX_LPC_ORDER];

@@ -55,7 +55,7 @@ typedef struct fo_config {
     int32_t lpc_order;             /* Qlpc.lpc_order, default 10 */
     int32_t quant_precision;       /* Qlpc.quant_precision, default 15 */
     int32_t use_direct_mse;        /* `experimental` feature: covariance-method LPC (src/lpc.rs:852-903) */
-    int32_t mae_optimization_steps;/* experimental only; must be 0 */
+    int32_t mae_optimization_steps;/* `experimental` feature: IRLS refinement steps of the direct-MSE estimate (src/lpc.rs:814-850) */
     int32_t window_type;           /* 0 = Rectangle, 1 = Tukey */
     float   tukey_alpha;           /* default 0.4 */
     int32_t prc_max_parameter;     /* Prc.max_parameter, default 30 */
@@ -116,11 +116,16 @@ void   fo_compute_error(const int16_t *q, int order, int shift, const int32_t *s
 void   fo_lpc_from_autocorr(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
                             double *coefs_out, double *corr_out /* nullable, lpc_order+1 */);
 
-/* `experimental` feature (src/lpc.rs:573-600, 76-87, 852-913) */
+/* `experimental` feature (src/lpc.rs:573-600, 76-87, 852-913; IRLS refinement :606-618, :814-850) */
 void   fo_lagged_outer_prod_sum(int order, const float *signal, int len, double *dest);
 int    fo_solve_sym(const double *mat, int n, double *v);
 void   fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
                               double *coefs_out, double *corr_out /* nullable */, double *covar_out /* nullable */);
+void   fo_compute_raw_errors(const int32_t *signal, int n, const double *coefs, int lpc_order, float *errors);
+float  fo_irls_weight(float err, float normalizer);
+void   fo_irls_weight_bits(uint32_t first_bits, uint64_t count, float normalizer, int threads, uint32_t *out_bits);
+void   fo_lpc_with_irls_mae(const int32_t *signal, int n, int window_type, float alpha, int lpc_order, int steps,
+                            double *coefs_out, float *sums_out /* nullable, steps + 1 */);
 
 /* ---- rice.rs ---- */
 uint32_t fo_encode_signbit(int32_t v);

@@ -137,6 +137,10 @@ def lib() -> C.CDLL:
             "fo_lagged_outer_prod_sum": (None, [C.c_int, f32p, C.c_int, f64p]),
             "fo_solve_sym": (C.c_int, [f64p, C.c_int, f64p]),
             "fo_lpc_with_direct_mse": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, f64p, f64p, f64p]),
+            "fo_compute_raw_errors": (None, [i32p, C.c_int, f64p, C.c_int, f32p]),
+            "fo_irls_weight": (C.c_float, [C.c_float, C.c_float]),
+            "fo_irls_weight_bits": (None, [C.c_uint32, C.c_uint64, C.c_float, C.c_int, C.c_void_p]),
+            "fo_lpc_with_irls_mae": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, f64p, f32p]),
             "fo_encode_signbit": (C.c_uint32, [C.c_int32]),
             "fo_decode_signbit": (C.c_int32, [C.c_uint32]),
             "fo_finest_partition_order": (C.c_int, [C.c_int, C.c_int]),
@@ -284,6 +288,36 @@ def lpc_with_direct_mse(signal, window_type: int, alpha: float, lpc_order: int):
     lib().fo_lpc_with_direct_mse(_p(s, C.c_int32), len(s), window_type, alpha, lpc_order, _p(coefs, C.c_double),
                                  _p(corr, C.c_double), _p(covar, C.c_double))
     return coefs[:lpc_order].copy(), corr, covar[:lpc_order, :lpc_order] if False else covar.reshape(-1)[: lpc_order * lpc_order].reshape(lpc_order, lpc_order)
+
+
+def compute_raw_errors(signal, coefs) -> np.ndarray:
+    """src/lpc.rs:606-618: f32 "prediction - signal" of unquantised coefficients (zeros before the order)"""
+    s = np.ascontiguousarray(signal, np.int32)
+    c = np.ascontiguousarray(coefs, np.float64)
+    e = np.zeros(len(s), np.float32)
+    lib().fo_compute_raw_errors(_p(s, C.c_int32), len(s), _p(c, C.c_double), len(c), _p(e, C.c_float))
+    return e
+
+
+def irls_weight(err: float, normalizer: float) -> float:
+    return float(lib().fo_irls_weight(err, normalizer))
+
+
+def irls_weight_bits(first: int, count: int, normalizer: float, threads: int = 8) -> np.ndarray:
+    """bits of the IRLS weight (host libm powf) of the raw errors with float bit patterns [first, first + count)"""
+    out = np.empty(count, np.uint32)
+    lib().fo_irls_weight_bits(first, count, normalizer, threads, out.ctypes.data)
+    return out
+
+
+def lpc_with_irls_mae(signal, window_type: int, alpha: float, lpc_order: int, steps: int):
+    """(coefs, the steps + 1 sums of |raw error|) of the `experimental` IRLS-MAE estimator (src/lpc.rs:814-850)"""
+    s = np.ascontiguousarray(signal, np.int32)
+    coefs = np.zeros(max(lpc_order, 1), np.float64)
+    sums = np.zeros(steps + 1, np.float32)
+    lib().fo_lpc_with_irls_mae(_p(s, C.c_int32), len(s), window_type, alpha, lpc_order, steps, _p(coefs, C.c_double),
+                               _p(sums, C.c_float))
+    return coefs[:lpc_order].copy(), sums
 
 
 def bit_table_from_errors(errors, offset: int) -> np.ndarray:

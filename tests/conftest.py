@@ -127,6 +127,8 @@ def fuzz_frame_case(rng):
     if rng.random() < 0.15:
         cfg["use_direct_mse"] = 1
     rate = int(rng.choice([8000, 44100, 48000, 96000, 11025]))
+    if cfg.get("use_direct_mse") and rng.random() < 0.5:  # (drawn last: earlier draws keep their values)
+        cfg["mae_optimization_steps"] = int(rng.integers(1, 4))
     return np.stack(chans, axis=1), channels, bps, rate, block, cfg
 
 
@@ -184,6 +186,8 @@ def random_case(rng):
     first = int(rng.choice([0, 1, 127, 128, 70000, (1 << 31) - 10]))
     if rng.random() < 0.2:  # (drawn last, so the cases above are the ones earlier versions of the suite ran)
         cfg["use_direct_mse"] = 1
+        if rng.random() < 0.5:
+            cfg["mae_optimization_steps"] = int(rng.integers(1, 4))
     return np.stack(chans, axis=1), channels, bps, rate, block, first, cfg
 
 

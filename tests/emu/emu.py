@@ -26,6 +26,8 @@ def lib():
         L.fbemu_log2f.argtypes = [C.c_float]
         L.fbemu_log2f_sweep.restype = C.c_ulonglong
         L.fbemu_log2f_sweep.argtypes = [C.c_uint32, C.c_ulonglong, C.c_int, C.POINTER(C.c_uint32)]
+        L.fbemu_irls_weight_bits.restype = None
+        L.fbemu_irls_weight_bits.argtypes = [C.c_uint32, C.c_ulonglong, C.c_float, C.c_int, C.c_void_p]
         L.fbemu_find_shift.restype = C.c_int
         L.fbemu_find_shift.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
         L.fbemu_config_default.argtypes = [C.POINTER(F.Config)]

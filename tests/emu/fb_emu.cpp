@@ -44,6 +44,19 @@ unsigned long long fbemu_log2f_sweep(uint32_t first, unsigned long long count, i
     return total;
 }
 
+// bits of the device-side IRLS weight (fb_irls_weight over fb_powf_pos) for raw errors with bit patterns [first, first + count)
+void fbemu_irls_weight_bits(uint32_t first, unsigned long long count, float normalizer, int threads, uint32_t *out) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; w++)
+        pool.emplace_back([&, w] {
+            const unsigned long long a = count * (unsigned long long)w / (unsigned long long)threads;
+            const unsigned long long b = count * (unsigned long long)(w + 1) / (unsigned long long)threads;
+            for (unsigned long long i = a; i < b; i++) out[i] = fb_f2u(fb_irls_weight(fb_u2f(first + (uint32_t)i), normalizer));
+        });
+    for (auto &t : pool) t.join();
+}
+
 int fbemu_find_shift(const double *coefs, int n, int precision) { return fb_find_shift(coefs, n, precision); }
 
 // Rice-search statistics: [0] narrow-window runs, [1] full-range reruns, [2] chunk-exact runs, [3] sum of widths
@@ -140,7 +153,16 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     for (uint32_t gv = 0; gv < nvars; gv++)
         fb_k1_dispatch(J, B.xv.data(), B.win_full.data(), B.win_tail.data(), B.ana.data(), B.taps.data(), gv);
     // K1C: direct-MSE estimator (tiles of 256 samples here, so that frames span several tiles)
-    if (cfg->use_direct_mse && cfg->use_lpc) {
+    if (cfg->use_direct_mse && cfg->use_lpc && cfg->mae_optimization_steps > 0) {
+        // K1I: IRLS-MAE refinement (same small tiles)
+        const int tile = 256;
+        std::vector<uint8_t> smem(fb_k1i_smem_bytes(J.cfg.lpc_order, tile) + 64);
+        for (uint32_t gv = 0; gv < nvars; gv++) {
+            memset(smem.data(), 0xAB, smem.size());
+            fb_k1i_body(J, B.xv.data(), nullptr, B.win_full.data(), B.win_tail.data(), B.ana.data(), B.taps.data(), gv, tile,
+                        smem.data());
+        }
+    } else if (cfg->use_direct_mse && cfg->use_lpc) {
         const int tile = 256;
         std::vector<uint8_t> smem(fb_k1c_smem_bytes(J.cfg.lpc_order, tile) + 64);
         for (uint32_t gv = 0; gv < nvars; gv++) {

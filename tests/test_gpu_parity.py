@@ -40,6 +40,8 @@ def make_config(**kw) -> Encoder:
             s.qlpc.quant_precision = v
         elif k == "use_direct_mse":
             s.qlpc.use_direct_mse = bool(v)
+        elif k == "mae_optimization_steps":
+            s.qlpc.mae_optimization_steps = v
         elif k == "window_type":
             s.qlpc.window.type = "Rectangle" if v == 0 else "Tukey"
         elif k == "tukey_alpha":
@@ -174,6 +176,65 @@ def test_experimental_config_c4_direct_mse():
     imp[1000] = 30000
     _compare(imp, 1, 16, 44100, 4096, use_direct_mse=1, window_type=0)
     _compare(sigen.noisy_sine_pcm(20000 * 2 + 5, 2, 16, 44100, config_id=8), 2, 16, 44100, 20000, use_direct_mse=1, window_type=0)
+
+
+def test_experimental_irls_mae_refinement():
+    """use_direct_mse + mae_optimization_steps > 0 (the IRLS-MAE refinement of src/lpc.rs:814-850, the estimator the
+    reference's own report/experimental.config.toml-style configs can select): byte-equal frames over step counts,
+    orders, windows, sample formats and degenerate signals; the winning coefficients bit-equal to the oracle's"""
+    x = sigen.noisy_sine_pcm(4096 * 6 + 1500, 2, 16, 44100, config_id=4)
+    _compare(x, 2, 16, 44100, 4096, use_direct_mse=1, mae_optimization_steps=2, window_type=0)
+    _compare(x[: 4096 * 3], 2, 16, 44100, 4096, use_direct_mse=1, mae_optimization_steps=1)
+    _compare(x[: 1024 * 5 + 77], 2, 16, 44100, 1024, use_direct_mse=1, mae_optimization_steps=4, lpc_order=24, tukey_alpha=0.1)
+    _compare(x[: 1024 * 5, 0], 1, 16, 44100, 1024, use_direct_mse=1, mae_optimization_steps=7, lpc_order=1, quant_precision=5)
+    y = sigen.noisy_sine_pcm(4608 * 3 + 100, 2, 24, 96000, config_id=3)
+    _compare(y, 2, 24, 96000, 4608, use_direct_mse=1, mae_optimization_steps=2, window_type=0, lpc_order=16)
+    _compare(np.zeros((3000, 2), np.int32), 2, 16, 44100, 1024, use_direct_mse=1, mae_optimization_steps=2, window_type=0)
+    c = np.full((3000, 1), 1000, np.int32)
+    c[1500:] = -77
+    _compare(c, 1, 16, 44100, 1024, use_direct_mse=1, mae_optimization_steps=3, window_type=0, use_constant=0)
+    imp = np.zeros((4096, 1), np.int32)
+    imp[1000] = 30000
+    _compare(imp, 1, 16, 44100, 4096, use_direct_mse=1, mae_optimization_steps=2, window_type=0)
+    _compare(sigen.noisy_sine_pcm(20000 * 2 + 5, 2, 16, 44100, config_id=8), 2, 16, 44100, 20000, use_direct_mse=1,
+             mae_optimization_steps=2, window_type=0)
+    z = sigen.noisy_sine_pcm(1024 * 4, 8, 24, 48000, config_id=5)
+    _compare(z, 8, 24, 48000, 1024, use_direct_mse=1, mae_optimization_steps=2)
+    # the steps are ignored unless the direct-MSE estimator is selected (src/coding.rs:337-351)
+    _compare(x[: 4096 * 3], 2, 16, 44100, 4096, use_direct_mse=0, mae_optimization_steps=3)
+    # float tier
+    sig = x[:4096, 0]
+    cfg = make_config(use_direct_mse=1, mae_optimization_steps=4, window_type=0).into_verified()
+    with Context(cfg, 1, 16, 44100, 4096) as ctx:
+        taps, nv = ctx.analyze(pack_pcm(sig.reshape(-1, 1), 2), 2, 4096)
+    assert nv == 1
+    coefs, sums = O.lpc_with_irls_mae(sig, 0, 0.0, 10, 4)
+    plain, corr, _ = O.lpc_with_direct_mse(sig, 0, 0.0, 10)
+    assert np.array_equal(np.array(taps[0].lpc[:10]), coefs) and np.array_equal(np.array(taps[0].autocorr[:11]), corr)
+    assert not np.array_equal(coefs, plain) and sums.min() < sums[0]
+
+
+def test_device_irls_weight_matches_libm_exhaustive():
+    """The device build of the IRLS weight (src/lpc.rs:828; powf(-1.2) by fb_powf_pos) against the host glibc's for every
+    non-negative raw-error bit pattern under one normalizer, slices under others and of the negative errors"""
+    lib = _ffi.lib()
+    threads = min(32, os.cpu_count() or 1)
+    step = 1 << 26
+    out = np.empty(step, np.uint32)
+
+    def sweep(first, end, norm):
+        while first < end:
+            cnt = min(step, end - first)
+            assert lib.fb200_debug_irls_weight(0, first, cnt, norm, out.ctypes.data) == 0
+            want = O.irls_weight_bits(first, cnt, norm, threads)
+            bad = np.flatnonzero(out[:cnt] != want)
+            assert len(bad) == 0, (norm, hex(first + int(bad[0])), hex(int(out[bad[0]])), hex(int(want[bad[0]])))
+            first += cnt
+
+    sweep(0, 0x7F800000 + 4096, 100.0)
+    for norm in (1.0, 3.0, 32767.0, 8388607.0, 0.0):
+        sweep(0x3F000000, 0x4C000000, norm)
+    sweep(0xBF000000, 0xC1000000, 1000.0)
 
 
 def test_rectangle_window_c4_shape():

@@ -86,7 +86,8 @@ def test_config_default_matches_reference_defaults():
     (lambda e: setattr(e.subframe_coding.qlpc, "lpc_order", 0), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "quant_precision", 16), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "use_direct_mse", True), True),   # the `experimental` covariance-method estimator is built
-    (lambda e: setattr(e.subframe_coding.qlpc, "mae_optimization_steps", 2), False),
+    (lambda e: setattr(e.subframe_coding.qlpc, "mae_optimization_steps", 2), True),   # ... and so is its IRLS-MAE refinement
+    (lambda e: setattr(e.subframe_coding.qlpc, "mae_optimization_steps", -1), False),  # (a usize in the reference)
     (lambda e: setattr(e.subframe_coding.qlpc, "window", Window.Tukey(1.5)), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "window", Window.Rectangle()), True),
     (lambda e: setattr(e.subframe_coding.prc, "max_parameter", 31), False),

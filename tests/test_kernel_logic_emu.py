@@ -382,6 +382,58 @@ def test_direct_mse_estimator_matches_oracle():
     assert np.array_equal(np.array(taps[0].lpc[:10]), coefs) and np.array_equal(np.array(taps[0].autocorr[:11]), corr)
 
 
+def test_irls_weight_matches_libm_exhaustive():
+    """fb_irls_weight -- the device code of the IRLS weight (/root/reference/src/lpc.rs:828: max, divide, max, then
+    powf(-1.2) through fb_powf_pos, a restatement of glibc's powf) compiled for the CPU -- against the oracle's, which
+    calls the host libm, for EVERY non-negative raw-error bit pattern (zero .. +inf and the first NaNs) under one
+    normalizer, and slices of it under others (incl. the normalizer 0 of a silent frame and negative errors)"""
+    L = E.lib()
+    threads = min(16, os.cpu_count() or 1)
+
+    def sweep(first, end, norm):
+        step = 1 << 26
+        while first < end:
+            cnt = min(step, end - first)
+            got = np.empty(cnt, np.uint32)
+            L.fbemu_irls_weight_bits(first, cnt, norm, threads, got.ctypes.data)
+            want = O.irls_weight_bits(first, cnt, norm, threads)
+            bad = np.flatnonzero(got != want)
+            assert len(bad) == 0, (norm, hex(first + int(bad[0])), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
+            first += cnt
+
+    sweep(0, 0x7F800000 + 4096, 100.0)          # weights from 0.01^-1.2 down to 0
+    for norm in (1.0, 3.0, 32767.0, 8388607.0, 0.0):
+        sweep(0x3F000000, 0x4C000000, norm)     # |err| in [0.5, 2^25): what 24-bit audio can produce
+    sweep(0xBF000000, 0xC1000000, 1000.0)       # negative errors
+
+
+def test_irls_mae_estimator_matches_oracle():
+    """K1I (the `experimental` IRLS-MAE refinement, /root/reference/src/lpc.rs:814-850) under emulation, frames spanning
+    several staging tiles, orders and step counts; whole frames byte-equal and coefficients bit-equal to the oracle"""
+    x = sigen.noisy_sine_pcm(1024 * 3 + 300, 2, 16, 44100, config_id=4)
+    _compare(x, 2, 16, 44100, 1024, use_direct_mse=1, mae_optimization_steps=2, window_type=0)
+    _compare(x[:2048], 2, 16, 44100, 1024, use_direct_mse=1, mae_optimization_steps=1)
+    _compare(x[:1500, 0], 1, 16, 44100, 500, use_direct_mse=1, mae_optimization_steps=3, lpc_order=24, tukey_alpha=0.1)
+    _compare(x[:1100, 1], 1, 16, 44100, 1000, use_direct_mse=1, mae_optimization_steps=5, lpc_order=1, quant_precision=5)
+    _compare(np.zeros((600, 2), np.int32), 2, 16, 44100, 256, use_direct_mse=1, mae_optimization_steps=2, window_type=0)
+    c = np.full((600, 1), 1000, np.int32)
+    c[300:] = -77
+    _compare(c, 1, 16, 44100, 256, use_direct_mse=1, mae_optimization_steps=2, window_type=0, use_constant=0)
+    y = sigen.noisy_sine_pcm(1152 + 100, 2, 24, 96000, config_id=3)
+    _compare(y, 2, 24, 96000, 1152, use_direct_mse=1, mae_optimization_steps=2, window_type=0, lpc_order=16)
+    # the steps are ignored unless the direct-MSE estimator is selected (src/coding.rs:337-351)
+    _compare(x[:2048], 2, 16, 44100, 1024, use_direct_mse=0, mae_optimization_steps=3)
+    # float tier: the winning coefficients are bit-identical to the oracle's, and the refinement does change them
+    sig = x[:1024, 0]
+    cfg = E.default_config(use_direct_mse=1, mae_optimization_steps=4, window_type=0)
+    rc, taps, nv = E.analyze(cfg, pack_pcm(sig.reshape(-1, 1), 2), 2, 1024, 1, 16, 44100, 1024)
+    assert rc == 0 and nv == 1
+    coefs, sums = O.lpc_with_irls_mae(sig, 0, 0.0, 10, 4)
+    plain, corr, _ = O.lpc_with_direct_mse(sig, 0, 0.0, 10)
+    assert np.array_equal(np.array(taps[0].lpc[:10]), coefs) and np.array_equal(np.array(taps[0].autocorr[:11]), corr)
+    assert not np.array_equal(coefs, plain) and sums.min() < sums[0]
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_fuzz_frames_at_reference_scale_emu(seed):
     """the reference's fuzz shape (one frame, block up to 32767, 1..8 channels, 8..24 bits, all toggles) under emulation;

@@ -610,3 +610,42 @@ def test_direct_mse_beats_autocorr_on_a_short_window_kat():
     snr_a = 10 * np.log10(se / energy(raw_errors(ca)[order:]))
     snr_d = 10 * np.log10(se / energy(raw_errors(cd)[order:]))
     assert snr_a < snr_d
+
+
+@pytest.mark.parametrize("block_size", [256, 512, 1024, 2048, 4096])
+def test_irls_mae_beats_direct_mse_in_mean_absolute_error_kat(block_size):
+    """src/lpc.rs:1448-1486 comparing_mse_vs_mae: on the sus109 clip (order 16, Rectangle window, 4 IRLS steps) the
+    IRLS-MAE coefficients have a mean absolute raw error no larger than the direct-MSE ones"""
+    sig = load_fixture("sus109", 0)[:block_size]
+    order = 16
+    c_mse, _, _ = O.lpc_with_direct_mse(sig, 0, 0.0, order)
+    c_mae, sums = O.lpc_with_irls_mae(sig, 0, 0.0, order, 4)
+    e_mse, e_mae = O.compute_raw_errors(sig, c_mse), O.compute_raw_errors(sig, c_mae)
+
+    def mae(e):  # the reference's sequential f32 sum of |x| / len
+        acc = np.float32(0.0)
+        n = np.float32(len(sig))
+        for v in np.abs(e):
+            acc = np.float32(acc + np.float32(v / n))
+        return float(acc)
+
+    assert mae(e_mse) >= mae(e_mae)
+    # step 0 of the refinement is the plain direct-MSE estimate; the winner's score is the smallest, earliest on ties
+    assert sums[0] == np.float32(np.add.accumulate(np.abs(e_mse), dtype=np.float32)[-1])
+    k = int(np.argmin(sums))
+    assert np.float32(np.add.accumulate(np.abs(e_mae), dtype=np.float32)[-1]) == sums[k]
+    # raw errors are zero before the order and follow the f32 fused-multiply-add chain after it
+    assert not e_mse[:order].any()
+    t = order + 5
+    acc = np.float32(-int(sig[t]))
+    for j in range(order):
+        acc = np.float32(np.float64(np.float32(c_mse[j])) * np.float64(np.float32(sig[t - 1 - j])) + np.float64(acc))
+    assert acc == e_mse[t]
+
+
+def test_irls_weight_kat():
+    """src/lpc.rs:828: (|err|.max(1) / normalizer).max(0.01).powf(-1.2) in f32"""
+    assert O.irls_weight(0.0, 1.0) == 1.0 and O.irls_weight(-0.5, 1.0) == 1.0
+    assert O.irls_weight(3.0, 1000.0) == float(np.float32(0.01) ** np.float32(-1.2)) or abs(O.irls_weight(3.0, 1000.0) - 251.18864) < 1e-3
+    assert abs(O.irls_weight(-500.0, 1000.0) - 0.5 ** -1.2) < 1e-6
+    assert O.irls_weight(5.0, 0.0) == 0.0  # silence: 1 / 0 = inf, inf^-1.2 = 0
