@@ -11,6 +11,7 @@ def run(ch, bps, cont, block, x, **kw):
     e = Encoder(block_size=block)
     if kw.get("lpc_order"): e.subframe_coding.qlpc.lpc_order = kw["lpc_order"]
     if kw.get("use_direct_mse"): e.subframe_coding.qlpc.use_direct_mse = True; e.subframe_coding.qlpc.window.type = "Rectangle"
+    e.subframe_coding.qlpc.mae_optimization_steps = kw.get("mae_optimization_steps", 0)
     n = len(x)
     with Context(e.into_verified(), ch, bps, 44100, block) as ctx:
         got, sizes, _ = ctx.encode_interleaved(pack_pcm(x, cont), cont, n)
@@ -32,6 +33,9 @@ big = crafted_huge_residual_stereo()
 run(2, 24, 3, 4096, np.concatenate([sig(2, 24, 4096), big, sig(2, 24, 4096, 7)]), lpc_order=24)
 # direct-MSE estimator: K1C (CTA per variant), then K1D and the thread-per-variant K1 forced on the same small inputs
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
+# ... and its IRLS-MAE refinement (K1I), frames of several staging tiles and a 24-bit 3-channel case
+run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1, mae_optimization_steps=2)
+run(3, 24, 3, 1500, sig(3, 24, 1500 * 2 + 77), use_direct_mse=1, mae_optimization_steps=1, lpc_order=24)
 os.environ["FB200_K1_SMALL"] = "0"
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 9 + 2728))
