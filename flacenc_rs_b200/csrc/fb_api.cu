@@ -71,25 +71,60 @@ __global__ void __launch_bounds__(256) fb_k0b_expand_pairs(FbJob J, const uint8_
     }
 }
 
-// K1S: the analysis of K1 for SMALL launches, one WARP per channel variant.  K1 gives every variant one thread that walks
-// the whole frame (the floats must be summed in the reference's sequential order), which is the right mapping when
-// there are tens of thousands of variants and a latency floor of two full walks when there are a few hundred (BASELINE
-// config 1: 432 variants).  The sequential chains are independent of one another, so here they are spread over lanes:
-//   * estimate_entropy (src/coding.rs:200-227): lane p sums partition p (its |e_k| in t order, f32) -- 16 chains of
-//     n / 16 samples instead of one of n; the zero-history differences at a partition start are rebuilt from the four
-//     samples before it
-//   * autocorrelation (src/lpc.rs:533-548): lane tau owns lag tau -- one sequential f64 FMA chain each, over tiles of
-//     y = (f32)x * w staged as doubles in shared memory
-// then lane 0 finishes with the same fb_k1_finish_ent / fb_k1_finish_lpc as K1: results are bit-identical.
-#define FB_K1S_TILE 2048
-#define FB_K1S_WARPS 4
-__global__ void __launch_bounds__(32 * FB_K1S_WARPS) fb_k1s_analyze(FbJob J, const int32_t *xt, const uint8_t *pcm,
-                                                                    const float *win_full, const float *win_tail, FbAnalysis *ana,
-                                                                    fb200_variant_taps *taps_all, uint32_t n_variants) {
+// K1S: the analysis of K1 for SMALL launches, one CTA of three warps per channel variant.  K1 gives every variant one
+// thread that walks the whole frame (the floats must be summed in the reference's sequential order), which is the right
+// mapping when there are tens of thousands of variants and a latency floor of two full walks when there are a few
+// hundred (BASELINE config 1: 432 variants).  Here the independent chains are spread over lanes and the two passes run
+// side by side:
+//   * warp 0, autocorrelation (src/lpc.rs:533-548): lane tau owns lag tau -- one sequential f64 FMA chain each, over
+//     tiles of y = (f32)x * w that warps 1 and 2 stage as doubles in four shared-memory buffers (named barriers: the
+//     chain never waits for memory after the first tile); lane 0 finishes with K1's fb_k1_finish_lpc
+//   * warps 1 and 2, estimate_entropy (src/coding.rs:200-227): every second partition each; the lanes take the samples
+//     of a partition 32 at a time, the zero-history differences in closed form (wrapping, like the chain of
+//     subtractions), |e_k| summed as INTEGERS -- every f32 addition of the reference is exact while the sum stays below
+//     2^24, so the order of addition does not matter then; partitions where some order reaches 2^24 (loud 24-bit material)
+//     are replayed afterwards one per lane with the sequential f32 additions.  Warp 1 finishes with fb_k1_finish_ent.
+// Results are bit-identical to K1's.
+#define FB_K1S_TILE 1024
+#define FB_K1S_NB 4
+#define FB_K1S_THREADS 96
+// sequential f32 replay of one estimate partition [t0, t1): the five sums of |e_k|
+static __device__ __noinline__ void fb_k1s_replay(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const FbVarRows &rows,
+                                                  int32_t mb, int32_t sh, uint32_t f, int t0, int t1, float *s) {
+    int32_t h[4];
+    for (int i = 0; i < 4; i++) h[i] = t0 - 1 - i >= 0 ? fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t0 - 1 - i) : 0;
+    int32_t pe0 = h[0];
+    int32_t pe1 = (int32_t)((uint32_t)h[0] - (uint32_t)h[1]);
+    int32_t pe2 = (int32_t)((uint32_t)h[0] - 2u * (uint32_t)h[1] + (uint32_t)h[2]);
+    int32_t pe3 = (int32_t)((uint32_t)h[0] - 3u * (uint32_t)h[1] + 3u * (uint32_t)h[2] - (uint32_t)h[3]);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+    for (int t = t0; t < t1; t++) {
+        const int32_t e0 = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+        const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)pe0);
+        const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)pe1);
+        const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)pe2);
+        const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)pe3);
+        pe0 = e0; pe1 = e1; pe2 = e2; pe3 = e3;
+        s0 = FB_FADD(fabsf((float)e0), s0);
+        s1 = FB_FADD(fabsf((float)e1), s1);
+        s2 = FB_FADD(fabsf((float)e2), s2);
+        s3 = FB_FADD(fabsf((float)e3), s3);
+        s4 = FB_FADD(fabsf((float)e4), s4);
+    }
+    s[0] = s0; s[1] = s1; s[2] = s2; s[3] = s3; s[4] = s4;
+}
+
+FB_DEV uint32_t fb_k1s_abs24(uint32_t e) { // min(|e|, 2^24) of a wrapped difference
+    const uint32_t a = (int32_t)e < 0 ? 0u - e : e;
+    return a < (1u << 24) ? a : (1u << 24);
+}
+
+__global__ void __launch_bounds__(FB_K1S_THREADS) fb_k1s_analyze(FbJob J, const int32_t *xt, const uint8_t *pcm,
+                                                                 const float *win_full, const float *win_tail, FbAnalysis *ana,
+                                                                 fb200_variant_taps *taps_all, uint32_t n_variants) {
     extern __shared__ __align__(16) uint8_t fb_smem_k1s[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t gv = blockIdx.x * FB_K1S_WARPS + warp;
-    if (gv >= n_variants) return;
+    const uint32_t gv = blockIdx.x;
     const uint32_t f = gv / (uint32_t)J.nvar;
     const int v = (int)(gv - f * (uint32_t)J.nvar);
     const FbK1Var V = fb_k1_var(J, f, v, win_full, win_tail);
@@ -99,91 +134,160 @@ __global__ void __launch_bounds__(32 * FB_K1S_WARPS) fb_k1s_analyze(FbJob J, con
     if (pcm) fb_pair_mix(v, &mb, &sh);
     FbAnalysis *out = ana + gv;
     fb200_variant_taps *taps = taps_all ? taps_all + gv : nullptr;
-    double *ys = (double *)fb_smem_k1s + (size_t)warp * (FB200_MAX_LPC_ORDER + FB_K1S_TILE);
+    // FB_K1S_NB tile buffers of y (each with the FB200_MAX_LPC_ORDER samples before the tile in front), filled by warps 1
+    // and 2 and walked by warp 0; named barriers 2 + b ("buffer b is full") and 2 + NB + b ("buffer b is free"), 96
+    // threads each.  Frames of up to NB tiles (4096 samples) are staged without ever waiting for the chain.
+    constexpr int YB = FB200_MAX_LPC_ORDER + FB_K1S_TILE, NB = FB_K1S_NB;
+    double *ys = (double *)fb_smem_k1s;                                   // [NB][YB] (+ slack: the chain reads ahead)
+    unsigned long long *xb = (unsigned long long *)(ys + NB * YB + 32);   // warp 2 -> warp 1: b0..b4
+    int32_t *xm = (int32_t *)(xb + 5);                                    // ... and min, max
+    const bool do_a = V.do_lpc && !J.cfg.use_direct_mse;
+    const int n_tiles = do_a ? (n + FB_K1S_TILE - 1) / FB_K1S_TILE : 0;
 
-    // ---- pass E: min / max over all samples, entropy estimate partition by partition
-    FbK1Ent S;
-    fb_k1_ent_init(S, n, V.psize, 0);
-    S.xmin = 2147483647;
-    S.xmax = -2147483647 - 1;
-    if (V.do_ent) {
-        const int parts = J.cfg.approx_ent_partitions;
-        for (int p = (int)lane; p < parts; p += 32) {
-            const int t0 = p * V.psize, t1 = t0 + V.psize < n ? t0 + V.psize : n;
-            if (t0 >= t1) continue; // (empty trailing partitions contribute nothing: NaN -> 0, src/coding.rs:219-222)
-            // e_k[t0 - 1] from the four samples before the partition (zeros before the frame)
-            int32_t h[4];
-            for (int i = 0; i < 4; i++) h[i] = t0 - 1 - i >= 0 ? fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t0 - 1 - i) : 0;
-            int32_t pe0 = h[0];
-            int32_t pe1 = (int32_t)((uint32_t)h[0] - (uint32_t)h[1]);
-            int32_t pe2 = (int32_t)((uint32_t)h[0] - 2u * (uint32_t)h[1] + (uint32_t)h[2]);
-            int32_t pe3 = (int32_t)((uint32_t)h[0] - 3u * (uint32_t)h[1] + 3u * (uint32_t)h[2] - (uint32_t)h[3]);
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
-            for (int t = t0; t < t1; t++) {
-                const int32_t e0 = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
-                S.xmin = e0 < S.xmin ? e0 : S.xmin;
-                S.xmax = e0 > S.xmax ? e0 : S.xmax;
-                const int32_t e1 = (int32_t)((uint32_t)e0 - (uint32_t)pe0);
-                const int32_t e2 = (int32_t)((uint32_t)e1 - (uint32_t)pe1);
-                const int32_t e3 = (int32_t)((uint32_t)e2 - (uint32_t)pe2);
-                const int32_t e4 = (int32_t)((uint32_t)e3 - (uint32_t)pe3);
-                pe0 = e0; pe1 = e1; pe2 = e2; pe3 = e3;
-                s0 = FB_FADD(fabsf((float)e0), s0);
-                s1 = FB_FADD(fabsf((float)e1), s1);
-                s2 = FB_FADD(fabsf((float)e2), s2);
-                s3 = FB_FADD(fabsf((float)e3), s3);
-                s4 = FB_FADD(fabsf((float)e4), s4);
-            }
-            S.b0 += fb_k1_part_bits(s0, 0, t1, t1 - t0);
-            S.b1 += fb_k1_part_bits(s1, 1, t1, t1 - t0);
-            S.b2 += fb_k1_part_bits(s2, 2, t1, t1 - t0);
-            S.b3 += fb_k1_part_bits(s3, 3, t1, t1 - t0);
-            S.b4 += fb_k1_part_bits(s4, 4, t1, t1 - t0);
-        }
-    } else {
-        for (int t = (int)lane; t < n; t += 32) {
-            const int32_t e0 = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
-            S.xmin = e0 < S.xmin ? e0 : S.xmin;
-            S.xmax = e0 > S.xmax ? e0 : S.xmax;
-        }
-    }
-    // bits are integers: any order of addition gives the reference's per-order totals
-    for (int d = 16; d; d >>= 1) {
-        S.b0 += __shfl_xor_sync(0xFFFFFFFFu, S.b0, d);
-        S.b1 += __shfl_xor_sync(0xFFFFFFFFu, S.b1, d);
-        S.b2 += __shfl_xor_sync(0xFFFFFFFFu, S.b2, d);
-        S.b3 += __shfl_xor_sync(0xFFFFFFFFu, S.b3, d);
-        S.b4 += __shfl_xor_sync(0xFFFFFFFFu, S.b4, d);
-        S.xmin = min(S.xmin, __shfl_xor_sync(0xFFFFFFFFu, S.xmin, d));
-        S.xmax = max(S.xmax, __shfl_xor_sync(0xFFFFFFFFu, S.xmax, d));
-    }
-    if (lane == 0) fb_k1_finish_ent(J, V, S, out, taps);
-
-    // ---- pass A: lane tau accumulates lag tau
-    double acc = 0.0;
-    if (V.do_lpc && !J.cfg.use_direct_mse) {
-        for (int tile0 = 0; tile0 < n; tile0 += FB_K1S_TILE) {
+    if (warp == 0) {
+        // ---- pass A: lane tau accumulates lag tau
+        double acc = 0.0;
+        for (int k = 0; k < n_tiles; k++) {
+            const int b = k % NB, tile0 = k * FB_K1S_TILE;
             const int tile1 = tile0 + FB_K1S_TILE < n ? tile0 + FB_K1S_TILE : n;
-            if (lane < FB200_MAX_LPC_ORDER) ys[lane] = tile0 == 0 ? 0.0 : ys[FB_K1S_TILE + lane];
-            __syncwarp();
-            for (int t = tile0 + (int)lane; t < tile1; t += 32) {
-                const int32_t x = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
-                ys[FB200_MAX_LPC_ORDER + (t - tile0)] = (double)FB_FMUL((float)x, V.win[t]);
-            }
-            __syncwarp();
+            asm volatile("bar.sync %0, 96;" ::"r"(2 + b) : "memory");
             if ((int)lane <= P) {
                 const int lo = P > tile0 ? P : tile0;
-                const double *pa = ys + FB200_MAX_LPC_ORDER - tile0 - (int)lane, *pb = ys + FB200_MAX_LPC_ORDER - tile0;
-#pragma unroll 4
+                const double *pb = ys + b * YB + FB200_MAX_LPC_ORDER - tile0, *pa = pb - (int)lane;
+                // (the loads of 16 steps are in flight ahead of the dependent DFMAs: 9.7 instead of 16.8 cycles per step)
+#pragma unroll 16
                 for (int t = lo; t < tile1; t++) acc = FB_FMA(pa[t], pb[t], acc);
             }
-            __syncwarp();
+            if (k + NB < n_tiles) asm volatile("bar.arrive %0, 96;" ::"r"(2 + NB + b) : "memory");
+        }
+        FbK1Acc<FB200_MAX_LPC_ORDER> A;
+#pragma unroll
+        for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) A.acc[i] = __shfl_sync(0xFFFFFFFFu, acc, i);
+        if (lane == 0) fb_k1_finish_lpc<FB200_MAX_LPC_ORDER>(J, V, A, out, taps);
+        return;
+    }
+
+    // ---- warps 1 and 2: stage tile k of y = (f32)x * w as doubles (src/lpc.rs:739-756), eight samples per thread in flight
+    auto stage_tile = [&](int k) {
+        const int b = k % NB, tile0 = k * FB_K1S_TILE;
+        const int tile1 = tile0 + FB_K1S_TILE < n ? tile0 + FB_K1S_TILE : n;
+        if (k >= NB) asm volatile("bar.sync %0, 96;" ::"r"(2 + NB + b) : "memory");
+        double *yb = ys + b * YB + FB200_MAX_LPC_ORDER - tile0;
+        const int lo = tile0 >= FB200_MAX_LPC_ORDER ? tile0 - FB200_MAX_LPC_ORDER : 0;
+        for (int t = lo + (int)threadIdx.x - 32; t < tile1; t += 512) {
+            int32_t x[8];
+            float wv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int ti = t + 64 * i;
+                x[i] = ti < tile1 ? fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, ti) : 0;
+                wv[i] = ti < tile1 ? V.win[ti] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int ti = t + 64 * i;
+                if (ti < tile1) yb[ti] = (double)FB_FMUL((float)x[i], wv[i]);
+            }
+        }
+        asm volatile("bar.arrive %0, 96;" ::"r"(2 + b) : "memory");
+    };
+    for (int k = 0; k < n_tiles && k < NB; k++) stage_tile(k);
+
+    // ---- pass E (warps 1 and 2): min / max over all samples, entropy estimate partition by partition
+    const int w = (int)warp - 1;
+    int32_t mn = 2147483647, mx = -2147483647 - 1;
+    unsigned long long bsum = 0; // lane k < 5: the bits of order k over this warp's partitions
+    if (V.do_ent) {
+        const int parts = J.cfg.approx_ent_partitions;
+        uint32_t flagged = 0; // local partitions (bit i = partition w + 2 i) that need the sequential replay
+        for (int p = w, i = 0; p < parts; p += 2, i++) {
+            const int t0 = p * V.psize, t1 = t0 + V.psize < n ? t0 + V.psize : n;
+            if (t0 >= t1) break; // (empty trailing partitions contribute nothing: NaN -> 0, src/coding.rs:219-222)
+            uint32_t j0 = 0, j1 = 0, j2 = 0, j3 = 0, j4 = 0;
+            for (int t = t0 + (int)lane; t < t1; t += 32) {
+                const uint32_t x0 = (uint32_t)fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+                const uint32_t x1 = t >= 1 ? (uint32_t)fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t - 1) : 0u;
+                const uint32_t x2 = t >= 2 ? (uint32_t)fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t - 2) : 0u;
+                const uint32_t x3 = t >= 3 ? (uint32_t)fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t - 3) : 0u;
+                const uint32_t x4 = t >= 4 ? (uint32_t)fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t - 4) : 0u;
+                mn = (int32_t)x0 < mn ? (int32_t)x0 : mn;
+                mx = (int32_t)x0 > mx ? (int32_t)x0 : mx;
+                // zero-history k-th differences (src/coding.rs:188-195), wrapping
+                const uint32_t d1 = x0 - x1, d1p = x1 - x2, d1pp = x2 - x3, d1ppp = x3 - x4;
+                const uint32_t d2 = d1 - d1p, d2p = d1p - d1pp, d2pp = d1pp - d1ppp;
+                const uint32_t d3 = d2 - d2p, d3p = d2p - d2pp;
+                const uint32_t d4 = d3 - d3p;
+                // (sums of clamped terms: at most 2^24 * 2048 rows of a lane -- block sizes are below 2^15 * 32 -- fits)
+                j0 += fb_k1s_abs24(x0);
+                j1 += fb_k1s_abs24(d1);
+                j2 += fb_k1s_abs24(d2);
+                j3 += fb_k1s_abs24(d3);
+                j4 += fb_k1s_abs24(d4);
+                j0 = j0 < (1u << 24) ? j0 : (1u << 24);
+                j1 = j1 < (1u << 24) ? j1 : (1u << 24);
+                j2 = j2 < (1u << 24) ? j2 : (1u << 24);
+                j3 = j3 < (1u << 24) ? j3 : (1u << 24);
+                j4 = j4 < (1u << 24) ? j4 : (1u << 24);
+            }
+            for (int d = 16; d; d >>= 1) { // (32 lanes x 2^24 fits)
+                j0 += __shfl_xor_sync(0xFFFFFFFFu, j0, d);
+                j1 += __shfl_xor_sync(0xFFFFFFFFu, j1, d);
+                j2 += __shfl_xor_sync(0xFFFFFFFFu, j2, d);
+                j3 += __shfl_xor_sync(0xFFFFFFFFu, j3, d);
+                j4 += __shfl_xor_sync(0xFFFFFFFFu, j4, d);
+            }
+            if ((j0 | j1 | j2 | j3 | j4) < (1u << 24)) {
+                // exact: the f32 sums of the reference are these integers; lane k estimates order k
+                const uint32_t js = lane == 0 ? j0 : lane == 1 ? j1 : lane == 2 ? j2 : lane == 3 ? j3 : j4;
+                if (lane < 5) bsum += fb_k1_part_bits((float)js, (int)lane, t1, t1 - t0);
+            } else {
+                flagged |= 1u << i;
+            }
+        }
+        if (flagged) { // (warp-uniform) lane i replays local partition i
+            unsigned long long r[5] = {0, 0, 0, 0, 0};
+            if ((flagged >> lane) & 1u) {
+                const int p = w + 2 * (int)lane;
+                const int t0 = p * V.psize, t1 = t0 + V.psize < n ? t0 + V.psize : n;
+                float s[5];
+                fb_k1s_replay(J, xt, pcm, rows, mb, sh, f, t0, t1, s);
+                for (int k = 0; k < 5; k++) r[k] = fb_k1_part_bits(s[k], k, t1, t1 - t0);
+            }
+            for (int k = 0; k < 5; k++) {
+                for (int d = 16; d; d >>= 1) r[k] += __shfl_xor_sync(0xFFFFFFFFu, r[k], d);
+                if ((int)lane == k) bsum += r[k];
+            }
+        }
+    } else {
+        for (int t = w * 32 + (int)lane; t < n; t += 64) {
+            const int32_t e0 = fb_k1c_sample(J, xt, pcm, rows, mb, sh, f, t);
+            mn = e0 < mn ? e0 : mn;
+            mx = e0 > mx ? e0 : mx;
         }
     }
-    FbK1Acc<FB200_MAX_LPC_ORDER> A;
-#pragma unroll
-    for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) A.acc[i] = __shfl_sync(0xFFFFFFFFu, acc, i);
-    if (lane == 0) fb_k1_finish_lpc<FB200_MAX_LPC_ORDER>(J, V, A, out, taps);
+    for (int d = 16; d; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    }
+    for (int k = NB; k < n_tiles; k++) stage_tile(k); // (frames of more than NB tiles: the chain waits for pass E once)
+    if (warp == 2) {
+        if (lane < 5) xb[lane] = bsum;
+        if (lane == 0) { xm[0] = mn; xm[1] = mx; }
+    }
+    asm volatile("bar.sync 1, 64;" ::: "memory"); // warps 1 and 2 only
+    if (warp == 1) {
+        if (lane < 5) bsum += xb[lane];
+        FbK1Ent S;
+        fb_k1_ent_init(S, n, V.psize, 0);
+        S.b0 = __shfl_sync(0xFFFFFFFFu, bsum, 0);
+        S.b1 = __shfl_sync(0xFFFFFFFFu, bsum, 1);
+        S.b2 = __shfl_sync(0xFFFFFFFFu, bsum, 2);
+        S.b3 = __shfl_sync(0xFFFFFFFFu, bsum, 3);
+        S.b4 = __shfl_sync(0xFFFFFFFFu, bsum, 4);
+        S.xmin = min(mn, xm[0]);
+        S.xmax = max(mx, xm[1]);
+        if (lane == 0) fb_k1_finish_ent(J, V, S, out, taps);
+    }
 }
 
 // K1C: direct-MSE LPC estimator, one CTA per channel variant (fb_kernels.cuh)
@@ -287,7 +391,6 @@ struct fb200_ctx {
     uint32_t ktab_chunk = 0; // CRC chunk length the uploaded tables were built for
     bool no_k1d = false;        // FB200_K1D=0: direct MSE always by the CTA-per-variant kernel (tests exercise both)
     int k1_small = -1;          // FB200_K1_SMALL=0/1: never / always analyse with a warp per variant (default: by launch size)
-    bool k1s_smem_set = false;
     bool no_pairs = false;      // FB200_KP_PAIRS=0: the pack kernel always stages planes (tests exercise both)
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
     uint64_t pipe_chunk_frames = 0; // FB200_CHUNK_FRAMES: frames per chunk of the pipelined host path (0 = default)
@@ -667,15 +770,11 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
         fb_k0_ingest<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(J, d_pcm, (int32_t *)S.xv.p, d_err, n_items);
     }
     FB_CUDA(ctx, cudaEventRecord(S.ev[2], st));
-    // small launches: a warp per variant (K1S) instead of a thread per variant (K1); same results
-    const bool k1_small = ctx->k1_small >= 0 ? ctx->k1_small != 0 : nvars <= 148u * 3u * FB_K1S_WARPS;
+    // small launches: a CTA per variant (K1S) instead of a thread per variant (K1); same results
+    const bool k1_small = ctx->k1_small >= 0 ? ctx->k1_small != 0 : nvars <= 148u * 12u;
     if (k1_small) {
-        const uint32_t smem = FB_K1S_WARPS * (FB200_MAX_LPC_ORDER + FB_K1S_TILE) * 8u;
-        if (!ctx->k1s_smem_set) {
-            FB_CUDA(ctx, cudaFuncSetAttribute(fb_k1s_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctx->k1s_smem_set = true;
-        }
-        fb_k1s_analyze<<<(nvars + FB_K1S_WARPS - 1) / FB_K1S_WARPS, 32 * FB_K1S_WARPS, smem, st>>>(
+        const uint32_t smem = FB_K1S_NB * (FB200_MAX_LPC_ORDER + FB_K1S_TILE) * 8u + 32u * 8u + 64u;
+        fb_k1s_analyze<<<nvars, FB_K1S_THREADS, smem, st>>>(
             J, (const int32_t *)S.xv.p, pcm_pairs, (const float *)ctx->win_full.p, P.d_win_tail, (FbAnalysis *)S.ana.p,
             A.analyze_only ? (fb200_variant_taps *)S.taps.p : nullptr, nvars);
     } else {
