@@ -1258,6 +1258,7 @@ FB_DEV void fb_k1c_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, c
                 const int lo = t_lo > tile0 ? t_lo : tile0, hi = t_hi < tile1 ? t_hi : tile1;
                 const double *pa = ys + FB200_MAX_LPC_ORDER - tile0 - a, *pb = ys + FB200_MAX_LPC_ORDER - tile0 - b;
                 double s = FB_K1C_ACC;
+#pragma unroll 8
                 for (int t = lo; t < hi; t++) s = FB_FMA(pa[t], pb[t], s);
                 FB_K1C_ACC = s;
             }
@@ -1445,9 +1446,11 @@ FB_DEV void fb_k1i_body(const FbJob &J, const int32_t *xt, const uint8_t *pcm, c
                     double s = FB_K1I_ACC;
                     if (k == 0) { // weights of 1: the products are exact
                         const double *pb = ys + H - tile0 - b;
+#pragma unroll 8
                         for (int u = lo; u < hi; u++) s = FB_FMA(pa[u], pb[u], s);
                     } else {
                         const float *pb = yf + H - tile0 - b, *pw = wt - tile0;
+#pragma unroll 8
                         for (int u = lo; u < hi; u++) s = FB_FMA(pa[u], (double)FB_FMUL(pw[u], pb[u]), s);
                     }
                     FB_K1I_ACC = s;
