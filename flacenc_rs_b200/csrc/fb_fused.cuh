@@ -878,7 +878,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 // One variant (one warp): fixed_lpc / estimated_qlpc / encode_subframe (src/coding.rs:298-418) on top
 // of K1's analysis.  Writes the decision record `out` (shared memory) and S->cand[v].
 // =====================================================================================================
-template <int G, bool ODD, int VMS>
+template <int G, bool ODD, int VMS, bool BC>
 FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, const FbAnalysis &A, int v,
                           uint8_t *smem, const FbKfLayout &L, fb200_subframe_info *out) {
     FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
@@ -927,14 +927,45 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
     }
     if (n < FB_MIN_PRED_BLOCK) return;
 
-    // candidates: 0 = fixed winner of K1's entropy estimate (src/coding.rs:298-331), 1 = LPC (src/coding.rs:360-381)
-    const int kf = J.cfg.use_fixed ? A.fixed_order : -1;
+    // candidates: 0 = fixed (src/coding.rs:298-331), 1 = LPC (src/coding.rs:360-381).  The fixed order is the winner of
+    // K1's entropy estimate (OrderSel::ApproxEnt) or, for OrderSel::BitCount (src/coding.rs:241-262), the first order
+    // minimising bps * order + code_bits of its exact Rice search: the orders are searched one after the other into
+    // result set 0 and the winner is searched again below unless it was the last one.  BC is a template parameter: the
+    // plan kernels of the default selector do not contain this loop at all (they are sensitive to their code size).
+    int kf = J.cfg.use_fixed ? A.fixed_order : -1;
+    int set0_order = -1;
+    if (BC && J.cfg.use_fixed && J.cfg.fixed_order_sel == 0) {
+        const int n_probe = (J.cfg.fixed_max_order < 4 ? J.cfg.fixed_max_order : 4) + 1;
+        unsigned long long best_key = 0;
+        kf = -1;
+#if FB_GPU
+#pragma unroll 1
+#endif
+        for (int k = 0; k < n_probe; k++) {
+            FbKfCand cd;
+            cd.kind = 0; cd.q = A.qlp; cd.order = k; cd.shift = 0; cd.narrow = true;
+            fb_kf_fixed_coefs(k, cd.fc);
+            fb_kf_search<G, ODD, VMS>(J, g, xa, xb, vm, cd, scratch, L, unit_bits, res[0]);
+            if (M->fail) return;
+            set0_order = k;
+            // code_bits of the search = the level total = res_bits without the 6 header bits and the RICE2 extra bits
+            const unsigned long long code_bits =
+                res[0]->res_bits - 6ull - (res[0]->rice2 ? (unsigned long long)(1 << res[0]->part_order) : 0ull);
+            const unsigned long long key = (unsigned long long)bps_v * (unsigned long long)k + code_bits;
+            if (kf < 0 || key < best_key) { kf = k; best_key = key; }
+        }
+        if (!(best_key < verbatim_bits)) kf = -1;
+    }
     unsigned long long cbits[2] = {0, 0};
 #if FB_GPU
 #pragma unroll 1
 #endif
     for (int c = 0; c < 2; c++) {
         if (c == 0 ? (kf < 0) : !J.cfg.use_lpc) continue;
+        if (BC && c == 0 && set0_order == kf) { // (the last order probed won, its results are in place)
+            cbits[0] = 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0]->res_bits;
+            continue;
+        }
         FbKfCand cd;
         cd.kind = c;
         cd.q = A.qlp;
@@ -1124,7 +1155,7 @@ FB_DEV void fb_kf_to_fallback(uint32_t *fb_list, uint32_t *fb_count, FbKfPlan *p
 // ---- KA: analysis and plan.  psubs: [frame][channels] chosen subframe records; poffs: [frame][channels][U_max+1]
 // VMS = 0: 32-bit planes staged from the planar store xv; VMS = FB_VM_PAIRS: the frame's packed 16-bit stereo PCM
 // (pcm) staged as one plane of pairs, xv is not read
-template <int G, bool ODD = false, int VMS = 0>
+template <int G, bool ODD = false, int VMS = 0, bool BC = false>
 FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, const FbAnalysis *ana, FbKfPlan *plan, fb200_subframe_info *vsubs,
                        fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                        uint32_t *fb_count, const uint32_t *ktab, uint32_t f, uint8_t *smem, const FbKfLayout &L) {
@@ -1164,7 +1195,7 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
 
     // ---- analysis: one warp per variant
     FB_WARPS_BEGIN(w, NW)
-        fb_kf_variant<G, ODD, VMS>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w]);
+        fb_kf_variant<G, ODD, VMS, BC>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w]);
         const FbKfMisc *M = (const FbKfMisc *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_misc);
         FB_WPHASE(lane)
             if (lane == 0 && M->fail) S->frame_fail = 1; // benign race between warps

@@ -122,11 +122,9 @@ inline int fbh_leaves_max(const FbJob &J) {
     return a > b ? a : b;
 }
 
-// The fused per-frame kernel (fb_fused.cuh) serves a batch when the fixed order comes from K1's entropy
-// estimate (OrderSel::ApproxEnt, the default; BitCount needs one Rice search per order and stays on the
-// generic kernels) and the frame's working set fits in shared memory.
+// The fused per-frame kernels (fb_fused.cuh) serve a batch when the frame's working set fits in shared memory (both
+// order selectors: ApproxEnt takes the fixed order from K1's entropy estimate, BitCount searches every order).
 inline bool fbh_fused_ok(const FbJob &J, int tail_n_call, FbKfLayout *Lout, bool x16 = false) {
-    if (J.cfg.use_fixed && J.cfg.fixed_order_sel != 1) return false;
     FbKfLayout L = fb_kf_layout(J.channels, J.nvar, J.bps, J.block_size, tail_n_call, x16);
     if (Lout) *Lout = L;
     if (L.total > FB_KF_SMEM_LIMIT) return false;

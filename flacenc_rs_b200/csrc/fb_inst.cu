@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
 // fused path (fb_fused.cuh), one CTA of 32 * nvar threads per frame: KA = analysis + plan, KP = pack + store
 // odd_mode (fb_kf_odd_mode): 0 = every frame has 4-sample aligned units; 1 = all but the last frame (its CTA comes
 // first: it is the slow one); 2 = none.  The ODD instance loads its windows sample by sample.
-#define FB_KA_KERNEL(NAME, BOUNDS, VMS)                                                                                          \
+#define FB_KA_KERNEL(NAME, BOUNDS, VMS, BC)                                                                                         \
     __global__ void BOUNDS NAME(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbAnalysis *ana, FbKfPlan *plan,           \
                                 fb200_subframe_info *vsubs, fb200_subframe_info *psubs, uint32_t *poffs, uint32_t *frame_bytes,  \
                                 fb200_frame_info *infos, uint32_t *fb_list, uint32_t *fb_count, const uint32_t *ktab,            \
@@ -93,15 +93,18 @@ __global__ void __launch_bounds__(FB_K3_THREADS) FB_NAME(fb_k3_pack_g)(FbJob J, 
         const bool odd = odd_mode == 2 || (odd_mode == 1 && blockIdx.x == 0);                                                    \
         const uint32_t f = odd_mode == 1 ? (blockIdx.x == 0 ? J.n_frames - 1u : blockIdx.x - 1u) : blockIdx.x;                   \
         if (odd)                                                                                                                 \
-            fb_ka_body<FB_INST_G, true, VMS>(J, xt, pcm, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count,  \
+            fb_ka_body<FB_INST_G, true, VMS, BC>(J, xt, pcm, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count,  \
                                              ktab, f, fb_smem, L);                                                               \
         else                                                                                                                     \
-            fb_ka_body<FB_INST_G, false, VMS>(J, xt, pcm, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, \
+            fb_ka_body<FB_INST_G, false, VMS, BC>(J, xt, pcm, ana, plan, vsubs, psubs, poffs, frame_bytes, infos, fb_list, fb_count, \
                                               ktab, f, fb_smem, L);                                                              \
     }
-FB_KA_KERNEL(FB_NAME(fb_ka_plan_g), FB_KA_BOUNDS, 0)
+FB_KA_KERNEL(FB_NAME(fb_ka_plan_g), FB_KA_BOUNDS, 0, false)
 // 16-bit stereo straight from the packed PCM: one plane of (left, right) pairs
-FB_KA_KERNEL(FB_NAME(fb_ka_planp_g), FB_KAP_BOUNDS, FB_VM_PAIRS)
+FB_KA_KERNEL(FB_NAME(fb_ka_planp_g), FB_KAP_BOUNDS, FB_VM_PAIRS, false)
+// OrderSel::BitCount: the instances that search every fixed order (src/coding.rs:241-262)
+FB_KA_KERNEL(FB_NAME(fb_ka_planb_g), FB_KA_BOUNDS, 0, true)
+FB_KA_KERNEL(FB_NAME(fb_ka_planpb_g), FB_KAP_BOUNDS, FB_VM_PAIRS, true)
 
 __global__ void FB_KP_BOUNDS FB_NAME(fb_kp_pack_g)(FbJob J, const int32_t *xt, const uint8_t *pcm, const FbKfPlan *plan,
                                                              const fb200_subframe_info *psubs, const uint32_t *poffs,
@@ -144,12 +147,18 @@ void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const uint8_t *p
                              fb200_subframe_info *vsubs, fb200_subframe_info *psubs,
                              uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                              uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-    if (pcm_pairs)
-        FB_NAME(fb_ka_planp_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, pcm_pairs, ana, (FbKfPlan *)plan, vsubs, psubs, poffs,
-                                                                          frame_bytes, infos, fb_list, fb_count, ktab, L, fb_kf_odd_mode(J));
-    else
-        FB_NAME(fb_ka_plan_g)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, nullptr, ana, (FbKfPlan *)plan, vsubs, psubs, poffs,
-                                                                         frame_bytes, infos, fb_list, fb_count, ktab, L, fb_kf_odd_mode(J));
+    const bool bitcount = J.cfg.use_fixed && J.cfg.fixed_order_sel == 0;
+#define FB_KA_LAUNCH(K, PCM)                                                                                                       \
+    FB_NAME(K)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, PCM, ana, (FbKfPlan *)plan, vsubs, psubs, poffs, frame_bytes, infos, \
+                                                         fb_list, fb_count, ktab, L, fb_kf_odd_mode(J))
+    if (pcm_pairs) {
+        if (bitcount) FB_KA_LAUNCH(fb_ka_planpb_g, pcm_pairs);
+        else FB_KA_LAUNCH(fb_ka_planp_g, pcm_pairs);
+    } else {
+        if (bitcount) FB_KA_LAUNCH(fb_ka_planb_g, nullptr);
+        else FB_KA_LAUNCH(fb_ka_plan_g, nullptr);
+    }
+#undef FB_KA_LAUNCH
 }
 
 void FB_NAME(fb_launch_kp_g)(const FbJob &J, const int32_t *xt, const uint8_t *pcm, const void *plan, const fb200_subframe_info *psubs,
@@ -169,6 +178,10 @@ cudaError_t FB_NAME(fb_set_smem_g)(int kernel, int bytes) {
         cudaError_t e = cudaFuncSetAttribute(FB_NAME(fb_ka_plan_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(FB_NAME(fb_ka_planp_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(FB_NAME(fb_ka_planb_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(FB_NAME(fb_ka_planpb_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(FB_NAME(fb_kp_pack_g), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     }

@@ -201,8 +201,8 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
             memset(smem.data(), 0xAB, smem.size());
 #define EMU_KA_ARGS B.ana.data(), plan.data(), B.choice.data(), psubs.data(), poffs.data(), B.frame_bytes.data(), B.infos.data(), list.data(), &count, ktab_a.data(), f, smem.data(), KL
 #define EMU_KA(GG) do { const bool odd__ = fb_kf_geom(fb_frame_len(J, f)).leaf_len & 3; \
-            if (ka_pairs) { if (odd__) fb_ka_body<GG, true, FB_VM_PAIRS>(J, nullptr, pcm8, EMU_KA_ARGS); else fb_ka_body<GG, false, FB_VM_PAIRS>(J, nullptr, pcm8, EMU_KA_ARGS); } \
-            else { if (odd__) fb_ka_body<GG, true, 0>(J, B.xv.data(), nullptr, EMU_KA_ARGS); else fb_ka_body<GG, false, 0>(J, B.xv.data(), nullptr, EMU_KA_ARGS); } } while (0)
+            if (ka_pairs) { if (odd__) fb_ka_body<GG, true, FB_VM_PAIRS, true>(J, nullptr, pcm8, EMU_KA_ARGS); else fb_ka_body<GG, false, FB_VM_PAIRS, true>(J, nullptr, pcm8, EMU_KA_ARGS); } \
+            else { if (odd__) fb_ka_body<GG, true, 0, true>(J, B.xv.data(), nullptr, EMU_KA_ARGS); else fb_ka_body<GG, false, 0, true>(J, B.xv.data(), nullptr, EMU_KA_ARGS); } } while (0)
             switch (fb_k1_ring(J.cfg.lpc_order)) {
             case 4: EMU_KA(4); break;
             case 8: EMU_KA(8); break;

@@ -335,7 +335,37 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     with Context(make_config(fixed_order_sel=0).into_verified(), 2, 16, 44100, 4096) as ctx:
         ctx.encode_interleaved(pack_pcm(x, 2), 2, n)
         t = ctx.timing()
-        assert (t.fused_frames, t.fallback_frames) == (0, 0)  # BitCount selection: generic kernels only
+        assert (t.fused_frames, t.fallback_frames) == (6, 0)  # BitCount selection runs on the fused kernels too
+
+
+def test_bitcount_order_selection_on_the_fused_path():
+    """OrderSel::BitCount (src/coding.rs:241-262) in the plan kernel: signals whose best fixed order differs, max orders
+    below 4, no LPC, a constant channel, RICE2 parameters, 24-bit order 24, 8 channels"""
+    t = np.arange(8192, dtype=np.float64)
+    rng = np.random.default_rng(21)
+    sigs = [
+        rng.integers(-20000, 20000, 8192),
+        np.cumsum(rng.integers(-300, 300, 8192)),
+        np.cumsum(np.cumsum(rng.integers(-3, 4, 8192))) % 30000,
+        (20000 * np.sin(t / 40.0)).astype(np.int64) + rng.integers(-2, 3, 8192),
+        (3000 * np.sin(t / 9.0) + 9000 * np.sin(t / 100.0)).astype(np.int64),
+    ]
+    for s in sigs:
+        x = np.stack([s, s[::-1]], axis=1).astype(np.int32)
+        _compare(x, 2, 16, 44100, 4096, fixed_order_sel=0)
+        _compare(x[:, :1], 1, 16, 44100, 2048, fixed_order_sel=0, use_lpc=0)
+    for mo in (0, 1, 2, 3):
+        _compare(np.stack([sigs[3], sigs[4]], axis=1).astype(np.int32), 2, 16, 44100, 4096, fixed_order_sel=0, fixed_max_order=mo)
+    _compare(np.stack([sigs[2], np.full(8192, 77)], axis=1).astype(np.int32), 2, 16, 44100, 1000, fixed_order_sel=0)
+    _compare(rng.integers(-(1 << 22), 1 << 22, (4096, 2)).astype(np.int32), 2, 24, 96000, 1024, fixed_order_sel=0)
+    y = sigen.noisy_sine_pcm(4608 * 3 + 100, 2, 24, 96000, config_id=3)
+    _compare(y, 2, 24, 96000, 4608, fixed_order_sel=0, lpc_order=24)
+    z = sigen.noisy_sine_pcm(1024 * 4 + 9, 8, 24, 48000, config_id=5)
+    _compare(z, 8, 24, 48000, 1024, fixed_order_sel=0)
+    with Context(make_config(fixed_order_sel=0).into_verified(), 2, 24, 96000, 4608) as ctx:
+        ctx.encode_interleaved(pack_pcm(y, 3), 3, len(y))
+        tm = ctx.timing()
+        assert (tm.fused_frames, tm.fallback_frames) == (4, 0)
 
 
 def test_pipelined_host_path_matches_oracle(monkeypatch):

@@ -209,7 +209,8 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     """Default config: every frame goes through the fused kernel, also tails whose finest Rice partitions are not
     a multiple of 4 samples (the 2728-sample tail: 8 x 341; the kernels' ODD instances).  Residuals >= 2^27 (the reference's chunked saturating
     sums become order dependent) and saturated table minima are handed to the generic kernels; BitCount order
-    selection and frames that do not fit shared memory never enter the fused kernel."""
+    selection (one Rice search per fixed order, /root/reference/src/coding.rs:241-262) also runs fused; frames that do
+    not fit shared memory never enter the fused kernel."""
     E.fused_counts()
     x = sigen.noisy_sine_pcm(4096 * 3 + 2728, 2, 16, 44100)
     _compare(x, 2, 16, 44100, 4096)
@@ -226,10 +227,43 @@ def test_fused_kernel_is_the_path_taken_and_falls_back_only_when_it_must():
     _compare(np.stack([smooth, smooth[::-1]], axis=1), 2, 24, 96000, 4096, lpc_order=12, prc_max_parameter=5)
     assert E.fused_counts() == [0, 1]  # saturated table minimum (max_parameter too small for the residuals)
     _compare(x, 2, 16, 44100, 4096, fixed_order_sel=0)
-    assert E.fused_counts() == [0, 0]
+    assert E.fused_counts() == [8, 0]
     y = sigen.noisy_sine_pcm(32767 + 500, 8, 24, 96000, config_id=7)
     _compare(y, 8, 24, 96000, 32767)
     assert E.fused_counts() == [0, 0]
+
+
+def test_bitcount_order_selection_on_the_fused_path():
+    """OrderSel::BitCount (/root/reference/src/coding.rs:241-262: bps * order + code_bits of an exact Rice search per
+    order, first minimum wins, accepted below the verbatim size) in the plan kernel: signals whose best order is each of
+    0..4, max orders below 4, no LPC, noise (verbatim), a constant channel, RICE2 parameters, and the reference's KAT
+    shapes ([255..], [256..], [128..] picks order 0, src/coding.rs:945-979)"""
+    E.fused_counts()
+    t = np.arange(2048, dtype=np.float64)
+    rng = np.random.default_rng(21)
+    sigs = [
+        rng.integers(-20000, 20000, 2048),                                             # order 0 / verbatim territory
+        np.cumsum(rng.integers(-300, 300, 2048)),                                      # order 1
+        np.cumsum(np.cumsum(rng.integers(-3, 4, 2048))) % 30000,                       # order 2
+        (20000 * np.sin(t / 40.0)).astype(np.int64) + rng.integers(-2, 3, 2048),       # higher orders
+        (3000 * np.sin(t / 9.0) + 9000 * np.sin(t / 100.0)).astype(np.int64),
+    ]
+    for s in sigs:
+        x = np.stack([s, s[::-1]], axis=1).astype(np.int32)
+        _compare(x, 2, 16, 44100, 1024, fixed_order_sel=0)
+        _compare(x[:, :1], 1, 16, 44100, 2048, fixed_order_sel=0, use_lpc=0)
+    for mo in (0, 1, 2, 3):
+        _compare(np.stack([sigs[3], sigs[4]], axis=1).astype(np.int32), 2, 16, 44100, 1024, fixed_order_sel=0, fixed_max_order=mo)
+    _compare(np.stack([sigs[2], np.full(2048, 77)], axis=1).astype(np.int32), 2, 16, 44100, 512, fixed_order_sel=0)
+    loud = (rng.integers(-(1 << 22), 1 << 22, (1024, 2))).astype(np.int32)           # Rice parameters above 14
+    _compare(loud, 2, 24, 96000, 512, fixed_order_sel=0)
+    for v in (255, 256, 128):
+        k = np.zeros((64, 1), np.int32)
+        k[::2] = v
+        _compare(np.tile(k, (4, 1)), 1, 16, 44100, 256, fixed_order_sel=0, use_lpc=0)
+    fused, fb = E.fused_counts()
+    # (the loud 24-bit noise is handed over: its order-4 differences reach 2^26, the zigzag values 2^27)
+    assert fused >= 50 and fb <= 2
 
 
 def test_crc8_closed_form_matches_bit_serial_definition():
