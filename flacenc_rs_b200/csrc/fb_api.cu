@@ -393,6 +393,7 @@ struct fb200_ctx {
     int k1_small = -1;          // FB200_K1_SMALL=0/1: never / always analyse with a warp per variant (default: by launch size)
     bool no_pairs = false;      // FB200_KP_PAIRS=0: the pack kernel always stages planes (tests exercise both)
     bool force_generic = false; // FB200_FORCE_GENERIC=1: never use the fused kernel (tests exercise both paths)
+    uint32_t serial_mib = 4096;     // FB200_SERIAL_MIB: working-set bound of a chunk of the serial (device-resident) path
     uint64_t pipe_chunk_frames = 0; // FB200_CHUNK_FRAMES: frames per chunk of the pipelined host path (0 = default)
     std::mutex mu;
 };
@@ -529,6 +530,8 @@ fb200_ctx *fb200_create(const fb200_config *cfg, int channels, int bits_per_samp
         if (ks) ctx->k1_small = ks[0] == '1' ? 1 : 0;
         const char *cf = getenv("FB200_CHUNK_FRAMES");
         if (cf) ctx->pipe_chunk_frames = strtoull(cf, nullptr, 10);
+        const char *sm = getenv("FB200_SERIAL_MIB");
+        if (sm && atoi(sm) >= 16) ctx->serial_mib = (uint32_t)atoi(sm);
         const char *ns = getenv("FB200_NSETS");
         if (ns) ctx->nsets = std::max(2, std::min(FB_NSETS_MAX, atoi(ns)));
     }
@@ -900,9 +903,10 @@ int fb_encode_serial(fb200_ctx *ctx, const EncodeArgs &A, const Plan &P) {
     ChunkSet &S = ctx->sets[0];
     cudaStream_t st = ctx->stream;
     int rc;
-    // chunking: bound the working set (planar variants + slots) to ~2 GiB per pass
+    // chunking: bound the working set (planar variants + slots) per pass (FB200_SERIAL_MIB, default 4 GiB: an hour of CD
+    // stereo is one chunk -- every extra chunk costs each kernel another partly filled last wave)
     const uint64_t per_frame = (uint64_t)P.nvar * P.stride * 4u + P.slot_bytes + 4096u;
-    uint64_t chunk_frames = std::max<uint64_t>(64, (2048ull << 20) / per_frame);
+    uint64_t chunk_frames = std::max<uint64_t>(64, ((uint64_t)ctx->serial_mib << 20) / per_frame);
     chunk_frames = std::min<uint64_t>(chunk_frames, P.total_frames);
     const uint64_t in_bytes_total = A.n_samples * (uint64_t)ctx->channels * (uint64_t)P.cb;
     uint64_t in_chunk = 0;

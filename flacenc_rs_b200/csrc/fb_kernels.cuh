@@ -898,15 +898,23 @@ FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
     static_assert(NC >= 2, "ring too small");
     const uint32_t group_bytes = (uint32_t)QG * T.pitch, slot_bytes = (uint32_t)GC * group_bytes;
     const uint32_t ring_end = T.ring + (uint32_t)NC * slot_bytes;
+#ifndef FB_X_NOSTAGE
 #pragma unroll 1
     for (int c = 0; c < D; c++) fb_k1_stage_issue_any<QC, PAIRS>(T, T.ring + (uint32_t)c * slot_bytes, c * QC);
+#else
+    for (uint32_t o = (threadIdx.x & 31u) * 4u; o < (uint32_t)NC * slot_bytes; o += 128u)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(T.ring + o), "r"(0) : "memory");
+    __syncwarp();
+#endif
     uint32_t slot_r = T.ring, slot_w = T.ring + (uint32_t)D * slot_bytes;
     int q_w = D * QC;
 #pragma unroll 1
     for (int g0 = 0; g0 < groups; g0 += GC) {
+#ifndef FB_X_NOSTAGE
         fb_k1_cp_wait<D - 1>(); // this chunk has landed (this lane's copies) ...
         __syncwarp();           // ... and everybody's; all lanes are also done reading the previous chunk
         fb_k1_stage_issue_any<QC, PAIRS>(T, slot_w, q_w);
+#endif
         q_w += QC;
         slot_w += slot_bytes;
         slot_w = slot_w == ring_end ? T.ring : slot_w;
@@ -930,7 +938,12 @@ FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &
         const int t0 = g * R;
         float ws[R];
         if (uniform && g > 0 && t0 + R <= n_w) {
+#ifdef FB_X_NOWIN
+#pragma unroll
+            for (int i = 0; i < R; i++) ws[i] = 1.0f;
+#else
             fb_k1_win_load<R, false>(V.win, t0, V.n, ws);
+#endif
             fb_k1_acc_group<R, false, SKIP>(A, xs, ws, t0, V.n, V.P);
         } else {
             fb_k1_win_load<R, true>(V.win, t0, V.n, ws);
@@ -1053,6 +1066,12 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
     FbAnalysis *out = ana + W.gve;
     fb200_variant_taps *taps = taps_all ? taps_all + W.gve : nullptr;
 
+#ifdef FB_X_ONLY_A
+    if (!role_a) return;
+#endif
+#ifdef FB_X_ONLY_E
+    if (role_a) return;
+#endif
     // ---- pass E
     if (!role_a) {
         FbK1Ent S;
