@@ -753,7 +753,15 @@ FB_HD int fb_k1_pitch_rows(int channels, int nvar) {
     return rows <= 16 ? 16 : (rows <= 32 ? 32 : 48);
 }
 #define FB_K1_THREADS 128
+#ifndef FB_K1_NQ
 #define FB_K1_NQ 32 // quads of every staged row in a warp's ring (128 samples)
+#endif
+#ifndef FB_K1_GCA
+#define FB_K1_GCA 2 // pass A, ring lengths 12 and 16: groups per staged chunk
+#endif
+#ifndef FB_K1_GCE
+#define FB_K1_GCE 4 // pass E: groups of 8 samples per staged chunk
+#endif
 // lane slots of a launch: the variants in order; a shorter last frame is moved to the next warp boundary
 FB_HD uint32_t fb_k1_full_variants(const FbJob &J, uint32_t n_variants) {
     return (J.n_frames > 1 && J.tail_n != J.block_size) ? n_variants - (uint32_t)J.nvar : n_variants;
@@ -934,7 +942,7 @@ FB_DEV void fb_k1_stream(const FbK1Stage &T, int groups, Body body) {
 
 template <int R, int SKIP, bool PAIRS>
 FB_DEV void fb_k1_warp_pass_a(const FbK1Stage &T, FbK1Acc<R> &A, const FbK1Var &V, int n_w, bool uniform) {
-    fb_k1_stream<R / 4, (R <= 8 ? 4 : (R <= 16 ? 2 : 1)), PAIRS>(T, (n_w + R - 1) / R, [&](int g, const int32_t *xs) {
+    fb_k1_stream<R / 4, (R <= 8 ? 4 : (R <= 16 ? FB_K1_GCA : 1)), PAIRS>(T, (n_w + R - 1) / R, [&](int g, const int32_t *xs) {
         const int t0 = g * R;
         float ws[R];
         if (uniform && g > 0 && t0 + R <= n_w) {
@@ -1081,12 +1089,12 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
         const bool ent_w = J.cfg.use_fixed && J.cfg.fixed_order_sel == 1 && n_w >= FB_MIN_PRED_BLOCK;
         const bool whole = uniform && (!ent_w || (V.psize & 7) == 0);
         if (ent_w)
-            fb_k1_stream<2, 4, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
+            fb_k1_stream<2, FB_K1_GCE, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
                 if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, true>(S, xs, g * 8);
                 else fb_k1_ent_group<true, true>(S, xs, g * 8);
             });
         else
-            fb_k1_stream<2, 4, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
+            fb_k1_stream<2, FB_K1_GCE, PAIRS>(T, (n_w + 7) / 8, [&](int g, const int32_t *xs) {
                 if (whole && g * 8 + 8 <= n_w) fb_k1_ent_group<false, false>(S, xs, g * 8);
                 else fb_k1_ent_group<true, false>(S, xs, g * 8);
             });
