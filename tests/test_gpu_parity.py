@@ -647,6 +647,25 @@ def test_device_resident_api_matches_host_api():
         assert d_out[:olen].cpu().numpy().tobytes() == host_bytes
 
 
+@pytest.mark.parametrize("fmt", [(2, 16, 2), (2, 24, 3), (3, 16, 2)])
+def test_device_resident_api_in_several_chunks(monkeypatch, fmt):
+    """the device-resident (serial) path cut into chunks by its working-set bound (FB200_SERIAL_MIB; default 4 GiB, so an
+    hour of CD stereo is one chunk): offsets continue across chunks on the device, bytes equal the oracle's"""
+    import torch
+    channels, bps, cont = fmt
+    monkeypatch.setenv("FB200_SERIAL_MIB", "16")  # ~190 stereo frames of 4096 samples per chunk
+    x = sigen.noisy_sine_pcm(4096 * 450 + 77, channels, bps, 44100, config_id=2)
+    pcm = pack_pcm(x, cont)
+    ref, ref_sizes = O.encode_frames(O.default_config(), x, channels, bps, 44100, 4096, nthreads=8)
+    with Context(Encoder().into_verified(), channels, bps, 44100, 4096) as ctx:
+        d_in = torch.from_numpy(pcm.copy()).cuda()
+        d_out = torch.empty(451 * ctx.max_frame_bytes(), dtype=torch.uint8, device="cuda")
+        olen, sizes = ctx.encode_device(d_in.data_ptr(), cont, len(x), d_out.data_ptr(), d_out.numel())
+        assert ctx.timing().launches > 16  # more than two chunks' worth of launches
+        assert list(sizes) == list(ref_sizes)
+        assert d_out[:olen].cpu().numpy().tobytes() == ref
+
+
 def test_device_resident_api_unaligned_pcm():
     """a device PCM pointer that is only 4-byte aligned: the ingest kernel's generic loads and the pack kernel's plane
     staging (the PCM-pair staging needs 16-byte alignment) give the same bytes"""
