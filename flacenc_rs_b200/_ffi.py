@@ -41,6 +41,7 @@ class Config(C.Structure):
         ("window_type", C.c_int32),
         ("tukey_alpha", C.c_float),
         ("prc_max_parameter", C.c_int32),
+        ("ext_lpc_order_search", C.c_int32),
     ]
 
 

@@ -72,6 +72,8 @@ class Qlpc:
     use_direct_mse: bool = False
     mae_optimization_steps: int = 0
     window: Window = field(default_factory=Window)
+    # extension beyond the reference (opt-in, see include/flacenc_b200.h): also try this many lower LPC orders
+    ext_order_search: int = 0
 
 
 @dataclass
@@ -110,7 +112,7 @@ class Encoder:
             lpc_order=q.lpc_order, quant_precision=q.quant_precision, use_direct_mse=int(q.use_direct_mse),
             mae_optimization_steps=q.mae_optimization_steps,
             window_type=0 if q.window.type == "Rectangle" else 1, tukey_alpha=float(q.window.alpha),
-            prc_max_parameter=s.prc.max_parameter)
+            prc_max_parameter=s.prc.max_parameter, ext_lpc_order_search=q.ext_order_search)
 
     def verify(self) -> None:
         """``Verify::verify`` (src/config.rs:109-130 and children); raises VerifyError."""

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(FB_K1S_THREADS) fb_k1s_analyze(FbJob J, const 
         FbK1Acc<FB200_MAX_LPC_ORDER> A;
 #pragma unroll
         for (int i = 0; i <= FB200_MAX_LPC_ORDER; i++) A.acc[i] = __shfl_sync(0xFFFFFFFFu, acc, i);
-        if (lane == 0) fb_k1_finish_lpc<FB200_MAX_LPC_ORDER>(J, V, A, out, taps);
+        if (lane == 0) fb_k1_finish_lpc<FB200_MAX_LPC_ORDER>(J, V, A, out, taps, gv);
         return;
     }
 
@@ -362,7 +362,7 @@ struct DevBuf {
 
 // Device buffers, events and pinned staging of one chunk in flight.  Set 0 also serves the serial path.
 struct ChunkSet {
-    DevBuf pcm, xv, xv4, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars, plan, psubs, poffs;
+    DevBuf pcm, xv, xv4, ana, taps, choice, slots, frame_bytes, offsets, out, infos, fb_list, scalars, plan, psubs, poffs, lpc_ext;
     // events: 0 H2D start, 1 H2D end, 2 ingest end, 3 analyze end, 4 rice/fused end, 5 pack/fallback end,
     //         6 gather end (= chunk done), 7 D2H start, 8 D2H end, 9 H2D end on the copy stream (pipelined path),
     //         10 start of the back half (fused kernel onwards) on its stream
@@ -564,7 +564,7 @@ void fb200_destroy(fb200_ctx *ctx) {
     cudaDeviceSynchronize();
     for (ChunkSet &S : ctx->sets) {
         DevBuf *bufs[] = {&S.pcm, &S.xv, &S.xv4, &S.ana, &S.taps, &S.choice, &S.slots, &S.frame_bytes, &S.offsets, &S.out,
-                          &S.infos, &S.fb_list, &S.scalars, &S.plan, &S.psubs, &S.poffs};
+                          &S.infos, &S.fb_list, &S.scalars, &S.plan, &S.psubs, &S.poffs, &S.lpc_ext};
         for (DevBuf *b : bufs)
             if (b->p) cudaFree(b->p);
         for (int i = 0; i < S.n_ev; i++) cudaEventDestroy(S.ev[i]);
@@ -726,6 +726,9 @@ int fb_reserve_set(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet 
     if ((rc = fb_reserve(ctx, S.xv, (fb_xt_words((int)P.stride, frames * (uint64_t)ctx->channels) + 64) * 4u))) return rc;
     if (!A.analyze_only && (rc = fb_reserve(ctx, S.xv4, (frames * (uint64_t)P.nvar * P.stride + 64) * 4u))) return rc;
     if ((rc = fb_reserve(ctx, S.ana, frames * (uint64_t)P.nvar * sizeof(FbAnalysis)))) return rc;
+    if (ctx->cfg.ext_lpc_order_search > 0 &&
+        (rc = fb_reserve(ctx, S.lpc_ext, frames * (uint64_t)P.nvar * FB_EXT_LPC_MAX * sizeof(FbLpcExt))))
+        return rc;
     if (in_bytes && (rc = fb_reserve(ctx, S.pcm, in_bytes + 16))) return rc;
     if (A.analyze_only) {
         if ((rc = fb_reserve(ctx, S.taps, frames * (uint64_t)P.nvar * sizeof(fb200_variant_taps)))) return rc;
@@ -754,6 +757,7 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     // analysis of the next chunk can overlap the fused kernel of this one
     FbJob J = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, P.cb, ns,
                            (uint32_t)(A.first_frame + f0));
+    if (ctx->cfg.ext_lpc_order_search > 0) J.lpc_ext = (FbLpcExt *)S.lpc_ext.p; // (extension: lower LPC orders, K1 -> KA / K2)
     const uint32_t nvars = J.n_frames * (uint32_t)J.nvar;
     uint32_t *d_err = (uint32_t *)S.scalars.p;
     unsigned long long *d_total = d_total_shared ? d_total_shared : (unsigned long long *)((uint8_t *)S.scalars.p + 8);

@@ -80,6 +80,26 @@ FB_DEV void fb_atomic_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
 FB_DEV void fb_atomic_add_u64(unsigned long long *p, unsigned long long v) { *p += v; }
 #endif
 
+// ---- EXTENSION beyond the reference (config.ext_lpc_order_search): the quantised coefficient sets of the lower LPC
+// orders of a channel variant, written by the analysis kernels and probed by the plan / rice kernels
+#define FB_EXT_LPC_MAX 8
+struct FbLpcExt {
+    int16_t qlp[32];
+    int32_t order, shift;   // order after tail-zero truncation (0: no such candidate)
+};
+// the orders tried besides P: P - i * ceil(P / (k + 1)), i = 1..k, while >= 1; returns their number
+FB_HD int fb_ext_lpc_orders(int P, int k, int *orders) {
+    int n = 0;
+    if (k <= 0) return 0;
+    const int step = (P + k) / (k + 1);
+    for (int i = 1; i <= k && i <= FB_EXT_LPC_MAX; i++) {
+        const int o = P - i * step;
+        if (o < 1) break;
+        orders[n++] = o;
+    }
+    return n;
+}
+
 // ---- job description passed by value to every kernel ----------------------------------------
 struct FbJob {
     fb200_config cfg;
@@ -96,6 +116,7 @@ struct FbJob {
     uint64_t n_samples;      // per channel
     uint32_t slot_bytes;     // stride of the per-frame output slots (multiple of 16)
     int32_t  pack_in_smem;   // 1: frames are assembled in shared memory, 0: in their global slot
+    FbLpcExt *lpc_ext;       // [n_frames * nvar][FB_EXT_LPC_MAX] or nullptr (extension off)
 };
 
 // Output of the analysis kernel (K1), one per channel variant.

@@ -880,7 +880,7 @@ FB_DEV void fb_kf_search(const FbJob &J, const FbKfGeom &g, const int32_t *xa, c
 // =====================================================================================================
 template <int G, bool ODD, int VMS, bool BC>
 FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, const FbAnalysis &A, int v,
-                          uint8_t *smem, const FbKfLayout &L, fb200_subframe_info *out) {
+                          uint8_t *smem, const FbKfLayout &L, fb200_subframe_info *out, const FbLpcExt *ext = nullptr) {
     FbKfFrame *S = (FbKfFrame *)(smem + L.off_frame);
     uint8_t *scratch = smem + L.off_scratch + (uint32_t)v * L.scratch_bytes;
     uint8_t *keep = smem + L.off_keep + (uint32_t)v * L.keep_bytes;
@@ -985,6 +985,47 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
         cbits[c] = c == 0 ? 8ull + (unsigned long long)bps_v * (unsigned long long)kf + res[0]->res_bits
                           : 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
                                 (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res[1]->res_bits;
+    }
+    if (BC && ext && J.cfg.use_lpc && J.cfg.ext_lpc_order_search > 0) {
+        // EXTENSION (config.ext_lpc_order_search): the lower-order coefficient sets K1 left in `ext` are searched into
+        // result set 1 one after the other; the fewest subframe bits win (the higher order on ties), the winner is
+        // searched again unless it was the last one, and its coefficients replace the staged analysis record.
+        int best = -1, last = -1; // -1: the primary set
+        unsigned long long best_bits = cbits[1];
+#if FB_GPU
+#pragma unroll 1
+#endif
+        for (int k = 0; k <= FB_EXT_LPC_MAX; k++) {
+            int pick_set;
+            if (k < FB_EXT_LPC_MAX && ext[k].order > 0) pick_set = k;       // probe set k
+            else if (best != last) pick_set = best;                           // the winner again, then done
+            else break;
+            const int16_t *qs = pick_set < 0 ? A.qlp : ext[pick_set].qlp;
+            const int o = pick_set < 0 ? A.qlp_order : ext[pick_set].order;
+            const int sh = pick_set < 0 ? A.qlp_shift : ext[pick_set].shift;
+            FbKfCand cd;
+            cd.kind = 1; cd.q = qs; cd.order = o; cd.shift = sh;
+            cd.fc[0] = cd.fc[1] = cd.fc[2] = cd.fc[3] = 0;
+            unsigned long long sumabs = 0;
+            for (int j = 0; j < o; j++) sumabs += (unsigned long long)(qs[j] < 0 ? -qs[j] : qs[j]);
+            cd.narrow = (unsigned long long)A.max_abs * sumabs < 0x7FFFFFFFull;
+            fb_kf_search<G, ODD, VMS>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)(L.U_max + 1), res[1]);
+            if (M->fail) return;
+            const unsigned long long bits = 8ull + (unsigned long long)bps_v * (unsigned long long)o + 4ull + 5ull +
+                                            (unsigned long long)J.cfg.quant_precision * (unsigned long long)o + res[1]->res_bits;
+            const bool probing = k < FB_EXT_LPC_MAX && ext[k].order > 0;
+            last = pick_set;
+            if (!probing) break;
+            if (bits < best_bits) { best = pick_set; best_bits = bits; }
+        }
+        if (best >= 0) {
+            FbAnalysis &Aw = const_cast<FbAnalysis &>(A); // (the staged copy in shared memory; this warp owns it)
+            FB_WPHASE(lane)
+                Aw.qlp[lane] = ext[best].qlp[lane];
+                if (lane == 0) { Aw.qlp_order = ext[best].order; Aw.qlp_shift = ext[best].shift; }
+            FB_WPHASE_END
+            cbits[1] = best_bits;
+        }
     }
     const unsigned long long fixed_bits = cbits[0], lpc_bits = cbits[1];
     const unsigned long long baseline_bits =
@@ -1195,7 +1236,8 @@ FB_DEV void fb_ka_body(const FbJob &J, const int32_t *xv, const uint8_t *pcm, co
 
     // ---- analysis: one warp per variant
     FB_WARPS_BEGIN(w, NW)
-        fb_kf_variant<G, ODD, VMS, BC>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w]);
+        fb_kf_variant<G, ODD, VMS, BC>(J, g, xs, ((const FbAnalysis *)(smem + L.off_ana))[w], w, smem, L, &choice[w],
+                                       (BC && J.lpc_ext) ? J.lpc_ext + ((size_t)f * (size_t)J.nvar + (size_t)w) * FB_EXT_LPC_MAX : nullptr);
         const FbKfMisc *M = (const FbKfMisc *)(smem + L.off_scratch + (uint32_t)w * L.scratch_bytes + L.s_misc);
         FB_WPHASE(lane)
             if (lane == 0 && M->fail) S->frame_fail = 1; // benign race between warps

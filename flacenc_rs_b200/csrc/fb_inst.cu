@@ -147,7 +147,8 @@ void FB_NAME(fb_launch_ka_g)(const FbJob &J, const int32_t *xt, const uint8_t *p
                              fb200_subframe_info *vsubs, fb200_subframe_info *psubs,
                              uint32_t *poffs, uint32_t *frame_bytes, fb200_frame_info *infos, uint32_t *fb_list,
                              uint32_t *fb_count, const uint32_t *ktab, const FbKfLayout &L, cudaStream_t st) {
-    const bool bitcount = J.cfg.use_fixed && J.cfg.fixed_order_sel == 0;
+    // the probing instances: OrderSel::BitCount, or the LPC order search extension
+    const bool bitcount = (J.cfg.use_fixed && J.cfg.fixed_order_sel == 0) || J.lpc_ext != nullptr;
 #define FB_KA_LAUNCH(K, PCM)                                                                                                       \
     FB_NAME(K)<<<J.n_frames, 32 * J.nvar, L.total, st>>>(J, xt, PCM, ana, (FbKfPlan *)plan, vsubs, psubs, poffs, frame_bytes, infos, \
                                                          fb_list, fb_count, ktab, L, fb_kf_odd_mode(J))

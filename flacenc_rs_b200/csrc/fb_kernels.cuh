@@ -640,7 +640,8 @@ FB_DEV void fb_k1_finish_ent(const FbJob &J, const FbK1Var &V, const FbK1Ent &S,
 
 // results of pass A: Levinson, quantiser
 template <int R>
-FB_DEV void fb_k1_finish_lpc(const FbJob &J, const FbK1Var &V, const FbK1Acc<R> &A, FbAnalysis *out, fb200_variant_taps *taps) {
+FB_DEV void fb_k1_finish_lpc(const FbJob &J, const FbK1Var &V, const FbK1Acc<R> &A, FbAnalysis *out, fb200_variant_taps *taps,
+                              uint32_t gv) {
     out->qlp_order = 0;
     out->qlp_shift = 0;
     if (taps) {
@@ -672,6 +673,22 @@ FB_DEV void fb_k1_finish_lpc(const FbJob &J, const FbK1Var &V, const FbK1Acc<R> 
         for (int i = 0; i < 32; i++) taps->qlp[i] = out->qlp[i];
         taps->qlp_order = order;
         taps->qlp_shift = shift;
+    }
+    if (J.lpc_ext && J.cfg.ext_lpc_order_search > 0) {
+        // EXTENSION: the Levinson solutions of the lower orders on the same autocorrelation, quantised alike
+        int orders[FB_EXT_LPC_MAX];
+        const int no = fb_ext_lpc_orders(V.P, J.cfg.ext_lpc_order_search, orders);
+        FbLpcExt *ext = J.lpc_ext + (size_t)gv * FB_EXT_LPC_MAX;
+        for (int k = 0; k < FB_EXT_LPC_MAX; k++) {
+            int ok = 0, sk = 0;
+            if (k < no) {
+                fb_levinson(corr, corr + 1, orders[k], lpc);
+                ok = fb_quantize(lpc, orders[k], J.cfg.quant_precision, q, &sk);
+            }
+            ext[k].order = ok;
+            ext[k].shift = sk;
+            for (int i = 0; i < 32; i++) ext[k].qlp[i] = i < ok ? q[i] : (int16_t)0;
+        }
     }
 }
 
@@ -743,7 +760,7 @@ FB_DEV void fb_k1_thread(const FbJob &J, const int32_t *xt, const float *win_ful
         default: fb_k1_pass_a<R, 3>(A, rows, V); break;
         }
     }
-    fb_k1_finish_lpc<R>(J, V, A, out, taps);
+    fb_k1_finish_lpc<R>(J, V, A, out, taps, gv);
 }
 
 // rows of xt that the 32 variants of one warp can span, rounded to the staging pitch (16, 32 or 48 rows)
@@ -1116,7 +1133,7 @@ FB_DEV void fb_k1_warp(const FbJob &J, const int32_t *xt, const uint8_t *pcm, co
         default: fb_k1_warp_pass_a<R, 3, PAIRS>(T, A, V, n_w, uniform); break;
         }
     }
-    if (valid) fb_k1_finish_lpc<R>(J, V, A, out, taps);
+    if (valid) fb_k1_finish_lpc<R>(J, V, A, out, taps, W.gve);
 }
 #endif
 
@@ -2145,10 +2162,30 @@ FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     // ---- LPC candidate (src/coding.rs:360-381)
     bool lpc_ok = false;
     unsigned long long lpc_bits = 0;
+    const int16_t *lq = A.qlp; // the LPC candidate's coefficients, order after truncation, shift
+    int lo = A.qlp_order, ls = A.qlp_shift;
     if (J.cfg.use_lpc) {
         fb_k2_rice_search<G>(J, x, n, 1, A.qlp_order, A.qlp, A.qlp_shift, smem, L, res_lpc);
         lpc_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
                    (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res_lpc->res_bits;
+        if (J.lpc_ext && J.cfg.ext_lpc_order_search > 0) {
+            // EXTENSION (config.ext_lpc_order_search): the lower-order sets of K1; fewest bits win, the higher order on ties
+            const FbLpcExt *ext = J.lpc_ext + (size_t)gv * FB_EXT_LPC_MAX;
+            for (int k = 0; k < FB_EXT_LPC_MAX && ext[k].order > 0; k++) {
+                fb_k2_rice_search<G>(J, x, n, 1, ext[k].order, ext[k].qlp, ext[k].shift, smem, L, res_tmp);
+                const unsigned long long bits = 8ull + (unsigned long long)bps_v * (unsigned long long)ext[k].order + 4ull + 5ull +
+                                                (unsigned long long)J.cfg.quant_precision * (unsigned long long)ext[k].order +
+                                                res_tmp->res_bits;
+                if (bits < lpc_bits) {
+                    lpc_bits = bits;
+                    lq = ext[k].qlp; lo = ext[k].order; ls = ext[k].shift;
+                    FB_PHASE(tid, T)
+                        for (int i = tid; i < (int)sizeof(FbRiceResult); i += T)
+                            ((uint8_t *)res_lpc)[i] = ((const uint8_t *)res_tmp)[i];
+                    FB_PHASE_END
+                }
+            }
+        }
         lpc_ok = lpc_bits < baseline_bits;
     }
 
@@ -2164,15 +2201,15 @@ FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     FB_PHASE(tid, T)
         if (tid == 0) {
             out->type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED;
-            out->order = pick == 1 ? A.qlp_order : kf;
+            out->order = pick == 1 ? lo : kf;
             out->precision = pick == 1 ? J.cfg.quant_precision : 0;
-            out->shift = pick == 1 ? A.qlp_shift : 0;
+            out->shift = pick == 1 ? ls : 0;
             out->partition_order = R->part_order;
             out->rice2 = R->rice2;
             out->bits = pick == 1 ? lpc_bits : fixed_bits;
         }
         if (pick == 1)
-            for (int i = tid; i < 32; i += T) out->qlp[i] = A.qlp[i];
+            for (int i = tid; i < 32; i += T) out->qlp[i] = lq[i];
         for (int i = tid; i < (1 << R->part_order); i += T) out->rice_params[i] = R->params[i];
     FB_PHASE_END
 }

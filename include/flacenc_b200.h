@@ -60,6 +60,12 @@ typedef struct fb200_config {
     int32_t window_type;            /* Window: 0 = Rectangle, 1 = Tukey (default) */
     float   tukey_alpha;            /* Window::Tukey.alpha (default 0.4, 0..=1) */
     int32_t prc_max_parameter;      /* Prc.max_parameter (default 30, 0..=30) */
+    /* ---- extensions beyond the reference (opt-in: any non-zero value gives frames the reference would not produce; they
+     *      decode to the same samples and are never larger) ---- */
+    int32_t ext_lpc_order_search;   /* 0 (default, off) .. 8: besides lpc_order P also try the k lower orders P - i * ceil(P / (k + 1)),
+                                       i = 1..k (those >= 1), each the Levinson solution of that order on the same autocorrelation;
+                                       the LPC candidate with the fewest subframe bits wins, the higher order on ties.
+                                       Autocorrelation estimator only (rejected with use_direct_mse). */
 } fb200_config;
 
 /* Subframe types (component::SubFrame, src/component/datatype.rs:1782-1795). */

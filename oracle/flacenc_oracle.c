@@ -39,6 +39,7 @@ void fo_config_default(fo_config *c) {
     c->window_type = 1;
     c->tukey_alpha = 0.4f;
     c->prc_max_parameter = FO_MAX_RICE_PARAMETER;
+    c->ext_lpc_order_search = 0;
 }
 
 /* src/config.rs:109-130 (Encoder), :198-204 (SubFrameCoding: note fixed.verify() is NOT called),
@@ -59,6 +60,8 @@ int fo_config_verify(const fo_config *c) {
         return 1;
     }
     if (c->prc_max_parameter < 0 || c->prc_max_parameter > FO_MAX_RICE_PARAMETER) return 1;
+    if (c->ext_lpc_order_search < 0 || c->ext_lpc_order_search > 8) return 1;
+    if (c->ext_lpc_order_search > 0 && c->use_direct_mse) return 1;
     return 0;
 }
 
@@ -786,15 +789,24 @@ static int fo_fixed_lpc(const fo_config *cfg, const int32_t *signal, int n, int 
     return 1;
 }
 
-/* src/coding.rs:360-381  estimated_qlpc */
-static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n, int bps, fo_subframe *out) {
-    int lpc_order = cfg->lpc_order;
-    double coefs[FO_MAX_LPC_ORDER];
-    /* src/coding.rs:333-351 perform_qlpc: the estimator the configuration names */
-    if (cfg->use_direct_mse && cfg->mae_optimization_steps > 0)
-        fo_lpc_with_irls_mae(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, cfg->mae_optimization_steps, coefs, NULL);
-    else if (cfg->use_direct_mse) fo_lpc_with_direct_mse(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL, NULL);
-    else fo_lpc_from_autocorr(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL);
+/* EXTENSION (not in the reference; config.ext_lpc_order_search = k > 0): the LPC orders tried besides P = lpc_order are
+ * P - i * ceil(P / (k + 1)), i = 1..k, as long as they are >= 1.  Returns the number of orders written (P first). */
+int fo_ext_lpc_orders(int lpc_order, int k, int *orders) {
+    int n = 0;
+    orders[n++] = lpc_order;
+    if (k <= 0) return n;
+    const int step = (lpc_order + k) / (k + 1);
+    for (int i = 1; i <= k; i++) {
+        const int o = lpc_order - i * step;
+        if (o < 1) break;
+        orders[n++] = o;
+    }
+    return n;
+}
+
+/* the LPC subframe of one set of unquantised coefficients (the second half of estimated_qlpc) */
+static void fo_qlpc_subframe(const fo_config *cfg, const double *coefs, int lpc_order, const int32_t *signal, int n, int bps,
+                             fo_subframe *out) {
     fo_subframe_reset(out, FO_SF_LPC, signal, n, bps);
     int16_t q[FO_MAX_LPC_ORDER];
     int shift;
@@ -809,6 +821,37 @@ static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n
     /* src/component/bitrepr.rs:492-499 */
     out->bits = 8 + (uint64_t)bps * order + 4 + 5 + (uint64_t)cfg->quant_precision * order + rbits;
     free(errors);
+}
+
+/* src/coding.rs:360-381  estimated_qlpc */
+static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n, int bps, fo_subframe *out) {
+    int lpc_order = cfg->lpc_order;
+    double coefs[FO_MAX_LPC_ORDER];
+    double corr[FO_MAX_LPC_ORDER + 1];
+    /* src/coding.rs:333-351 perform_qlpc: the estimator the configuration names */
+    if (cfg->use_direct_mse && cfg->mae_optimization_steps > 0)
+        fo_lpc_with_irls_mae(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, cfg->mae_optimization_steps, coefs, NULL);
+    else if (cfg->use_direct_mse) fo_lpc_with_direct_mse(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL, NULL);
+    else fo_lpc_from_autocorr(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, corr);
+    fo_qlpc_subframe(cfg, coefs, lpc_order, signal, n, bps, out);
+    if (cfg->ext_lpc_order_search > 0 && !cfg->use_direct_mse) {
+        /* EXTENSION: the Levinson solutions of lower orders on the same autocorrelation; fewest bits wins, the higher
+         * order (the earlier candidate) on ties */
+        int orders[16];
+        const int no = fo_ext_lpc_orders(lpc_order, cfg->ext_lpc_order_search, orders);
+        for (int k = 1; k < no; k++) {
+            double ck[FO_MAX_LPC_ORDER];
+            fo_levinson_f64(corr, corr + 1, orders[k], ck);
+            fo_subframe cand;
+            fo_qlpc_subframe(cfg, ck, orders[k], signal, n, bps, &cand);
+            if (cand.bits < out->bits) {
+                free(out->residual);
+                *out = cand;
+            } else {
+                free(cand.residual);
+            }
+        }
+    }
 }
 
 static void fo_subframe_free(fo_subframe *sf) {

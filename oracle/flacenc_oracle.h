@@ -59,6 +59,7 @@ typedef struct fo_config {
     int32_t window_type;           /* 0 = Rectangle, 1 = Tukey */
     float   tukey_alpha;           /* default 0.4 */
     int32_t prc_max_parameter;     /* Prc.max_parameter, default 30 */
+    int32_t ext_lpc_order_search;  /* EXTENSION beyond the reference (0 = off): lower LPC orders tried, see fo_ext_lpc_orders */
 } fo_config;
 
 enum { FO_SF_CONSTANT = 0, FO_SF_VERBATIM = 1, FO_SF_FIXED = 2, FO_SF_LPC = 3 };
@@ -122,6 +123,7 @@ int    fo_solve_sym(const double *mat, int n, double *v);
 void   fo_lpc_with_direct_mse(const int32_t *signal, int n, int window_type, float alpha, int lpc_order,
                               double *coefs_out, double *corr_out /* nullable */, double *covar_out /* nullable */);
 void   fo_compute_raw_errors(const int32_t *signal, int n, const double *coefs, int lpc_order, float *errors);
+int    fo_ext_lpc_orders(int lpc_order, int k, int *orders /* up to k + 1 */); /* EXTENSION, see fo_config */
 float  fo_irls_weight(float err, float normalizer);
 void   fo_irls_weight_bits(uint32_t first_bits, uint64_t count, float normalizer, int threads, uint32_t *out_bits);
 void   fo_lpc_with_irls_mae(const int32_t *signal, int n, int window_type, float alpha, int lpc_order, int steps,

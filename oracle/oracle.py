@@ -42,6 +42,7 @@ class Config(C.Structure):
         ("window_type", C.c_int32),
         ("tukey_alpha", C.c_float),
         ("prc_max_parameter", C.c_int32),
+        ("ext_lpc_order_search", C.c_int32),
     ]
 
 
@@ -138,6 +139,7 @@ def lib() -> C.CDLL:
             "fo_solve_sym": (C.c_int, [f64p, C.c_int, f64p]),
             "fo_lpc_with_direct_mse": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, f64p, f64p, f64p]),
             "fo_compute_raw_errors": (None, [i32p, C.c_int, f64p, C.c_int, f32p]),
+            "fo_ext_lpc_orders": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
             "fo_irls_weight": (C.c_float, [C.c_float, C.c_float]),
             "fo_irls_weight_bits": (None, [C.c_uint32, C.c_uint64, C.c_float, C.c_int, C.c_void_p]),
             "fo_lpc_with_irls_mae": (None, [i32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, f64p, f32p]),
@@ -301,6 +303,13 @@ def compute_raw_errors(signal, coefs) -> np.ndarray:
 
 def irls_weight(err: float, normalizer: float) -> float:
     return float(lib().fo_irls_weight(err, normalizer))
+
+
+def ext_lpc_orders(lpc_order: int, k: int):
+    """the LPC orders the ext_lpc_order_search extension tries (lpc_order first)"""
+    buf = (C.c_int * 16)()
+    n = lib().fo_ext_lpc_orders(lpc_order, k, buf)
+    return list(buf[:n])
 
 
 def irls_weight_bits(first: int, count: int, normalizer: float, threads: int = 8) -> np.ndarray:

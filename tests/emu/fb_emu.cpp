@@ -104,6 +104,7 @@ struct EmuBuffers {
     std::vector<int32_t> xv, xv4;
     std::vector<float> win_full, win_tail;
     std::vector<FbAnalysis> ana;
+    std::vector<FbLpcExt> lpc_ext;
     std::vector<fb200_variant_taps> taps;
     std::vector<fb200_subframe_info> choice;
     std::vector<uint8_t> slots;
@@ -132,6 +133,13 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.block_size, B.win_full.data());
     fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.tail_n, B.win_tail.data());
     B.ana.resize(nvars);
+    if (cfg->ext_lpc_order_search > 0) {
+        FbLpcExt poison;
+        memset(&poison, 0x5A, sizeof(poison));
+        B.lpc_ext.assign(nvars * FB_EXT_LPC_MAX, poison);
+        J.lpc_ext = B.lpc_ext.data();
+        Jout = J;
+    }
     B.taps.resize(nvars);
     B.choice.resize(nvars);
     uint32_t err_flag = 0;

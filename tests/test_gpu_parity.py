@@ -42,6 +42,8 @@ def make_config(**kw) -> Encoder:
             s.qlpc.use_direct_mse = bool(v)
         elif k == "mae_optimization_steps":
             s.qlpc.mae_optimization_steps = v
+        elif k == "ext_lpc_order_search":
+            s.qlpc.ext_order_search = v
         elif k == "window_type":
             s.qlpc.window.type = "Rectangle" if v == 0 else "Tukey"
         elif k == "tukey_alpha":
@@ -366,6 +368,50 @@ def test_bitcount_order_selection_on_the_fused_path():
         ctx.encode_interleaved(pack_pcm(y, 3), 3, len(y))
         tm = ctx.timing()
         assert (tm.fused_frames, tm.fallback_frames) == (4, 0)
+
+
+def test_ext_lpc_order_search_extension():
+    """EXTENSION beyond the reference (config.ext_lpc_order_search, opt-in): lower LPC orders from the same
+    autocorrelation, fewest bits wins.  The kernels (fused probing instances, generic, both analysis kernels) are
+    byte-equal to the oracle's statement of it; streams decode to the input and are never larger."""
+    rng = np.random.default_rng(33)
+    n = 4096 * 5 + 700
+    t = np.arange(n, dtype=np.float64)
+    ar2 = np.zeros(n)
+    e = rng.normal(0, 300, n)
+    for i in range(2, n):
+        ar2[i] = 1.027 * ar2[i - 1] - 0.9025 * ar2[i - 2] + 1.5 * e[i]
+    sigs = [
+        np.stack([ar2, np.roll(ar2, 7)], axis=1),
+        np.stack([8000 * np.sin(t / 15.0) + rng.normal(0, 30, n), 3000 * np.sin(t / 4.0) + rng.normal(0, 300, n)], axis=1),
+        sigen.noisy_sine_pcm(n, 2, 16, 44100, config_id=2),
+    ]
+    for x in sigs:
+        x = np.clip(np.round(x), -32768, 32767).astype(np.int32)
+        base, _ = O.encode_frames(O.default_config(), x, 2, 16, 44100, 4096, nthreads=8)
+        for k in (1, 4, 8):
+            _compare(x, 2, 16, 44100, 4096, ext_lpc_order_search=k)
+            ext, _ = O.encode_frames(O.default_config(ext_lpc_order_search=k), x, 2, 16, 44100, 4096, nthreads=8)
+            assert len(ext) <= len(base)
+    x = np.clip(np.round(sigs[0]), -32768, 32767).astype(np.int32)
+    small, _ = O.encode_frames(O.default_config(ext_lpc_order_search=4), x, 2, 16, 44100, 4096, nthreads=8)
+    base, _ = O.encode_frames(O.default_config(), x, 2, 16, 44100, 4096, nthreads=8)
+    assert len(small) < len(base)
+    _compare(x, 2, 16, 44100, 4096, ext_lpc_order_search=8, lpc_order=24)
+    _compare(x, 2, 16, 44100, 1000, ext_lpc_order_search=3, lpc_order=3, quant_precision=7)
+    _compare(x[:, :1], 1, 16, 44100, 512, ext_lpc_order_search=2, lpc_order=1)
+    _compare(x, 2, 16, 44100, 4096, ext_lpc_order_search=2, fixed_order_sel=0)
+    _compare(x, 2, 16, 44100, 4096, ext_lpc_order_search=2, use_fixed=0, window_type=0)
+    y = sigen.noisy_sine_pcm(4608 * 2 + 100, 3, 24, 96000, config_id=3)
+    _compare(y, 3, 24, 96000, 4608, ext_lpc_order_search=4, lpc_order=16)
+    z = sigen.noisy_sine_pcm(1024 * 3 + 9, 8, 24, 48000, config_id=5)
+    _compare(z, 8, 24, 48000, 1024, ext_lpc_order_search=2)
+    _compare(np.zeros((3000, 2), np.int32), 2, 16, 44100, 1024, ext_lpc_order_search=2, use_constant=0)
+    _compare(crafted_huge_residual_stereo(), 2, 24, 96000, 4096, lpc_order=24, ext_lpc_order_search=3)  # a fallback frame
+    with pytest.raises(VerifyError):
+        make_config(ext_lpc_order_search=1, use_direct_mse=1).into_verified()
+    with pytest.raises(VerifyError):
+        make_config(ext_lpc_order_search=9).into_verified()
 
 
 def test_pipelined_host_path_matches_oracle(monkeypatch):

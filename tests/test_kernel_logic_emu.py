@@ -266,6 +266,51 @@ def test_bitcount_order_selection_on_the_fused_path():
     assert fused >= 50 and fb <= 2
 
 
+def test_ext_lpc_order_search_extension():
+    """EXTENSION beyond the reference (config.ext_lpc_order_search, opt-in): besides lpc_order the lower orders
+    P - i * ceil(P / (k + 1)) are tried, each the Levinson solution of that order on the same autocorrelation; the LPC
+    candidate with the fewest bits wins.  Emulated kernels (fused and generic) byte-equal to the oracle's statement of it;
+    the streams decode to the input (inside _compare) and are never larger than the reference-compatible ones."""
+    assert O.ext_lpc_orders(10, 1) == [10, 5] and O.ext_lpc_orders(10, 4) == [10, 8, 6, 4, 2]
+    assert O.ext_lpc_orders(24, 8) == [24, 21, 18, 15, 12, 9, 6, 3] and O.ext_lpc_orders(3, 8) == [3, 2, 1]
+    assert O.ext_lpc_orders(1, 3) == [1]
+    rng = np.random.default_rng(33)
+    t = np.arange(3000, dtype=np.float64)
+    ar2 = np.zeros(3000)
+    e = rng.normal(0, 200, 3000)
+    for i in range(2, 3000):
+        ar2[i] = 1.027 * ar2[i - 1] - 0.9025 * ar2[i - 2] + 1.5 * e[i]  # a resonant order-2 process: high orders only cost bits
+    sigs = [
+        np.stack([ar2, np.roll(ar2, 7)], axis=1),
+        np.stack([8000 * np.sin(t / 15.0) + rng.normal(0, 30, 3000), 3000 * np.sin(t / 4.0) + rng.normal(0, 300, 3000)], axis=1),
+        sigen.noisy_sine_pcm(3000, 2, 16, 44100, config_id=2),
+    ]
+    for x in sigs:
+        x = np.clip(np.round(x), -32768, 32767).astype(np.int32)
+        base, _ = O.encode_frames(O.default_config(), x, 2, 16, 44100, 1024)
+        for k in (1, 2, 4, 8):
+            _compare(x, 2, 16, 44100, 1024, ext_lpc_order_search=k)
+            ext, _ = O.encode_frames(O.default_config(ext_lpc_order_search=k), x, 2, 16, 44100, 1024)
+            assert len(ext) <= len(base)
+    x = np.clip(np.round(sigs[0]), -32768, 32767).astype(np.int32)
+    small, _ = O.encode_frames(O.default_config(ext_lpc_order_search=4), x, 2, 16, 44100, 1024)
+    base, _ = O.encode_frames(O.default_config(), x, 2, 16, 44100, 1024)
+    assert len(small) < len(base)   # the order-2 process really is cheaper at a lower order
+    # with other orders / precisions / selectors / formats
+    _compare(x, 2, 16, 44100, 1024, ext_lpc_order_search=8, lpc_order=24)
+    _compare(x, 2, 16, 44100, 1000, ext_lpc_order_search=3, lpc_order=3, quant_precision=7)
+    _compare(x[:, :1], 1, 16, 44100, 512, ext_lpc_order_search=2, lpc_order=1)
+    _compare(x, 2, 16, 44100, 1024, ext_lpc_order_search=2, fixed_order_sel=0)
+    _compare(x, 2, 16, 44100, 1024, ext_lpc_order_search=2, use_fixed=0, window_type=0)
+    y = sigen.noisy_sine_pcm(1152 * 2 + 100, 3, 24, 96000, config_id=3)
+    _compare(y, 3, 24, 96000, 1152, ext_lpc_order_search=4, lpc_order=16)
+    _compare(np.zeros((600, 2), np.int32), 2, 16, 44100, 256, ext_lpc_order_search=2, use_constant=0)
+    # the estimators of the `experimental` feature have no lower orders to offer: rejected
+    bad = E.default_config(ext_lpc_order_search=1, use_direct_mse=1)
+    assert E.lib().fbemu_config_verify(bad) != 0
+    assert E.lib().fbemu_config_verify(E.default_config(ext_lpc_order_search=9)) != 0
+
+
 def test_crc8_closed_form_matches_bit_serial_definition():
     """CRC-8/SMBUS (poly 0x07, init 0): the kernels' closed-form byte step against the bit-serial definition, for every
     byte value and for random strings"""
