@@ -12,6 +12,10 @@ def run(ch, bps, cont, block, x, **kw):
     if kw.get("lpc_order"): e.subframe_coding.qlpc.lpc_order = kw["lpc_order"]
     if kw.get("use_direct_mse"): e.subframe_coding.qlpc.use_direct_mse = True; e.subframe_coding.qlpc.window.type = "Rectangle"
     e.subframe_coding.qlpc.mae_optimization_steps = kw.get("mae_optimization_steps", 0)
+    e.subframe_coding.qlpc.ext_order_search = kw.get("ext_lpc_order_search", 0)
+    if kw.get("bitcount"):
+        from flacenc_rs_b200.config import OrderSel
+        e.subframe_coding.fixed.order_sel = OrderSel.BitCount()
     n = len(x)
     with Context(e.into_verified(), ch, bps, 44100, block) as ctx:
         got, sizes, _ = ctx.encode_interleaved(pack_pcm(x, cont), cont, n)
@@ -36,6 +40,10 @@ run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
 # ... and its IRLS-MAE refinement (K1I), frames of several staging tiles and a 24-bit 3-channel case
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1, mae_optimization_steps=2)
 run(3, 24, 3, 1500, sig(3, 24, 1500 * 2 + 77), use_direct_mse=1, mae_optimization_steps=1, lpc_order=24)
+# the probing instances of the plan kernel: BitCount order selection, the LPC order search extension (with a fallback frame)
+run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), bitcount=1)
+run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), ext_lpc_order_search=4)
+run(2, 24, 3, 4096, np.concatenate([sig(2, 24, 4096), big]), lpc_order=24, ext_lpc_order_search=3, bitcount=1)
 os.environ["FB200_K1_SMALL"] = "0"
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 9 + 2728))
