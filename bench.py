@@ -345,9 +345,10 @@ CONFIG_CASES = [
     ("C4-irls2", "CD stereo 2 min, C4's config + mae_optimization_steps = 2 (IRLS-MAE refinement, 3 weighted solves per channel variant)",
      2, 16, 44100, 4096, 120, {"window_type": 0, "use_direct_mse": 1, "mae_optimization_steps": 2}),
     ("C5-slice", "48 kHz / 24-bit 8 channels, 2 min (1407 frames)", 8, 24, 48000, 4096, 120, {}),
-    ("C2-ext-orders4", "CD stereo 10 min, default config + the opt-in extension ext_lpc_order_search = 4 (LPC orders 10, 8, 6, 4, 2 "
-     "from one autocorrelation; not reference-compatible frames, compared with the oracle's statement of the extension)",
-     2, 16, 44100, 4096, 600, {"ext_lpc_order_search": 4}),
+    ("C2-ext-o4p4", "CD stereo 10 min, default config + the opt-in extensions ext_lpc_order_search = 4 (LPC orders 10, 8, 6, 4, 2 "
+     "from one autocorrelation) and ext_lpc_precision_search = 4 (15..11 coefficient bits); not reference-compatible frames, "
+     "compared with the oracle's statement of the extensions",
+     2, 16, 44100, 4096, 600, {"ext_lpc_order_search": 4, "ext_lpc_precision_search": 4}),
     ("C2-bitcount", "CD stereo 10 min, default config with fixed.order_sel = BitCount (an exact Rice search per fixed order)",
      2, 16, 44100, 4096, 600, {"fixed_order_sel": 0}),
 ]
@@ -364,6 +365,7 @@ def make_cfg(kw):
         e.subframe_coding.qlpc.use_direct_mse = True
     e.subframe_coding.qlpc.mae_optimization_steps = kw.get("mae_optimization_steps", 0)
     e.subframe_coding.qlpc.ext_order_search = kw.get("ext_lpc_order_search", 0)
+    e.subframe_coding.qlpc.ext_precision_search = kw.get("ext_lpc_precision_search", 0)
     if kw.get("fixed_order_sel") == 0:
         from flacenc_rs_b200.config import OrderSel
         e.subframe_coding.fixed.order_sel = OrderSel.BitCount()

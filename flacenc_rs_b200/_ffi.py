@@ -42,6 +42,7 @@ class Config(C.Structure):
         ("tukey_alpha", C.c_float),
         ("prc_max_parameter", C.c_int32),
         ("ext_lpc_order_search", C.c_int32),
+        ("ext_lpc_precision_search", C.c_int32),
     ]
 
 

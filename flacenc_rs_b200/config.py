@@ -74,6 +74,7 @@ class Qlpc:
     window: Window = field(default_factory=Window)
     # extension beyond the reference (opt-in, see include/flacenc_b200.h): also try this many lower LPC orders
     ext_order_search: int = 0
+    ext_precision_search: int = 0
 
 
 @dataclass
@@ -112,7 +113,8 @@ class Encoder:
             lpc_order=q.lpc_order, quant_precision=q.quant_precision, use_direct_mse=int(q.use_direct_mse),
             mae_optimization_steps=q.mae_optimization_steps,
             window_type=0 if q.window.type == "Rectangle" else 1, tukey_alpha=float(q.window.alpha),
-            prc_max_parameter=s.prc.max_parameter, ext_lpc_order_search=q.ext_order_search)
+            prc_max_parameter=s.prc.max_parameter, ext_lpc_order_search=q.ext_order_search,
+            ext_lpc_precision_search=q.ext_precision_search)
 
     def verify(self) -> None:
         """``Verify::verify`` (src/config.rs:109-130 and children); raises VerifyError."""

@@ -676,6 +676,10 @@ int fb_make_plan(fb200_ctx *ctx, const EncodeArgs &A, Plan &P) {
     const int leaves_tail = 1 << fb_finest_partition_order(P.tail_n);
     P.L = fb_k2_layout(ctx->block_size, std::max(leaves_max, leaves_tail));
     P.k2_smem = P.L.total + 3 * sizeof(FbRiceResult);
+    if (P.k2_smem > 227u * 1024u) { // (block sizes 30720 .. 32512 with 256+ finest partitions: without the bank padding)
+        P.L = fb_k2_layout(ctx->block_size, std::max(leaves_max, leaves_tail), 31);
+        P.k2_smem = P.L.total + 3 * sizeof(FbRiceResult);
+    }
     P.k3_smem = fb_k3_smem_bytes(P.mb, ctx->block_size, J0.pack_in_smem);
     if (P.k2_smem > 227u * 1024u || P.k3_smem > 227u * 1024u) {
         ctx->last_error = "internal: shared memory budget exceeded";
@@ -726,7 +730,7 @@ int fb_reserve_set(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, ChunkSet 
     if ((rc = fb_reserve(ctx, S.xv, (fb_xt_words((int)P.stride, frames * (uint64_t)ctx->channels) + 64) * 4u))) return rc;
     if (!A.analyze_only && (rc = fb_reserve(ctx, S.xv4, (frames * (uint64_t)P.nvar * P.stride + 64) * 4u))) return rc;
     if ((rc = fb_reserve(ctx, S.ana, frames * (uint64_t)P.nvar * sizeof(FbAnalysis)))) return rc;
-    if (ctx->cfg.ext_lpc_order_search > 0 &&
+    if ((ctx->cfg.ext_lpc_order_search > 0 || ctx->cfg.ext_lpc_precision_search > 0) &&
         (rc = fb_reserve(ctx, S.lpc_ext, frames * (uint64_t)P.nvar * FB_EXT_LPC_MAX * sizeof(FbLpcExt))))
         return rc;
     if (in_bytes && (rc = fb_reserve(ctx, S.pcm, in_bytes + 16))) return rc;
@@ -757,7 +761,8 @@ int fb_enqueue_kernels(fb200_ctx *ctx, const Plan &P, const EncodeArgs &A, Chunk
     // analysis of the next chunk can overlap the fused kernel of this one
     FbJob J = fbh_make_job(ctx->cfg, ctx->channels, ctx->bps, ctx->sample_rate, ctx->block_size, P.cb, ns,
                            (uint32_t)(A.first_frame + f0));
-    if (ctx->cfg.ext_lpc_order_search > 0) J.lpc_ext = (FbLpcExt *)S.lpc_ext.p; // (extension: lower LPC orders, K1 -> KA / K2)
+    if (ctx->cfg.ext_lpc_order_search > 0 || ctx->cfg.ext_lpc_precision_search > 0)
+        J.lpc_ext = (FbLpcExt *)S.lpc_ext.p; // (extensions: alternative LPC sets, K1 -> KA / K2)
     const uint32_t nvars = J.n_frames * (uint32_t)J.nvar;
     uint32_t *d_err = (uint32_t *)S.scalars.p;
     unsigned long long *d_total = d_total_shared ? d_total_shared : (unsigned long long *)((uint8_t *)S.scalars.p + 8);

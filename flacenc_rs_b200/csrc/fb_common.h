@@ -86,6 +86,7 @@ FB_DEV void fb_atomic_add_u64(unsigned long long *p, unsigned long long v) { *p 
 struct FbLpcExt {
     int16_t qlp[32];
     int32_t order, shift;   // order after tail-zero truncation (0: no such candidate)
+    int32_t precision;      // quantiser precision of this set
 };
 // the orders tried besides P: P - i * ceil(P / (k + 1)), i = 1..k, while >= 1; returns their number
 FB_HD int fb_ext_lpc_orders(int P, int k, int *orders) {

@@ -986,7 +986,8 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
                           : 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
                                 (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res[1]->res_bits;
     }
-    if (BC && ext && J.cfg.use_lpc && J.cfg.ext_lpc_order_search > 0) {
+    int win_prec = J.cfg.quant_precision; // (BC: precision of the winning LPC set)
+    if (BC && ext && J.cfg.use_lpc) {
         // EXTENSION (config.ext_lpc_order_search): the lower-order coefficient sets K1 left in `ext` are searched into
         // result set 1 one after the other; the fewest subframe bits win (the higher order on ties), the winner is
         // searched again unless it was the last one, and its coefficients replace the staged analysis record.
@@ -1003,6 +1004,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             const int16_t *qs = pick_set < 0 ? A.qlp : ext[pick_set].qlp;
             const int o = pick_set < 0 ? A.qlp_order : ext[pick_set].order;
             const int sh = pick_set < 0 ? A.qlp_shift : ext[pick_set].shift;
+            const int pr = pick_set < 0 ? J.cfg.quant_precision : ext[pick_set].precision;
             FbKfCand cd;
             cd.kind = 1; cd.q = qs; cd.order = o; cd.shift = sh;
             cd.fc[0] = cd.fc[1] = cd.fc[2] = cd.fc[3] = 0;
@@ -1012,7 +1014,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
             fb_kf_search<G, ODD, VMS>(J, g, xa, xb, vm, cd, scratch, L, unit_bits + (size_t)(L.U_max + 1), res[1]);
             if (M->fail) return;
             const unsigned long long bits = 8ull + (unsigned long long)bps_v * (unsigned long long)o + 4ull + 5ull +
-                                            (unsigned long long)J.cfg.quant_precision * (unsigned long long)o + res[1]->res_bits;
+                                            (unsigned long long)pr * (unsigned long long)o + res[1]->res_bits;
             const bool probing = k < FB_EXT_LPC_MAX && ext[k].order > 0;
             last = pick_set;
             if (!probing) break;
@@ -1025,6 +1027,7 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
                 if (lane == 0) { Aw.qlp_order = ext[best].order; Aw.qlp_shift = ext[best].shift; }
             FB_WPHASE_END
             cbits[1] = best_bits;
+            win_prec = ext[best].precision;
         }
     }
     const unsigned long long fixed_bits = cbits[0], lpc_bits = cbits[1];
@@ -1060,6 +1063,11 @@ FB_DEV void fb_kf_variant(const FbJob &J, const FbKfGeom &g, const int32_t *xs, 
         if (pick == 1) out->qlp[lane] = A.qlp[lane];
         for (int i = lane; i < (1 << R->part_order); i += 32) out->rice_params[i] = R->params[i];
     FB_WPHASE_END
+    if (BC && pick == 1 && win_prec != J.cfg.quant_precision) { // (precision search extension: the winner's precision)
+        FB_WPHASE(lane)
+            if (lane == 0) { out->precision = win_prec; S->vh[v].precision = (int16_t)win_prec; }
+        FB_WPHASE_END
+    }
 }
 
 // ORs the k (1..32) low bits of v (v < 2^k) into the MSB-first bit stream at bit position pos.  The buffer is

@@ -27,6 +27,7 @@ inline void fbh_config_default(fb200_config *c) {
     c->tukey_alpha = 0.4f;
     c->prc_max_parameter = 30;
     c->ext_lpc_order_search = 0;
+    c->ext_lpc_precision_search = 0;
 }
 
 // Verify for Encoder and children (src/config.rs:109-130,198-204,224-229,299-326,371-387).
@@ -52,7 +53,9 @@ inline int fbh_config_verify(const fb200_config *c) {
     if (c->prc_max_parameter < 0 || c->prc_max_parameter > 30) return FB200_ERR_CONFIG;
     // extension (not in the reference): lower LPC orders from the same autocorrelation
     if (c->ext_lpc_order_search < 0 || c->ext_lpc_order_search > FB_EXT_LPC_MAX) return FB200_ERR_CONFIG;
-    if (c->ext_lpc_order_search > 0 && c->use_direct_mse) return FB200_ERR_CONFIG;
+    if (c->ext_lpc_precision_search < 0 || c->ext_lpc_precision_search > 4) return FB200_ERR_CONFIG;
+    if (c->ext_lpc_order_search + c->ext_lpc_precision_search > FB_EXT_LPC_MAX) return FB200_ERR_CONFIG;
+    if ((c->ext_lpc_order_search > 0 || c->ext_lpc_precision_search > 0) && c->use_direct_mse) return FB200_ERR_CONFIG;
     if (c->fixed_max_order < 0) return FB200_ERR_CONFIG;
     if (c->fixed_order_sel != 0 && c->fixed_order_sel != 1) return FB200_ERR_CONFIG;
     if (c->fixed_order_sel == 1 && (c->approx_ent_partitions < 1 || c->approx_ent_partitions > FB_MAX_ENT_PARTS))

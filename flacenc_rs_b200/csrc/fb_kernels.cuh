@@ -674,19 +674,28 @@ FB_DEV void fb_k1_finish_lpc(const FbJob &J, const FbK1Var &V, const FbK1Acc<R> 
         taps->qlp_order = order;
         taps->qlp_shift = shift;
     }
-    if (J.lpc_ext && J.cfg.ext_lpc_order_search > 0) {
-        // EXTENSION: the Levinson solutions of the lower orders on the same autocorrelation, quantised alike
+    if (J.lpc_ext) {
+        // EXTENSIONS: the Levinson solutions of the lower orders on the same autocorrelation, quantised alike, then the
+        // order-P solution quantised with fewer bits; unused entries get order 0
         int orders[FB_EXT_LPC_MAX];
         const int no = fb_ext_lpc_orders(V.P, J.cfg.ext_lpc_order_search, orders);
         FbLpcExt *ext = J.lpc_ext + (size_t)gv * FB_EXT_LPC_MAX;
+        double lpc_p[FB200_MAX_LPC_ORDER];
+        for (int i = 0; i < FB200_MAX_LPC_ORDER; i++) lpc_p[i] = lpc[i];
+        int np = 0; // precision candidates written so far
         for (int k = 0; k < FB_EXT_LPC_MAX; k++) {
-            int ok = 0, sk = 0;
+            int ok = 0, sk = 0, pk = J.cfg.quant_precision;
             if (k < no) {
                 fb_levinson(corr, corr + 1, orders[k], lpc);
-                ok = fb_quantize(lpc, orders[k], J.cfg.quant_precision, q, &sk);
+                ok = fb_quantize(lpc, orders[k], pk, q, &sk);
+            } else if (np < J.cfg.ext_lpc_precision_search && J.cfg.quant_precision - (np + 1) >= 1) {
+                np++;
+                pk = J.cfg.quant_precision - np;
+                ok = fb_quantize(lpc_p, V.P, pk, q, &sk);
             }
             ext[k].order = ok;
             ext[k].shift = sk;
+            ext[k].precision = pk;
             for (int i = 0; i < 32; i++) ext[k].qlp[i] = i < ok ? q[i] : (int16_t)0;
         }
     }
@@ -1760,12 +1769,17 @@ FB_HD int fb_uidx(int t) { return t + (t >> 5); }
 // shared-memory layout of K2 (offsets in bytes), identical on host and device
 struct FbK2Layout {
     uint32_t off_u, off_tbl_a, off_tbl_b, off_part, off_lvl_params, off_lvl_bits, off_unit_sum, off_misc, total;
+    int32_t u_shift;
 };
 
-FB_HD FbK2Layout fb_k2_layout(int n_max, int leaves_max) {
+// index of residual t in K2's buffer: one pad word per 32 (u_shift 5) keeps strided readers off one bank; the few large
+// block sizes with 256 or more finest partitions (30720 .. 32512) only fit without the padding (u_shift 31)
+FB_HD int fb_uidx2(int t, int u_shift) { return t + (t >> u_shift); }
+FB_HD FbK2Layout fb_k2_layout(int n_max, int leaves_max, int u_shift = 5) {
     FbK2Layout L;
     uint32_t o = 0;
-    L.off_u = o;          o += (uint32_t)((n_max + (n_max >> 5) + 4 + 3) & ~3) * 4u; // padded, see fb_uidx
+    L.u_shift = u_shift;
+    L.off_u = o;          o += (uint32_t)((n_max + (n_max >> u_shift) + 4 + 3) & ~3) * 4u; // padded, see fb_uidx2
     L.off_tbl_a = o;      o += (uint32_t)leaves_max * 32u * 4u;
     L.off_tbl_b = o;      o += (uint32_t)leaves_max * 32u * 4u;
     uint32_t units = (uint32_t)(leaves_max > FB_K2_THREADS ? leaves_max : FB_K2_THREADS);
@@ -1848,7 +1862,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
 #pragma unroll
             for (int i = 0; i < FB_RUN; i++) {
                 const int t = run * FB_RUN + i;
-                if (t < n) u[fb_uidx(t)] = uu[i];
+                if (t < n) u[fb_uidx2(t, L.u_shift)] = uu[i];
                 mx = uu[i] > mx ? uu[i] : mx;
             }
         }
@@ -1868,7 +1882,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
             int t = a0 + (m > 0 ? (tid % m) : 0);
             unsigned long long sacc = 0;
             for (int i = 0; i < m; i++) {
-                sacc += u[fb_uidx(t)];
+                sacc += u[fb_uidx2(t, L.u_shift)];
                 t = (t + 1 < a1) ? t + 1 : a0;
             }
             unit_sum[unit] = sacc;
@@ -1924,7 +1938,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
                         const int p0 = a + pc;
                         int t = tstart;
                         for (int i = 0; i < m; i++) {
-                            uint32_t v = u[fb_uidx(t)] >> p0;
+                            uint32_t v = u[fb_uidx2(t, L.u_shift)] >> p0;
                             c0 += v; c1 += v >> 1; c2 += v >> 2; c3 += v >> 3;
                             t = (t + 1 < a1) ? t + 1 : a0;
                         }
@@ -1958,7 +1972,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
                     uint32_t accv = 0;
                     for (int c = start; c < end; c += 16) {
                         int ce = c + 16 < end ? c + 16 : end;
-                        for (int t = c; t < ce; t++) accv += u[fb_uidx(t)] >> p;
+                        for (int t = c; t < ce; t++) accv += u[fb_uidx2(t, L.u_shift)] >> p;
                         accv = accv < FB_RICE_SAT ? accv : FB_RICE_SAT;
                     }
                     accv += 4u + (uint32_t)(end - start) * (uint32_t)(p + 1);
@@ -2065,7 +2079,7 @@ FB_DEV void fb_k2_rice_search(const FbJob &J, const int32_t *x, int n, int kind,
                 int pj = (int)((float)t * inv_plen);
                 if ((pj + 1) * plen <= t) pj++;
                 if (pj * plen > t) pj--;
-                if (t >= warm) local += u[fb_uidx(t)] >> lvl_params[pbase + pj];
+                if (t >= warm) local += u[fb_uidx2(t, L.u_shift)] >> lvl_params[pbase + pj];
             }
             if (local) fb_atomic_add_u64(&M->sum_q, local);
         FB_PHASE_END
@@ -2163,22 +2177,22 @@ FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
     bool lpc_ok = false;
     unsigned long long lpc_bits = 0;
     const int16_t *lq = A.qlp; // the LPC candidate's coefficients, order after truncation, shift
-    int lo = A.qlp_order, ls = A.qlp_shift;
+    int lo = A.qlp_order, ls = A.qlp_shift, lp = J.cfg.quant_precision;
     if (J.cfg.use_lpc) {
         fb_k2_rice_search<G>(J, x, n, 1, A.qlp_order, A.qlp, A.qlp_shift, smem, L, res_lpc);
         lpc_bits = 8ull + (unsigned long long)bps_v * (unsigned long long)A.qlp_order + 4ull + 5ull +
                    (unsigned long long)J.cfg.quant_precision * (unsigned long long)A.qlp_order + res_lpc->res_bits;
-        if (J.lpc_ext && J.cfg.ext_lpc_order_search > 0) {
-            // EXTENSION (config.ext_lpc_order_search): the lower-order sets of K1; fewest bits win, the higher order on ties
+        if (J.lpc_ext) {
+            // EXTENSIONS (config.ext_lpc_*_search): the alternative sets of K1; fewest bits win, the earlier set on ties
             const FbLpcExt *ext = J.lpc_ext + (size_t)gv * FB_EXT_LPC_MAX;
             for (int k = 0; k < FB_EXT_LPC_MAX && ext[k].order > 0; k++) {
                 fb_k2_rice_search<G>(J, x, n, 1, ext[k].order, ext[k].qlp, ext[k].shift, smem, L, res_tmp);
                 const unsigned long long bits = 8ull + (unsigned long long)bps_v * (unsigned long long)ext[k].order + 4ull + 5ull +
-                                                (unsigned long long)J.cfg.quant_precision * (unsigned long long)ext[k].order +
+                                                (unsigned long long)ext[k].precision * (unsigned long long)ext[k].order +
                                                 res_tmp->res_bits;
                 if (bits < lpc_bits) {
                     lpc_bits = bits;
-                    lq = ext[k].qlp; lo = ext[k].order; ls = ext[k].shift;
+                    lq = ext[k].qlp; lo = ext[k].order; ls = ext[k].shift; lp = ext[k].precision;
                     FB_PHASE(tid, T)
                         for (int i = tid; i < (int)sizeof(FbRiceResult); i += T)
                             ((uint8_t *)res_lpc)[i] = ((const uint8_t *)res_tmp)[i];
@@ -2202,7 +2216,7 @@ FB_DEV void fb_k2_body(const FbJob &J, const int32_t *xv, const FbAnalysis *ana,
         if (tid == 0) {
             out->type = pick == 1 ? FB200_SF_LPC : FB200_SF_FIXED;
             out->order = pick == 1 ? lo : kf;
-            out->precision = pick == 1 ? J.cfg.quant_precision : 0;
+            out->precision = pick == 1 ? lp : 0;
             out->shift = pick == 1 ? ls : 0;
             out->partition_order = R->part_order;
             out->rice2 = R->rice2;

@@ -66,6 +66,9 @@ typedef struct fb200_config {
                                        i = 1..k (those >= 1), each the Levinson solution of that order on the same autocorrelation;
                                        the LPC candidate with the fewest subframe bits wins, the higher order on ties.
                                        Autocorrelation estimator only (rejected with use_direct_mse). */
+    int32_t ext_lpc_precision_search; /* 0 (default, off) .. 4: also quantise the order-P coefficients with quant_precision - 1 ..
+                                       quant_precision - k bits (those >= 1) and take the cheapest; candidates are ranked after
+                                       the lower orders.  ext_lpc_order_search + ext_lpc_precision_search <= 8. */
 } fb200_config;
 
 /* Subframe types (component::SubFrame, src/component/datatype.rs:1782-1795). */

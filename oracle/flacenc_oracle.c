@@ -40,6 +40,7 @@ void fo_config_default(fo_config *c) {
     c->tukey_alpha = 0.4f;
     c->prc_max_parameter = FO_MAX_RICE_PARAMETER;
     c->ext_lpc_order_search = 0;
+    c->ext_lpc_precision_search = 0;
 }
 
 /* src/config.rs:109-130 (Encoder), :198-204 (SubFrameCoding: note fixed.verify() is NOT called),
@@ -61,7 +62,9 @@ int fo_config_verify(const fo_config *c) {
     }
     if (c->prc_max_parameter < 0 || c->prc_max_parameter > FO_MAX_RICE_PARAMETER) return 1;
     if (c->ext_lpc_order_search < 0 || c->ext_lpc_order_search > 8) return 1;
-    if (c->ext_lpc_order_search > 0 && c->use_direct_mse) return 1;
+    if (c->ext_lpc_precision_search < 0 || c->ext_lpc_precision_search > 4) return 1;
+    if (c->ext_lpc_order_search + c->ext_lpc_precision_search > 8) return 1;
+    if ((c->ext_lpc_order_search > 0 || c->ext_lpc_precision_search > 0) && c->use_direct_mse) return 1;
     return 0;
 }
 
@@ -805,21 +808,21 @@ int fo_ext_lpc_orders(int lpc_order, int k, int *orders) {
 }
 
 /* the LPC subframe of one set of unquantised coefficients (the second half of estimated_qlpc) */
-static void fo_qlpc_subframe(const fo_config *cfg, const double *coefs, int lpc_order, const int32_t *signal, int n, int bps,
-                             fo_subframe *out) {
+static void fo_qlpc_subframe(const fo_config *cfg, const double *coefs, int lpc_order, int precision, const int32_t *signal,
+                             int n, int bps, fo_subframe *out) {
     fo_subframe_reset(out, FO_SF_LPC, signal, n, bps);
     int16_t q[FO_MAX_LPC_ORDER];
     int shift;
-    int order = fo_quantize_parameters(coefs, lpc_order, cfg->quant_precision, q, &shift);
+    int order = fo_quantize_parameters(coefs, lpc_order, precision, q, &shift);
     for (int i = 0; i < FO_MAX_LPC_ORDER; i++) out->qlp[i] = i < order ? q[i] : 0;
     out->order = order;
     out->shift = shift;
-    out->precision = cfg->quant_precision;
+    out->precision = precision;
     int32_t *errors = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
     fo_compute_error(q, order, shift, signal, n, errors);
     uint64_t rbits = fo_encode_residual(cfg->prc_max_parameter, errors, n, order, out);
     /* src/component/bitrepr.rs:492-499 */
-    out->bits = 8 + (uint64_t)bps * order + 4 + 5 + (uint64_t)cfg->quant_precision * order + rbits;
+    out->bits = 8 + (uint64_t)bps * order + 4 + 5 + (uint64_t)precision * order + rbits;
     free(errors);
 }
 
@@ -833,7 +836,7 @@ static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n
         fo_lpc_with_irls_mae(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, cfg->mae_optimization_steps, coefs, NULL);
     else if (cfg->use_direct_mse) fo_lpc_with_direct_mse(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, NULL, NULL);
     else fo_lpc_from_autocorr(signal, n, cfg->window_type, cfg->tukey_alpha, lpc_order, coefs, corr);
-    fo_qlpc_subframe(cfg, coefs, lpc_order, signal, n, bps, out);
+    fo_qlpc_subframe(cfg, coefs, lpc_order, cfg->quant_precision, signal, n, bps, out);
     if (cfg->ext_lpc_order_search > 0 && !cfg->use_direct_mse) {
         /* EXTENSION: the Levinson solutions of lower orders on the same autocorrelation; fewest bits wins, the higher
          * order (the earlier candidate) on ties */
@@ -843,7 +846,21 @@ static void fo_estimated_qlpc(const fo_config *cfg, const int32_t *signal, int n
             double ck[FO_MAX_LPC_ORDER];
             fo_levinson_f64(corr, corr + 1, orders[k], ck);
             fo_subframe cand;
-            fo_qlpc_subframe(cfg, ck, orders[k], signal, n, bps, &cand);
+            fo_qlpc_subframe(cfg, ck, orders[k], cfg->quant_precision, signal, n, bps, &cand);
+            if (cand.bits < out->bits) {
+                free(out->residual);
+                *out = cand;
+            } else {
+                free(cand.residual);
+            }
+        }
+    }
+    if (cfg->ext_lpc_precision_search > 0 && !cfg->use_direct_mse) {
+        /* EXTENSION: the order-P coefficients quantised with fewer bits (ranked after the lower orders; strictly fewer
+         * subframe bits to win) */
+        for (int k = 1; k <= cfg->ext_lpc_precision_search && cfg->quant_precision - k >= 1; k++) {
+            fo_subframe cand;
+            fo_qlpc_subframe(cfg, coefs, lpc_order, cfg->quant_precision - k, signal, n, bps, &cand);
             if (cand.bits < out->bits) {
                 free(out->residual);
                 *out = cand;

@@ -60,6 +60,7 @@ typedef struct fo_config {
     float   tukey_alpha;           /* default 0.4 */
     int32_t prc_max_parameter;     /* Prc.max_parameter, default 30 */
     int32_t ext_lpc_order_search;  /* EXTENSION beyond the reference (0 = off): lower LPC orders tried, see fo_ext_lpc_orders */
+    int32_t ext_lpc_precision_search; /* EXTENSION (0 = off): lower quantiser precisions tried for the order-P coefficients */
 } fo_config;
 
 enum { FO_SF_CONSTANT = 0, FO_SF_VERBATIM = 1, FO_SF_FIXED = 2, FO_SF_LPC = 3 };

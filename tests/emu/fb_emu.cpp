@@ -133,7 +133,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.block_size, B.win_full.data());
     fbh_window_weights(cfg->window_type, cfg->tukey_alpha, J.tail_n, B.win_tail.data());
     B.ana.resize(nvars);
-    if (cfg->ext_lpc_order_search > 0) {
+    if (cfg->ext_lpc_order_search > 0 || cfg->ext_lpc_precision_search > 0) {
         FbLpcExt poison;
         memset(&poison, 0x5A, sizeof(poison));
         B.lpc_ext.assign(nvars * FB_EXT_LPC_MAX, poison);
@@ -236,6 +236,7 @@ static int emu_run(const fb200_config *cfg, const void *pcm, const int32_t *plan
     {
         int nmax = J.block_size;
         FbK2Layout L = fb_k2_layout(nmax, fbh_leaves_max(J));
+        if (L.total + 3 * sizeof(FbRiceResult) > 227u * 1024u) L = fb_k2_layout(nmax, fbh_leaves_max(J), 31); // (like the library)
         std::vector<uint8_t> smem(L.total + 3 * sizeof(FbRiceResult) + 64);
         for (uint32_t f : todo)
           for (uint32_t gv = f * J.nvar; gv < (f + 1) * (uint32_t)J.nvar; gv++) {

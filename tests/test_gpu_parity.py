@@ -44,6 +44,8 @@ def make_config(**kw) -> Encoder:
             s.qlpc.mae_optimization_steps = v
         elif k == "ext_lpc_order_search":
             s.qlpc.ext_order_search = v
+        elif k == "ext_lpc_precision_search":
+            s.qlpc.ext_precision_search = v
         elif k == "window_type":
             s.qlpc.window.type = "Rectangle" if v == 0 else "Tukey"
         elif k == "tukey_alpha":
@@ -408,10 +410,36 @@ def test_ext_lpc_order_search_extension():
     _compare(z, 8, 24, 48000, 1024, ext_lpc_order_search=2)
     _compare(np.zeros((3000, 2), np.int32), 2, 16, 44100, 1024, ext_lpc_order_search=2, use_constant=0)
     _compare(crafted_huge_residual_stereo(), 2, 24, 96000, 4096, lpc_order=24, ext_lpc_order_search=3)  # a fallback frame
+    # second extension: fewer quantiser bits for the order-P coefficients, alone and with the order search
+    for ko, kp in ((0, 1), (0, 4), (4, 4), (5, 3)):
+        _compare(x, 2, 16, 44100, 4096, ext_lpc_order_search=ko, ext_lpc_precision_search=kp)
+        ext, _ = O.encode_frames(O.default_config(ext_lpc_order_search=ko, ext_lpc_precision_search=kp), x, 2, 16, 44100, 4096,
+                                 nthreads=8)
+        assert len(ext) <= len(base)
+    _compare(x, 2, 16, 44100, 1000, ext_lpc_precision_search=4, quant_precision=3, lpc_order=5)
+    _compare(y, 3, 24, 96000, 4608, ext_lpc_order_search=3, ext_lpc_precision_search=2, lpc_order=16)
+    _compare(crafted_huge_residual_stereo(), 2, 24, 96000, 4096, lpc_order=24, ext_lpc_precision_search=2)
+    with pytest.raises(VerifyError):
+        make_config(ext_lpc_order_search=6, ext_lpc_precision_search=3).into_verified()
     with pytest.raises(VerifyError):
         make_config(ext_lpc_order_search=1, use_direct_mse=1).into_verified()
     with pytest.raises(VerifyError):
         make_config(ext_lpc_order_search=9).into_verified()
+
+
+def test_large_blocks_with_256_finest_partitions():
+    """block sizes 30720 .. 32512 in steps of 256 (2^8 finest Rice partitions at nearly the maximum length): the generic
+    rice kernel fits them in shared memory only without its bank padding -- found by the fuzz campaign (31744), where the
+    library answered with its "shared memory budget exceeded" error"""
+    rng = np.random.default_rng(77)
+    for block in (31744, 32512, 30720, 32000):
+        x = (rng.normal(0, 2000, (block + 300, 2)).cumsum(axis=0) % 60000 - 30000).astype(np.int32)
+        _compare(x, 2, 16, 44100, block)
+    x4 = (rng.normal(0, 200000, (31744, 4))).astype(np.int32)
+    _compare(x4, 4, 24, 44100, 31744, lpc_order=6, quant_precision=10, fixed_order_sel=0, prc_max_parameter=6, use_midside=0,
+             ext_lpc_order_search=6, ext_lpc_precision_search=2)
+    x8 = (rng.normal(0, 100000, (32512 + 50, 8))).astype(np.int32)
+    _compare(x8, 8, 24, 48000, 32512)
 
 
 def test_pipelined_host_path_matches_oracle(monkeypatch):

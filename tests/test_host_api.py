@@ -48,7 +48,7 @@ def test_version_and_strerror_need_no_gpu():
 
 def test_struct_sizes_match_header():
     # sizes computed by hand from include/flacenc_b200.h
-    assert C.sizeof(_ffi.Config) == 20 * 4  # 19 fields of config::Encoder + 1 opt-in extension
+    assert C.sizeof(_ffi.Config) == 21 * 4  # 19 fields of config::Encoder + 2 opt-in extensions
     assert C.sizeof(_ffi.SubframeInfo) == 8 * 4 + 64 + 256 + 8
     assert C.sizeof(_ffi.FrameInfo) == 16 + 8 * C.sizeof(_ffi.SubframeInfo)
     assert C.sizeof(_ffi.VariantTaps) == 25 * 8 + 24 * 8 + 64 + 4 * 4 + 5 * 8
@@ -90,6 +90,9 @@ def test_config_default_matches_reference_defaults():
     (lambda e: setattr(e.subframe_coding.qlpc, "mae_optimization_steps", -1), False),  # (a usize in the reference)
     (lambda e: setattr(e.subframe_coding.qlpc, "ext_order_search", 8), True),    # extension beyond the reference (opt-in)
     (lambda e: setattr(e.subframe_coding.qlpc, "ext_order_search", 9), False),
+    (lambda e: setattr(e.subframe_coding.qlpc, "ext_precision_search", 4), True),
+    (lambda e: setattr(e.subframe_coding.qlpc, "ext_precision_search", 5), False),
+    (lambda e: (setattr(e.subframe_coding.qlpc, "ext_order_search", 6), setattr(e.subframe_coding.qlpc, "ext_precision_search", 3)), False),
     (lambda e: (setattr(e.subframe_coding.qlpc, "ext_order_search", 1), setattr(e.subframe_coding.qlpc, "use_direct_mse", True)), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "window", Window.Tukey(1.5)), False),
     (lambda e: setattr(e.subframe_coding.qlpc, "window", Window.Rectangle()), True),

@@ -305,10 +305,34 @@ def test_ext_lpc_order_search_extension():
     y = sigen.noisy_sine_pcm(1152 * 2 + 100, 3, 24, 96000, config_id=3)
     _compare(y, 3, 24, 96000, 1152, ext_lpc_order_search=4, lpc_order=16)
     _compare(np.zeros((600, 2), np.int32), 2, 16, 44100, 256, ext_lpc_order_search=2, use_constant=0)
+    # second extension: the order-P coefficients quantised with fewer bits (config.ext_lpc_precision_search), alone and
+    # together with the order search
+    base, _ = O.encode_frames(O.default_config(), x, 2, 16, 44100, 1024)
+    for ko, kp in ((0, 1), (0, 4), (4, 4), (2, 3), (5, 3)):
+        _compare(x, 2, 16, 44100, 1024, ext_lpc_order_search=ko, ext_lpc_precision_search=kp)
+        ext, _ = O.encode_frames(O.default_config(ext_lpc_order_search=ko, ext_lpc_precision_search=kp), x, 2, 16, 44100, 1024)
+        assert len(ext) <= len(base)
+    _compare(x, 2, 16, 44100, 1000, ext_lpc_precision_search=4, quant_precision=3, lpc_order=5)   # precisions 2 and 1 only
+    _compare(x, 2, 16, 44100, 1024, ext_lpc_precision_search=2, fixed_order_sel=0, lpc_order=24)
+    _compare(y, 3, 24, 96000, 1152, ext_lpc_order_search=3, ext_lpc_precision_search=2, lpc_order=16)
+    assert E.lib().fbemu_config_verify(E.default_config(ext_lpc_precision_search=5)) != 0
+    assert E.lib().fbemu_config_verify(E.default_config(ext_lpc_order_search=6, ext_lpc_precision_search=3)) != 0
+    assert E.lib().fbemu_config_verify(E.default_config(ext_lpc_precision_search=1, use_direct_mse=1)) != 0
     # the estimators of the `experimental` feature have no lower orders to offer: rejected
     bad = E.default_config(ext_lpc_order_search=1, use_direct_mse=1)
     assert E.lib().fbemu_config_verify(bad) != 0
     assert E.lib().fbemu_config_verify(E.default_config(ext_lpc_order_search=9)) != 0
+
+
+def test_large_blocks_with_256_finest_partitions():
+    """block sizes 30720 .. 32512 in steps of 256 have 2^8 finest Rice partitions AND nearly the maximum length: the generic
+    rice kernel's shared-memory layout only fits them without its bank padding (found by the fuzz campaign: 31744)"""
+    rng = np.random.default_rng(77)
+    for block in (31744, 32512, 30720):
+        x = (rng.normal(0, 2000, (block + 300, 2)).cumsum(axis=0) % 60000 - 30000).astype(np.int32)
+        _compare(x, 2, 16, 44100, block)
+    x4 = (rng.normal(0, 200000, (31744, 4))).astype(np.int32)
+    _compare(x4, 4, 24, 44100, 31744, lpc_order=6, quant_precision=10, fixed_order_sel=0, prc_max_parameter=6, use_midside=0)
 
 
 def test_crc8_closed_form_matches_bit_serial_definition():

@@ -27,7 +27,8 @@ for seed in range(first, first + count):
         else:
             x, channels, bps, rate, block, first_frame, cfg = random_case(rng)
         if seed % 5 == 0 and not cfg.get("use_direct_mse"):
-            cfg["ext_lpc_order_search"] = int(rng.integers(1, 9))   # the opt-in extension, against the oracle's statement
+            cfg["ext_lpc_order_search"] = int(rng.integers(0, 9))   # the opt-in extensions, against the oracle's statement
+            cfg["ext_lpc_precision_search"] = int(rng.integers(0, min(4, 8 - cfg["ext_lpc_order_search"]) + 1))
         T._compare(x, channels, bps, rate, block, first_frame=first_frame, oracle_threads=8, **cfg)
         for k in cfg:
             kinds[k] = kinds.get(k, 0) + 1

@@ -13,6 +13,7 @@ def run(ch, bps, cont, block, x, **kw):
     if kw.get("use_direct_mse"): e.subframe_coding.qlpc.use_direct_mse = True; e.subframe_coding.qlpc.window.type = "Rectangle"
     e.subframe_coding.qlpc.mae_optimization_steps = kw.get("mae_optimization_steps", 0)
     e.subframe_coding.qlpc.ext_order_search = kw.get("ext_lpc_order_search", 0)
+    e.subframe_coding.qlpc.ext_precision_search = kw.get("ext_lpc_precision_search", 0)
     if kw.get("bitcount"):
         from flacenc_rs_b200.config import OrderSel
         e.subframe_coding.fixed.order_sel = OrderSel.BitCount()
@@ -42,7 +43,7 @@ run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1, mae_optimizati
 run(3, 24, 3, 1500, sig(3, 24, 1500 * 2 + 77), use_direct_mse=1, mae_optimization_steps=1, lpc_order=24)
 # the probing instances of the plan kernel: BitCount order selection, the LPC order search extension (with a fallback frame)
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), bitcount=1)
-run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), ext_lpc_order_search=4)
+run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), ext_lpc_order_search=4, ext_lpc_precision_search=3)
 run(2, 24, 3, 4096, np.concatenate([sig(2, 24, 4096), big]), lpc_order=24, ext_lpc_order_search=3, bitcount=1)
 os.environ["FB200_K1_SMALL"] = "0"
 run(2, 16, 2, 4096, sig(2, 16, 4096 * 3 + 100), use_direct_mse=1)
