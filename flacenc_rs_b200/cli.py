@@ -41,19 +41,32 @@ def main(argv: List[str] | None = None) -> int:
     enc = sub.add_parser("encode", help="encode WAV file(s) to FLAC on the GPU")
     enc.add_argument("-o", "--output", required=True, help="output FLAC path (with several sources: a directory-less prefix, "
                                                            "outputs are PREFIX<i>.flac)")
-    enc.add_argument("--block-size", type=int, default=4096)
+    enc.add_argument("-c", "--config", default=None, help="encoder configuration in the reference's TOML form "
+                                                          "(flacenc-bin --config, src/config.rs:20-60)")
+    enc.add_argument("--dump-config", default=None, help="write the configuration used to this path (flacenc-bin --dump-config)")
+    enc.add_argument("--block-size", type=int, default=None)
     enc.add_argument("--lpc-order", type=int, default=None)
     enc.add_argument("--direct-mse", action="store_true", help="the `experimental` covariance-method LPC estimator")
     enc.add_argument("--devices", default="0", help="comma-separated device ordinals")
     enc.add_argument("source", nargs="+")
     args = ap.parse_args(argv)
 
-    cfg = Encoder(block_size=args.block_size)
+    if args.config:
+        with open(args.config, "r", encoding="utf-8") as f:
+            cfg = Encoder.from_toml(f.read())
+    else:
+        cfg = Encoder()
+    if args.block_size is not None:
+        cfg.block_size = args.block_size
+    args.block_size = cfg.block_size
     if args.lpc_order is not None:
         cfg.subframe_coding.qlpc.lpc_order = args.lpc_order
     if args.direct_mse:
         cfg.subframe_coding.qlpc.use_direct_mse = True
     vcfg = cfg.into_verified()
+    if args.dump_config:
+        with open(args.dump_config, "w", encoding="utf-8") as f:
+            f.write(cfg.to_toml())
     devices = [int(d) for d in args.devices.split(",")]
     srcs = [wav_source(p) for p in args.source]
     t0 = time.perf_counter()

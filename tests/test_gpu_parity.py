@@ -836,6 +836,17 @@ def test_cli_encodes_wav_files(tmp_path):
         assert data == O.encode_stream(O.default_config(), x, ch, bps, rate, 4096)
         dec, info = O.decode_stream(data)
         assert np.array_equal(dec, x)
+    # --config: the reference's TOML form (here report/experimental.config.toml's content), --dump-config writes it back
+    toml = str(tmp_path / "experimental.config.toml")
+    with open(toml, "w") as f:
+        f.write("[subframe_coding.qlpc]\nuse_direct_mse = true\n\n[subframe_coding.qlpc.window]\ntype = \"Rectangle\"\n")
+    out = str(tmp_path / "c4.flac")
+    dump = str(tmp_path / "used.toml")
+    assert cli.main(["encode", "-c", toml, "--dump-config", dump, "-o", out, paths[0]]) == 0
+    x, ch, bps, rate = sigs[0]
+    assert open(out, "rb").read() == O.encode_stream(O.default_config(use_direct_mse=1, window_type=0), x, ch, bps, rate, 4096)
+    used = Encoder.from_toml(open(dump).read())
+    assert used.subframe_coding.qlpc.use_direct_mse and used.subframe_coding.qlpc.window.type == "Rectangle"
     # two files of one format as a batch
     assert cli.main(["encode", "-o", str(tmp_path / "b"), paths[0], paths[0]]) == 0
     assert open(str(tmp_path / "b0.flac"), "rb").read() == open(str(tmp_path / "b1.flac"), "rb").read() == open(str(tmp_path / "out0.flac"), "rb").read()

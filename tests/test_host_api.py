@@ -112,6 +112,69 @@ def test_config_verify(mutate, ok):
             e.into_verified()
 
 
+def test_config_toml_form_of_the_reference():
+    """config::Encoder's serde layout (src/config.rs:20-60; every table `serde(default)`): the module doc's example, the
+    shapes of the reference's report/*.config.toml files, a dump / load round trip, and rejects"""
+    doc = """
+block_size = 4096
+multithread = true
+
+[stereo_coding]
+use_leftside = true
+use_rightside = true
+use_midside = true
+
+[subframe_coding]
+use_constant = true
+use_fixed = true
+use_lpc = true
+
+[subframe_coding.fixed]
+max_order = 4
+
+[subframe_coding.fixed.order_sel]
+type = "ApproxEnt"
+partitions = 32
+
+[subframe_coding.qlpc]
+lpc_order = 10
+quant_precision = 15
+use_direct_mse = false
+mae_optimization_steps = 0
+
+[subframe_coding.qlpc.window]
+type = "Tukey"
+alpha = 0.4
+
+[subframe_coding.prc]
+max_parameter = 14
+"""
+    e = Encoder.from_toml(doc)
+    assert e.subframe_coding.fixed.order_sel == OrderSel.ApproxEnt(32) and e.subframe_coding.prc.max_parameter == 14
+    assert Encoder.from_toml("") == Encoder()                                  # all defaults
+    st = Encoder.from_toml("multithread = false\n")                           # report/st.config.toml's shape
+    assert st.multithread is False and st.subframe_coding == Encoder().subframe_coding
+    mt = Encoder.from_toml("multithread = true\nworkers = 1\n")               # report/mt1.config.toml's shape
+    assert mt.workers == 1
+    ex = Encoder.from_toml('[subframe_coding.qlpc]\nuse_direct_mse = true\n[subframe_coding.qlpc.window]\ntype = "Rectangle"\n')
+    assert ex.subframe_coding.qlpc.use_direct_mse and ex.subframe_coding.qlpc.window == Window.Rectangle()
+    bc = Encoder.from_toml('[subframe_coding.fixed.order_sel]\ntype = "BitCount"\n')
+    assert bc.subframe_coding.fixed.order_sel.type == "BitCount"
+    for cfg in (e, st, mt, ex, bc):
+        assert Encoder.from_toml(cfg.to_toml()) == cfg
+    x = Encoder()
+    x.subframe_coding.qlpc.ext_order_search, x.subframe_coding.qlpc.ext_precision_search = 4, 2
+    x.subframe_coding.qlpc.window = Window.Tukey(0.25)
+    assert Encoder.from_toml(x.to_toml()) == x and "ext_order_search" not in Encoder().to_toml()
+    for bad in ("block_size = \"big\"\n", "blocksize = 4096\n", "[subframe_coding.qlpc]\nlpc_order = true\n",
+                '[subframe_coding.qlpc.window]\ntype = "Hann"\n', "[subframe_coding\n", '[subframe_coding.fixed.order_sel]\ntype = 3\n'):
+        with pytest.raises(VerifyError):
+            Encoder.from_toml(bad)
+    # what loads still goes through Verify
+    with pytest.raises(VerifyError):
+        Encoder.from_toml("[subframe_coding.qlpc]\nlpc_order = 25\n").into_verified()
+
+
 def test_error_code_mapping():
     raise_for_code(0)
     with pytest.raises(VerifyError):
