@@ -13,6 +13,13 @@ import test_gpu_parity as T  # noqa: E402
 
 first, count = int(sys.argv[1]), int(sys.argv[2])
 budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
+# "pipe": only the multi-frame generator, every signal repeated five times and the host pipeline cut into chunks of two
+# frames (FB200_CHUNK_FRAMES), so that the chunked H2D / kernels / D2H path with its rotating buffer sets sees every
+# configuration too
+PIPE = len(sys.argv) > 4 and sys.argv[4] == "pipe"
+if PIPE:
+    import os
+    os.environ["FB200_CHUNK_FRAMES"] = "2"
 t0 = time.time()
 done = bad = 0
 kinds = {}
@@ -21,11 +28,14 @@ for seed in range(first, first + count):
         break
     rng = np.random.default_rng(seed)
     try:
-        if seed % 2 == 0:
+        if seed % 2 == 0 and not PIPE:
             x, channels, bps, rate, block, cfg = fuzz_frame_case(rng)
             first_frame = 0
         else:
             x, channels, bps, rate, block, first_frame, cfg = random_case(rng)
+            if PIPE:
+                x = np.concatenate([x, x[::-1], x, -x[::-1] // 2, x[: len(x) // 3]], axis=0)
+                first_frame = min(first_frame, (1 << 31) - 64)
         if seed % 5 == 0 and not cfg.get("use_direct_mse"):
             cfg["ext_lpc_order_search"] = int(rng.integers(0, 9))   # the opt-in extensions, against the oracle's statement
             cfg["ext_lpc_precision_search"] = int(rng.integers(0, min(4, 8 - cfg["ext_lpc_order_search"]) + 1))
