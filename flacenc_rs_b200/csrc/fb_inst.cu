@@ -11,6 +11,8 @@
 
 #if FB_INST_G >= 20
 #define FB_K1_BOUNDS __maxnreg__(168)
+#elif defined(FB_K1_MINB)
+#define FB_K1_BOUNDS __launch_bounds__(FB_K1_THREADS, FB_K1_MINB) // (experiment: more resident CTAs, fewer registers)
 #else
 #define FB_K1_BOUNDS __launch_bounds__(FB_K1_THREADS)
 #endif
