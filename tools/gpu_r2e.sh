@@ -1,3 +1,4 @@
+# one-off (round 2): direct-MSE / IRLS tests, K1C / K1D / K1I timing at 2 min of CD stereo, then the ncu capture r2e
 python -m pytest tests -m gpu -x -q -k "direct_mse or irls" 2>&1 | tail -2
 python - <<'PY'
 import sys, os
