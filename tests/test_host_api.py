@@ -46,6 +46,19 @@ def test_version_and_strerror_need_no_gpu():
     assert b"no CPU fallback" in L.fb200_strerror(3)
 
 
+def test_integration_doc_declares_every_symbol_of_the_header():
+    """INTEGRATION.md's Rust `extern "C"` block (the reference-side binding a maintainer would add) names every entry point
+    include/flacenc_b200.h declares"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "flacenc_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    symbols = sorted(set(re.findall(r"\b(fb200_[a-z0-9_]+)\s*\(", header)))
+    assert len(symbols) >= 20
+    missing = [f for f in symbols if f"pub fn {f}(" not in doc]
+    assert not missing, missing
+
+
 def test_struct_sizes_match_header():
     # sizes computed by hand from include/flacenc_b200.h
     assert C.sizeof(_ffi.Config) == 21 * 4  # 19 fields of config::Encoder + 2 opt-in extensions
